@@ -1,0 +1,140 @@
+/* tpgsr_b200 — C ABI of the B200-native TPGSR hot path (libtpgsr_b200.so).
+ *
+ * Conventions
+ *   - every entry point returns 0 (TPGSR_OK) or a negative error code; none throws, allocates, or synchronises;
+ *   - all tensor pointers are CALLER-OWNED DEVICE memory (torch: tensor.data_ptr()); scalars are passed by value;
+ *   - work is enqueued on the given cudaStream_t, so a whole train step can be captured in a CUDA graph;
+ *   - scratch space is passed in (`workspace`, `workspace_bytes`), sized by the matching *_workspace_bytes() query;
+ *   - activations inside the library are NHWC fp32 ("pixel rows": m = (b*H + h)*W + w, `ld*` = row pitch in floats);
+ *     the module boundary (what the reference's nn.Module callers see) stays NCHW fp32 — see tpgsr_nchw_to_nhwc /
+ *     tpgsr_nhwc_to_nchw and the TPGSR_OUT_NCHW epilogue;
+ *   - parameter layouts are the reference's state_dict layouts (OIHW conv weights, [3H,I]/[4H,I] RNN weights), so
+ *     reference checkpoints load unchanged;
+ *   - parameter-gradient outputs take `accumulate` (0: overwrite, 1: +=) because a shared SR model is used once per
+ *     cascade stage (interfaces/super_resolution.py:306-386).
+ *
+ * Each declaration cites the reference call site (paths relative to the reference repo) whose library kernel it replaces;
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ */
+#ifndef TPGSR_B200_H
+#define TPGSR_B200_H
+
+#include <stddef.h>
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPGSR_OK 0
+#define TPGSR_ERR_BAD_ARG (-1)
+#define TPGSR_ERR_LAUNCH (-2)
+#define TPGSR_ERR_WORKSPACE (-3)
+#define TPGSR_ERR_UNSUPPORTED (-4)
+#define TPGSR_ERR_DRIVER (-5)
+
+#define TPGSR_ACT_NONE 0
+#define TPGSR_ACT_RELU 1
+#define TPGSR_ACT_PRELU 2
+#define TPGSR_ACT_MISH 3
+#define TPGSR_ACT_TANH 4
+
+#define TPGSR_OUT_NHWC 0
+#define TPGSR_OUT_NCHW 1
+
+/* ---- convolution / linear as gather-GEMM (fp32 CUDA cores) ------------------------------------------------------
+ * nn.Conv2d / nn.Linear forward + backward: model/tsrn.py:26-43,376-381,467,495; model/stn_head.py:12-53;
+ * model/crnn/crnn.py:35-67,11,24 (cuDNN / cuBLAS in the reference). */
+int tpgsr_pack_conv_weights(const float* w_oihw, float* wk_fwd, float* wk_dgrad, int Co, int Ci, int KH, int KW,
+                            cudaStream_t stream);
+int tpgsr_conv2d_igemm(const float* x, const float* wk, const float* bias, float* y, int B, int Hi, int Wi, int Ci,
+                       int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int act,
+                       const float* act_param, int out_mode, int accumulate, cudaStream_t stream);
+size_t tpgsr_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW);
+int tpgsr_conv2d_wgrad(const float* x, const float* dy, float* dw_oihw, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
+                       int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int accumulate, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- batch norm, activations, pooling, reshuffles -----------------------------------------------------------------
+ * nn.BatchNorm2d/1d (model/tsrn.py:377,382,38; model/stn_head.py:19,51; model/crnn/crnn.py:48), mish
+ * (model/tsrn.py:480-488), nn.PReLU (model/tsrn.py:28), nn.MaxPool2d (model/stn_head.py:36-44;
+ * model/crnn/crnn.py:56-66), nn.PixelShuffle + mish (model/tsrn.py:464-477), torch.tanh (model/tsrn.py:74). */
+size_t tpgsr_colreduce_workspace_bytes(long M, int C);
+int tpgsr_bn_stats(const float* x, long M, int C, int ldx, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, float* mean_rstd, float* scale_shift, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+int tpgsr_bn_eval_prepare(int C, const float* gamma, const float* beta, const float* running_mean,
+                          const float* running_var, float eps, float* mean_rstd, float* scale_shift, cudaStream_t stream);
+int tpgsr_bn_apply(const float* x, float* y, const float* scale_shift, long M, int C, int ldx, int ldy, int act,
+                   const float* residual, int ldr, cudaStream_t stream);
+size_t tpgsr_bn_bwd_workspace_bytes(long M, int C);
+int tpgsr_bn_bwd(const float* dy, const float* x, float* dx, const float* scale_shift, const float* mean_rstd, long M,
+                 int C, int lddy, int ldx, int lddx, int act, int train, float* dgamma, float* dbeta, int accumulate,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int tpgsr_colsum(const float* x, long M, int C, int ldx, float* out, int accumulate, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
+int tpgsr_act_fwd(const float* x, float* y, long n, int act, const float* slope, cudaStream_t stream);
+size_t tpgsr_act_bwd_workspace_bytes(long n);
+int tpgsr_act_bwd(const float* dy, const float* ref, float* dx, long n, int act, const float* slope, float* dslope,
+                  int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int tpgsr_add(const float* a, const float* b, float* y, long n, cudaStream_t stream);
+int tpgsr_copy_cols(const float* src, int lds, float* dst, int ldd, long M, int C, float alpha, int accumulate,
+                    cudaStream_t stream);
+int tpgsr_add_i64(long long* x, long n, long long v, cudaStream_t stream);
+int tpgsr_maxpool_fwd(const float* x, float* y, int* argmax, int B, int Hi, int Wi, int C, int kh, int kw, int sh,
+                      int sw, int ph, int pw, cudaStream_t stream);
+int tpgsr_maxpool_bwd(const float* dy, const int* argmax, float* dx, int B, int Hi, int Wi, int C, int kh, int kw,
+                      int sh, int sw, int ph, int pw, cudaStream_t stream);
+int tpgsr_pixelshuffle_mish_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
+int tpgsr_pixelshuffle_mish_bwd(const float* dy, const float* x, float* dx, int B, int H, int W, int C,
+                                cudaStream_t stream);
+int tpgsr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, long sb, long sc, long sh, long sw,
+                       int ldd, const float* tanh_out, cudaStream_t stream);
+int tpgsr_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, int lds, cudaStream_t stream);
+
+/* ---- bidirectional GRU recurrence ----------------------------------------------------------------------------------
+ * nn.GRU(64, 32, bidirectional=True, batch_first=True) in GruBlock: model/tsrn.py:491-508 (cuDNN RNN). */
+int tpgsr_gru_fwd(const float* gx, const float* whh, const float* bhh, float* y, int ldy, const float* residual,
+                  int ldr, float* ysum, int ldys, float* stash, int S, int T, int inner, long outer_stride,
+                  long inner_stride, long t_stride, cudaStream_t stream);
+size_t tpgsr_gru_bwd_workspace_bytes(int S);
+int tpgsr_gru_bwd(const float* dy, int lddy, const float* y, int ldy, const float* stash, const float* whh, float* dgx,
+                  float* dwhh, float* dbhh, float* dbih, int accumulate, int S, int T, int inner, long outer_stride,
+                  long inner_stride, long t_stride, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- TPS rectification + bilinear sampler ---------------------------------------------------------------------------
+ * TPSSpatialTransformer.forward + F.grid_sample: model/tps_spatial_transformer.py:10-18,97-112 (2 bmm + ATen gather). */
+int tpgsr_tps_sample_fwd(const float* img, const float* ctrl, const float* inv_kernel, const float* reprT, float* out,
+                         float* src, int B, int H, int W, int C, cudaStream_t stream);
+int tpgsr_tps_sample_bwd(const float* dout, const float* img, const float* src, const float* inv_kernel,
+                         const float* reprT, float* dctrl, int B, int H, int W, int C, int accumulate,
+                         cudaStream_t stream);
+
+/* ---- losses --------------------------------------------------------------------------------------------------------
+ * ImageLoss / GradientPriorLoss: loss/image_loss.py:19-51; SemanticLoss: loss/semantic_loss.py:21-38. */
+size_t tpgsr_loss_workspace_bytes(long n);
+int tpgsr_image_loss_fwd(const float* out, const float* target, int B, int C, int H, int W, int gradient, float w0,
+                         float w1, float out_scale, float* loss, int accumulate, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
+int tpgsr_image_loss_bwd(const float* out, const float* target, const float* upstream, float scale, int B, int C, int H,
+                         int W, int gradient, float w0, float w1, float* dout, int accumulate, cudaStream_t stream);
+int tpgsr_semantic_loss_fwd(const float* pred, const float* gt, long n, float out_scale, float* loss, int accumulate,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int tpgsr_semantic_loss_bwd(const float* pred, const float* gt, long n, const float* upstream, float scale, float* dpred,
+                            int accumulate, cudaStream_t stream);
+
+/* ---- optimiser step --------------------------------------------------------------------------------------------------
+ * clip_grad_norm_(SR params, 0.25) + optim.Adam(lr, (beta1, 0.999)): interfaces/super_resolution.py:419-424,
+ * interfaces/base.py:449-450 (ATen foreach kernels). */
+size_t tpgsr_optim_workspace_bytes(long n);
+int tpgsr_optim_prepare(const float* grads, long n_clipped, float max_norm, float beta1, float beta2, float grad_scale,
+                        float* state, int advance, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int tpgsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, long n_clipped,
+                    const float* state, float lr, float beta1, float beta2, float eps, float grad_scale,
+                    cudaStream_t stream);
+int tpgsr_scale_inplace(float* x, long n, const float* coef, float s, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPGSR_B200_H */

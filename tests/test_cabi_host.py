@@ -1,0 +1,100 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/tpgsr_b200.h declares, the drop-in modules
+expose the reference's state_dict surface, the flat parameter store aliases correctly, and the product never falls
+back to CPU or to the oracle."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KW = dict(scale_factor=2, width=128, height=32, STN=True, mask=True, srb_nums=5, hidden_units=32)
+
+
+def test_library_exports_every_declared_symbol():
+    from tpgsr_b200 import _lib
+    decls = _lib.parse_header()
+    assert len(decls) >= 35
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r'\b(tpgsr_\w+)\b', out))
+    missing = sorted(set(decls) - exported)
+    assert not missing, missing
+    for name in decls:                       # ctypes signatures were attached at import
+        assert getattr(_lib.LIB, name).argtypes is not None
+
+
+def test_workspace_queries_run_without_gpu():
+    from tpgsr_b200 import _lib
+    assert _lib.query('tpgsr_conv2d_wgrad_workspace_bytes', 48, 16, 64, 64, 16, 64, 64, 3, 3) > 0
+    assert _lib.query('tpgsr_colreduce_workspace_bytes', 49152, 64) > 0
+    assert _lib.query('tpgsr_gru_bwd_workspace_bytes', 768) > 0
+
+
+@pytest.mark.parametrize('cls_name,key', [('TSRN', 'tsrn_train'), ('TSRN_TL', 'tsrn_tl_train')])
+def test_state_dict_surface_matches_reference(shapes, cls_name, key):
+    from tpgsr_b200.model import tsrn
+    net = getattr(tsrn, cls_name)(**KW)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(shapes[key].keys())
+    for k, shp in shapes[key].items():
+        assert list(sd[k].shape) == shp, k
+    # reference KAT: STN head initialised to the constant control points (model/stn_head.py:73-90)
+    from oracle.weights import stn_fc2_bias
+    assert torch.allclose(net.stn_head.stn_fc2.bias, stn_fc2_bias(20)) and float(net.stn_head.stn_fc2.weight.abs().sum()) == 0
+    # TPS buffers reproduce the fixture recorded from the reference
+    from conftest import load_golden
+    g = load_golden('tps')
+    for name in ('inverse_kernel', 'target_coordinate_repr', 'target_control_points', 'padding_matrix'):
+        assert torch.allclose(getattr(net.tps, name), torch.from_numpy(g['tps.' + name]), rtol=1e-4, atol=2e-4), name
+    assert torch.equal(net.tps.reprT, net.tps.target_coordinate_repr.t())
+
+
+def test_flat_state_aliases_parameters():
+    from tpgsr_b200.model.tsrn import TSRN
+    net = TSRN(**KW)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    st = net._flat
+    st.ensure()
+    assert st.is_current()
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    total = sum(p.numel() for p in net.parameters())
+    assert st.n == total
+    # every parameter is a view of the flat buffer; fused RNN views cover forward+reverse
+    for name, p in net.named_parameters():
+        off, n = st.offsets[name]
+        assert p.data_ptr() == st.flat.data_ptr() + 4 * off and n == p.numel()
+    wih = st.views['block2.gru1.gru.weight_ih']
+    assert wih.shape == (192, 64)
+    assert torch.equal(wih[:96], net.block2.gru1.gru.weight_ih_l0) and torch.equal(wih[96:], net.block2.gru1.gru.weight_ih_l0_reverse)
+    whh = st.views['block6.gru2.gru.weight_hh']
+    assert whh.shape == (2, 96, 32) and torch.equal(whh[1], net.block6.gru2.gru.weight_hh_l0_reverse)
+    # writes through the flat buffer are visible through the module
+    st.flat.zero_()
+    assert float(net.block1[0].weight.abs().sum()) == 0
+    # load_state_dict keeps the aliasing
+    net.load_state_dict(before)
+    assert st.is_current() and torch.equal(net.block1[0].weight, before['block1.0.weight'])
+
+
+def test_no_cpu_fallback():
+    from tpgsr_b200.loss.image_loss import ImageLoss
+    from tpgsr_b200.model.tsrn import TSRN
+    net = TSRN(**KW)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        net(torch.rand(1, 4, 16, 64))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ImageLoss()(torch.rand(1, 4, 32, 128), torch.rand(1, 4, 32, 128))
+
+
+def test_layout_rules_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'tpgsr_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    assert 'TEST INFRASTRUCTURE' in open(os.path.join(ROOT, 'oracle', '__init__.py')).read()

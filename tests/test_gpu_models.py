@@ -1,0 +1,153 @@
+"""GPU parity tests, module / step level: the drop-in nn.Modules (tpgsr_b200.model.*) through their public
+forward()/backward() against the CPU oracle on identical seeded weights and inputs, and against the golden fixtures
+recorded from the reference's own modules."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_fp_close, fingerprint, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(scale_factor=2, width=128, height=32, STN=True, mask=True, srb_nums=5, hidden_units=32)
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def _load(module, sd):
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all('reprT' in m or m.startswith('tps.') for m in missing), missing
+    return module
+
+
+def _synth(shapes, key, seed, golden=None):
+    from oracle.weights import synth_state_dict
+    sd = synth_state_dict(shapes[key], seed)
+    if golden is not None:
+        for k, v in golden.items():
+            if k.startswith('tps.'):
+                sd[k] = torch.from_numpy(v)
+    return sd
+
+
+def _grad_report(named_params, oracle_grads, tol, skip=()):
+    worst = []
+    for k, p in named_params:
+        if any(s in k for s in skip):
+            continue
+        want = oracle_grads[k]
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        if float(want.norm()) < 2e-3:          # mathematically-zero grads (bias before train-mode BN)
+            assert float(got.norm()) < 5e-2, (k, float(got.norm()))
+            continue
+        worst.append((rel_err(got, want), k))
+    worst.sort(reverse=True)
+    assert worst[0][0] < tol, worst[:8]
+    return worst[0]
+
+
+@pytest.mark.parametrize('smooth', [True, False])
+def test_tsrn_train_forward_backward_vs_oracle(shapes, smooth):
+    from oracle import models, ops as o, step
+    from oracle.weights import synth_images
+    from tpgsr_b200.loss.image_loss import ImageLoss
+    from tpgsr_b200.model.tsrn import TSRN
+    g = load_golden('tsrn_train')
+    sd = _synth(shapes, 'tsrn_train', 1, g)
+    lr, hr = synth_images(3, seed=20 if smooth else 21, smooth=smooth)
+    # oracle
+    p = {k: v.clone() for k, v in sd.items()}
+    leaves = {k: v.requires_grad_(True) for k, v in p.items() if step.is_param(k)}
+    sr_o = models.tsrn(lr, p, True, stn=True)
+    loss_o = o.image_loss(sr_o, hr) * 100
+    loss_o.backward()
+    og = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    # CUDA path through the public nn.Module API
+    net = _load(TSRN(**KW), sd).to(_dev()).train()
+    crit = ImageLoss(gradient=True, loss_weight=[1, 1e-4])
+    sr = net(lr.to(_dev()))
+    loss = crit(sr, hr.to(_dev())).mean() * 100
+    loss.backward()
+    assert sr.shape == (3, 4, 32, 128)
+    assert rel_err(sr, sr_o) < (1e-4 if smooth else 5e-4), rel_err(sr, sr_o)
+    assert abs(float(loss) - float(loss_o)) < 1e-4 * abs(float(loss_o))
+    _grad_report(net.named_parameters(), og, 2e-3 if smooth else 3e-2)
+    for k, b in net.named_buffers():
+        if 'running_' in k:
+            assert rel_err(b, p[k]) < 1e-4, k
+        if k.endswith('num_batches_tracked'):
+            assert int(b) == 1
+    if not smooth:
+        # same inputs as the fixture recorded from the reference modules
+        assert rel_err(sr, g['sr']) < 5e-4
+        assert abs(float(loss) - float(g['loss'])) < 1e-4 * abs(float(g['loss']))
+        for k, q in net.named_parameters():
+            assert_fp_close(fingerprint(q.grad), g['g/' + k], k, rtol=3e-2, atol=1e-3, check_head=False)
+
+
+def test_tsrn_eval_vs_golden(shapes):
+    from tpgsr_b200.model.tsrn import TSRN
+    g = load_golden('tsrn_eval')
+    net = _load(TSRN(**KW), _synth(shapes, 'tsrn_train', 1, g)).to(_dev()).eval()
+    with torch.no_grad():
+        sr = net(torch.from_numpy(g['lr']).to(_dev()))
+    assert rel_err(sr, g['sr']) < 5e-5
+    # PSNR / SSIM of our output vs the reference output agree to 3 dp with reference-vs-itself (inf / 1.0 excluded):
+    from oracle import ops as o
+    hr = torch.from_numpy(g['hr'])
+    assert abs(float(o.calculate_psnr(sr.cpu(), hr)) - float(o.calculate_psnr(torch.from_numpy(g['sr']), hr))) < 5e-4
+    assert abs(float(o.ssim(sr.cpu(), hr)) - float(o.ssim(torch.from_numpy(g['sr']), hr))) < 5e-4
+
+
+def test_tsrn_state_dict_roundtrip_and_grad_accumulation(shapes):
+    from tpgsr_b200.loss.image_loss import ImageLoss
+    from tpgsr_b200.model.tsrn import TSRN
+    from oracle.weights import synth_images
+    sd = _synth(shapes, 'tsrn_train', 1, load_golden('tsrn_train'))
+    net = _load(TSRN(**KW), sd).to(_dev()).train()
+    out = net.state_dict()
+    assert list(out.keys()) == list(shapes['tsrn_train'].keys())
+    for k, v in sd.items():
+        assert torch.equal(out[k].cpu(), v), k
+    lr, hr = synth_images(2, seed=5, smooth=True)
+    crit = ImageLoss()
+    net.zero_grad()
+    (crit(net(lr.to(_dev())), hr.to(_dev())) * 100).backward()
+    g1 = {k: p.grad.clone() for k, p in net.named_parameters()}
+    # a second backward without zero_grad accumulates (running stats differ slightly, so compare loosely)
+    (crit(net(lr.to(_dev())), hr.to(_dev())) * 100).backward()
+    for k, p in net.named_parameters():
+        if float(g1[k].norm()) > 1e-2:
+            assert rel_err(p.grad, 2 * g1[k]) < 1e-3, k
+
+
+def test_tsrn_three_graphed_steps_vs_golden_and_oracle(shapes):
+    """TSRNTrainStep (CUDA-graphed fwd+loss+bwd+clip+Adam) reproduces the reference's 3-step trajectory."""
+    from oracle import step
+    from oracle.weights import synth_images
+    from tpgsr_b200.model.tsrn import TSRN
+    from tpgsr_b200.train import TSRNTrainStep
+    g = load_golden('tsrn_steps')
+    sd = _synth(shapes, 'tsrn_train', 1, load_golden('tsrn_train'))
+    for use_graph in (False, True):
+        net = _load(TSRN(**KW), copy.deepcopy(sd)).to(_dev()).train()
+        ts = TSRNTrainStep(net, batch=4, use_graph=use_graph)
+        for it in range(3):
+            lr, hr = synth_images(4, seed=50 + it)
+            loss = float(ts(lr.to(_dev()), hr.to(_dev())))
+            assert abs(loss - g['losses'][it]) < 3e-4 * g['losses'][it], (use_graph, it, loss, g['losses'][it])
+            gn = ts.opt.grad_norm
+            tol = 2e-3 if it == 0 else 0.25
+            assert abs(gn - g['grad_norms'][it]) < tol * g['grad_norms'][it], (use_graph, it, gn, g['grad_norms'][it])
+        for k, v in net.state_dict().items():
+            if k.startswith('tps.') or 'stn_head.' in k:
+                continue
+            if k.endswith('num_batches_tracked'):
+                assert int(v) == 3, k
+                continue
+            assert_fp_close(fingerprint(v.float()), g['p/' + k], k, rtol=5e-3, atol=7e-3, noise_floor=0.0)

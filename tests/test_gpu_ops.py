@@ -1,0 +1,266 @@
+"""GPU parity tests, op level: every C-ABI kernel family vs the CPU oracle (oracle/ops.py) on seeded inputs.
+Tolerances are fp32 round-off (1e-5 .. 1e-4 relative to the tensor norm) unless stated."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.from_numpy(np.random.RandomState(seed).randn(*shape).astype(np.float32) * scale)
+
+
+@pytest.mark.parametrize('B,Ci,Co,H,W,k,pad', [
+    (2, 64, 64, 16, 64, 3, 1),      # SRB conv
+    (2, 4, 64, 16, 64, 9, 4),       # block1
+    (1, 64, 4, 32, 128, 9, 4),      # final conv (small-N path)
+    (2, 96, 64, 16, 64, 1, 0),      # gru1 1x1 conv (TL)
+    (2, 64, 256, 16, 64, 3, 1),     # upsample conv
+    (3, 1, 64, 32, 100, 3, 1),      # CRNN conv0 (scalar gather path)
+    (3, 512, 512, 2, 27, 2, 0),     # CRNN conv6 (valid 2x2)
+    (5, 36, 40, 1, 1, 1, 0),        # linear with ragged N/K
+    (2, 3, 64, 32, 128, 9, 4),      # SRCNN conv1 (Cin=3)
+])
+def test_conv_fwd_dgrad_wgrad(B, Ci, Co, H, W, k, pad):
+    from tpgsr_b200 import ops
+    x = rnd(B, Ci, H, W, seed=1).requires_grad_(True)
+    w = (rnd(Co, Ci, k, k, seed=2) / np.sqrt(Ci * k * k)).requires_grad_(True)
+    b = rnd(Co, seed=3, scale=0.1).requires_grad_(True)
+    y = F.conv2d(x, w, b, padding=pad)
+    gy = rnd(*y.shape, seed=4)
+    (y * gy).sum().backward()
+    d = _dev()
+    xd, wd_, bd, gyd = nhwc(x.detach()).to(d), w.detach().to(d), b.detach().to(d), nhwc(gy).to(d)
+    wf, wdg = ops.pack_conv_weights(wd_, True)
+    yd = ops.conv_fwd(xd, wf, bd, Co, k, k, pad, pad)
+    assert rel_err(nchw(yd), y) < 2e-5
+    dx = ops.conv_dgrad(gyd, wdg, (H, W), Ci, k, k, pad, pad)
+    assert rel_err(nchw(dx), x.grad) < 2e-5
+    dw = torch.full_like(wd_, 7.0)
+    ops.conv_wgrad(xd, gyd, dw, k, k, pad, pad, False)
+    assert rel_err(dw, w.grad) < 5e-5
+    ops.conv_wgrad(xd, gyd, dw, k, k, pad, pad, True)          # accumulate
+    assert rel_err(dw, 2 * w.grad) < 5e-5
+    db = torch.zeros(Co, device=d)
+    ops.colsum(gyd.view(-1, Co), db, False)
+    assert rel_err(db, b.grad) < 2e-5
+    # NCHW epilogue + fused tanh
+    y2 = ops.conv_fwd(xd, wf, bd, Co, k, k, pad, pad, act=ops.ACT_TANH, out_nchw=True)
+    assert rel_err(y2, torch.tanh(y)) < 2e-5
+
+
+@pytest.mark.parametrize('act', ['none', 'relu', 'mish'])
+@pytest.mark.parametrize('M,C', [(2 * 16 * 64, 64), (5, 512), (777, 32)])
+def test_batchnorm_train_eval(act, M, C):
+    from oracle import ops as o
+    from tpgsr_b200 import ops
+    x = (rnd(M, C, seed=5) * 1.5 + 0.3).requires_grad_(True)
+    g = (1 + 0.1 * rnd(C, seed=6)).requires_grad_(True)
+    b = (0.1 * rnd(C, seed=7)).requires_grad_(True)
+    rm, rv = 0.1 * rnd(C, seed=8), 1 + 0.1 * rnd(C, seed=9).abs()
+    rm_o, rv_o = rm.clone(), rv.clone()
+    res = rnd(M, C, seed=10)
+    f = {'none': lambda t: t, 'relu': torch.relu, 'mish': o.mish}[act]
+    y = f(o.batchnorm(x, g, b, rm_o, rv_o, True)) + res
+    gy = rnd(M, C, seed=11)
+    (y * gy).sum().backward()
+    d = _dev()
+    code = {'none': ops.ACT_NONE, 'relu': ops.ACT_RELU, 'mish': ops.ACT_MISH}[act]
+    xd, gd, bd, rmd, rvd = x.detach().to(d), g.detach().to(d), b.detach().to(d), rm.to(d), rv.to(d)
+    mean_rstd, ss = ops.bn_stats(xd, gd, bd, rmd, rvd)
+    yd = ops.bn_apply(xd, ss, code, res.to(d))
+    assert rel_err(yd, y) < 1e-5
+    assert rel_err(rmd, rm_o) < 1e-5 and rel_err(rvd, rv_o) < 1e-5
+    dg, db = torch.zeros(C, device=d), torch.zeros(C, device=d)
+    dx = ops.bn_bwd(gy.to(d), xd, ss, mean_rstd, code, True, dg, db, False)
+    assert rel_err(dx, x.grad) < 5e-5
+    assert rel_err(dg, g.grad) < 5e-5 and rel_err(db, b.grad) < 5e-5
+    # eval mode
+    ye = f(o.batchnorm(x.detach(), g.detach(), b.detach(), rm_o, rv_o, False))
+    mr, ss_e = ops.bn_eval_prepare(gd, bd, rmd, rvd)
+    assert rel_err(ops.bn_apply(xd, ss_e, code), ye) < 1e-5
+
+
+@pytest.mark.parametrize('vertical', [False, True])
+def test_gru_block_recurrence(vertical):
+    """BiGRU recurrence + BPTT vs the explicit oracle loop, rows (gru2) and columns (gru1, the reference's transpose)."""
+    from oracle import ops as o
+    from tpgsr_b200 import ops
+    B, H, W, Hd = 2, 16, 64, 32
+    r = np.random.RandomState(3)
+    kk = 1 / np.sqrt(Hd)
+    p = {}
+    for suf in ('', '_reverse'):
+        p['weight_ih_l0' + suf] = torch.from_numpy(r.uniform(-kk, kk, (96, 64)).astype(np.float32)).requires_grad_(True)
+        p['weight_hh_l0' + suf] = torch.from_numpy(r.uniform(-kk, kk, (96, 32)).astype(np.float32)).requires_grad_(True)
+        p['bias_ih_l0' + suf] = torch.from_numpy(r.uniform(-kk, kk, 96).astype(np.float32)).requires_grad_(True)
+        p['bias_hh_l0' + suf] = torch.from_numpy(r.uniform(-kk, kk, 96).astype(np.float32)).requires_grad_(True)
+    x = rnd(B, 64, H, W, seed=12).requires_grad_(True)
+    xs = x.transpose(-1, -2) if vertical else x
+    b_, c_, h_, w_ = xs.shape
+    seq = xs.permute(0, 2, 3, 1).reshape(b_ * h_, w_, c_)
+    y = o.bigru(seq, p, '').reshape(b_, h_, w_, 64).permute(0, 3, 1, 2)
+    if vertical:
+        y = y.transpose(-1, -2)
+    gy = rnd(B, 64, H, W, seed=13)
+    (y * gy).sum().backward()
+    d = _dev()
+    xd = nhwc(x.detach()).to(d)
+    wih = torch.cat([p['weight_ih_l0'], p['weight_ih_l0_reverse']], 0).detach().to(d)
+    bih = torch.cat([p['bias_ih_l0'], p['bias_ih_l0_reverse']], 0).detach().to(d)
+    whh = torch.stack([p['weight_hh_l0'], p['weight_hh_l0_reverse']], 0).detach().to(d).contiguous()
+    bhh = torch.stack([p['bias_hh_l0'], p['bias_hh_l0_reverse']], 0).detach().to(d).contiguous()
+    wf, wdg = ops.pack_conv_weights(wih.view(192, 64, 1, 1), True)
+    gx = ops.conv_fwd(xd, wf, bih, 192, 1, 1, 0, 0)
+    res = rnd(B, H, W, 64, seed=14).to(d)
+    yd, ysum, stash = ops.gru_fwd(gx.view(-1, 192), whh, bhh, B, H, W, vertical, residual=res.view(-1, 64))
+    assert rel_err(nchw(yd.view(B, H, W, 64)), y) < 2e-5
+    assert rel_err(ysum, yd + res.view(-1, 64)) < 1e-6
+    dwhh, dbhh, dbih = torch.zeros_like(whh), torch.zeros_like(bhh), torch.zeros(192, device=d)
+    dgx = ops.gru_bwd(nhwc(gy).to(d).view(-1, 64), yd, stash, whh, dwhh, dbhh, dbih, False, B, H, W, vertical)
+    dx = ops.conv_dgrad(dgx.view(B, H, W, 192), wdg, (H, W), 64, 1, 1, 0, 0)
+    assert rel_err(nchw(dx), x.grad) < 5e-5
+    ref_dwhh = torch.stack([p['weight_hh_l0'].grad, p['weight_hh_l0_reverse'].grad], 0)
+    ref_dbhh = torch.stack([p['bias_hh_l0'].grad, p['bias_hh_l0_reverse'].grad], 0)
+    ref_dbih = torch.cat([p['bias_ih_l0'].grad, p['bias_ih_l0_reverse'].grad], 0)
+    assert rel_err(dwhh, ref_dwhh) < 5e-5 and rel_err(dbhh, ref_dbhh) < 5e-5 and rel_err(dbih, ref_dbih) < 5e-5
+    dwih = torch.zeros(192, 64, 1, 1, device=d)
+    ops.conv_wgrad(xd, dgx.view(B, H, W, 192), dwih, 1, 1, 0, 0, False)
+    ref_dwih = torch.cat([p['weight_ih_l0'].grad, p['weight_ih_l0_reverse'].grad], 0)
+    assert rel_err(dwih.view(192, 64), ref_dwih) < 5e-5
+
+
+@pytest.mark.parametrize('k,s,p,shape', [((2, 2), (2, 2), (0, 0), (2, 16, 64, 32)), ((1, 2), (1, 2), (0, 0), (2, 1, 4, 256)),
+                                         ((2, 2), (2, 1), (0, 1), (3, 8, 25, 256))])
+def test_maxpool(k, s, p, shape):
+    from tpgsr_b200 import ops
+    x = rnd(*shape, seed=15)
+    xc = nchw(x).requires_grad_(True)
+    y = F.max_pool2d(xc, k, s, p)
+    gy = rnd(*y.shape, seed=16)
+    (y * gy).sum().backward()
+    d = _dev()
+    yd, arg = ops.maxpool_fwd(x.to(d), k, s, p)
+    assert rel_err(nchw(yd), y) == 0.0
+    dx = ops.maxpool_bwd(nhwc(gy).to(d), arg, tuple(shape), k, s, p)
+    assert rel_err(nchw(dx), xc.grad) < 1e-6
+
+
+def test_pixelshuffle_mish_and_acts():
+    from oracle import ops as o
+    from tpgsr_b200 import ops
+    x = rnd(2, 256, 16, 64, seed=17).requires_grad_(True)
+    y = o.mish(o.pixel_shuffle(x, 2))
+    gy = rnd(*y.shape, seed=18)
+    (y * gy).sum().backward()
+    d = _dev()
+    xd = nhwc(x.detach()).to(d)
+    yd = ops.pixelshuffle_mish_fwd(xd)
+    assert rel_err(nchw(yd), y) < 1e-6
+    dx = ops.pixelshuffle_mish_bwd(nhwc(gy).to(d), xd)
+    assert rel_err(nchw(dx), x.grad) < 1e-5
+    # PReLU fwd/bwd with slope gradient
+    a = torch.tensor([0.25], requires_grad=True)
+    z = rnd(3, 16, 64, 64, seed=19).requires_grad_(True)
+    yz = o.prelu(z, a)
+    gz = rnd(*z.shape, seed=20)
+    (yz * gz).sum().backward()
+    ad = a.detach().to(d)
+    assert rel_err(ops.act_fwd(z.detach().to(d), ops.ACT_PRELU, ad), yz) < 1e-6
+    da = torch.zeros(1, device=d)
+    dz = ops.act_bwd(gz.to(d), z.detach().to(d), ops.ACT_PRELU, ad, da, False)
+    assert rel_err(dz, z.grad) < 1e-6 and rel_err(da, a.grad) < 1e-4
+    # layout round trip on a strided channel-sliced view (callers pass images[:, :3])
+    img = rnd(3, 4, 16, 64, seed=21).to(d)
+    v = img[:, :3]
+    assert torch.equal(ops.nchw_to_nhwc(v), v.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(ops.nchw_to_nhwc(img)), img)
+
+
+def test_tps_sampler_against_golden_and_oracle():
+    from oracle import ops as o
+    from tpgsr_b200 import ops
+    g = load_golden('tps')
+    d = _dev()
+    inv = torch.from_numpy(g['tps.inverse_kernel']).to(d)
+    rep = torch.from_numpy(g['tps.target_coordinate_repr'])
+    reprT = rep.t().contiguous().to(d)
+    img = torch.from_numpy(g['img'])
+    ctrl = torch.from_numpy(g['ctrl'])
+    out, src = ops.tps_sample_fwd(nhwc(img).to(d), ctrl.to(d), inv, reprT)
+    assert rel_err(src, g['src']) < 2e-5
+    assert rel_err(nchw(out), g['out']) < 1e-4
+    dctrl = ops.tps_sample_bwd(nhwc(torch.from_numpy(g['w'])).to(d), nhwc(img).to(d), src, inv, reprT)
+    assert rel_err(dctrl, g['grad_ctrl']) < 2e-3
+    # identity control points reproduce the pixel grid (KAT, SURVEY §4 iv)
+    tcp = torch.from_numpy(g['tps.target_control_points']).expand(3, 20, 2).contiguous()
+    ident, _ = ops.tps_sample_fwd(nhwc(img).to(d), tcp.to(d), inv, reprT)
+    assert rel_err(nchw(ident), g['out_identity']) < 1e-4
+    # smooth image: gradient w.r.t. control points is well conditioned -> tight check against the oracle
+    from oracle.weights import synth_images
+    lr, _ = synth_images(4, seed=2, smooth=True)
+    c2 = (torch.from_numpy(g['ctrl'][:1]).expand(4, 20, 2) * 0.97 + 0.01).clone().requires_grad_(True)
+    buf = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('tps.')}
+    oo, _ = o.tps_forward(lr, c2, buf, 16, 64)
+    w = rnd(*oo.shape, seed=22)
+    (oo * w).sum().backward()
+    out2, src2 = ops.tps_sample_fwd(nhwc(lr).to(d), c2.detach().to(d), inv, reprT)
+    assert rel_err(nchw(out2), oo) < 2e-5
+    dc2 = ops.tps_sample_bwd(nhwc(w).to(d), nhwc(lr).to(d), src2, inv, reprT)
+    assert rel_err(dc2, c2.grad) < 2e-4
+
+
+def test_losses_against_golden():
+    from tpgsr_b200 import ops
+    d = _dev()
+    g = load_golden('image_loss')
+    sr, hr = torch.from_numpy(g['sr']).to(d), torch.from_numpy(g['hr']).to(d)
+    loss = ops.image_loss_fwd(sr, hr, True, 1.0, 1e-4)
+    assert abs(float(loss) - float(g['loss'])) < 2e-6 * abs(float(g['loss']))
+    dsr = ops.image_loss_bwd(sr, hr, True, 1.0, 1e-4)
+    assert rel_err(dsr, g['grad']) < 2e-5
+    assert abs(float(ops.image_loss_fwd(sr, hr, False, 1.0, 1e-4)) - float(g['loss_nograd'])) < 1e-7
+    # x100 scale + accumulate + upstream
+    l2 = ops.image_loss_fwd(sr, hr, True, 1.0, 1e-4, out_scale=100.0, loss=loss, accumulate=True)
+    assert abs(float(l2) - 101 * float(g['loss'])) < 1e-4 * 101 * float(g['loss'])
+    up = torch.tensor([2.0], device=d)
+    assert rel_err(ops.image_loss_bwd(sr, hr, True, 1.0, 1e-4, 100.0, upstream=up), 200 * torch.from_numpy(g['grad'])) < 2e-5
+    s = load_golden('semantic_loss')
+    pr, gt = torch.from_numpy(s['pred']).to(d), torch.from_numpy(s['gt']).to(d)
+    assert abs(float(ops.semantic_loss_fwd(pr, gt)) - float(s['loss'])) < 2e-6
+    assert rel_err(ops.semantic_loss_bwd(pr, gt), s['grad']) < 2e-5
+
+
+def test_clip_and_adam_against_oracle():
+    from oracle import ops as o
+    from tpgsr_b200.optim import FlatAdam
+    d = _dev()
+    n, n_clip = 10007, 6001
+    p = rnd(n, seed=30)
+    opt = FlatAdam(p.clone().to(d), n_clipped=n_clip, lr=1e-3, betas=(0.5, 0.999), max_norm=0.25)
+    p_o, m_o, v_o = p.clone(), torch.zeros(n), torch.zeros(n)
+    for step in range(1, 4):
+        g = rnd(n, seed=30 + step, scale=0.01 * step)
+        opt.grads.copy_(g.to(d))
+        opt.step()
+        g_o = g.clone()
+        norm = o.clip_grad_norm([g_o[:n_clip]], 0.25)
+        o.adam_step(p_o, g_o, m_o, v_o, step)
+        assert abs(float(opt.state[3]) - float(norm)) < 1e-5 * float(norm)
+        assert rel_err(opt.params, p_o) < 1e-6

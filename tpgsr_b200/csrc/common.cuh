@@ -1,0 +1,65 @@
+// Shared device/host helpers for the tpgsr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define TPGSR_OK 0
+#define TPGSR_ERR_BAD_ARG (-1)
+#define TPGSR_ERR_LAUNCH (-2)
+#define TPGSR_ERR_WORKSPACE (-3)
+#define TPGSR_ERR_UNSUPPORTED (-4)
+#define TPGSR_ERR_DRIVER (-5)
+
+// activation codes shared by conv epilogues / BN-apply / act-bwd
+#define TPGSR_ACT_NONE 0
+#define TPGSR_ACT_RELU 1
+#define TPGSR_ACT_PRELU 2   // one shared slope, passed by device pointer
+#define TPGSR_ACT_MISH 3
+#define TPGSR_ACT_TANH 4
+
+// output layout of conv epilogues
+#define TPGSR_OUT_NHWC 0
+#define TPGSR_OUT_NCHW 1
+
+static inline int tpgsr_launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TPGSR_OK : TPGSR_ERR_LAUNCH;
+}
+
+static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float softplus_f(float x) {
+    // F.softplus(beta=1, threshold=20)
+    return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float mish_f(float x) { return x * tanhf(softplus_f(x)); }
+__device__ __forceinline__ float mish_grad_f(float x) {
+    // d/dx [x * tanh(sp(x))] = tanh(sp) + x * (1 - tanh(sp)^2) * sigmoid(x)   (sp' = sigmoid for x<=20, 1 above)
+    float sp = softplus_f(x);
+    float t = tanhf(sp);
+    float sg = x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
+    return t + x * (1.f - t * t) * sg;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    switch (act) {
+        case TPGSR_ACT_RELU: return v > 0.f ? v : 0.f;
+        case TPGSR_ACT_PRELU: return v >= 0.f ? v : slope * v;
+        case TPGSR_ACT_MISH: return mish_f(v);
+        case TPGSR_ACT_TANH: return tanhf(v);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,573 @@
+// Normalisation, activation, pooling and reshuffle kernels on NHWC fp32 tensors (HBM/L2-bound elementwise + column reductions).
+//
+// Reference ops replaced: nn.BatchNorm2d/1d train+eval (model/tsrn.py:377,382,38; model/stn_head.py:19,51;
+// model/crnn/crnn.py:48), mish (model/tsrn.py:480-488), nn.PReLU (model/tsrn.py:28), nn.ReLU, nn.MaxPool2d
+// (model/stn_head.py:36-44, model/crnn/crnn.py:56-66), nn.PixelShuffle(2)+mish (model/tsrn.py:464-477), torch.tanh
+// (model/tsrn.py:74), bias gradients, NCHW<->NHWC boundary transposes.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// generic 2-value column reduction over a [M, C] row-major matrix: partial[rb][v][c]
+// ------------------------------------------------------------------------------------------------
+struct StatsF {   // sum x, sum x^2
+    const float* x; int ld;
+    __device__ float2 operator()(long r, int c) const { float v = x[(size_t)r * ld + c]; return make_float2(v, v * v); }
+};
+struct SumF {     // sum x (bias gradients)
+    const float* x; int ld;
+    __device__ float2 operator()(long r, int c) const { return make_float2(x[(size_t)r * ld + c], 0.f); }
+};
+struct BnBwdF {   // sum dy', sum dy'*xhat with dy' = dy * act'(y_pre)
+    const float* dy; const float* x; const float* scale_shift; const float* mean_rstd; int C, ldx, lddy, act;
+    __device__ float2 operator()(long r, int c) const {
+        float xv = x[(size_t)r * ldx + c];
+        float g = dy[(size_t)r * lddy + c];
+        float yp = xv * scale_shift[c] + scale_shift[C + c];
+        if (act == TPGSR_ACT_RELU) g = yp > 0.f ? g : 0.f;
+        else if (act == TPGSR_ACT_MISH) g *= mish_grad_f(yp);
+        float xh = (xv - mean_rstd[c]) * mean_rstd[C + c];
+        return make_float2(g, g * xh);
+    }
+};
+
+template <class F>
+__global__ void __launch_bounds__(256) col_reduce2_kernel(F f, long M, int C, long rows_per_block, float* __restrict__ partial) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long r0 = (long)blockIdx.y * rows_per_block;
+    long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    float s1 = 0.f, s2 = 0.f;
+    if (c < C)
+        for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+            float2 v = f(r, c);
+            s1 += v.x;
+            s2 += v.y;
+        }
+    __shared__ float sh[2][8][33];
+    sh[0][threadIdx.y][threadIdx.x] = s1;
+    sh[1][threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
+        partial[((size_t)blockIdx.y * 2 + 0) * C + c] = a;
+        partial[((size_t)blockIdx.y * 2 + 1) * C + c] = b;
+    }
+}
+
+inline void reduce_plan(long M, int C, int& row_blocks, long& rows_per_block) {
+    int col_blocks = ceil_div(C, 32);
+    long want = (148L * 4 + col_blocks - 1) / col_blocks;
+    long maxb = (M + 63) / 64;
+    long rb = want < maxb ? want : maxb;
+    if (rb < 1) rb = 1;
+    rows_per_block = (M + rb - 1) / rb;
+    rows_per_block = (rows_per_block + 7) / 8 * 8;
+    row_blocks = (int)((M + rows_per_block - 1) / rows_per_block);
+}
+
+template <class F>
+int launch_col_reduce(F f, long M, int C, float* partial, int& row_blocks, cudaStream_t s) {
+    long rpb;
+    reduce_plan(M, C, row_blocks, rpb);
+    dim3 grid(ceil_div(C, 32), row_blocks), block(32, 8);
+    col_reduce2_kernel<F><<<grid, block, 0, s>>>(f, M, C, rpb, partial);
+    return tpgsr_launch_status();
+}
+
+// BN forward finalize: mean / rstd / folded scale+shift / running stats
+__global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int row_blocks, long M, int C,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* __restrict__ mean_rstd, float* __restrict__ scale_shift,
+                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                       float momentum, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < row_blocks; ++b) {
+        s1 += partial[((size_t)b * 2 + 0) * C + c];
+        s2 += partial[((size_t)b * 2 + 1) * C + c];
+    }
+    double mean = s1 / (double)M;
+    double var = s2 / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mean_rstd[c] = (float)mean;
+    mean_rstd[C + c] = rstd;
+    float sc = gamma[c] * rstd;
+    scale_shift[c] = sc;
+    scale_shift[C + c] = beta[c] - (float)mean * sc;
+    if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// eval mode: fold running stats into scale/shift (mean_rstd also written so the same bwd code could run)
+__global__ void bn_eval_prepare_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                       float eps, float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float rstd = 1.f / sqrtf(running_var[c] + eps);
+    float sc = gamma[c] * rstd;
+    mean_rstd[c] = running_mean[c];
+    mean_rstd[C + c] = rstd;
+    scale_shift[c] = sc;
+    scale_shift[C + c] = beta[c] - running_mean[c] * sc;
+}
+
+// y = act(x*scale + shift) (+ residual)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                        const float* __restrict__ scale_shift, long M, int C, int ldx,
+                                                        int ldy, int act, const float* __restrict__ residual, int ldr) {
+    const int cq = C >> 2;
+    const long total = M * cq;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long r = i / cq;
+        int c = (int)(i - r * cq) * 4;
+        float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
+        float4 sc = *reinterpret_cast<const float4*>(scale_shift + c);
+        float4 sh = *reinterpret_cast<const float4*>(scale_shift + C + c);
+        v.x = apply_act(fmaf(v.x, sc.x, sh.x), act, 0.f);
+        v.y = apply_act(fmaf(v.y, sc.y, sh.y), act, 0.f);
+        v.z = apply_act(fmaf(v.z, sc.z, sh.z), act, 0.f);
+        v.w = apply_act(fmaf(v.w, sc.w, sh.w), act, 0.f);
+        if (residual) {
+            float4 rr = *reinterpret_cast<const float4*>(residual + (size_t)r * ldr + c);
+            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(y + (size_t)r * ldy + c) = v;
+    }
+}
+
+// BN backward finalize: dgamma, dbeta (+)=, and per-channel coefficients for the apply pass
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int row_blocks, long M, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
+                                       int accumulate) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < row_blocks; ++b) {
+        s1 += partial[((size_t)b * 2 + 0) * C + c];
+        s2 += partial[((size_t)b * 2 + 1) * C + c];
+    }
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s1 : (float)s1;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)s2 : (float)s2;
+    coef[c] = (float)(s1 / (double)M);
+    coef[C + c] = (float)(s2 / (double)M);
+}
+
+// dx = scale * (dy' - mean(dy') - xhat * mean(dy'*xhat))
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            float* __restrict__ dx, const float* __restrict__ scale_shift,
+                                                            const float* __restrict__ mean_rstd, const float* __restrict__ coef,
+                                                            long M, int C, int lddy, int ldx, int lddx, int act, int train) {
+    const long total = M * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long r = i / C;
+        int c = (int)(i - r * C);
+        float xv = x[(size_t)r * ldx + c];
+        float g = dy[(size_t)r * lddy + c];
+        float sc = scale_shift[c];
+        float yp = fmaf(xv, sc, scale_shift[C + c]);
+        if (act == TPGSR_ACT_RELU) g = yp > 0.f ? g : 0.f;
+        else if (act == TPGSR_ACT_MISH) g *= mish_grad_f(yp);
+        float out;
+        if (train) {
+            float xh = (xv - mean_rstd[c]) * mean_rstd[C + c];
+            out = sc * (g - coef[c] - xh * coef[C + c]);
+        } else {
+            out = sc * g;
+        }
+        dx[(size_t)r * lddx + c] = out;
+    }
+}
+
+// column sums finalize (bias grads)
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int row_blocks, int C, float* __restrict__ out,
+                                       int accumulate) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int b = 0; b < row_blocks; ++b) s += partial[((size_t)b * 2) * C + c];
+    out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise activations
+// ------------------------------------------------------------------------------------------------
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n, int act,
+                               const float* __restrict__ slope_p) {
+    float slope = slope_p ? __ldg(slope_p) : 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = apply_act(x[i], act, slope);
+}
+
+// dx = dy * act'(.)  — `ref` is the pre-activation for PRELU/MISH, the OUTPUT for RELU/TANH.
+// For PRELU also accumulates d(slope) = sum dy * x * [x<0] into partial[blockIdx.x].
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ ref,
+                                                       float* __restrict__ dx, long n, int act,
+                                                       const float* __restrict__ slope_p, float* __restrict__ partial) {
+    float slope = slope_p ? __ldg(slope_p) : 0.f;
+    float ds = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        float g = dy[i], r = ref[i], o;
+        switch (act) {
+            case TPGSR_ACT_RELU: o = r > 0.f ? g : 0.f; break;
+            case TPGSR_ACT_TANH: o = g * (1.f - r * r); break;
+            case TPGSR_ACT_MISH: o = g * mish_grad_f(r); break;
+            case TPGSR_ACT_PRELU: o = r >= 0.f ? g : slope * g; if (r < 0.f) ds += g * r; break;
+            default: o = g;
+        }
+        dx[i] = o;
+    }
+    if (partial) {
+        __shared__ float sh[8];
+        ds = warp_sum(ds);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ds;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+            partial[blockIdx.x] = s;
+        }
+    }
+}
+
+__global__ void scalar_finalize_kernel(const float* __restrict__ partial, int n, float* __restrict__ out, int accumulate) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += partial[i];
+        out[0] = accumulate ? out[0] + (float)s : (float)s;
+    }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = a[i] + b[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool (NHWC), argmax stored as the flattened input pixel index within the image (h*W + w)
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int* __restrict__ arg, int B,
+                                   int Hi, int Wi, int C, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw) {
+    const long total = (long)B * Ho * Wo * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long p = i / C;
+        int wo = (int)(p % Wo);
+        long q = p / Wo;
+        int ho = (int)(q % Ho);
+        int b = (int)(q / Ho);
+        float best = -INFINITY;
+        int bi = -1;
+        for (int a = 0; a < kh; ++a) {
+            int h = ho * sh - ph + a;
+            if ((unsigned)h >= (unsigned)Hi) continue;
+            for (int d = 0; d < kw; ++d) {
+                int w = wo * sw - pw + d;
+                if ((unsigned)w >= (unsigned)Wi) continue;
+                float v = x[((size_t)(b * Hi + h) * Wi + w) * C + c];
+                if (v > best || bi < 0) { best = v; bi = h * Wi + w; }   // first max wins, like ATen
+            }
+        }
+        y[i] = best;
+        if (arg) arg[i] = bi;
+    }
+}
+
+// gather formulation (deterministic): every input pixel sums the gradients of the windows that selected it
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const int* __restrict__ arg, float* __restrict__ dx,
+                                   int B, int Hi, int Wi, int C, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph,
+                                   int pw) {
+    const long total = (long)B * Hi * Wi * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long p = i / C;
+        int w = (int)(p % Wi);
+        long q = p / Wi;
+        int h = (int)(q % Hi);
+        int b = (int)(q / Hi);
+        int me = h * Wi + w;
+        float s = 0.f;
+        int ho_lo = (h + ph - kh + sh) / sh;  if (h + ph - kh + 1 <= 0) ho_lo = 0;
+        int wo_lo = (w + pw - kw + sw) / sw;  if (w + pw - kw + 1 <= 0) wo_lo = 0;
+        int ho_hi = (h + ph) / sh, wo_hi = (w + pw) / sw;
+        if (ho_hi > Ho - 1) ho_hi = Ho - 1;
+        if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+        for (int ho = ho_lo; ho <= ho_hi; ++ho)
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                size_t o = ((size_t)(b * Ho + ho) * Wo + wo) * C + c;
+                if (arg[o] == me) s += dy[o];
+            }
+        dx[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PixelShuffle(2) + mish on NHWC: x [B,H,W,4C] -> y [B,2H,2W,C];  y[b,2h+i,2w+j,c] = mish(x[b,h,w,4c+2i+j])
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pixelshuffle_mish_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                      int B, int H, int W, int C) {
+    // one thread per (input pixel, output channel c): reads a float4 (the 2x2 sub-pixels of channel c), writes 4 scalars
+    const long total = (long)B * H * W * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long p = i / C;
+        int w = (int)(p % W);
+        long q = p / W;
+        int h = (int)(q % H);
+        int b = (int)(q / H);
+        float4 v = *reinterpret_cast<const float4*>(x + (size_t)p * 4 * C + 4 * c);
+        size_t o = (((size_t)b * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
+        y[o] = mish_f(v.x);
+        y[o + C] = mish_f(v.y);
+        y[o + (size_t)2 * W * C] = mish_f(v.z);
+        y[o + (size_t)2 * W * C + C] = mish_f(v.w);
+    }
+}
+
+__global__ void __launch_bounds__(256) pixelshuffle_mish_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                      float* __restrict__ dx, int B, int H, int W, int C) {
+    const long total = (long)B * H * W * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long p = i / C;
+        int w = (int)(p % W);
+        long q = p / W;
+        int h = (int)(q % H);
+        int b = (int)(q / H);
+        float4 v = *reinterpret_cast<const float4*>(x + (size_t)p * 4 * C + 4 * c);
+        size_t o = (((size_t)b * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
+        float4 g;
+        g.x = dy[o] * mish_grad_f(v.x);
+        g.y = dy[o + C] * mish_grad_f(v.y);
+        g.z = dy[o + (size_t)2 * W * C] * mish_grad_f(v.z);
+        g.w = dy[o + (size_t)2 * W * C + C] * mish_grad_f(v.w);
+        *reinterpret_cast<float4*>(dx + (size_t)p * 4 * C + 4 * c) = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary transposes (strided NCHW view <-> dense NHWC), optional tanh-backward fused into the NCHW->NHWC direction
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W,
+                                    long sb, long sc, long sh, long sw, int ldd, const float* __restrict__ tanh_out) {
+    const long total = (long)B * H * W * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long p = i / C;
+        int w = (int)(p % W);
+        long q = p / W;
+        int h = (int)(q % H);
+        int b = (int)(q / H);
+        size_t so = (size_t)(b * sb + c * sc + h * sh + w * sw);
+        float v = src[so];
+        if (tanh_out) { float t = tanh_out[so]; v *= (1.f - t * t); }
+        dst[(size_t)p * ldd + c] = v;
+    }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W, int lds) {
+    const long total = (long)B * C * H * W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int w = (int)(i % W);
+        long q = i / W;
+        int h = (int)(q % H);
+        long r = q / H;
+        int c = (int)(r % C);
+        int b = (int)(r / C);
+        dst[i] = src[((size_t)(b * H + h) * W + w) * lds + c];
+    }
+}
+
+// dst[m, c] = (accumulate ? dst : 0) + alpha * src[m, c] for a [M, C] window of two pitched matrices
+__global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, long M, int C,
+                                 float alpha, int accumulate) {
+    const long total = M * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long r = i / C;
+        int c = (int)(i - r * C);
+        float v = alpha * src[(size_t)r * lds + c];
+        float* d = dst + (size_t)r * ldd + c;
+        *d = accumulate ? *d + v : v;
+    }
+}
+
+__global__ void add_i64_kernel(long long* __restrict__ x, long n, long long v) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] += v;
+}
+
+inline int ew_grid(long n) {
+    long b = (n + 255) / 256;
+    return (int)(b > 148L * 16 ? 148L * 16 : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tpgsr_colreduce_workspace_bytes(long M, int C) {
+    int rb; long rpb;
+    reduce_plan(M, C, rb, rpb);
+    return (size_t)rb * 2 * C * sizeof(float);
+}
+
+// Training-mode BN statistics of x[M,C] (+ running-stat update) -> mean_rstd[2C], scale_shift[2C]
+int tpgsr_bn_stats(const float* x, long M, int C, int ldx, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, float* mean_rstd, float* scale_shift, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream) {
+    if (!x || !gamma || !beta || !mean_rstd || !scale_shift || !workspace || M <= 0 || C <= 0) return TPGSR_ERR_BAD_ARG;
+    if (workspace_bytes < tpgsr_colreduce_workspace_bytes(M, C)) return TPGSR_ERR_WORKSPACE;
+    int rb;
+    int rc = launch_col_reduce(StatsF{x, ldx > 0 ? ldx : C}, M, C, static_cast<float*>(workspace), rb, stream);
+    if (rc) return rc;
+    bn_fwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(static_cast<float*>(workspace), rb, M, C, gamma, beta,
+                                                                 mean_rstd, scale_shift, running_mean, running_var, momentum, eps);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_bn_eval_prepare(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                          float eps, float* mean_rstd, float* scale_shift, cudaStream_t stream) {
+    if (!gamma || !beta || !running_mean || !running_var || !mean_rstd || !scale_shift) return TPGSR_ERR_BAD_ARG;
+    bn_eval_prepare_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(C, gamma, beta, running_mean, running_var, eps, mean_rstd, scale_shift);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_bn_apply(const float* x, float* y, const float* scale_shift, long M, int C, int ldx, int ldy, int act,
+                   const float* residual, int ldr, cudaStream_t stream) {
+    if (!x || !y || !scale_shift || (C & 3)) return TPGSR_ERR_BAD_ARG;
+    ldx = ldx > 0 ? ldx : C; ldy = ldy > 0 ? ldy : C; ldr = ldr > 0 ? ldr : C;
+    if ((ldx & 3) || (ldy & 3) || (ldr & 3)) return TPGSR_ERR_BAD_ARG;
+    bn_apply_kernel<<<ew_grid(M * (C / 4)), 256, 0, stream>>>(x, y, scale_shift, M, C, ldx, ldy, act, residual, ldr);
+    return tpgsr_launch_status();
+}
+
+// BN backward (train: full formula; eval: dx = scale*dy').  act' of the fused activation is applied to dy first.
+int tpgsr_bn_bwd(const float* dy, const float* x, float* dx, const float* scale_shift, const float* mean_rstd, long M, int C,
+                 int lddy, int ldx, int lddx, int act, int train, float* dgamma, float* dbeta, int accumulate,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!dy || !x || !dx || !scale_shift || !mean_rstd || !workspace) return TPGSR_ERR_BAD_ARG;
+    lddy = lddy > 0 ? lddy : C; ldx = ldx > 0 ? ldx : C; lddx = lddx > 0 ? lddx : C;
+    size_t need = tpgsr_colreduce_workspace_bytes(M, C) + 2 * (size_t)C * sizeof(float);
+    if (workspace_bytes < need) return TPGSR_ERR_WORKSPACE;
+    float* partial = static_cast<float*>(workspace);
+    float* coef = partial + tpgsr_colreduce_workspace_bytes(M, C) / sizeof(float);
+    int rb;
+    int rc = launch_col_reduce(BnBwdF{dy, x, scale_shift, mean_rstd, C, ldx, lddy, act}, M, C, partial, rb, stream);
+    if (rc) return rc;
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(partial, rb, M, C, dgamma, dbeta, coef, accumulate);
+    rc = tpgsr_launch_status();
+    if (rc) return rc;
+    bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, stream>>>(dy, x, dx, scale_shift, mean_rstd, coef, M, C, lddy, ldx, lddx, act, train);
+    return tpgsr_launch_status();
+}
+
+size_t tpgsr_bn_bwd_workspace_bytes(long M, int C) { return tpgsr_colreduce_workspace_bytes(M, C) + 2 * (size_t)C * sizeof(float); }
+
+// out[C] (+)= column sums of x[M,C]  (bias gradients)
+int tpgsr_colsum(const float* x, long M, int C, int ldx, float* out, int accumulate, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+    if (!x || !out || !workspace) return TPGSR_ERR_BAD_ARG;
+    if (workspace_bytes < tpgsr_colreduce_workspace_bytes(M, C)) return TPGSR_ERR_WORKSPACE;
+    int rb;
+    int rc = launch_col_reduce(SumF{x, ldx > 0 ? ldx : C}, M, C, static_cast<float*>(workspace), rb, stream);
+    if (rc) return rc;
+    colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(static_cast<float*>(workspace), rb, C, out, accumulate);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_act_fwd(const float* x, float* y, long n, int act, const float* slope, cudaStream_t stream) {
+    if (!x || !y) return TPGSR_ERR_BAD_ARG;
+    act_fwd_kernel<<<ew_grid(n), 256, 0, stream>>>(x, y, n, act, slope);
+    return tpgsr_launch_status();
+}
+
+size_t tpgsr_act_bwd_workspace_bytes(long n) { return (size_t)ew_grid(n) * sizeof(float); }
+
+// dx = dy*act'(ref); for PRELU also dslope (+)= sum(dy*x*[x<0]) (needs workspace)
+int tpgsr_act_bwd(const float* dy, const float* ref, float* dx, long n, int act, const float* slope, float* dslope,
+                  int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!dy || !ref || !dx) return TPGSR_ERR_BAD_ARG;
+    int grid = ew_grid(n);
+    float* partial = nullptr;
+    if (act == TPGSR_ACT_PRELU && dslope) {
+        if (!workspace || workspace_bytes < (size_t)grid * sizeof(float)) return TPGSR_ERR_WORKSPACE;
+        partial = static_cast<float*>(workspace);
+    }
+    act_bwd_kernel<<<grid, 256, 0, stream>>>(dy, ref, dx, n, act, slope, partial);
+    int rc = tpgsr_launch_status();
+    if (rc || !partial) return rc;
+    scalar_finalize_kernel<<<1, 32, 0, stream>>>(partial, grid, dslope, accumulate);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_add(const float* a, const float* b, float* y, long n, cudaStream_t stream) {
+    if (!a || !b || !y) return TPGSR_ERR_BAD_ARG;
+    add_kernel<<<ew_grid(n), 256, 0, stream>>>(a, b, y, n);
+    return tpgsr_launch_status();
+}
+
+// dst window (+)= alpha * src window (pitched [M,C] matrices): concat / slice / scale / residual accumulation
+int tpgsr_copy_cols(const float* src, int lds, float* dst, int ldd, long M, int C, float alpha, int accumulate,
+                    cudaStream_t stream) {
+    if (!src || !dst || M <= 0 || C <= 0) return TPGSR_ERR_BAD_ARG;
+    copy_cols_kernel<<<ew_grid(M * C), 256, 0, stream>>>(src, lds, dst, ldd, M, C, alpha, accumulate);
+    return tpgsr_launch_status();
+}
+
+// x[i] += v on an int64 buffer (BatchNorm num_batches_tracked counters kept in one flat buffer)
+int tpgsr_add_i64(long long* x, long n, long long v, cudaStream_t stream) {
+    if (!x || n <= 0) return TPGSR_ERR_BAD_ARG;
+    add_i64_kernel<<<ew_grid(n), 256, 0, stream>>>(x, n, v);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_maxpool_fwd(const float* x, float* y, int* argmax, int B, int Hi, int Wi, int C, int kh, int kw, int sh, int sw,
+                      int ph, int pw, cudaStream_t stream) {
+    if (!x || !y) return TPGSR_ERR_BAD_ARG;
+    int Ho = (Hi + 2 * ph - kh) / sh + 1, Wo = (Wi + 2 * pw - kw) / sw + 1;
+    maxpool_fwd_kernel<<<ew_grid((long)B * Ho * Wo * C), 256, 0, stream>>>(x, y, argmax, B, Hi, Wi, C, Ho, Wo, kh, kw, sh, sw, ph, pw);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_maxpool_bwd(const float* dy, const int* argmax, float* dx, int B, int Hi, int Wi, int C, int kh, int kw, int sh,
+                      int sw, int ph, int pw, cudaStream_t stream) {
+    if (!dy || !argmax || !dx) return TPGSR_ERR_BAD_ARG;
+    int Ho = (Hi + 2 * ph - kh) / sh + 1, Wo = (Wi + 2 * pw - kw) / sw + 1;
+    maxpool_bwd_kernel<<<ew_grid((long)B * Hi * Wi * C), 256, 0, stream>>>(dy, argmax, dx, B, Hi, Wi, C, Ho, Wo, kh, kw, sh, sw, ph, pw);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_pixelshuffle_mish_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream) {
+    if (!x || !y) return TPGSR_ERR_BAD_ARG;
+    pixelshuffle_mish_fwd_kernel<<<ew_grid((long)B * H * W * C), 256, 0, stream>>>(x, y, B, H, W, C);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_pixelshuffle_mish_bwd(const float* dy, const float* x, float* dx, int B, int H, int W, int C, cudaStream_t stream) {
+    if (!dy || !x || !dx) return TPGSR_ERR_BAD_ARG;
+    pixelshuffle_mish_bwd_kernel<<<ew_grid((long)B * H * W * C), 256, 0, stream>>>(dy, x, dx, B, H, W, C);
+    return tpgsr_launch_status();
+}
+
+// strided NCHW view -> dense NHWC (pitch ldd); if tanh_out != NULL, multiplies by (1 - tanh_out^2) (same strides as src)
+int tpgsr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, long sb, long sc, long sh, long sw, int ldd,
+                       const float* tanh_out, cudaStream_t stream) {
+    if (!src || !dst) return TPGSR_ERR_BAD_ARG;
+    nchw_to_nhwc_kernel<<<ew_grid((long)B * C * H * W), 256, 0, stream>>>(src, dst, B, C, H, W, sb, sc, sh, sw, ldd > 0 ? ldd : C, tanh_out);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, int lds, cudaStream_t stream) {
+    if (!src || !dst) return TPGSR_ERR_BAD_ARG;
+    nhwc_to_nchw_kernel<<<ew_grid((long)B * C * H * W), 256, 0, stream>>>(src, dst, B, C, H, W, lds > 0 ? lds : C);
+    return tpgsr_launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+"""Hand-sequenced forward/backward of the TPGSR building blocks on top of the C ABI (no autograd inside).
+
+Every block is a pair ``*_fwd(ctx, ...) -> (out, saved)`` / ``*_bwd(ctx, saved, dout) -> din`` that enqueues kernels on the
+current stream.  ``Ctx`` resolves reference-named parameters (``state_dict`` keys) to device tensors, hands out gradient
+buffers (views of one flat buffer) and caches the packed weights for the lifetime of one forward(+backward).
+
+Layout: activations are NHWC fp32 tensors [B,H,W,C]; ``x.view(-1, C)`` is the [M,C] pixel-row matrix the kernels see.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_MISH, ACT_NONE, ACT_PRELU, ACT_RELU, ACT_TANH
+
+Tensor = torch.Tensor
+
+
+class Ctx:
+    """Parameter / gradient resolver for one forward(+backward) pass of one module."""
+
+    def __init__(self, params: Dict[str, Tensor], grads: Optional[Dict[str, Tensor]], training: bool,
+                 need_input_grad: bool = False):
+        self.params = params          # name -> tensor (parameters and buffers, reference state_dict names + fused views)
+        self.grads = grads            # name -> tensor (same names as params) or None when no backward is wanted
+        self.training = training
+        self.need_input_grad = need_input_grad
+        self._packed: Dict[str, tuple] = {}
+        self._written = set()
+
+    def P(self, name: str) -> Tensor:
+        return self.params[name]
+
+    def G(self, name: str):
+        """(grad tensor, accumulate?) — first write in a backward overwrites, later writes accumulate."""
+        acc = name in self._written or getattr(self, 'always_accumulate', False)
+        self._written.add(name)
+        return self.grads[name], acc
+
+    def packed(self, name: str, need_dgrad: bool = True, as4d=None):
+        key = name
+        hit = self._packed.get(key)
+        if hit is None or (need_dgrad and hit[1] is None):
+            w = self.params[name]
+            if as4d is not None:
+                w = w.view(*as4d)
+            elif w.dim() == 2:
+                w = w.view(w.shape[0], w.shape[1], 1, 1)
+            hit = ops.pack_conv_weights(w, need_dgrad)
+            self._packed[key] = hit
+        return hit
+
+
+# ------------------------------------------------------------------------------------------------------------ conv
+def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=ACT_NONE, act_param: Optional[Tensor] = None,
+             out_nchw: bool = False, need_dgrad: bool = True, as4d=None, ldx: int = 0, out: Optional[Tensor] = None):
+    w = ctx.P(wname)
+    Co = w.shape[0]
+    kh, kw = k if isinstance(k, tuple) else (k, k)
+    ph, pw = pad if isinstance(pad, tuple) else (pad, pad)
+    wf, _ = ctx.packed(wname, need_dgrad and ctx.grads is not None, as4d)
+    y = ops.conv_fwd(x, wf, ctx.P(bname) if bname else None, Co, kh, kw, ph, pw, act, act_param, out_nchw, out=out, ldx=ldx)
+    saved = (x, wname, bname, kh, kw, ph, pw, as4d, ldx)
+    return y, saved
+
+
+def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional[Tensor] = None, dx_accumulate: bool = False):
+    """dy: NHWC gradient w.r.t. the conv's pre-activation output."""
+    x, wname, bname, kh, kw, ph, pw, as4d, ldx = saved
+    w = ctx.P(wname)
+    Co = w.shape[0]
+    Ci = (w.numel() // Co) // (kh * kw)
+    gw, acc = ctx.G(wname)
+    ops.conv_wgrad(x, dy, gw, kh, kw, ph, pw, acc, ldx=ldx, Ci=Ci)
+    if bname:
+        gb, accb = ctx.G(bname)
+        ops.colsum(dy.view(-1, Co), gb, accb)
+    if not need_dx:
+        return None
+    _, wd = ctx.packed(wname, True, as4d)
+    return ops.conv_dgrad(dy, wd, (x.shape[1], x.shape[2]), Ci, kh, kw, ph, pw, out=dx_out, accumulate=dx_accumulate)
+
+
+# ------------------------------------------------------------------------------------------------------------ batch norm
+def bn_fwd(ctx: Ctx, x: Tensor, pre: str, act=ACT_NONE, residual: Optional[Tensor] = None, out: Optional[Tensor] = None,
+           ldy: int = 0):
+    """x [...,C] -> act(BN(x)) (+ residual).  Training: batch stats + running-stat update; eval: running stats."""
+    C = x.shape[-1]
+    x2 = x.view(-1, C)
+    if ctx.training:
+        mean_rstd, ss = ops.bn_stats(x2, ctx.P(pre + 'weight'), ctx.P(pre + 'bias'), ctx.P(pre + 'running_mean'),
+                                     ctx.P(pre + 'running_var'))
+    else:
+        mean_rstd, ss = ops.bn_eval_prepare(ctx.P(pre + 'weight'), ctx.P(pre + 'bias'), ctx.P(pre + 'running_mean'),
+                                            ctx.P(pre + 'running_var'))
+    y = ops.bn_apply(x2, ss, act, residual.view(-1, C) if residual is not None else None,
+                     out=out.view(-1, out.shape[-1]) if out is not None else None, ldy=ldy)
+    if out is None:
+        y = y.view(x.shape)
+    else:
+        y = out
+    return y, (x, pre, act, mean_rstd, ss, ctx.training)
+
+
+def bn_bwd(ctx: Ctx, saved, dy: Tensor, lddy: int = 0) -> Tensor:
+    x, pre, act, mean_rstd, ss, train = saved
+    C = x.shape[-1]
+    gg, acc = ctx.G(pre + 'weight')
+    gb, _ = ctx.G(pre + 'bias')
+    dx = ops.bn_bwd(dy.view(-1, dy.shape[-1]) if lddy == 0 else dy, x.view(-1, C), ss, mean_rstd, act, train, gg, gb, acc, lddy=lddy)
+    return dx.view(x.shape)
+
+
+# ------------------------------------------------------------------------------------------------------------ GruBlock
+def gru_block_fwd(ctx: Ctx, x: Tensor, pre: str, vertical: bool, residual: Optional[Tensor] = None, ldx: int = 0):
+    """GruBlock (model/tsrn.py:491-508): 1x1 conv -> BiGRU along W (or along H when ``vertical``: the reference's
+    transpose trick).  Returns (y or y+residual) as [B,H,W,64]."""
+    B, H, W, _ = x.shape
+    y1, s_conv = conv_fwd(ctx, x, pre + 'conv1.weight', pre + 'conv1.bias', 1, 0, ldx=ldx)
+    gx, s_ih = conv_fwd(ctx, y1, pre + 'gru.weight_ih', pre + 'gru.bias_ih', 1, 0)
+    whh, bhh = ctx.P(pre + 'gru.weight_hh'), ctx.P(pre + 'gru.bias_hh')
+    y, ysum, stash = ops.gru_fwd(gx.view(-1, 192), whh, bhh, B, H, W, vertical,
+                                 residual.view(-1, 64) if residual is not None else None, need_stash=ctx.grads is not None)
+    out = (ysum if residual is not None else y).view(B, H, W, 64)
+    return out, (s_conv, s_ih, y, stash, pre, vertical, (B, H, W))
+
+
+def gru_block_bwd(ctx: Ctx, saved, dout: Tensor, need_dx: bool = True, dx_out: Optional[Tensor] = None,
+                  dx_accumulate: bool = False):
+    s_conv, s_ih, y, stash, pre, vertical, (B, H, W) = saved
+    whh = ctx.P(pre + 'gru.weight_hh')
+    gwhh, acc = ctx.G(pre + 'gru.weight_hh')
+    gbhh, _ = ctx.G(pre + 'gru.bias_hh')
+    gbih, _ = ctx.G(pre + 'gru.bias_ih')
+    dgx = ops.gru_bwd(dout.view(-1, 64), y, stash, whh, gwhh, gbhh, gbih, acc, B, H, W, vertical).view(B, H, W, 192)
+    # input projection (bias grad already produced by the recurrence kernel)
+    x_ih, wname, _, kh, kw, ph, pw, as4d, ldx = s_ih
+    dy1 = conv_bwd(ctx, (x_ih, wname, None, kh, kw, ph, pw, as4d, ldx), dgx)
+    return conv_bwd(ctx, s_conv, dy1, need_dx, dx_out, dx_accumulate)
+
+
+# ------------------------------------------------------------------------------------------------------------ SRB
+def srb_fwd(ctx: Ctx, x: Tensor, pre: str, text: Optional[Tensor] = None):
+    """RecurrentResidualBlock / RecurrentResidualBlockTL (model/tsrn.py:373-426)."""
+    B, H, W, C = x.shape
+    c1, s_c1 = conv_fwd(ctx, x, pre + 'conv1.weight', pre + 'conv1.bias', 3, 1)
+    a1, s_bn1 = bn_fwd(ctx, c1, pre + 'bn1.', ACT_MISH)
+    c2, s_c2 = conv_fwd(ctx, a1, pre + 'conv2.weight', pre + 'conv2.bias', 3, 1)
+    if text is None:
+        r2, s_bn2 = bn_fwd(ctx, c2, pre + 'bn2.')
+        cat = r2
+    else:
+        Ct = text.shape[-1]
+        cat = ops.new((B, H, W, C + Ct), x)
+        _, s_bn2 = bn_fwd(ctx, c2, pre + 'bn2.', out=cat, ldy=C + Ct)
+        ops.copy_cols(text, Ct, cat, C + Ct, B * H * W, Ct, dst_off=C)
+    r1sum, s_g1 = gru_block_fwd(ctx, cat, pre + 'gru1.', True, residual=x)     # x + gru1(...)
+    out, s_g2 = gru_block_fwd(ctx, r1sum, pre + 'gru2.', False)
+    return out, (s_c1, s_bn1, s_c2, s_bn2, s_g1, s_g2, text is not None, (B, H, W, C))
+
+
+def srb_bwd(ctx: Ctx, saved, dout: Tensor, dtext: Optional[Tensor] = None):
+    s_c1, s_bn1, s_c2, s_bn2, s_g1, s_g2, has_text, (B, H, W, C) = saved
+    dsum = gru_block_bwd(ctx, s_g2, dout)                       # d(x + r1)
+    dcat = gru_block_bwd(ctx, s_g1, dsum)                       # [B,H,W,64(+Ct)]
+    if has_text:
+        Ctot = dcat.shape[-1]
+        Ct = Ctot - C
+        ops.copy_cols(dcat, Ctot, dtext, Ct, B * H * W, Ct, accumulate=True, src_off=C)
+        dc2 = bn_bwd(ctx, s_bn2, dcat.view(-1, Ctot), lddy=Ctot)
+    else:
+        dc2 = bn_bwd(ctx, s_bn2, dcat)
+    da1 = conv_bwd(ctx, s_c2, dc2)
+    dc1 = bn_bwd(ctx, s_bn1, da1)
+    # dx = dgrad(conv1) + dsum : accumulate into the dsum buffer
+    return conv_bwd(ctx, s_c1, dc1, True, dx_out=dsum, dx_accumulate=True)
+
+
+# ------------------------------------------------------------------------------------------------------------ STN head
+_STN_POOLS = {0: (2, 2), 2: (2, 2), 4: (2, 2), 6: (2, 2), 8: (1, 2)}
+
+
+def stn_head_fwd(ctx: Ctx, x: Tensor, pre: str = 'stn_head.'):
+    """STNHead.forward (model/stn_head.py:92-106).  x NHWC [B,16,64,4] -> (img_feat [B,512], ctrl [B,20,2])."""
+    saved = []
+    need_dgrad_first = False
+    for i in (0, 2, 4, 6, 8, 10):
+        q = f'{pre}stn_convnet.{i}.'
+        c, s_c = conv_fwd(ctx, x, q + '0.weight', q + '0.bias', 3, 1, need_dgrad=(i != 0) or need_dgrad_first)
+        a, s_bn = bn_fwd(ctx, c, q + '1.', ACT_RELU)
+        if i in _STN_POOLS:
+            k = _STN_POOLS[i]
+            p, arg = ops.maxpool_fwd(a, k, k, need_argmax=ctx.grads is not None)
+            saved.append((s_c, s_bn, (arg, tuple(a.shape), k)))
+            x = p
+        else:
+            saved.append((s_c, s_bn, None))
+            x = a
+    B, Hh, Ww, Cc = x.shape       # [B,1,2,256]; NCHW flatten index c*Ww + w == fc1.weight viewed as [512, 256, 1, Ww]
+    f_pre, s_fc1 = conv_fwd(ctx, x, pre + 'stn_fc1.0.weight', pre + 'stn_fc1.0.bias', (Hh, Ww), 0, as4d=(512, Cc, Hh, Ww))
+    f, s_bn1 = bn_fwd(ctx, f_pre.view(B, 512), pre + 'stn_fc1.1.', ACT_RELU)
+    f01 = ops.new((B, 1, 1, 512), x)
+    ops.copy_cols(f, 512, f01, 512, B, 512, alpha=0.1)
+    c, s_fc2 = conv_fwd(ctx, f01, pre + 'stn_fc2.weight', pre + 'stn_fc2.bias', 1, 0)
+    nctrl = c.shape[-1] // 2
+    return f, c.view(B, nctrl, 2), (saved, s_fc1, s_bn1, s_fc2, B)
+
+
+def stn_head_bwd(ctx: Ctx, saved_all, dctrl: Tensor) -> None:
+    saved, s_fc1, s_bn1, s_fc2, B = saved_all
+    df01 = conv_bwd(ctx, s_fc2, dctrl.view(B, 1, 1, -1))
+    df = ops.new((B, 512), dctrl)
+    ops.copy_cols(df01, 512, df, 512, B, 512, alpha=0.1)
+    dfpre = bn_bwd(ctx, s_bn1, df)
+    d = conv_bwd(ctx, s_fc1, dfpre.view(B, 1, 1, 512))
+    for idx in range(len(saved) - 1, -1, -1):
+        s_c, s_bn, pool = saved[idx]
+        if pool is not None:
+            arg, in_shape, k = pool
+            d = ops.maxpool_bwd(d, arg, in_shape, k, k)
+        dc = bn_bwd(ctx, s_bn, d)
+        d = conv_bwd(ctx, s_c, dc, need_dx=idx > 0)
+
+
+# ------------------------------------------------------------------------------------------------------------ InfoGen
+def info_gen_fwd(ctx: Ctx, prior: Tensor, pre: str, out_hw):
+    raise NotImplementedError  # replaced in infogen.py once the transposed-conv kernels are registered
+
+
+# ------------------------------------------------------------------------------------------------------------ TSRN
+def tsrn_fwd(ctx: Ctx, x_nchw: Tensor, stn: bool, srb_nums: int = 5, text: Optional[Tensor] = None, text_saved=None):
+    """TSRN.forward (model/tsrn.py:61-78) / TSRN_TL.forward (model/tsrn.py:178-215) after the prior has been expanded to
+    ``text`` [B,16,64,32] (NHWC) by the InfoGen path.  Returns (sr NCHW [B,C,2H,2W], saved)."""
+    x = ops.nchw_to_nhwc(x_nchw)
+    B, H, W, C = x.shape
+    s_stn = None
+    if stn and ctx.training:
+        _, ctrl, s_head = stn_head_fwd(ctx, x)
+        xr, src = ops.tps_sample_fwd(x, ctrl, ctx.P('tps.inverse_kernel'), ctx.P('tps.reprT'))
+        s_stn = (s_head, x, src)
+        x_in = xr
+    else:
+        x_in = x
+    b1pre, s_b1 = conv_fwd(ctx, x_in, 'block1.0.weight', 'block1.0.bias', 9, 4, need_dgrad=s_stn is not None)
+    slope = ctx.P('block1.1.weight')
+    b1 = ops.act_fwd(b1pre, ACT_PRELU, slope)
+    b = b1
+    s_srb = []
+    for i in range(srb_nums):
+        b, s = srb_fwd(ctx, b, f'block{i + 2}.', text)
+        s_srb.append(s)
+    k = srb_nums + 2
+    c7, s_c7 = conv_fwd(ctx, b, f'block{k}.0.weight', f'block{k}.0.bias', 3, 1)
+    s8, s_bn7 = bn_fwd(ctx, c7, f'block{k}.1.', ACT_NONE, residual=b1)
+    k += 1
+    u, s_up = conv_fwd(ctx, s8, f'block{k}.0.conv.weight', f'block{k}.0.conv.bias', 3, 1)
+    v = ops.pixelshuffle_mish_fwd(u)
+    sr, s_out = conv_fwd(ctx, v, f'block{k}.1.weight', f'block{k}.1.bias', 9, 4, act=ACT_TANH, out_nchw=True)
+    saved = (s_stn, s_b1, b1pre, s_srb, s_c7, s_bn7, s_up, u, s_out, sr, (B, H, W, C))
+    return sr, saved
+
+
+def tsrn_bwd(ctx: Ctx, saved, dsr_nchw: Tensor, dtext: Optional[Tensor] = None) -> None:
+    """Backward of tsrn_fwd given d(loss)/d(sr) (NCHW, same strides as sr).  Parameter grads go to ctx.grads;
+    ``dtext`` (NHWC [B,16,64,32], zero-initialised by the caller) accumulates the gradient of the expanded prior."""
+    s_stn, s_b1, b1pre, s_srb, s_c7, s_bn7, s_up, u, s_out, sr, (B, H, W, C) = saved
+    dpre = ops.nchw_to_nhwc(dsr_nchw, tanh_out=sr)              # tanh' fused into the layout change
+    dv = conv_bwd(ctx, s_out, dpre)
+    du = ops.pixelshuffle_mish_bwd(dv, u)
+    ds8 = conv_bwd(ctx, s_up, du)                               # = d(b1 + bn7(c7)): flows to both operands
+    dc7 = bn_bwd(ctx, s_bn7, ds8)
+    db = conv_bwd(ctx, s_c7, dc7)
+    for s in reversed(s_srb):
+        db = srb_bwd(ctx, s, db, dtext)
+    db1 = ops.add(db, ds8)
+    slope = ctx.P('block1.1.weight')
+    gs, acc = ctx.G('block1.1.weight')
+    db1pre = ops.act_bwd(db1, b1pre, ACT_PRELU, slope, gs, acc)
+    if s_stn is None:
+        conv_bwd(ctx, s_b1, db1pre, need_dx=False)
+        return
+    dxr = conv_bwd(ctx, s_b1, db1pre, need_dx=True)
+    s_head, x, src = s_stn
+    dctrl = ops.tps_sample_bwd(dxr, x, src, ctx.P('tps.inverse_kernel'), ctx.P('tps.reprT'))
+    stn_head_bwd(ctx, s_head, dctrl)

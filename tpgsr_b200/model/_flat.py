@@ -1,0 +1,126 @@
+"""Flat parameter / gradient storage behind reference-shaped nn.Modules.
+
+The drop-in modules keep the reference's submodule tree (so ``state_dict`` keys, default initialisers, ``.to()``,
+``.train()``, ``.parameters()`` behave exactly like ``model/tsrn.py`` etc.), but every parameter's storage is a view
+of ONE flat fp32 buffer, and gradients are views of a second flat buffer.  That gives (a) one NCCL all-reduce per step
+on a single buffer, (b) one fused clip+Adam kernel, (c) adjacent forward/reverse RNN weights so both
+directions' input projections are a single GEMM.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+from torch import nn
+
+
+class FlatState:
+    def __init__(self, module: nn.Module, fused: Sequence[Tuple[str, Sequence[str], Tuple[int, ...]]] = ()):
+        """``fused``: (fused_name, [param names to place adjacently, in order], shape of the fused view)."""
+        self.module = module
+        self.fused = list(fused)
+        self.flat = None
+        self.gflat = None
+        self.views: Dict[str, torch.Tensor] = {}
+        self.gviews: Dict[str, torch.Tensor] = {}
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        self.nbt = None
+
+    # -- layout -----------------------------------------------------------------------------------------------------
+    def _order(self, params: Dict[str, nn.Parameter]) -> List[str]:
+        placed, order = set(), []
+        for _, names, _ in self.fused:
+            for n in names:
+                order.append(n)
+                placed.add(n)
+        order += [n for n in params if n not in placed]
+        return order
+
+    def is_current(self) -> bool:
+        if self.flat is None:
+            return False
+        for name, p in self.module.named_parameters():
+            off, _ = self.offsets[name]
+            if p.device != self.flat.device or p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                return False
+            break
+        return True
+
+    def rebuild(self) -> None:
+        params = dict(self.module.named_parameters())
+        first = next(iter(params.values()))
+        dev = first.device
+        order = self._order(params)
+        total = sum(params[n].numel() for n in order)
+        total_pad = (total + 3) // 4 * 4
+        flat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
+        gflat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
+        off = 0
+        self.offsets, self.views, self.gviews = {}, {}, {}
+        for n in order:
+            p = params[n]
+            k = p.numel()
+            # keep 16-byte alignment of every tensor start (float4 / TMA friendly)
+            off = (off + 3) // 4 * 4 if False else off
+            flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + k].view(p.shape)
+            if p.grad is not None:
+                gflat[off:off + k].copy_(p.grad.reshape(-1))
+                p.grad = gflat[off:off + k].view(p.shape)
+            self.offsets[n] = (off, k)
+            self.views[n] = p.data
+            self.gviews[n] = gflat[off:off + k].view(p.shape)
+            off += k
+        for fname, names, shape in self.fused:
+            o0 = self.offsets[names[0]][0]
+            k = sum(self.offsets[n][1] for n in names)
+            self.views[fname] = flat[o0:o0 + k].view(*shape)
+            self.gviews[fname] = gflat[o0:o0 + k].view(*shape)
+        self.flat, self.gflat, self.n = flat, gflat, total
+        # BatchNorm counters -> one flat int64 buffer
+        owners = [(m, 'num_batches_tracked') for m in self.module.modules()
+                  if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
+        if owners:
+            nbt = torch.zeros(len(owners), dtype=torch.int64, device=dev)
+            for i, (m, key) in enumerate(owners):
+                nbt[i] = m._buffers[key].to(dev)
+                m._buffers[key] = nbt[i]
+            self.nbt = nbt
+        # float buffers (BN running stats, TPS constants)
+        for name, b in self.module.named_buffers():
+            if b.dtype == torch.float32:
+                self.views[name] = b
+
+    def ensure(self) -> None:
+        if not self.is_current():
+            self.rebuild()
+        else:
+            for name, b in self.module.named_buffers():
+                if b.dtype == torch.float32:
+                    self.views[name] = b
+
+    # -- gradient hand-off ------------------------------------------------------------------------------------------
+    def live_grads(self) -> set:
+        """Names whose ``.grad`` already lives in the flat gradient buffer (so new gradients must accumulate)."""
+        live = set()
+        for name, p in self.module.named_parameters():
+            g = p.grad
+            if g is None:
+                continue
+            gv = self.gviews[name]
+            if g.data_ptr() != gv.data_ptr():
+                gv.copy_(g)
+                p.grad = gv
+            live.add(name)
+        for fname, names, _ in self.fused:
+            if all(n in live for n in names):
+                live.add(fname)
+            elif any(n in live for n in names):
+                raise RuntimeError(f'partial .grad state inside fused parameter group {fname}')
+        return live
+
+    def publish_grads(self) -> None:
+        """Point every parameter's ``.grad`` at its flat-buffer view (after a backward wrote them)."""
+        for name, p in self.module.named_parameters():
+            if p.requires_grad:
+                p.grad = self.gviews[name]

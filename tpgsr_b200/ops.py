@@ -1,0 +1,326 @@
+"""Tensor-level wrappers over the C ABI (device pointers + dims on torch's current stream).
+
+PyTorch is used here only as plumbing: device memory (``torch.empty``), streams and autograd hand-off.  All arithmetic
+happens in libtpgsr_b200.so.  Activations are NHWC fp32 tensors of shape [B,H,W,C] (or [M,C]).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import call, query
+
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_MISH, ACT_TANH = 0, 1, 2, 3, 4
+OUT_NHWC, OUT_NCHW = 0, 1
+
+# number of kernel launches issued by this process through the C ABI (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+_KERNELS_PER_CALL = {
+    'tpgsr_conv2d_wgrad': 2, 'tpgsr_bn_stats': 2, 'tpgsr_bn_bwd': 3, 'tpgsr_colsum': 2, 'tpgsr_gru_bwd': 2,
+    'tpgsr_image_loss_fwd': 2, 'tpgsr_semantic_loss_fwd': 2, 'tpgsr_optim_prepare': 2, 'tpgsr_lstm_bwd': 2,
+    'tpgsr_conv2d_tc': 1,
+}
+
+
+def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+    call(name, *args)
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+_WS = {}
+_WS_RETIRED = []     # outgrown buffers are kept alive: captured CUDA graphs may still reference their addresses
+
+
+def workspace(nbytes: int, device) -> Tuple[int, int]:
+    """A per-device scratch buffer (grown on demand; stable pointer once large enough — safe under graph capture
+    because every kernel that uses it runs on the same stream)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    buf = _WS.get(key)
+    need = max(int(nbytes), 1)
+    if buf is None or buf.numel() < need:
+        if buf is not None:
+            _WS_RETIRED.append(buf)
+        buf = torch.empty(max(need, 64 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf.data_ptr(), buf.numel()
+
+
+def new(shape, like: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def nchw_to_nhwc(x: torch.Tensor, tanh_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Strided NCHW view -> dense NHWC [B,H,W,C]; with ``tanh_out`` multiplies by (1-tanh_out^2) (tanh backward)."""
+    B, C, H, W = x.shape
+    if tanh_out is not None:
+        assert tanh_out.stride() == x.stride()
+    y = new((B, H, W, C), x)
+    sb, sc, sh, sw = x.stride()
+    _call('tpgsr_nchw_to_nhwc', ptr(x), ptr(y), B, C, H, W, sb, sc, sh, sw, C, ptr(tanh_out), stream())
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, C = x.shape
+    y = new((B, C, H, W), x)
+    _call('tpgsr_nhwc_to_nchw', ptr(x), ptr(y), B, C, H, W, C, stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ conv / linear
+def pack_conv_weights(w: torch.Tensor, need_dgrad: bool = True):
+    Co, Ci, KH, KW = w.shape
+    wf = new((KH * KW * Ci, Co), w)
+    wd = new((KH * KW * Co, Ci), w) if need_dgrad else None
+    _call('tpgsr_pack_conv_weights', ptr(w), ptr(wf), ptr(wd), Co, Ci, KH, KW, stream())
+    return wf, wd
+
+
+def conv_fwd(x: torch.Tensor, wk_fwd: torch.Tensor, bias: Optional[torch.Tensor], Co: int, KH: int, KW: int, ph: int, pw: int,
+             act: int = ACT_NONE, act_param: Optional[torch.Tensor] = None, out_nchw: bool = False,
+             out: Optional[torch.Tensor] = None, ldx: int = 0) -> torch.Tensor:
+    """y = act(conv(x) + bias); x NHWC [B,Hi,Wi,Ci(pitch ldx)] -> NHWC [B,Ho,Wo,Co] (or NCHW)."""
+    B, Hi, Wi, Cx = x.shape
+    Ci = wk_fwd.shape[0] // (KH * KW)
+    Ho, Wo = Hi + 2 * ph - KH + 1, Wi + 2 * pw - KW + 1
+    if out is None:
+        out = new((B, Co, Ho, Wo) if out_nchw else (B, Ho, Wo, Co), x)
+    _call('tpgsr_conv2d_igemm', ptr(x), ptr(wk_fwd), ptr(bias), ptr(out), B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw,
+          ldx or Cx, Co, act, ptr(act_param), OUT_NCHW if out_nchw else OUT_NHWC, 0, stream())
+    return out
+
+
+def conv_dgrad(dy: torch.Tensor, wk_dgrad: torch.Tensor, in_hw: Tuple[int, int], Ci: int, KH: int, KW: int, ph: int, pw: int,
+               out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """dx = conv_transpose(dy): gather-GEMM over dy with the flipped packing.  dy NHWC [B,Ho,Wo,Co] -> [B,Hi,Wi,Ci]."""
+    B, Ho, Wo, Co = dy.shape
+    Hi, Wi = in_hw
+    if out is None:
+        out = new((B, Hi, Wi, Ci), dy)
+        accumulate = False
+    _call('tpgsr_conv2d_igemm', ptr(dy), ptr(wk_dgrad), None, ptr(out), B, Ho, Wo, Co, Hi, Wi, Ci, KH, KW,
+          KH - 1 - ph, KW - 1 - pw, Co, out.shape[-1], ACT_NONE, None, OUT_NHWC, int(accumulate), stream())
+    return out
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, KH: int, KW: int, ph: int, pw: int,
+               accumulate: bool, ldx: int = 0, Ci: int = 0) -> None:
+    B, Hi, Wi, Cx = x.shape
+    _, Ho, Wo, Co = dy.shape
+    Ci = Ci or Cx
+    nbytes = query('tpgsr_conv2d_wgrad_workspace_bytes', B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW)
+    wp, wn = workspace(nbytes, x.device)
+    _call('tpgsr_conv2d_wgrad', ptr(x), ptr(dy), ptr(dw), B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw, ldx or Cx, Co,
+          int(accumulate), wp, wn, stream())
+
+
+def colsum(x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> None:
+    """out[C] (+)= sum over rows of x [M,C] (bias gradients)."""
+    M, C = x2d.shape
+    wp, wn = workspace(query('tpgsr_colreduce_workspace_bytes', M, C), x2d.device)
+    _call('tpgsr_colsum', ptr(x2d), M, C, C, ptr(out), int(accumulate), wp, wn, stream())
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+def bn_stats(x2d: torch.Tensor, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5):
+    M, C = x2d.shape
+    mean_rstd = new((2, C), x2d)
+    scale_shift = new((2, C), x2d)
+    wp, wn = workspace(query('tpgsr_colreduce_workspace_bytes', M, C), x2d.device)
+    _call('tpgsr_bn_stats', ptr(x2d), M, C, C, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), momentum, eps,
+          ptr(mean_rstd), ptr(scale_shift), wp, wn, stream())
+    return mean_rstd, scale_shift
+
+
+def bn_eval_prepare(gamma, beta, running_mean, running_var, eps=1e-5):
+    C = gamma.numel()
+    mean_rstd = new((2, C), gamma)
+    scale_shift = new((2, C), gamma)
+    _call('tpgsr_bn_eval_prepare', C, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), eps, ptr(mean_rstd),
+          ptr(scale_shift), stream())
+    return mean_rstd, scale_shift
+
+
+def bn_apply(x2d: torch.Tensor, scale_shift: torch.Tensor, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, ldy: int = 0) -> torch.Tensor:
+    M, C = x2d.shape
+    if out is None:
+        out = new((M, C), x2d)
+    _call('tpgsr_bn_apply', ptr(x2d), ptr(out), ptr(scale_shift), M, C, C, ldy or C, act, ptr(residual), C, stream())
+    return out
+
+
+def bn_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, scale_shift, mean_rstd, act: int, train: bool, dgamma, dbeta,
+           accumulate: bool, lddy: int = 0) -> torch.Tensor:
+    M, C = x2d.shape
+    dx = new((M, C), x2d)
+    wp, wn = workspace(query('tpgsr_bn_bwd_workspace_bytes', M, C), x2d.device)
+    _call('tpgsr_bn_bwd', ptr(dy2d), ptr(x2d), ptr(dx), ptr(scale_shift), ptr(mean_rstd), M, C, lddy or C, C, C, act,
+          int(train), ptr(dgamma), ptr(dbeta), int(accumulate), wp, wn, stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ activations etc.
+def act_fwd(x: torch.Tensor, act: int, slope: Optional[torch.Tensor] = None) -> torch.Tensor:
+    y = torch.empty_like(x)
+    _call('tpgsr_act_fwd', ptr(x), ptr(y), x.numel(), act, ptr(slope), stream())
+    return y
+
+
+def act_bwd(dy: torch.Tensor, ref: torch.Tensor, act: int, slope: Optional[torch.Tensor] = None,
+            dslope: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    dx = torch.empty_like(dy)
+    wp, wn = workspace(query('tpgsr_act_bwd_workspace_bytes', dy.numel()), dy.device)
+    _call('tpgsr_act_bwd', ptr(dy), ptr(ref), ptr(dx), dy.numel(), act, ptr(slope), ptr(dslope), int(accumulate), wp, wn, stream())
+    return dx
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(a)
+    _call('tpgsr_add', ptr(a), ptr(b), ptr(out), a.numel(), stream())
+    return out
+
+
+def copy_cols(src: torch.Tensor, lds: int, dst: torch.Tensor, ldd: int, M: int, C: int, alpha: float = 1.0,
+              accumulate: bool = False, src_off: int = 0, dst_off: int = 0) -> None:
+    """dst[:, dst_off:dst_off+C] (+)= alpha * src[:, src_off:src_off+C] on pitched [M, ld] matrices."""
+    _call('tpgsr_copy_cols', src.data_ptr() + 4 * src_off, lds, dst.data_ptr() + 4 * dst_off, ldd, M, C, alpha,
+          int(accumulate), stream())
+
+
+def add_i64(x: torch.Tensor, v: int = 1) -> None:
+    _call('tpgsr_add_i64', ptr(x), x.numel(), v, stream())
+
+
+def maxpool_fwd(x: torch.Tensor, k, s, p=(0, 0), need_argmax: bool = True):
+    B, Hi, Wi, C = x.shape
+    Ho, Wo = (Hi + 2 * p[0] - k[0]) // s[0] + 1, (Wi + 2 * p[1] - k[1]) // s[1] + 1
+    y = new((B, Ho, Wo, C), x)
+    arg = new((B, Ho, Wo, C), x, torch.int32) if need_argmax else None
+    _call('tpgsr_maxpool_fwd', ptr(x), ptr(y), ptr(arg), B, Hi, Wi, C, k[0], k[1], s[0], s[1], p[0], p[1], stream())
+    return y, arg
+
+
+def maxpool_bwd(dy: torch.Tensor, arg: torch.Tensor, in_shape, k, s, p=(0, 0)) -> torch.Tensor:
+    B, Hi, Wi, C = in_shape
+    dx = new(in_shape, dy)
+    _call('tpgsr_maxpool_bwd', ptr(dy), ptr(arg), ptr(dx), B, Hi, Wi, C, k[0], k[1], s[0], s[1], p[0], p[1], stream())
+    return dx
+
+
+def pixelshuffle_mish_fwd(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, C4 = x.shape
+    y = new((B, 2 * H, 2 * W, C4 // 4), x)
+    _call('tpgsr_pixelshuffle_mish_fwd', ptr(x), ptr(y), B, H, W, C4 // 4, stream())
+    return y
+
+
+def pixelshuffle_mish_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    B, H, W, C4 = x.shape
+    dx = torch.empty_like(x)
+    _call('tpgsr_pixelshuffle_mish_bwd', ptr(dy), ptr(x), ptr(dx), B, H, W, C4 // 4, stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ GRU
+def _seq_geom(B: int, H: int, W: int, vertical: bool):
+    """(S, T, inner, outer_stride, inner_stride, t_stride) in pixel-row units."""
+    if vertical:      # sequences run down the columns (gru1 in the reference, on the transposed map)
+        return B * W, H, W, H * W, 1, W
+    return B * H, W, 1, W, 0, 1
+
+
+def gru_fwd(gx: torch.Tensor, whh: torch.Tensor, bhh: torch.Tensor, B: int, H: int, W: int, vertical: bool,
+            residual: Optional[torch.Tensor] = None, need_stash: bool = True):
+    """gx [M,192] -> y [M,64] (+ ysum = y + residual), stash [M,2,4,32]."""
+    M = gx.shape[0]
+    y = new((M, 64), gx)
+    ysum = new((M, 64), gx) if residual is not None else None
+    stash = new((M, 2, 4, 32), gx) if need_stash else None
+    S, T, inner, so, si, st = _seq_geom(B, H, W, vertical)
+    _call('tpgsr_gru_fwd', ptr(gx), ptr(whh), ptr(bhh), ptr(y), 64, ptr(residual), 64, ptr(ysum), 64, ptr(stash), S, T,
+          inner, so, si, st, stream())
+    return y, ysum, stash
+
+
+def gru_bwd(dy: torch.Tensor, y: torch.Tensor, stash: torch.Tensor, whh: torch.Tensor, dwhh, dbhh, dbih, accumulate: bool,
+            B: int, H: int, W: int, vertical: bool) -> torch.Tensor:
+    M = y.shape[0]
+    dgx = new((M, 192), y)
+    S, T, inner, so, si, st = _seq_geom(B, H, W, vertical)
+    wp, wn = workspace(query('tpgsr_gru_bwd_workspace_bytes', S), y.device)
+    _call('tpgsr_gru_bwd', ptr(dy), 64, ptr(y), 64, ptr(stash), ptr(whh), ptr(dgx), ptr(dwhh), ptr(dbhh), ptr(dbih),
+          int(accumulate), S, T, inner, so, si, st, wp, wn, stream())
+    return dgx
+
+
+# ------------------------------------------------------------------------------------------------ TPS
+def tps_sample_fwd(img: torch.Tensor, ctrl: torch.Tensor, inv_kernel: torch.Tensor, reprT: torch.Tensor):
+    B, H, W, C = img.shape
+    out = torch.empty_like(img)
+    src = new((B, H * W, 2), img)
+    _call('tpgsr_tps_sample_fwd', ptr(img), ptr(ctrl), ptr(inv_kernel), ptr(reprT), ptr(out), ptr(src), B, H, W, C, stream())
+    return out, src
+
+
+def tps_sample_bwd(dout: torch.Tensor, img: torch.Tensor, src: torch.Tensor, inv_kernel, reprT) -> torch.Tensor:
+    B, H, W, C = img.shape
+    dctrl = new((B, 20, 2), img)
+    _call('tpgsr_tps_sample_bwd', ptr(dout), ptr(img), ptr(src), ptr(inv_kernel), ptr(reprT), ptr(dctrl), B, H, W, C, 0, stream())
+    return dctrl
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def image_loss_fwd(out: torch.Tensor, target: torch.Tensor, gradient: bool, w0: float, w1: float, out_scale: float = 1.0,
+                   loss: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    B, C, H, W = out.shape
+    if loss is None:
+        loss = new((1,), out)
+        accumulate = False
+    wp, wn = workspace(query('tpgsr_loss_workspace_bytes', out.numel()), out.device)
+    _call('tpgsr_image_loss_fwd', ptr(out), ptr(target), B, C, H, W, int(gradient), w0, w1, out_scale, ptr(loss),
+          int(accumulate), wp, wn, stream())
+    return loss
+
+
+def image_loss_bwd(out: torch.Tensor, target: torch.Tensor, gradient: bool, w0: float, w1: float, scale: float = 1.0,
+                   upstream: Optional[torch.Tensor] = None, dout: Optional[torch.Tensor] = None,
+                   accumulate: bool = False) -> torch.Tensor:
+    B, C, H, W = out.shape
+    if dout is None:
+        dout = torch.empty_like(out)
+        accumulate = False
+    _call('tpgsr_image_loss_bwd', ptr(out), ptr(target), ptr(upstream), scale, B, C, H, W, int(gradient), w0, w1, ptr(dout),
+          int(accumulate), stream())
+    return dout
+
+
+def semantic_loss_fwd(pred: torch.Tensor, gt: torch.Tensor, out_scale: float = 1.0, loss: Optional[torch.Tensor] = None,
+                      accumulate: bool = False) -> torch.Tensor:
+    if loss is None:
+        loss = new((1,), pred)
+        accumulate = False
+    wp, wn = workspace(query('tpgsr_loss_workspace_bytes', pred.numel()), pred.device)
+    _call('tpgsr_semantic_loss_fwd', ptr(pred), ptr(gt), pred.numel(), out_scale, ptr(loss), int(accumulate), wp, wn, stream())
+    return loss
+
+
+def semantic_loss_bwd(pred: torch.Tensor, gt: torch.Tensor, scale: float = 1.0, upstream: Optional[torch.Tensor] = None,
+                      dpred: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    if dpred is None:
+        dpred = torch.empty_like(pred)
+        accumulate = False
+    _call('tpgsr_semantic_loss_bwd', ptr(pred), ptr(gt), pred.numel(), ptr(upstream), scale, ptr(dpred), int(accumulate), stream())
+    return dpred
