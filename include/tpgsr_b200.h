@@ -55,6 +55,16 @@ int tpgsr_conv2d_wgrad(const float* x, const float* dy, float* dw_oihw, int B, i
                        int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int accumulate, void* workspace,
                        size_t workspace_bytes, cudaStream_t stream);
 
+/* ---- convolution on tensor cores: TMA-staged NHWC tiles -> tcgen05.mma (bf16 x {1,3} products, fp32 accumulate in TMEM) -------
+ * nn.Conv2d with Cin % 64 == 0, 'same' padding (model/tsrn.py:37,376,381,467,495,43); operands are bf16 hi/lo planes. */
+int tpgsr_split_bf16(const float* x, int ldx, void* hi, void* lo, long M, int C, cudaStream_t stream);
+int tpgsr_pack_conv_weights_bf16(const float* w_oihw, void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, int Co,
+                                 int Ci, int KH, int KW, cudaStream_t stream);
+int tpgsr_conv2d_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW);
+int tpgsr_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y,
+                    int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
+                    const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream);
+
 /* ---- batch norm, activations, pooling, reshuffles -----------------------------------------------------------------
  * nn.BatchNorm2d/1d (model/tsrn.py:377,382,38; model/stn_head.py:19,51; model/crnn/crnn.py:48), mish
  * (model/tsrn.py:480-488), nn.PReLU (model/tsrn.py:28), nn.MaxPool2d (model/stn_head.py:36-44;

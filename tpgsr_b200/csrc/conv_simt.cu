@@ -320,18 +320,26 @@ conv_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY, flo
 }
 
 // sum the split partials and scatter to OIHW:  dW[n][ci][kh][kw] (+)= sum_z ws[z][k][n]
+// blockDim = (32, 8): 32 consecutive (k,n) elements x 8 lanes over the splits, fixed-order shared-memory tree.
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, int splits, int K, int N,
                                          int Ci, int KH, int KW, int accumulate) {
-    int total = K * N;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        int n = idx % N, k = idx / N;
-        float s = 0.f;
-        for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + idx];
-        int tap = k / Ci, ci = k - tap * Ci;
-        int kh = tap / KW, kw = tap - kh * KW;
-        size_t o = ((size_t)(n * Ci + ci) * KH + kh) * KW + kw;
-        dW[o] = accumulate ? dW[o] + s : s;
-    }
+    const int total = K * N;
+    const int idx = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (idx < total)
+        for (int z = threadIdx.y; z < splits; z += 8) s += ws[(size_t)z * total + idx];
+    __shared__ float sh[8][33];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y != 0 || idx >= total) return;
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
+    int n = idx % N, k = idx / N;
+    int tap = k / Ci, ci = k - tap * Ci;
+    int kh = tap / KW, kw = tap - kh * KW;
+    size_t o = ((size_t)(n * Ci + ci) * KH + kh) * KW + kw;
+    dW[o] = accumulate ? dW[o] + s : s;
 }
 
 int wgrad_splits(const ConvGeom& g, int BN) {
@@ -425,7 +433,7 @@ int tpgsr_conv2d_wgrad(const float* x, const float* dy, float* dw_oihw, int B, i
     rc = tpgsr_launch_status();
     if (rc) return rc;
     int total = g.K * g.Co;
-    conv_wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(ws, dw_oihw, splits, g.K, g.Co, Ci, KH, KW, accumulate);
+    conv_wgrad_reduce_kernel<<<ceil_div(total, 32), dim3(32, 8), 0, stream>>>(ws, dw_oihw, splits, g.K, g.Co, Ci, KH, KW, accumulate);
     return tpgsr_launch_status();
 }
 

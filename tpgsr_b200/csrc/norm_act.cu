@@ -78,19 +78,36 @@ int launch_col_reduce(F f, long M, int C, float* partial, int& row_blocks, cudaS
     return tpgsr_launch_status();
 }
 
+// Sum the [row_blocks][2][C] partials of column c.  blockDim = (32, 8): the 8 y-lanes split the row blocks, results are
+// valid on threadIdx.y == 0 (other lanes must not use them).  Deterministic (fixed summation tree).
+__device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int row_blocks, int C, int c, bool two,
+                                             double& s1, double& s2) {
+    double a = 0.0, b = 0.0;
+    if (c < C)
+        for (int rb = threadIdx.y; rb < row_blocks; rb += 8) {
+            a += partial[((size_t)rb * 2 + 0) * C + c];
+            if (two) b += partial[((size_t)rb * 2 + 1) * C + c];
+        }
+    __shared__ double shp[2][8][33];
+    shp[0][threadIdx.y][threadIdx.x] = a;
+    shp[1][threadIdx.y][threadIdx.x] = b;
+    __syncthreads();
+    s1 = 0.0; s2 = 0.0;
+    if (threadIdx.y == 0)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1 += shp[0][i][threadIdx.x]; s2 += shp[1][i][threadIdx.x]; }
+}
+
 // BN forward finalize: mean / rstd / folded scale+shift / running stats
 __global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int row_blocks, long M, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ mean_rstd, float* __restrict__ scale_shift,
                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                        float momentum, float eps) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < row_blocks; ++b) {
-        s1 += partial[((size_t)b * 2 + 0) * C + c];
-        s2 += partial[((size_t)b * 2 + 1) * C + c];
-    }
+    int c = blockIdx.x * 32 + threadIdx.x;
+    double s1, s2;
+    sum_partials(partial, row_blocks, C, c, true, s1, s2);
+    if (c >= C || threadIdx.y != 0) return;
     double mean = s1 / (double)M;
     double var = s2 / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -149,13 +166,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int row_blocks, long M, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
                                        int accumulate) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < row_blocks; ++b) {
-        s1 += partial[((size_t)b * 2 + 0) * C + c];
-        s2 += partial[((size_t)b * 2 + 1) * C + c];
-    }
+    int c = blockIdx.x * 32 + threadIdx.x;
+    double s1, s2;
+    sum_partials(partial, row_blocks, C, c, true, s1, s2);
+    if (c >= C || threadIdx.y != 0) return;
     if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s1 : (float)s1;
     if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)s2 : (float)s2;
     coef[c] = (float)(s1 / (double)M);
@@ -191,10 +205,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 // column sums finalize (bias grads)
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int row_blocks, int C, float* __restrict__ out,
                                        int accumulate) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0;
-    for (int b = 0; b < row_blocks; ++b) s += partial[((size_t)b * 2) * C + c];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    double s, unused;
+    sum_partials(partial, row_blocks, C, c, false, s, unused);
+    if (c >= C || threadIdx.y != 0) return;
     out[c] = accumulate ? out[c] + (float)s : (float)s;
 }
 
@@ -427,7 +441,7 @@ int tpgsr_bn_stats(const float* x, long M, int C, int ldx, const float* gamma, c
     int rb;
     int rc = launch_col_reduce(StatsF{x, ldx > 0 ? ldx : C}, M, C, static_cast<float*>(workspace), rb, stream);
     if (rc) return rc;
-    bn_fwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(static_cast<float*>(workspace), rb, M, C, gamma, beta,
+    bn_fwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(static_cast<float*>(workspace), rb, M, C, gamma, beta,
                                                                  mean_rstd, scale_shift, running_mean, running_var, momentum, eps);
     return tpgsr_launch_status();
 }
@@ -461,7 +475,7 @@ int tpgsr_bn_bwd(const float* dy, const float* x, float* dx, const float* scale_
     int rb;
     int rc = launch_col_reduce(BnBwdF{dy, x, scale_shift, mean_rstd, C, ldx, lddy, act}, M, C, partial, rb, stream);
     if (rc) return rc;
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(partial, rb, M, C, dgamma, dbeta, coef, accumulate);
+    bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(partial, rb, M, C, dgamma, dbeta, coef, accumulate);
     rc = tpgsr_launch_status();
     if (rc) return rc;
     bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, stream>>>(dy, x, dx, scale_shift, mean_rstd, coef, M, C, lddy, ldx, lddx, act, train);
@@ -478,7 +492,7 @@ int tpgsr_colsum(const float* x, long M, int C, int ldx, float* out, int accumul
     int rb;
     int rc = launch_col_reduce(SumF{x, ldx > 0 ? ldx : C}, M, C, static_cast<float*>(workspace), rb, stream);
     if (rc) return rc;
-    colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(static_cast<float*>(workspace), rb, C, out, accumulate);
+    colsum_finalize_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(static_cast<float*>(workspace), rb, C, out, accumulate);
     return tpgsr_launch_status();
 }
 

@@ -28,6 +28,8 @@ class Ctx:
         self.training = training
         self.need_input_grad = need_input_grad
         self._packed: Dict[str, tuple] = {}
+        self._packed_bf16: Dict[str, tuple] = {}
+        self._planes: Dict[int, tuple] = {}
         self._written = set()
 
     def P(self, name: str) -> Tensor:
@@ -38,6 +40,27 @@ class Ctx:
         acc = name in self._written or getattr(self, 'always_accumulate', False)
         self._written.add(name)
         return self.grads[name], acc
+
+    def planes(self, x: Tensor):
+        """bf16 hi/lo operand planes of an activation (cached: an activation feeds forward conv and weight-gradient)."""
+        key = id(x)
+        hit = self._planes.get(key)
+        if hit is None:
+            hit = (x, ops.split_bf16(x, ops.CONV_MODE == 'bf16x3'))
+            self._planes[key] = hit
+        return hit[1]
+
+    def packed_bf16(self, name: str, as4d=None):
+        hit = self._packed_bf16.get(name)
+        if hit is None:
+            w = self.params[name]
+            if as4d is not None:
+                w = w.view(*as4d)
+            elif w.dim() == 2:
+                w = w.view(w.shape[0], w.shape[1], 1, 1)
+            hit = ops.pack_conv_weights_bf16(w, self.grads is not None, ops.CONV_MODE == 'bf16x3')
+            self._packed_bf16[name] = hit
+        return hit
 
     def packed(self, name: str, need_dgrad: bool = True, as4d=None):
         key = name
@@ -54,15 +77,28 @@ class Ctx:
 
 
 # ------------------------------------------------------------------------------------------------------------ conv
+def _tc_ok(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: int, ldx: int) -> bool:
+    B, H, W, Cx = x.shape
+    return (ldx in (0, Cx) and Cx == Ci and 2 * ph == kh - 1 and 2 * pw == kw - 1 and x.is_contiguous()
+            and ops.tc_supported(B, H, W, Ci, H, W, Co, kh, kw))
+
+
 def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=ACT_NONE, act_param: Optional[Tensor] = None,
              out_nchw: bool = False, need_dgrad: bool = True, as4d=None, ldx: int = 0, out: Optional[Tensor] = None):
     w = ctx.P(wname)
     Co = w.shape[0]
     kh, kw = k if isinstance(k, tuple) else (k, k)
     ph, pw = pad if isinstance(pad, tuple) else (pad, pad)
-    wf, _ = ctx.packed(wname, need_dgrad and ctx.grads is not None, as4d)
-    y = ops.conv_fwd(x, wf, ctx.P(bname) if bname else None, Co, kh, kw, ph, pw, act, act_param, out_nchw, out=out, ldx=ldx)
+    Ci = (w.numel() // Co) // (kh * kw)
     saved = (x, wname, bname, kh, kw, ph, pw, as4d, ldx)
+    bias = ctx.P(bname) if bname else None
+    if out is None and _tc_ok(x, Ci, Co, kh, kw, ph, pw, ldx):
+        B, H, W, _ = x.shape
+        wf, _ = ctx.packed_bf16(wname, as4d)
+        y = ops.conv_tc(ctx.planes(x), wf, bias, B, H, W, Ci, Co, kh, kw, ph, pw, act, act_param, out_nchw)
+        return y, saved
+    wf, _ = ctx.packed(wname, need_dgrad and ctx.grads is not None, as4d)
+    y = ops.conv_fwd(x, wf, bias, Co, kh, kw, ph, pw, act, act_param, out_nchw, out=out, ldx=ldx)
     return y, saved
 
 
@@ -79,6 +115,12 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
         ops.colsum(dy.view(-1, Co), gb, accb)
     if not need_dx:
         return None
+    B, H, W, _ = x.shape
+    dense_out = dx_out is None or dx_out.shape[-1] == Ci
+    if dense_out and _tc_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
+        _, wd = ctx.packed_bf16(wname, as4d)
+        return ops.conv_tc(ctx.planes(dy), wd, None, B, H, W, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out,
+                           accumulate=dx_accumulate)
     _, wd = ctx.packed(wname, True, as4d)
     return ops.conv_dgrad(dy, wd, (x.shape[1], x.shape[2]), Ci, kh, kw, ph, pw, out=dx_out, accumulate=dx_accumulate)
 

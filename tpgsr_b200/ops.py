@@ -5,11 +5,12 @@ happens in libtpgsr_b200.so.  Activations are NHWC fp32 tensors of shape [B,H,W,
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
 
-from ._lib import call, query
+from ._lib import LIB, call, query
 
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_MISH, ACT_TANH = 0, 1, 2, 3, 4
 OUT_NHWC, OUT_NCHW = 0, 1
@@ -123,6 +124,51 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, KH: int, KW:
     wp, wn = workspace(nbytes, x.device)
     _call('tpgsr_conv2d_wgrad', ptr(x), ptr(dy), ptr(dw), B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw, ldx or Cx, Co,
           int(accumulate), wp, wn, stream())
+
+
+# ---- tensor-core path (tcgen05): bf16 hi/lo operand planes -------------------------------------------------------------
+# 'bf16x3' = split-bf16, three MMAs per K step, fp32-class accuracy (the parity mode); 'bf16' = one MMA (throughput mode,
+# misses the 1e-3 parity budget — every number measured in it is labelled); 'fp32' = CUDA-core path only.
+CONV_MODE = os.environ.get('TPGSR_CONV_MODE', 'bf16x3')
+
+
+def tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW) -> bool:
+    return CONV_MODE != 'fp32' and bool(LIB.tpgsr_conv2d_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW))
+
+
+def split_bf16(x: torch.Tensor, need_lo: bool = True):
+    """fp32 NHWC [..., C] (dense) -> (hi, lo) bf16 planes of the same shape; lo is None in 'bf16' mode."""
+    C = x.shape[-1]
+    M = x.numel() // C
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if need_lo else None
+    _call('tpgsr_split_bf16', ptr(x), C, ptr(hi), ptr(lo), M, C, stream())
+    return hi, lo
+
+
+def pack_conv_weights_bf16(w: torch.Tensor, need_dgrad: bool, need_lo: bool = True):
+    Co, Ci, KH, KW = w.shape
+    mk = lambda r, c: torch.empty((r, c), dtype=torch.bfloat16, device=w.device)
+    f_hi = mk(Co, KH * KW * Ci)
+    f_lo = mk(Co, KH * KW * Ci) if need_lo else None
+    d_hi = mk(Ci, KH * KW * Co) if need_dgrad else None
+    d_lo = mk(Ci, KH * KW * Co) if (need_dgrad and need_lo) else None
+    _call('tpgsr_pack_conv_weights_bf16', ptr(w), ptr(f_hi), ptr(f_lo), ptr(d_hi), ptr(d_lo), Co, Ci, KH, KW, stream())
+    return (f_hi, f_lo), (d_hi, d_lo)
+
+
+def conv_tc(x_planes, w_planes, bias, B, Hi, Wi, Ci, Co, KH, KW, ph, pw, act=ACT_NONE, act_param=None, out_nchw=False,
+            out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """Tensor-core conv on pre-split operands ('same' geometry: Ho=Hi, Wo=Wi)."""
+    hi, lo = x_planes
+    if out is None:
+        out = torch.empty((B, Co, Hi, Wi) if out_nchw else (B, Hi, Wi, Co), dtype=torch.float32, device=hi.device)
+        accumulate = False
+    nprod = 3 if (CONV_MODE == 'bf16x3' and lo is not None and w_planes[1] is not None) else 1
+    _call('tpgsr_conv2d_tc', ptr(hi), ptr(lo), ptr(w_planes[0]), ptr(w_planes[1]), ptr(bias), ptr(out), B, Hi, Wi, Ci, Hi, Wi,
+          Co, KH, KW, ph, pw, out.shape[-1] if not out_nchw else Co, act, ptr(act_param), OUT_NCHW if out_nchw else OUT_NHWC,
+          int(accumulate), nprod, stream())
+    return out
 
 
 def colsum(x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> None:
