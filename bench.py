@@ -290,6 +290,7 @@ def run_ours(args):
     }
     if world == 1:
         line['roofline'] = time_dominant_kernel(dev, B, peaks)
+    if world == 1 and not os.environ.get('TPGSR_BENCH_NO_CPU'):     # (developer switch: skip the ~60 s CPU leg)
         threads = os.cpu_count() or 1
         ips, sec_cpu = cpu_port_images_per_s(12, 2, 1, threads)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cpu_port_images_per_s.threads_used, 'host_cpus': threads, 'kind': 'port',

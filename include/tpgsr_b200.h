@@ -60,6 +60,7 @@ int tpgsr_conv2d_wgrad(const float* x, const float* dy, float* dw_oihw, int B, i
 int tpgsr_split_bf16(const float* x, int ldx, void* hi, void* lo, long M, int C, cudaStream_t stream);
 int tpgsr_pack_conv_weights_bf16(const float* w_oihw, void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, int Co,
                                  int Ci, int KH, int KW, cudaStream_t stream);
+int tpgsr_conv2d_tc_set_debug(long long* dbg);
 int tpgsr_conv2d_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW);
 int tpgsr_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y,
                     int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldy, int act,

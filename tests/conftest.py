@@ -55,9 +55,9 @@ def assert_fp_close(got, want, name, rtol=2e-3, atol=2e-5, noise_floor=2e-3, che
     scale = max(abs(want[0]), 1e-12)
     assert abs(got[0] - want[0]) <= rtol * scale + atol, f'{name}: norm {got[0]} vs {want[0]}'
     # the sum is a cancellation-prone statistic: tolerate rtol*norm*few
-    assert abs(got[1] - want[1]) <= 20 * rtol * scale + atol, f'{name}: sum {got[1]} vs {want[1]}'
-    if not check_head:
+    if not check_head:          # norm-only mode (chaotic trajectories: element signs of +-lr Adam steps differ)
         return
+    assert abs(got[1] - want[1]) <= 20 * rtol * scale + atol, f'{name}: sum {got[1]} vs {want[1]}'
     assert np.all(np.abs(got[2:] - want[2:]) <= rtol * np.maximum(np.abs(want[2:]), scale * 5e-2) + atol), \
         f'{name}: head {got[2:]} vs {want[2:]}'
 

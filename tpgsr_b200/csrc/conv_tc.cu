@@ -34,10 +34,11 @@ struct TcConvParams {
     const float* bias;
     const float* act_param;
     float* y;
+    long long* dbg;            // optional [grid][8] clock64 timestamps (developer instrumentation)
 };
 
 template <int NPROD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcConvParams p,
                int stages) {
@@ -51,6 +52,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* empty = full + stages;
     uint64_t* tmem_full = empty + stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);      // [n_tile]
 
     const int cblks = p.Ci / BLOCK_K;
     const int nkb = p.KH * p.KW * cblks;
@@ -61,6 +63,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.n_tile) tmem_cols <<= 1;
 
+    long long t_start = 0;
+    if (p.dbg && threadIdx.x == 0) t_start = clock64();
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmA_hi);
         tc::prefetch_tmap(&tmB_hi);
@@ -73,10 +77,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc::tmem_alloc(tmem_slot, tmem_cols);
         tc::tmem_relinquish();
     }
+    if (warp >= 2) {     // bias for this N tile -> shared (the epilogue reads it as a broadcast)
+        for (int i = threadIdx.x - 64; i < p.n_tile; i += 128)
+            bias_s[i] = (p.bias && n0 + i < p.Co) ? __ldg(p.bias + n0 + i) : 0.f;
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.dbg && threadIdx.x == 0) { p.dbg[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 + 0] = t_start; p.dbg[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 + 1] = clock64(); }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -107,6 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t ph = (kb / stages) & 1;
                 tc::mbar_wait(&full[s], ph);
                 tc::tc_fence_after();
+                if (p.dbg && kb == 0) p.dbg[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 + 2] = clock64();
                 const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t a_hi = st, a_lo = st + A_PLANE_BYTES;
                 const uint32_t b_hi = st + planes * A_PLANE_BYTES, b_lo = b_hi + b_plane_bytes;
@@ -126,51 +136,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tc::tc_commit(&empty[s]);                 // frees this smem stage once the MMAs above have read it
             }
             tc::tc_commit(tmem_full);                      // accumulator complete
+            if (p.dbg) p.dbg[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 + 3] = clock64();
         }
     } else {
         // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+        // TMEM -> registers (+bias, activation) -> shared staging tile (reuses the drained pipeline stages) -> coalesced
+        // 16-byte global stores.  (Direct per-thread row stores ran at ~300 GB/s: every lane hit a different 128-byte line.)
         const int q = warp & 3;
+        const int et = (warp - 2) * 32 + lane;             // 0..127
         tc::mbar_wait(tmem_full, 0);
         tc::tc_fence_after();
+        if (p.dbg && et == 0) p.dbg[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 + 4] = clock64();
         const int r = q * 32 + lane;                       // row of the tile = pixel
-        const int hl = r / p.tile_w, wl = r - hl * p.tile_w;
-        const int ho = h0 + hl;
-        const bool valid = ho < p.Ho;
-        const long m = ((long)b * p.Ho + ho) * p.Wo + wl;
+        const int pitch = p.n_tile + 4;                    // floats: keeps 16-byte alignment, spreads banks
+        float* stg = reinterpret_cast<float*>(smem);
         const float slope = (p.act == TPGSR_ACT_PRELU && p.act_param) ? __ldg(p.act_param) : 0.f;
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
             float v[32];
             tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tc::tmem_ld_wait();
-            if (!valid) continue;
+            float* d = stg + (size_t)r * pitch + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = n0 + c0 + j;
-                if (n < p.Co) {
-                    float x = v[j] + (p.bias ? __ldg(p.bias + n) : 0.f);
-                    v[j] = apply_act(x, p.act, slope);
-                }
+            for (int j = 0; j < 32; j += 4) {
+                float o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[u] = apply_act(v[j + u] + bias_s[c0 + j + u], p.act, slope);
+                if (c0 + j < p.n_tile) *reinterpret_cast<float4*>(d + j) = make_float4(o[0], o[1], o[2], o[3]);
             }
-            if (p.out_mode == TPGSR_OUT_NHWC) {
-                float* dst = p.y + (size_t)m * p.ldy + n0 + c0;
-                if (!p.accumulate && n0 + c0 + 32 <= p.Co && (p.ldy & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c0 + j < p.Co) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+        if (p.dbg && et == 0) p.dbg[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 + 5] = clock64();
+        const long m0 = ((long)b * p.Ho + h0) * p.Wo;      // the tile is 128 consecutive pixel rows
+        const int ncols = (p.Co - n0) < p.n_tile ? (p.Co - n0) : p.n_tile;
+        if (p.out_mode == TPGSR_OUT_NHWC) {
+            if ((ncols & 3) == 0 && (p.ldy & 3) == 0 && (n0 & 3) == 0) {
+                const int c4n = ncols >> 2;
+                for (int i = et; i < TILE_M * c4n; i += 128) {
+                    const int row = i / c4n, c4 = i - row * c4n;
+                    float4 val = *reinterpret_cast<const float4*>(stg + (size_t)row * pitch + c4 * 4);
+                    float4* dst = reinterpret_cast<float4*>(p.y + (size_t)(m0 + row) * p.ldy + n0 + c4 * 4);
+                    if (p.accumulate) {
+                        float4 o = *dst;
+                        val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                    }
+                    *dst = val;
                 }
             } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < p.Co) {
-                        float* d = p.y + (((size_t)b * p.Co + n) * p.Ho + ho) * p.Wo + wl;
-                        *d = p.accumulate ? *d + v[j] : v[j];
-                    }
+                for (int i = et; i < TILE_M * ncols; i += 128) {
+                    const int row = i / ncols, c = i - row * ncols;
+                    float val = stg[(size_t)row * pitch + c];
+                    float* dst = p.y + (size_t)(m0 + row) * p.ldy + n0 + c;
+                    *dst = p.accumulate ? *dst + val : val;
                 }
+            }
+        } else {
+            // NCHW: for a fixed channel the tile's 128 pixels are contiguous ((h0*Wo + row) because tile_w == Wo)
+            for (int n = 0; n < ncols; ++n) {
+                float val = stg[(size_t)et * pitch + n];
+                float* dst = p.y + (((size_t)b * p.Co + n0 + n) * p.Ho + h0) * p.Wo + et;
+                *dst = p.accumulate ? *dst + val : val;
             }
         }
     }
@@ -231,7 +255,12 @@ __global__ void pack_conv_weights_bf16_kernel(const float* __restrict__ w, __nv_
 
 }  // namespace
 
+static long long* g_tc_dbg = nullptr;
+
 extern "C" {
+
+// developer instrumentation: per-CTA clock64 timestamps of the next conv_tc launches are written to dbg[grid][8]
+int tpgsr_conv2d_tc_set_debug(long long* dbg) { g_tc_dbg = dbg; return TPGSR_OK; }
 
 int tpgsr_split_bf16(const float* x, int ldx, void* hi, void* lo, long M, int C, cudaStream_t stream) {
     if (!x || !hi || (C & 3) || (ldx & 3)) return TPGSR_ERR_BAD_ARG;
@@ -280,6 +309,7 @@ int tpgsr_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const 
     if (Co > 256 && Co % 256 != 0) return TPGSR_ERR_UNSUPPORTED;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
     p.bias = bias; p.act_param = act_param; p.y = y;
+    p.dbg = g_tc_dbg;
 
     const uint64_t K = (uint64_t)KH * KW * Ci;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -300,10 +330,15 @@ int tpgsr_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const 
     }
     const int planes = nprod == 3 ? 2 : 1;
     const int stage_bytes = planes * (A_PLANE_BYTES + p.n_tile * BLOCK_K * 2);
-    int stages = (200 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
+    // Two CTAs per SM when a 2-deep ring fits in half the shared memory (prologue/epilogue of one tile then overlaps the
+    // L2-bound main loop of the other); otherwise one CTA with as deep a ring as fits.
+    int stages = (110 * 1024) / stage_bytes;
+    if (stages < 2) stages = (200 * 1024) / stage_bytes;
+    if (stages > 4) stages = 4;
     if (stages < 2) return TPGSR_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    // the staging tile of the epilogue reuses the ring: 128 x (n_tile + 4) floats must fit
+    while ((size_t)stages * stage_bytes < (size_t)TILE_M * (p.n_tile + 4) * 4) ++stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;     // + alignment slack, barriers, bias
     dim3 grid(B * p.tiles_per_img, (Co + p.n_tile - 1) / p.n_tile);
     cudaError_t e;
     if (nprod == 3) {
