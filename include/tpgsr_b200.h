@@ -65,6 +65,14 @@ int tpgsr_conv2d_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int
 int tpgsr_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y,
                     int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
                     const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream);
+int tpgsr_conv2d_wgrad_reduce(const float* ws, float* dw_oihw, int splits, int K, int N, int Ci, int KH, int KW, int accumulate,
+                              cudaStream_t stream);
+int tpgsr_split_bf16_pad(const float* x, int ldx, void* hi, void* lo, long M, int C, int Cout, cudaStream_t stream);
+int tpgsr_conv2d_wgrad_tc_supported(int B, int H, int W, int Ci, int Co, int Cpad, int KH, int KW, int nprod);
+size_t tpgsr_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Ci, int Co, int Cpad, int KH, int KW, int nprod);
+int tpgsr_conv2d_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw_oihw, int B,
+                          int H, int W, int Ci, int Co, int Cpad, int KH, int KW, int ph, int pw, int accumulate, int nprod,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- batch norm, activations, pooling, reshuffles -----------------------------------------------------------------
  * nn.BatchNorm2d/1d (model/tsrn.py:377,382,38; model/stn_head.py:19,51; model/crnn/crnn.py:48), mish

@@ -399,6 +399,14 @@ int tpgsr_conv2d_igemm(const float* x, const float* wk, const float* bias, float
     return tpgsr_launch_status();
 }
 
+// shared by the CUDA-core and tensor-core weight-gradient paths: dW (OIHW) (+)= sum over splits of ws[z][k][n]
+int tpgsr_conv2d_wgrad_reduce(const float* ws, float* dw_oihw, int splits, int K, int N, int Ci, int KH, int KW, int accumulate,
+                              cudaStream_t stream) {
+    if (!ws || !dw_oihw || splits <= 0) return TPGSR_ERR_BAD_ARG;
+    conv_wgrad_reduce_kernel<<<ceil_div((long)K * N, 32), dim3(32, 8), 0, stream>>>(ws, dw_oihw, splits, K, N, Ci, KH, KW, accumulate);
+    return tpgsr_launch_status();
+}
+
 size_t tpgsr_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW) {
     ConvGeom g;
     if (fill_geom(g, B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, 0, 0, 0, 0)) return 0;

@@ -50,6 +50,14 @@ class Ctx:
             self._planes[key] = hit
         return hit[1]
 
+    def planes_padded(self, x: Tensor, c_out: int):
+        key = (id(x), c_out)
+        hit = self._planes.get(key)
+        if hit is None:
+            hit = (x, ops.split_bf16_pad(x, c_out, ops.CONV_MODE == 'bf16x3'))
+            self._planes[key] = hit
+        return hit[1]
+
     def packed_bf16(self, name: str, as4d=None):
         hit = self._packed_bf16.get(name)
         if hit is None:
@@ -109,13 +117,18 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     Co = w.shape[0]
     Ci = (w.numel() // Co) // (kh * kw)
     gw, acc = ctx.G(wname)
-    ops.conv_wgrad(x, dy, gw, kh, kw, ph, pw, acc, ldx=ldx, Ci=Ci)
+    B, H, W, Cx = x.shape
+    if (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 2 * ph == kh - 1 and 2 * pw == kw - 1
+            and ops.wgrad_tc_supported(B, H, W, Ci, Co, kh, kw)):
+        dyp = ctx.planes(dy) if Co % 64 == 0 else ctx.planes_padded(dy, (Co + 63) // 64 * 64)
+        ops.conv_wgrad_tc(ctx.planes(x), dyp, gw, B, H, W, Ci, Co, kh, kw, ph, pw, acc)
+    else:
+        ops.conv_wgrad(x, dy, gw, kh, kw, ph, pw, acc, ldx=ldx, Ci=Ci)
     if bname:
         gb, accb = ctx.G(bname)
         ops.colsum(dy.view(-1, Co), gb, accb)
     if not need_dx:
         return None
-    B, H, W, _ = x.shape
     dense_out = dx_out is None or dx_out.shape[-1] == Ci
     if dense_out and _tc_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)

@@ -20,7 +20,7 @@ LAUNCHES = 0
 _KERNELS_PER_CALL = {
     'tpgsr_conv2d_wgrad': 2, 'tpgsr_bn_stats': 2, 'tpgsr_bn_bwd': 3, 'tpgsr_colsum': 2, 'tpgsr_gru_bwd': 2,
     'tpgsr_image_loss_fwd': 2, 'tpgsr_semantic_loss_fwd': 2, 'tpgsr_optim_prepare': 2, 'tpgsr_lstm_bwd': 2,
-    'tpgsr_conv2d_tc': 1,
+    'tpgsr_conv2d_tc': 1, 'tpgsr_conv2d_wgrad_tc': 2,
 }
 
 
@@ -169,6 +169,33 @@ def conv_tc(x_planes, w_planes, bias, B, Hi, Wi, Ci, Co, KH, KW, ph, pw, act=ACT
           Co, KH, KW, ph, pw, out.shape[-1] if not out_nchw else Co, act, ptr(act_param), OUT_NCHW if out_nchw else OUT_NHWC,
           int(accumulate), nprod, stream())
     return out
+
+
+def split_bf16_pad(x: torch.Tensor, c_out: int, need_lo: bool = True):
+    """fp32 NHWC [..., C] -> bf16 planes [..., c_out] with zero channels beyond C (ragged Co for the wgrad B' operand)."""
+    C = x.shape[-1]
+    M = x.numel() // C
+    shape = tuple(x.shape[:-1]) + (c_out,)
+    hi = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(shape, dtype=torch.bfloat16, device=x.device) if need_lo else None
+    _call('tpgsr_split_bf16_pad', ptr(x), C, ptr(hi), ptr(lo), M, C, c_out, stream())
+    return hi, lo
+
+
+def wgrad_tc_supported(B, H, W, Ci, Co, KH, KW) -> bool:
+    if CONV_MODE == 'fp32':
+        return False
+    cpad = (Co + 63) // 64 * 64
+    return bool(LIB.tpgsr_conv2d_wgrad_tc_supported(B, H, W, Ci, Co, cpad, KH, KW, 3 if CONV_MODE == 'bf16x3' else 1))
+
+
+def conv_wgrad_tc(x_planes, dy_planes, dw: torch.Tensor, B, H, W, Ci, Co, KH, KW, ph, pw, accumulate: bool) -> None:
+    cpad = dy_planes[0].shape[-1]
+    nprod = 3 if (CONV_MODE == 'bf16x3' and x_planes[1] is not None and dy_planes[1] is not None) else 1
+    nbytes = query('tpgsr_conv2d_wgrad_tc_workspace_bytes', B, H, W, Ci, Co, cpad, KH, KW, nprod)
+    wp, wn = workspace(nbytes, dw.device)
+    _call('tpgsr_conv2d_wgrad_tc', ptr(x_planes[0]), ptr(x_planes[1]), ptr(dy_planes[0]), ptr(dy_planes[1]), ptr(dw), B, H, W, Ci,
+          Co, cpad, KH, KW, ph, pw, int(accumulate), nprod, wp, wn, stream())
 
 
 def colsum(x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> None:
