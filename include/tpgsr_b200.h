@@ -50,6 +50,11 @@ int tpgsr_pack_conv_weights(const float* w_oihw, float* wk_fwd, float* wk_dgrad,
 int tpgsr_conv2d_igemm(const float* x, const float* wk, const float* bias, float* y, int B, int Hi, int Wi, int Ci,
                        int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int act,
                        const float* act_param, int out_mode, int accumulate, cudaStream_t stream);
+size_t tpgsr_conv2d_igemm_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW);
+int tpgsr_conv2d_igemm_ws(const float* x, const float* wk, const float* bias, float* y, int B, int Hi, int Wi, int Ci,
+                          int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int act,
+                          const float* act_param, int out_mode, int accumulate, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream);
 size_t tpgsr_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW);
 int tpgsr_conv2d_wgrad(const float* x, const float* dy, float* dw_oihw, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
                        int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int accumulate, void* workspace,

@@ -39,7 +39,7 @@ template <int BN, int TN, bool VEC>
 __global__ void __launch_bounds__(256)
 conv_igemm_kernel(const float* __restrict__ X, const float* __restrict__ Wk, const float* __restrict__ bias,
                   float* __restrict__ Y, ConvGeom g, int act, const float* __restrict__ act_param, int out_mode,
-                  int accumulate) {
+                  int accumulate, int kt_per_split) {
     constexpr int BM = 128, BK = 16, TM = 8;
     constexpr int NTN = BN / TN;
     static_assert((BM / TM) * NTN == 256, "thread layout");
@@ -52,7 +52,14 @@ conv_igemm_kernel(const float* __restrict__ X, const float* __restrict__ Wk, con
     const long m0 = (long)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int K = g.K, N = g.Co;
-    const int nkt = (K + BK - 1) / BK;
+    const int nkt_all = (K + BK - 1) / BK;
+    // split-K (tiny-M, large-K layers such as the STN head): blockIdx.z owns a k-tile range and writes a raw partial tile
+    int kt0 = 0, nkt = nkt_all;
+    if (kt_per_split > 0) {
+        kt0 = blockIdx.z * kt_per_split;
+        nkt = kt0 + kt_per_split < nkt_all ? kt0 + kt_per_split : nkt_all;
+        Y += (size_t)blockIdx.z * (size_t)g.M * N;
+    }
 
     // ---- per-thread A-row bookkeeping
     constexpr int A_ROWS = VEC ? 2 : 8;
@@ -134,11 +141,11 @@ conv_igemm_kernel(const float* __restrict__ X, const float* __restrict__ Wk, con
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    load_tile(0);
+    load_tile(kt0);
     store_tile(0);
     __syncthreads();
-    for (int kt = 0; kt < nkt; ++kt) {
-        int buf = kt & 1;
+    for (int kt = kt0; kt < nkt; ++kt) {
+        int buf = (kt - kt0) & 1;
         if (kt + 1 < nkt) load_tile(kt + 1);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
@@ -319,6 +326,33 @@ conv_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY, flo
     }
 }
 
+// split-K finalize: y = act(sum_z ws[z][m][n] + bias) with the usual epilogue options
+__global__ void conv_splitk_finalize_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ bias,
+                                            float* __restrict__ Y, ConvGeom g, int act, const float* __restrict__ act_param,
+                                            int out_mode, int accumulate) {
+    const long total = g.M * g.Co;
+    const float slope = (act == TPGSR_ACT_PRELU && act_param) ? __ldg(act_param) : 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long m = i / g.Co;
+        int n = (int)(i - m * g.Co);
+        float v = bias ? __ldg(bias + n) : 0.f;
+        for (int z = 0; z < splits; ++z) v += ws[(size_t)z * total + i];
+        v = apply_act(v, act, slope);
+        size_t off;
+        if (out_mode == TPGSR_OUT_NCHW) {
+            int wo = (int)(m % g.Wo);
+            long r = m / g.Wo;
+            int ho = (int)(r % g.Ho);
+            int b = (int)(r / g.Ho);
+            off = ((size_t)(b * g.Co + n) * g.Ho + ho) * g.Wo + wo;
+        } else {
+            off = (size_t)m * g.ldy + n;
+        }
+        if (accumulate) v += Y[off];
+        Y[off] = v;
+    }
+}
+
 // sum the split partials and scatter to OIHW:  dW[n][ci][kh][kw] (+)= sum_z ws[z][k][n]
 // blockDim = (32, 8): 32 consecutive (k,n) elements x 8 lanes over the splits, fixed-order shared-memory tree.
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, int splits, int K, int N,
@@ -379,24 +413,67 @@ int tpgsr_pack_conv_weights(const float* w_oihw, float* wk_fwd, float* wk_dgrad,
 
 // Generic gather-GEMM used for both the forward conv (wk = Wk_fwd, geometry as given) and the data gradient
 // (x := dY, wk = Wk_dgrad, Ci := conv Co, Co := conv Ci, ph := KH-1-ph, pw := KW-1-pw, (Hi,Wi) := dY dims, (Ho,Wo) := dX dims).
-int tpgsr_conv2d_igemm(const float* x, const float* wk, const float* bias, float* y, int B, int Hi, int Wi, int Ci,
-                       int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int act,
-                       const float* act_param, int out_mode, int accumulate, cudaStream_t stream) {
+static int igemm_splits(const ConvGeom& g, bool small_n) {
+    long tiles = (long)ceil_div(g.M, 128) * ceil_div(g.Co, small_n ? 16 : 64);
+    int nkt = (g.K + 15) / 16;
+    if (tiles >= 74 || nkt < 16) return 1;
+    long s = (148L * 2) / tiles;
+    if (s > nkt / 4) s = nkt / 4;
+    return s < 2 ? 1 : (int)s;
+}
+
+size_t tpgsr_conv2d_igemm_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int KH, int KW) {
+    ConvGeom g;
+    if (fill_geom(g, B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, 0, 0, 0, 0)) return 0;
+    int s = igemm_splits(g, Co <= 16);
+    return s > 1 ? (size_t)s * g.M * g.Co * sizeof(float) : 0;
+}
+
+int tpgsr_conv2d_igemm_ws(const float* x, const float* wk, const float* bias, float* y, int B, int Hi, int Wi, int Ci,
+                          int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int act,
+                          const float* act_param, int out_mode, int accumulate, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream) {
     ConvGeom g;
     int rc = fill_geom(g, B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw, ldx, ldy);
     if (rc) return rc;
     if (!x || !wk || !y) return TPGSR_ERR_BAD_ARG;
     bool vec = (Ci % 4 == 0) && (g.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     bool small_n = Co <= 16;
-    dim3 grid(ceil_div(g.M, 128), ceil_div(Co, small_n ? 16 : 64));
+    int splits = igemm_splits(g, small_n);
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * g.M * g.Co * sizeof(float))) splits = 1;
+    const int nkt = (g.K + 15) / 16;
+    const int kps = splits > 1 ? (nkt + splits - 1) / splits : 0;
+    if (splits > 1) splits = (nkt + kps - 1) / kps;
+    dim3 grid(ceil_div(g.M, 128), ceil_div(Co, small_n ? 16 : 64), splits > 1 ? splits : 1);
+    float* out = splits > 1 ? static_cast<float*>(workspace) : y;
+    ConvGeom gk = g;
+    if (splits > 1) gk.ldy = Co;
+    const float* kb = splits > 1 ? nullptr : bias;
+    const int kact = splits > 1 ? TPGSR_ACT_NONE : act;
+    const int kom = splits > 1 ? TPGSR_OUT_NHWC : out_mode;
+    const int kacc = splits > 1 ? 0 : accumulate;
     if (small_n) {
-        if (vec) conv_igemm_kernel<16, 1, true><<<grid, 256, 0, stream>>>(x, wk, bias, y, g, act, act_param, out_mode, accumulate);
-        else conv_igemm_kernel<16, 1, false><<<grid, 256, 0, stream>>>(x, wk, bias, y, g, act, act_param, out_mode, accumulate);
+        if (vec) conv_igemm_kernel<16, 1, true><<<grid, 256, 0, stream>>>(x, wk, kb, out, gk, kact, act_param, kom, kacc, kps);
+        else conv_igemm_kernel<16, 1, false><<<grid, 256, 0, stream>>>(x, wk, kb, out, gk, kact, act_param, kom, kacc, kps);
     } else {
-        if (vec) conv_igemm_kernel<64, 4, true><<<grid, 256, 0, stream>>>(x, wk, bias, y, g, act, act_param, out_mode, accumulate);
-        else conv_igemm_kernel<64, 4, false><<<grid, 256, 0, stream>>>(x, wk, bias, y, g, act, act_param, out_mode, accumulate);
+        if (vec) conv_igemm_kernel<64, 4, true><<<grid, 256, 0, stream>>>(x, wk, kb, out, gk, kact, act_param, kom, kacc, kps);
+        else conv_igemm_kernel<64, 4, false><<<grid, 256, 0, stream>>>(x, wk, kb, out, gk, kact, act_param, kom, kacc, kps);
     }
+    rc = tpgsr_launch_status();
+    if (rc || splits <= 1) return rc;
+    long total = g.M * g.Co;
+    conv_splitk_finalize_kernel<<<ceil_div(total, 256) > 1184 ? 1184 : ceil_div(total, 256), 256, 0, stream>>>(
+        static_cast<float*>(workspace), splits, bias, y, g, act, act_param, out_mode, accumulate);
     return tpgsr_launch_status();
+}
+
+// Generic gather-GEMM used for both the forward conv (wk = Wk_fwd, geometry as given) and the data gradient
+// (x := dY, wk = Wk_dgrad, Ci := conv Co, Co := conv Ci, ph := KH-1-ph, pw := KW-1-pw, (Hi,Wi) := dY dims, (Ho,Wo) := dX dims).
+int tpgsr_conv2d_igemm(const float* x, const float* wk, const float* bias, float* y, int B, int Hi, int Wi, int Ci,
+                       int Ho, int Wo, int Co, int KH, int KW, int ph, int pw, int ldx, int ldy, int act,
+                       const float* act_param, int out_mode, int accumulate, cudaStream_t stream) {
+    return tpgsr_conv2d_igemm_ws(x, wk, bias, y, B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw, ldx, ldy, act, act_param, out_mode,
+                                 accumulate, nullptr, 0, stream);
 }
 
 // shared by the CUDA-core and tensor-core weight-gradient paths: dW (OIHW) (+)= sum over splits of ws[z][k][n]

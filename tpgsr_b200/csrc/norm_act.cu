@@ -78,24 +78,25 @@ int launch_col_reduce(F f, long M, int C, float* partial, int& row_blocks, cudaS
     return tpgsr_launch_status();
 }
 
-// Sum the [row_blocks][2][C] partials of column c.  blockDim = (32, 8): the 8 y-lanes split the row blocks, results are
-// valid on threadIdx.y == 0 (other lanes must not use them).  Deterministic (fixed summation tree).
+// Sum the [row_blocks][2][C] partials of column c.  blockDim = (32, 32): the 32 y-lanes split the row blocks (so the serial,
+// latency-bound part is ~row_blocks/32 loads), results are valid on threadIdx.y == 0.  Deterministic (fixed summation tree).
+constexpr int FIN_Y = 32;
 __device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int row_blocks, int C, int c, bool two,
                                              double& s1, double& s2) {
-    double a = 0.0, b = 0.0;
+    float a = 0.f, b = 0.f;
     if (c < C)
-        for (int rb = threadIdx.y; rb < row_blocks; rb += 8) {
+        for (int rb = threadIdx.y; rb < row_blocks; rb += FIN_Y) {
             a += partial[((size_t)rb * 2 + 0) * C + c];
             if (two) b += partial[((size_t)rb * 2 + 1) * C + c];
         }
-    __shared__ double shp[2][8][33];
+    __shared__ float shp[2][FIN_Y][33];
     shp[0][threadIdx.y][threadIdx.x] = a;
     shp[1][threadIdx.y][threadIdx.x] = b;
     __syncthreads();
     s1 = 0.0; s2 = 0.0;
     if (threadIdx.y == 0)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s1 += shp[0][i][threadIdx.x]; s2 += shp[1][i][threadIdx.x]; }
+        for (int i = 0; i < FIN_Y; ++i) { s1 += (double)shp[0][i][threadIdx.x]; s2 += (double)shp[1][i][threadIdx.x]; }
 }
 
 // BN forward finalize: mean / rstd / folded scale+shift / running stats
@@ -441,7 +442,7 @@ int tpgsr_bn_stats(const float* x, long M, int C, int ldx, const float* gamma, c
     int rb;
     int rc = launch_col_reduce(StatsF{x, ldx > 0 ? ldx : C}, M, C, static_cast<float*>(workspace), rb, stream);
     if (rc) return rc;
-    bn_fwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(static_cast<float*>(workspace), rb, M, C, gamma, beta,
+    bn_fwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, FIN_Y), 0, stream>>>(static_cast<float*>(workspace), rb, M, C, gamma, beta,
                                                                  mean_rstd, scale_shift, running_mean, running_var, momentum, eps);
     return tpgsr_launch_status();
 }
@@ -475,7 +476,7 @@ int tpgsr_bn_bwd(const float* dy, const float* x, float* dx, const float* scale_
     int rb;
     int rc = launch_col_reduce(BnBwdF{dy, x, scale_shift, mean_rstd, C, ldx, lddy, act}, M, C, partial, rb, stream);
     if (rc) return rc;
-    bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(partial, rb, M, C, dgamma, dbeta, coef, accumulate);
+    bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, FIN_Y), 0, stream>>>(partial, rb, M, C, dgamma, dbeta, coef, accumulate);
     rc = tpgsr_launch_status();
     if (rc) return rc;
     bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, stream>>>(dy, x, dx, scale_shift, mean_rstd, coef, M, C, lddy, ldx, lddx, act, train);
@@ -492,7 +493,7 @@ int tpgsr_colsum(const float* x, long M, int C, int ldx, float* out, int accumul
     int rb;
     int rc = launch_col_reduce(SumF{x, ldx > 0 ? ldx : C}, M, C, static_cast<float*>(workspace), rb, stream);
     if (rc) return rc;
-    colsum_finalize_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, stream>>>(static_cast<float*>(workspace), rb, C, out, accumulate);
+    colsum_finalize_kernel<<<ceil_div(C, 32), dim3(32, FIN_Y), 0, stream>>>(static_cast<float*>(workspace), rb, C, out, accumulate);
     return tpgsr_launch_status();
 }
 

@@ -97,8 +97,9 @@ def conv_fwd(x: torch.Tensor, wk_fwd: torch.Tensor, bias: Optional[torch.Tensor]
     Ho, Wo = Hi + 2 * ph - KH + 1, Wi + 2 * pw - KW + 1
     if out is None:
         out = new((B, Co, Ho, Wo) if out_nchw else (B, Ho, Wo, Co), x)
-    _call('tpgsr_conv2d_igemm', ptr(x), ptr(wk_fwd), ptr(bias), ptr(out), B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw,
-          ldx or Cx, Co, act, ptr(act_param), OUT_NCHW if out_nchw else OUT_NHWC, 0, stream())
+    wp, wn = workspace(query('tpgsr_conv2d_igemm_workspace_bytes', B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW), x.device)
+    _call('tpgsr_conv2d_igemm_ws', ptr(x), ptr(wk_fwd), ptr(bias), ptr(out), B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw,
+          ldx or Cx, Co, act, ptr(act_param), OUT_NCHW if out_nchw else OUT_NHWC, 0, wp, wn, stream())
     return out
 
 
@@ -110,8 +111,9 @@ def conv_dgrad(dy: torch.Tensor, wk_dgrad: torch.Tensor, in_hw: Tuple[int, int],
     if out is None:
         out = new((B, Hi, Wi, Ci), dy)
         accumulate = False
-    _call('tpgsr_conv2d_igemm', ptr(dy), ptr(wk_dgrad), None, ptr(out), B, Ho, Wo, Co, Hi, Wi, Ci, KH, KW,
-          KH - 1 - ph, KW - 1 - pw, Co, out.shape[-1], ACT_NONE, None, OUT_NHWC, int(accumulate), stream())
+    wp, wn = workspace(query('tpgsr_conv2d_igemm_workspace_bytes', B, Ho, Wo, Co, Hi, Wi, Ci, KH, KW), dy.device)
+    _call('tpgsr_conv2d_igemm_ws', ptr(dy), ptr(wk_dgrad), None, ptr(out), B, Ho, Wo, Co, Hi, Wi, Ci, KH, KW,
+          KH - 1 - ph, KW - 1 - pw, Co, out.shape[-1], ACT_NONE, None, OUT_NHWC, int(accumulate), wp, wn, stream())
     return out
 
 
