@@ -116,6 +116,35 @@ int tpgsr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W,
                        int ldd, const float* tanh_out, cudaStream_t stream);
 int tpgsr_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, int lds, cudaStream_t stream);
 
+/* ---- resampling / prior formatting of the text-prior branch -------------------------------------------------------------------
+ * parse_crnn_data (interfaces/base.py:806-829); F.interpolate bilinear align_corners=True (model/tsrn.py:196); InfoGen's
+ * ConvTranspose2d on H=1 maps as zero-upsample + conv (model/tsrn.py:81-108); softmax + permute + prior dropout
+ * (interfaces/super_resolution.py:319-321,376-382). */
+int tpgsr_bicubic_gray_fwd(const float* in, long sb, long sc, long sh, long sw, int B, int Hi, int Wi, float* out, int Ho,
+                           int Wo, cudaStream_t stream);
+int tpgsr_bicubic_gray_bwd(const float* dout, int B, int Hi, int Wi, int Ho, int Wo, float* din, long sb, long sc, long sh,
+                           long sw, int accumulate, cudaStream_t stream);
+int tpgsr_bilinear_rows_fwd(const float* in, float* out, int B, int Wi, int C, int Ho, int Wo, int ldo, cudaStream_t stream);
+int tpgsr_bilinear_rows_bwd(const float* dout, float* din, int B, int Wi, int C, int Ho, int Wo, int ldo, cudaStream_t stream);
+int tpgsr_zero_upsample_w(const float* x, float* y, int B, int W, int C, int stride, cudaStream_t stream);
+int tpgsr_zero_upsample_w_bwd(const float* dy, float* dx, int B, int W, int C, int stride, cudaStream_t stream);
+int tpgsr_tconv_weight_fwd(const float* wt, float* wc, int Ci, int Co, int KH, int KW, int kh_mid, cudaStream_t stream);
+int tpgsr_tconv_weight_bwd(const float* dwc, float* dwt, int Ci, int Co, int KH, int KW, int kh_mid, int accumulate,
+                           cudaStream_t stream);
+int tpgsr_softmax_prior_fwd(const float* logits, float* probs, float* prior, int T, int B, int C, int drop_first,
+                            cudaStream_t stream);
+int tpgsr_softmax_prior_bwd(const float* probs, const float* dprobs, const float* dprior, float* dlogits, int T, int B, int C,
+                            int drop_first, cudaStream_t stream);
+
+/* ---- bidirectional LSTM recurrence -----------------------------------------------------------------------------------------------
+ * nn.LSTM(nIn, 256, bidirectional=True) in BidirectionalLSTM: model/crnn/crnn.py:5-26 (cuDNN RNN). */
+int tpgsr_lstm_transpose_whh(const float* whh, float* whhT, cudaStream_t stream);
+int tpgsr_lstm_fwd(const float* gx, const float* whhT, const float* bhh, float* y, float* stash, int T, int B, int hidden,
+                   int batch_first, cudaStream_t stream);
+int tpgsr_lstm_bwd(const float* dy, const float* stash, const float* whh, float* dgx, int T, int B, int hidden,
+                   int batch_first, cudaStream_t stream);
+int tpgsr_lstm_shift_h(const float* y, float* hprev, int T, int B, int hidden, int batch_first, cudaStream_t stream);
+
 /* ---- bidirectional GRU recurrence ----------------------------------------------------------------------------------
  * nn.GRU(64, 32, bidirectional=True, batch_first=True) in GruBlock: model/tsrn.py:491-508 (cuDNN RNN). */
 int tpgsr_gru_fwd(const float* gx, const float* whh, const float* bhh, float* y, int ldy, const float* residual,

@@ -1,0 +1,216 @@
+"""GPU parity for the text-prior branch: parse_crnn_data (bicubic+gray), prior formatting, InfoGen, BiLSTM, CRNN, TSRN_TL —
+kernels vs the CPU oracle and the fixtures recorded from the reference's modules."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_fp_close, fingerprint, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+KW = dict(scale_factor=2, width=128, height=32, STN=True, mask=True, srb_nums=5, hidden_units=32)
+T = torch.from_numpy
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.from_numpy(np.random.RandomState(seed).randn(*shape).astype(np.float32) * scale)
+
+
+def _synth(shapes, key, seed, golden=None):
+    from oracle.weights import synth_state_dict
+    sd = synth_state_dict(shapes[key], seed)
+    if golden is not None:
+        for k, v in golden.items():
+            if k.startswith('tps.'):
+                sd[k] = T(v)
+    return sd
+
+
+def test_parse_crnn_data_fwd_bwd_vs_golden():
+    from tpgsr_b200 import ops_prior
+    g = load_golden('parse_crnn_data')
+    d = _dev()
+    lr, hr = T(g['lr']).to(d), T(g['hr']).to(d)
+    gl = ops_prior.bicubic_gray_fwd(lr[:, :3])          # strided channel-sliced view, as the reference callers pass
+    gh = ops_prior.bicubic_gray_fwd(hr)
+    assert rel_err(gl, g['gray_lr']) < 2e-6 and rel_err(gh, g['gray_hr']) < 2e-6
+    w = T(g['w']).to(d)
+    dl = torch.zeros_like(lr)
+    dh = torch.zeros_like(hr)
+    ops_prior.bicubic_gray_bwd(w, dl, False)
+    ops_prior.bicubic_gray_bwd(w, dh, False)
+    assert rel_err(dl, g['grad_lr']) < 5e-6 and rel_err(dh, g['grad_hr']) < 5e-6
+    ops_prior.bicubic_gray_bwd(w, dh, True)
+    assert rel_err(dh, 2 * T(g['grad_hr'])) < 5e-6
+
+
+def test_softmax_prior_formatting():
+    from oracle import models
+    from tpgsr_b200 import ops_prior
+    logits = rnd(26, 8, 37, seed=3, scale=2.0).requires_grad_(True)
+    probs, prior = models.prior_from_logits(logits, True)           # drops the first B//4 = 2 samples
+    wp, wq = rnd(26, 8, 37, seed=4), rnd(8, 37, 1, 26, seed=5)
+    ((probs * wp).sum() + (prior * wq).sum()).backward()
+    d = _dev()
+    p_d, prior_d = ops_prior.softmax_prior_fwd(logits.detach().to(d), 2)
+    assert rel_err(p_d, probs) < 1e-6
+    assert rel_err(prior_d.permute(0, 3, 1, 2), prior) < 1e-6       # NHWC [B,1,T,C] -> NCHW [B,C,1,T]
+    dprior_nhwc = wq.permute(0, 2, 3, 1).contiguous().to(d)
+    dl = ops_prior.softmax_prior_bwd(p_d, wp.to(d), dprior_nhwc, 2)
+    assert rel_err(dl, logits.grad) < 1e-5
+
+
+def test_infogen_vs_golden_and_oracle(shapes):
+    from oracle import models, ops as o, step
+    from tpgsr_b200 import engine, infogen
+    from tpgsr_b200.model.tsrn import TSRN_TL
+    g = load_golden('infogen')
+    sd = {'infoGen.' + k: v for k, v in _synth(shapes, 'infogen', 6).items()}
+    p = {k: v.clone() for k, v in sd.items()}
+    leaves = {k: v.requires_grad_(True) for k, v in p.items() if step.is_param(k)}
+    prior = T(g['prior']).requires_grad_(True)
+    t_o = models.info_gen(prior, p, 'infoGen.', True)
+    ti_o = o.resize_separable(t_o, o.bilinear_ac_matrix(1, 16), o.bilinear_ac_matrix(203, 64))
+    (ti_o * T(g['w'])).sum().backward()
+    net = TSRN_TL(**KW)
+    net.load_state_dict(sd, strict=False)
+    net = net.to(_dev()).train()
+    st = net._flat
+    st.ensure()
+    ctx = engine.Ctx(st.views, st.gviews, True)
+    x = torch.zeros(3, 4, 16, 64, device=_dev())
+    text, s_text = infogen.info_gen_fwd(ctx, x, prior.detach().to(_dev()), 37)
+    assert rel_err(text.permute(0, 3, 1, 2), g['t_interp']) < 5e-5
+    dtext = T(g['w']).permute(0, 2, 3, 1).contiguous().to(_dev())
+    dprior = infogen.info_gen_bwd(ctx, s_text, dtext, True)
+    assert rel_err(dprior, g['grad_prior']) < 1e-3
+    for k, v in leaves.items():
+        if float(v.grad.norm()) > 2e-3:
+            assert rel_err(st.gviews[k], v.grad) < 2e-3, k
+
+
+def test_bilstm_recurrence_vs_oracle():
+    from oracle import ops as o
+    from tpgsr_b200 import ops, ops_prior
+    Tn, B, I, H = 26, 11, 256, 256          # B = 11: one full batch chunk of 8 plus a ragged one
+    r = np.random.RandomState(9)
+    k = 1 / np.sqrt(H)
+    p = {}
+    for suf in ('', '_reverse'):
+        p['weight_ih_l0' + suf] = T(r.uniform(-k, k, (4 * H, I)).astype(np.float32)).requires_grad_(True)
+        p['weight_hh_l0' + suf] = T(r.uniform(-k, k, (4 * H, H)).astype(np.float32)).requires_grad_(True)
+        p['bias_ih_l0' + suf] = T(r.uniform(-k, k, 4 * H).astype(np.float32)).requires_grad_(True)
+        p['bias_hh_l0' + suf] = T(r.uniform(-k, k, 4 * H).astype(np.float32)).requires_grad_(True)
+    x = rnd(Tn, B, I, seed=10).requires_grad_(True)
+    y = o.bilstm(x, p, '')
+    gy = rnd(Tn, B, 2 * H, seed=11)
+    (y * gy).sum().backward()
+    d = _dev()
+    for bf in (False, True):
+        perm = (lambda t: t.transpose(0, 1).contiguous()) if bf else (lambda t: t)
+        xd = perm(x.detach()).reshape(Tn * B, I).to(d)
+        wih = torch.cat([p['weight_ih_l0'], p['weight_ih_l0_reverse']], 0).detach().to(d)
+        bih = torch.cat([p['bias_ih_l0'], p['bias_ih_l0_reverse']], 0).detach().to(d)
+        whh = torch.stack([p['weight_hh_l0'], p['weight_hh_l0_reverse']], 0).detach().to(d).contiguous()
+        bhh = torch.stack([p['bias_hh_l0'], p['bias_hh_l0_reverse']], 0).detach().to(d).contiguous()
+        wf, wdg = ops.pack_conv_weights(wih.view(8 * H, I, 1, 1), True)
+        gx = ops.conv_fwd(xd.view(Tn * B, 1, 1, I), wf, bih, 8 * H, 1, 1, 0, 0).view(Tn * B, 8 * H)
+        yd, stash = ops_prior.lstm_fwd(gx, ops_prior.lstm_transpose_whh(whh), bhh, Tn, B, True, batch_first=bf)
+        y_ref = perm(y.detach()).reshape(Tn * B, 2 * H)
+        assert rel_err(yd, y_ref) < 2e-5, bf
+        dgx = ops_prior.lstm_bwd(perm(gy).reshape(Tn * B, 2 * H).to(d), stash, whh, Tn, B, batch_first=bf)
+        dx = ops.conv_dgrad(dgx.view(Tn * B, 1, 1, 8 * H), wdg, (1, 1), I, 1, 1, 0, 0).view(Tn * B, I)
+        assert rel_err(dx, perm(x.grad).reshape(Tn * B, I)) < 5e-5, bf
+        db = torch.zeros(8 * H, device=d)
+        ops.colsum(dgx, db, False)
+        assert rel_err(db, torch.cat([p['bias_ih_l0'].grad, p['bias_ih_l0_reverse'].grad])) < 5e-5
+        hprev = ops_prior.lstm_shift_h(yd, Tn, B, batch_first=bf)
+        from tpgsr_b200.crnn_engine import _wgrad_pitched
+        for di, suf in enumerate(('', '_reverse')):
+            dw = torch.zeros(4 * H, H, device=d)
+            _wgrad_pitched(hprev, di * H, 2 * H, dgx, di * 4 * H, 8 * H, dw, Tn * B, H, 4 * H, False)
+            assert rel_err(dw, p['weight_hh_l0' + suf].grad) < 5e-5, (bf, suf)
+
+
+def test_crnn_train_and_eval_vs_golden_and_oracle(shapes):
+    from oracle import models, step
+    from tpgsr_b200.model.crnn import CRNN
+    g = load_golden('crnn_train')
+    sd = _synth(shapes, 'crnn', 7)
+    p = {k: v.clone() for k, v in sd.items()}
+    leaves = {k: v.requires_grad_(True) for k, v in p.items() if step.is_param(k)}
+    gray_o = T(g['gray']).requires_grad_(True)
+    lg_o = models.crnn(gray_o, p, True)
+    (lg_o * T(g['w'])).sum().backward()
+    net = CRNN(32, 1, 37, 256)
+    net.load_state_dict(sd)
+    net = net.to(_dev()).train()
+    gray = T(g['gray']).to(_dev()).requires_grad_(True)
+    lg = net(gray)
+    assert lg.shape == (26, 3, 37)
+    (lg * T(g['w']).to(_dev())).sum().backward()
+    assert rel_err(lg, g['logits']) < 2e-4 and rel_err(lg, lg_o) < 2e-4
+    assert rel_err(gray.grad, gray_o.grad) < 2e-2          # ReLU / max-pool / batch-3 BN switches (see test_oracle_golden)
+    worst = []
+    for k, q in net.named_parameters():
+        want = leaves[k].grad
+        if float(want.norm()) < 2e-3:
+            continue
+        worst.append((rel_err(q.grad, want), k))
+        assert_fp_close(fingerprint(q.grad), g['g/' + k], k, rtol=5e-2, atol=1e-3, check_head=False)
+    worst.sort(reverse=True)
+    assert worst[0][0] < 3e-2, worst[:6]
+    for k, b in net.named_buffers():
+        if 'running_' in k:
+            assert rel_err(b, p[k]) < 1e-4, k
+    ge = load_golden('crnn_eval')
+    net2 = CRNN(32, 1, 37, 256)
+    net2.load_state_dict(sd)
+    net2 = net2.to(_dev()).eval()
+    with torch.no_grad():
+        assert rel_err(net2(T(ge['gray']).to(_dev())), ge['logits']) < 1e-4
+
+
+def test_tsrn_tl_train_and_eval_vs_golden_and_oracle(shapes):
+    from oracle import models, ops as o, step
+    from tpgsr_b200.loss.image_loss import ImageLoss
+    from tpgsr_b200.model.tsrn import TSRN_TL
+    g = load_golden('tsrn_tl_train')
+    sd = _synth(shapes, 'tsrn_tl_train', 2, g)
+    p = {k: v.clone() for k, v in sd.items()}
+    leaves = {k: v.requires_grad_(True) for k, v in p.items() if step.is_param(k)}
+    prior_o = T(g['prior']).requires_grad_(True)
+    sr_o = models.tsrn(T(g['lr']), p, True, stn=True, text_emb=prior_o, tl=True)
+    (o.image_loss(sr_o, T(g['hr'])) * 100).backward()
+    net = TSRN_TL(**KW)
+    net.load_state_dict(sd, strict=False)
+    net = net.to(_dev()).train()
+    prior = T(g['prior']).to(_dev()).requires_grad_(True)
+    sr = net(T(g['lr']).to(_dev()), prior)
+    loss = ImageLoss(gradient=True, loss_weight=[1, 1e-4])(sr, T(g['hr']).to(_dev())) * 100
+    loss.backward()
+    assert rel_err(sr, g['sr']) < 1e-3 and rel_err(sr, sr_o) < 1e-3
+    assert abs(float(loss) - float(g['loss'])) < 2e-4 * abs(float(g['loss']))
+    assert rel_err(prior.grad, prior_o.grad) < 3e-2
+    worst = []
+    for k, q in net.named_parameters():
+        want = leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])
+        if 'stn_head.' in k or float(want.norm()) < 2e-3:
+            continue
+        worst.append((rel_err(q.grad, want), k))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 3e-2, worst[:6]
+    ge = load_golden('tsrn_tl_eval')
+    net.eval()
+    with torch.no_grad():
+        sr_e = net(T(ge['lr']).to(_dev()), T(ge['prior']).to(_dev()))
+        sr_none = net(T(ge['lr']).to(_dev()))                      # text_emb=None -> zero prior (model/tsrn.py:191-193)
+    assert sr_none.shape == sr_e.shape
+    # eval uses the running statistics that the training forward above just updated, so compare against the oracle in
+    # the same state rather than the fixture (which was recorded from freshly loaded weights)
+    with torch.no_grad():
+        sr_eo = models.tsrn(T(ge['lr']), p, False, stn=True, text_emb=T(ge['prior']), tl=True)
+    assert rel_err(sr_e, sr_eo) < 2e-4
