@@ -22,15 +22,17 @@ class Ctx:
     """Parameter / gradient resolver for one forward(+backward) pass of one module."""
 
     def __init__(self, params: Dict[str, Tensor], grads: Optional[Dict[str, Tensor]], training: bool,
-                 need_input_grad: bool = False):
+                 need_input_grad: bool = False, share: Optional['Ctx'] = None):
         self.params = params          # name -> tensor (parameters and buffers, reference state_dict names + fused views)
         self.grads = grads            # name -> tensor (same names as params) or None when no backward is wanted
         self.training = training
         self.need_input_grad = need_input_grad
-        self._packed: Dict[str, tuple] = {}
-        self._packed_bf16: Dict[str, tuple] = {}
+        # a second pass over the same module inside one step (shared SR model in the cascade) reuses the packed weights
+        # and the first-write/accumulate bookkeeping of the first pass
+        self._packed: Dict[str, tuple] = share._packed if share is not None else {}
+        self._packed_bf16: Dict[str, tuple] = share._packed_bf16 if share is not None else {}
         self._planes: Dict[int, tuple] = {}
-        self._written = set()
+        self._written = share._written if share is not None else set()
 
     def P(self, name: str) -> Tensor:
         return self.params[name]

@@ -18,13 +18,18 @@ from .ops import ACT_RELU
 _LAYERS = [(2, 1), (2, 1), (2, 1), (1, 0)]
 
 
-def info_gen_fwd(ctx: engine.Ctx, x_nchw: torch.Tensor, text_emb: Optional[torch.Tensor], emb_cls: int):
+def info_gen_fwd(ctx: engine.Ctx, x_nchw: torch.Tensor, text_emb: Optional[torch.Tensor], emb_cls: int,
+                 prior_nhwc: Optional[torch.Tensor] = None):
+    """``text_emb`` is the reference's NCHW prior [B,37,1,26]; the fused train step passes the NHWC prior [B,1,26,37] that the
+    softmax/prior kernel already produced (``prior_nhwc``) and skips the layout change."""
     B, _, H, W = x_nchw.shape
-    if text_emb is None:
+    if prior_nhwc is not None:
+        text_emb = prior_nhwc
+    elif text_emb is None:
         text_emb = torch.zeros((B, emb_cls, 1, 26), dtype=torch.float32, device=x_nchw.device)
     if not text_emb.is_cuda:
         raise RuntimeError('tpgsr_b200 runs on CUDA only — text_emb must live on the same device as the images')
-    t = ops.nchw_to_nhwc(text_emb)                                  # [B,1,26,37]
+    t = prior_nhwc if prior_nhwc is not None else ops.nchw_to_nhwc(text_emb)      # [B,1,26,37]
     saved = []
     for i, (stride, pad_t) in enumerate(_LAYERS, 1):
         wname = f'infoGen.tconv{i}.weight'
@@ -42,7 +47,7 @@ def info_gen_fwd(ctx: engine.Ctx, x_nchw: torch.Tensor, text_emb: Optional[torch
     return text, {'layers': saved, 'text': text, 'w_last': t.shape[2], 'prior_shape': tuple(text_emb.shape)}
 
 
-def info_gen_bwd(ctx: engine.Ctx, s_text, dtext: torch.Tensor, need_dprior: bool):
+def info_gen_bwd(ctx: engine.Ctx, s_text, dtext: torch.Tensor, need_dprior: bool, nhwc_out: bool = False):
     d = ops_prior.bilinear_rows_bwd(dtext, s_text['w_last'])        # [B,1,203,32]
     layers = s_text['layers']
     for idx in range(len(layers) - 1, -1, -1):
@@ -56,4 +61,4 @@ def info_gen_bwd(ctx: engine.Ctx, s_text, dtext: torch.Tensor, need_dprior: bool
             return None
         dup = ops.conv_dgrad(dc, wd, (1, up.shape[2]), Ci, 1, KW, 0, pad)
         d = ops_prior.zero_upsample_w_bwd(dup, w_in, stride) if stride > 1 else dup
-    return ops.nhwc_to_nchw(d)                                       # [B,37,1,26]
+    return d if nhwc_out else ops.nhwc_to_nchw(d)                    # [B,1,26,37] or the reference's [B,37,1,26]

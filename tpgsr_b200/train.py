@@ -108,3 +108,186 @@ class TSRNTrainStep:
     def __call__(self, images_lr: torch.Tensor, images_hr: torch.Tensor) -> torch.Tensor:
         self.load_batch(images_lr, images_hr)
         return self.run()
+
+
+class TPGSRTrainStep:
+    """The cascade step of ``interfaces/super_resolution.py:297-424`` (arch ``tsrn_tl_cascade``, ``--sr_share``) as CUDA graphs:
+
+        teacher prior  : CRNN(eval)(parse_crnn_data(HR)) -> softmax                      (no grad)
+        for i < stu_iter: gray = parse_crnn_data(cascade); logits = student_i(gray); probs, prior = softmax / permute / dropout
+                          loss += 100 * SemanticLoss(probs, teacher) [use_distill]; cascade = TSRN_TL(LR, prior)
+                          loss += 100 * ImageLoss(cascade, HR)
+        backward through every stage (the stage-i SR output feeds stage i+1's recogniser un-detached),
+        clip_grad_norm_(SR params, 0.25), Adam over SR + student parameters.
+
+    Configs 3 (stu_iter=1) and 4 (stu_iter=3) of BASELINE.json.  ``students`` may hold one module (``tpg_share``) or stu_iter."""
+
+    def __init__(self, model, students, teacher, batch: int, stu_iter: int = 1, use_distill: bool = True, gradient: bool = True,
+                 loss_weight=(1.0, 1e-4), lr: float = 1e-3, beta1: float = 0.5, max_norm: float = 0.25, use_graph: bool = True,
+                 process_group=None):
+        from . import crnn_engine, infogen, ops_prior  # noqa: F401
+        self.model, self.students, self.teacher = model, list(students), teacher
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError('tpgsr_b200 runs on CUDA only — move the models to a B200 first')
+        self.dev = p0.device
+        self.stu_iter, self.use_distill = stu_iter, use_distill
+        self.gradient, self.w0, self.w1 = bool(gradient), float(loss_weight[0]), float(loss_weight[1])
+        self.tpg_share = len(self.students) == 1 and stu_iter > 1
+        assert self.tpg_share or len(self.students) == stu_iter
+        for m in [model] + self.students + [teacher]:
+            m._flat.ensure()
+        self.opt_sr = FlatAdam(model._flat.flat, n_clipped=model._flat.n, lr=lr, betas=(beta1, 0.999), max_norm=max_norm,
+                               grads=model._flat.gflat)
+        self.opt_stu = [FlatAdam(s._flat.flat, n_clipped=0, lr=lr, betas=(beta1, 0.999), max_norm=0.0, grads=s._flat.gflat)
+                        for s in self.students]
+        H, W = model.tps_inputsize
+        self.lr_buf = torch.zeros(batch, model.in_planes, H, W, device=self.dev)
+        self.hr_buf = torch.zeros(batch, model.in_planes, 2 * H, 2 * W, device=self.dev)
+        self.batch = batch
+        self.loss = torch.zeros(1, device=self.dev)
+        self.loss_img = torch.zeros(1, device=self.dev)
+        self.loss_distill = torch.zeros(1, device=self.dev)
+        self.sr = None
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        self.use_graph = use_graph
+        self._g_fb = None
+        self._g_opt = None
+        ops.workspace(256 << 20, self.dev)
+
+    def _fwd_bwd(self):
+        from . import crnn_engine, infogen, ops_prior
+        m = self.model
+        B = self.batch
+        drop = B // 4
+        st_sr = m._flat
+        # ---- teacher prior (eval mode, no grad)
+        tctx = engine.Ctx(self.teacher._flat.views, None, False)
+        gray_hr = ops_prior.bicubic_gray_fwd(self.hr_buf)
+        logits_hr, _ = crnn_engine.crnn_fwd(tctx, gray_hr)
+        label_hr, _ = ops_prior.softmax_prior_fwd(logits_hr, 0, need_prior=False)
+        # ---- cascade forward
+        stages = []
+        cascade = self.lr_buf
+        sr_ctx0 = None
+        stu_ctx = {}
+        first_img, first_dis = True, True
+        for i in range(self.stu_iter):
+            si = 0 if self.tpg_share else i
+            stu = self.students[si]
+            sctx = engine.Ctx(stu._flat.views, stu._flat.gviews, True, share=stu_ctx.get(si))
+            stu_ctx.setdefault(si, sctx)
+            if stu._flat.nbt is not None:
+                ops.add_i64(stu._flat.nbt, 1)
+            gray = ops_prior.bicubic_gray_fwd(cascade)
+            logits, s_crnn = crnn_engine.crnn_fwd(sctx, gray, need_input_grad=i > 0)
+            probs, prior = ops_prior.softmax_prior_fwd(logits, drop)
+            if self.use_distill:
+                ops.semantic_loss_fwd(probs, label_hr, 100.0, loss=self.loss_distill, accumulate=not first_dis)
+                first_dis = False
+            ctx = engine.Ctx(st_sr.views, st_sr.gviews, True, share=sr_ctx0)
+            sr_ctx0 = sr_ctx0 or ctx
+            if st_sr.nbt is not None:
+                ops.add_i64(st_sr.nbt, 1)
+            text, s_text = infogen.info_gen_fwd(ctx, self.lr_buf, None, m.emb_cls, prior_nhwc=prior)
+            sr, s_sr = engine.tsrn_fwd(ctx, self.lr_buf, m.stn, m.srb_nums, text)
+            ops.image_loss_fwd(sr, self.hr_buf, self.gradient, self.w0, self.w1, 100.0, loss=self.loss_img, accumulate=not first_img)
+            first_img = False
+            stages.append((sctx, s_crnn, probs, ctx, s_text, s_sr, sr))
+            cascade = sr
+        if not self.use_distill:
+            self.loss_distill.zero_()
+        ops.add(self.loss_img, self.loss_distill, out=self.loss)
+        # ---- cascade backward
+        dnext = None                                  # d(loss)/d(SR output of the stage) contributed by the NEXT stage's recogniser
+        for i in range(self.stu_iter - 1, -1, -1):
+            sctx, s_crnn, probs, ctx, s_text, s_sr, sr = stages[i]
+            dsr = ops.image_loss_bwd(sr, self.hr_buf, self.gradient, self.w0, self.w1, 100.0, dout=dnext, accumulate=dnext is not None)
+            dtext = torch.zeros_like(s_text['text'])
+            engine.tsrn_bwd(ctx, s_sr, dsr, dtext)
+            dprior = infogen.info_gen_bwd(ctx, s_text, dtext, True, nhwc_out=True)
+            dprobs = ops.semantic_loss_bwd(probs, label_hr, 100.0) if self.use_distill else None
+            dlogits = ops_prior.softmax_prior_bwd(probs, dprobs, dprior, drop)
+            dgray = crnn_engine.crnn_bwd(sctx, s_crnn, dlogits)
+            if i > 0:
+                dnext = torch.zeros_like(stages[i - 1][6])
+                ops_prior.bicubic_gray_bwd(dgray, dnext, False)
+        self.sr = stages[-1][6]
+
+    def _optim(self):
+        self.opt_sr.step(1.0 / self.world)
+        for o in self.opt_stu:
+            o.step(1.0 / self.world)
+
+    def _all_reduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.model._flat.gflat, group=self.pg)
+            for s in self.students:
+                torch.distributed.all_reduce(s._flat.gflat, group=self.pg)
+
+    def _capture(self):
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        mods = [self.model] + self.students
+        opts = [self.opt_sr] + self.opt_stu
+        with torch.cuda.stream(s):
+            snap = [(m._flat.flat.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.state.clone(),
+                     {k: v.clone() for k, v in m._flat.views.items() if 'running_' in k},
+                     m._flat.nbt.clone() if m._flat.nbt is not None else None) for m, o in zip(mods, opts)]
+            self._fwd_bwd()
+            self._optim()
+            for (m, o), sn in zip(zip(mods, opts), snap):
+                m._flat.flat.copy_(sn[0]); o.exp_avg.copy_(sn[1]); o.exp_avg_sq.copy_(sn[2]); o.state.copy_(sn[3])
+                for k, v in sn[4].items():
+                    m._flat.views[k].copy_(v)
+                if sn[5] is not None:
+                    m._flat.nbt.copy_(sn[5])
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self._g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fb):
+            self._fwd_bwd()
+        self._g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
+            self._optim()
+
+    def load_batch(self, images_lr, images_hr):
+        self.lr_buf.copy_(images_lr, non_blocking=True)
+        self.hr_buf.copy_(images_hr, non_blocking=True)
+
+    def run(self):
+        if self.use_graph:
+            if self._g_fb is None:
+                self._capture()
+            self._g_fb.replay()
+            self._all_reduce()
+            self._g_opt.replay()
+        else:
+            self._fwd_bwd()
+            self._all_reduce()
+            self._optim()
+        return self.loss
+
+    def __call__(self, images_lr, images_hr):
+        self.load_batch(images_lr, images_hr)
+        return self.run()
+
+
+@torch.no_grad()
+def tpgsr_infer(model, students, images_lr: torch.Tensor, stu_iter: int = 1) -> torch.Tensor:
+    """Evaluation data-flow of ``interfaces/super_resolution.py:748-768`` (eval mode: no STN, running BN stats, no prior
+    dropout) on the CUDA kernels; ``model`` / ``students`` must be in ``.eval()``."""
+    from . import crnn_engine, infogen, ops_prior
+    model._flat.ensure()
+    cascade = images_lr
+    for i in range(stu_iter):
+        stu = students[0 if len(students) == 1 else i]
+        stu._flat.ensure()
+        sctx = engine.Ctx(stu._flat.views, None, False)
+        logits, _ = crnn_engine.crnn_fwd(sctx, ops_prior.bicubic_gray_fwd(cascade))
+        _, prior = ops_prior.softmax_prior_fwd(logits, 0)
+        ctx = engine.Ctx(model._flat.views, None, False)
+        text, _ = infogen.info_gen_fwd(ctx, images_lr, None, model.emb_cls, prior_nhwc=prior)
+        cascade, _ = engine.tsrn_fwd(ctx, images_lr, model.stn, model.srb_nums, text)
+    return cascade
