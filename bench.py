@@ -171,32 +171,40 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------------------------------
 def time_dominant_kernel(device, batch: int, peaks):
-    """3x3 64->64 conv forward on [batch,16,64,64] NHWC: CUDA-event timing on the launch stream, L2 flushed between launches."""
+    """3x3 64->64 conv forward on [batch,16,64,64] NHWC through the tcgen05 kernel (tpgsr_conv2d_tc) in the active
+    CONV_MODE: CUDA-event timing on the launch stream (torch's current stream = the stream the C ABI is handed), L2
+    flushed between launches.  achieved = ALGORITHMIC flops (2*M*N*K, one product — the 3 MMAs of split-bf16 are not
+    counted three times) / launch time."""
     from tpgsr_b200 import ops
     x = torch.randn(batch, 16, 64, 64, device=device)
     w = torch.randn(64, 64, 3, 3, device=device) * 0.05
     b = torch.zeros(64, device=device)
-    wf, _ = ops.pack_conv_weights(w, False)
+    need_lo = ops.CONV_MODE == 'bf16x3'
+    xp = ops.split_bf16(x, need_lo)
+    (wf, _) = ops.pack_conv_weights_bf16(w, False, need_lo)
     y = torch.empty(batch, 16, 64, 64, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    run = lambda: ops.conv_tc(xp, wf, b, batch, 16, 64, 64, 64, 3, 3, 1, 1, out=y)
     for _ in range(3):
-        ops.conv_fwd(x, wf, b, 64, 3, 3, 1, 1, out=y)
+        run()
     torch.cuda.synchronize(device)
     durs = []
-    for _ in range(10):
+    for _ in range(20):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv_fwd(x, wf, b, 64, 3, 3, 1, 1, out=y)
+        run()
         e1.record()
         e1.synchronize()
         durs.append(e0.elapsed_time(e1) * 1e-3)
-    dur = sorted(durs)[len(durs) // 2]
+    dur = sum(durs) / len(durs)
     flops = 2.0 * batch * 16 * 64 * 64 * 576
     ach = flops / dur / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv_igemm_kernel<64,4,true> (3x3, 64->64, M=%d, fp32 CUDA cores)' % (batch * 1024),
+    nprod = 3 if need_lo else 1
+    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel<%d> (tcgen05+TMA implicit GEMM, 3x3, 64->64, M=%d, N=64, K=576, mode %s)' % (nprod, batch * 1024, ops.CONV_MODE),
             'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops_burst'],
-            'traffic': None, 'launch_us': dur * 1e6, 'algorithmic_flops_per_launch': flops,
+            'traffic': None, 'launch_us': dur * 1e6, 'launch_us_min': min(durs) * 1e6, 'algorithmic_flops_per_launch': flops,
+            'mma_flops_per_launch': flops * nprod, 'tensor_pipe_tflops': ach * nprod,
             'peak_source': peaks['source'] + ', bf16 burst (kernel timed alone)'}
 
 
@@ -259,7 +267,10 @@ def run_ours(args):
 
     with ClockSampler(local) as clocks:
         sec, wall, last_loss = timed(dev_batches, False)
-    sec_e2e, wall_e2e, _ = timed(host_batches, True)
+    if args.no_e2e:          # developer switch for profiler runs (ncu launch lists): one timed leg only
+        sec_e2e, wall_e2e = sec, wall
+    else:
+        sec_e2e, wall_e2e, _ = timed(host_batches, True)
     sec_e2e = max(sec_e2e, wall_e2e) if world == 1 else sec_e2e      # host-visible time when the D2H sync dominates
 
     imgs = B * world * args.steps
@@ -274,7 +285,7 @@ def run_ours(args):
         'metric': 'SR images/sec (16x64->32x128), TSRN train step', 'value': value, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32 (CUDA-core fp32 contractions; reference is fp32 end to end)', 'data': 'synthetic',
+        'dtype': 'f32 I/O; conv contractions ' + ops.CONV_MODE + ' on tcgen05 (fp32 accumulate in TMEM); recurrences/BN/losses/Adam fp32', 'data': 'synthetic',
         'config': {'workload': 'BASELINE configs[1]: TSRN single-stage TRAIN step, STN on, mask, ImageLoss(gradient,[1,1e-4])*100, '
                                'clip_grad_norm 0.25, Adam(1e-3,(0.5,0.999))', 'per_gpu_batch': B, 'global_batch': B * world,
                    'lr_hw': [16, 64], 'hr_hw': [32, 128], 'parallelism': f'dp{world}', 'cuda_graph': not args.no_graph,
@@ -288,7 +299,7 @@ def run_ours(args):
         'step_tflops': value * GFLOP_PER_IMG_STEP / 1e3,
         'step_frac_of_sustained_bf16_peak': value * GFLOP_PER_IMG_STEP / 1e3 / peaks['tflops_sustained'],
     }
-    if world == 1:
+    if world == 1 and not os.environ.get('TPGSR_BENCH_NO_ROOFLINE'):
         line['roofline'] = time_dominant_kernel(dev, B, peaks)
     if world == 1 and not os.environ.get('TPGSR_BENCH_NO_CPU'):     # (developer switch: skip the ~60 s CPU leg)
         threads = os.cpu_count() or 1
@@ -308,6 +319,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='developer switch: skip the host-buffer leg (profiler runs)')
     args = ap.parse_args()
     if os.environ.get('TPGSR_BENCH_TRACE'):
         import faulthandler

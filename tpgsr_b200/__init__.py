@@ -1,6 +1,6 @@
 """tpgsr_b200 — B200-native (sm_100a) implementation of the TPGSR hot path behind the reference's nn.Module API.
 
-Importing this package loads ``libtpgsr_b200.so`` (built by ``python -m tpgsr_b200.build``); there is no CPU or
+Importing this package loads ``libtpgsr_b200.so`` (built by ``python tpgsr_b200/build.py``); there is no CPU or
 PyTorch fallback.  Public surface (mirrors the reference's import paths):
 
     tpgsr_b200.model.tsrn.TSRN / TSRN_TL         model/tsrn.py

@@ -49,7 +49,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f'{LIB_PATH} not found. tpgsr_b200 has no CPU/PyTorch fallback: build the CUDA library first with '
-            f'`python -m tpgsr_b200.build` (or `python -c "import __graft_entry__ as g; g.build()"`).')
+            f'`python tpgsr_b200/build.py` (or `python -c "import __graft_entry__ as g; g.build()"`).')
     lib = ctypes.CDLL(LIB_PATH)
     decls = parse_header()
     for name, (ret, types) in decls.items():
