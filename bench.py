@@ -180,11 +180,16 @@ def time_dominant_kernel(device, batch: int, peaks):
     w = torch.randn(64, 64, 3, 3, device=device) * 0.05
     b = torch.zeros(64, device=device)
     need_lo = ops.CONV_MODE == 'bf16x3'
-    xp = ops.split_bf16(x, need_lo)
     (wf, _) = ops.pack_conv_weights_bf16(w, False, need_lo)
     y = torch.empty(batch, 16, 64, 64, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    run = lambda: ops.conv_tc(xp, wf, b, batch, 16, 64, 64, 64, 3, 3, 1, 1, out=y)
+    flat = ops.flat_supported(batch, 16, 64, 1, 64, 64, 3, 3, 1, 1)
+    if flat:
+        fp = ops.split_bf16_flat(x, 1, need_lo)
+        run = lambda: ops.conv_flat(fp, wf, b, 64, 3, 3, 1, 1, out=y)
+    else:
+        xp = ops.split_bf16(x, need_lo)
+        run = lambda: ops.conv_tc(xp, wf, b, batch, 16, 64, 64, 64, 3, 3, 1, 1, out=y)
     for _ in range(3):
         run()
     torch.cuda.synchronize(device)
@@ -201,7 +206,8 @@ def time_dominant_kernel(device, batch: int, peaks):
     flops = 2.0 * batch * 16 * 64 * 64 * 576
     ach = flops / dur / 1e12
     nprod = 3 if need_lo else 1
-    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel<%d> (tcgen05+TMA implicit GEMM, 3x3, 64->64, M=%d, N=64, K=576, mode %s)' % (nprod, batch * 1024, ops.CONV_MODE),
+    kname = 'conv_flat_kernel' if flat else 'conv_tc_kernel'
+    return {'bound': 'tensor', 'kernel': '%s<%d> (tcgen05+TMA implicit GEMM, 3x3, 64->64, M=%d, N=64, K=576, mode %s)' % (kname, nprod, batch * 1024, ops.CONV_MODE),
             'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops_burst'],
             'traffic': None, 'launch_us': dur * 1e6, 'launch_us_min': min(durs) * 1e6, 'algorithmic_flops_per_launch': flops,
             'mma_flops_per_launch': flops * nprod, 'tensor_pipe_tflops': ach * nprod,

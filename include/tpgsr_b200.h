@@ -79,6 +79,24 @@ int tpgsr_conv2d_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi,
                           int H, int W, int Ci, int Co, int Cpad, int KH, int KW, int ph, int pw, int accumulate, int nprod,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* ---- "padded-flat" tensor-core convolutions: halo rows staged ONCE in shared memory, every tap = a row offset of the same buffer ----
+ * Same reference ops as tpgsr_conv2d_tc (nn.Conv2d 'same', 64 input channels: model/tsrn.py:37,376,381,467,495,43), but the
+ * bf16 planes are stored [B][H+P][W+P][C] with zero pad rows/columns (tpgsr_split_bf16_flat) so shifted taps are row offsets. */
+int tpgsr_tc_set_desc_mode(int mode);
+int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, int H, int W, int C, int Cout, int P,
+                          cudaStream_t stream);
+int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod);
+size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, int* out);
+size_t tpgsr_conv2d_wgrad_flat_plan(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, int* out);
+int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, int B,
+                      int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
+                      const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream);
+int tpgsr_conv2d_wgrad_flat_supported(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod);
+size_t tpgsr_conv2d_wgrad_flat_workspace_bytes(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod);
+int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw_oihw, int B,
+                            int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int ph, int pw, int accumulate,
+                            int nprod, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- batch norm, activations, pooling, reshuffles -----------------------------------------------------------------
  * nn.BatchNorm2d/1d (model/tsrn.py:377,382,38; model/stn_head.py:19,51; model/crnn/crnn.py:48), mish
  * (model/tsrn.py:480-488), nn.PReLU (model/tsrn.py:28), nn.MaxPool2d (model/stn_head.py:36-44;

@@ -1,21 +1,37 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, bench (both arms), ncu launch list of one eager step, ncu --set full of the top kernels.
-# Usage (from the repo root, on the GPU box): bash scripts/gpu_check.sh [tests] [bench] [launches] [full]   (default: all)
+# One gpurun call: probes, GPU parity tests, bench (both arms), ncu launch list of one eager step, ncu --set full of the top kernels.
+# Usage (repo root, on the GPU box): bash scripts/gpu_check.sh [probe] [flat] [timing] [tests] [smoke] [bench] [refarm] [launches] [full]
 set -u
 mkdir -p gpurun_out
 what="${*:-tests bench launches full}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
+if [[ $what == *probe* ]]; then
+  timeout 300 python scripts/probe_flat.py > gpurun_out/probe_flat.log 2>&1; echo "probe rc=$?"; cat gpurun_out/probe_flat.log | tail -12
+fi
+if [[ $what == *flat* ]]; then
+  timeout 600 python -m pytest tests/test_gpu_flat.py -m gpu -q -x > gpurun_out/pytest_flat.log 2>&1; echo "pytest flat rc=$?"
+  tail -15 gpurun_out/pytest_flat.log; cat gpurun_out/desc_mode.txt 2>/dev/null
+fi
+# pick the descriptor flavour the probe validated (default 0); fall back to the per-tap kernels when neither reproduces F.conv2d
+if [[ -f gpurun_out/desc_mode.txt ]]; then
+  export TPGSR_DESC_MODE=$(sed -n 's/^desc_mode=\([01]\).*/\1/p' gpurun_out/desc_mode.txt)
+elif [[ $what == *flat* ]]; then
+  export TPGSR_FLAT=0; echo "flat kernels NOT validated: running the rest with TPGSR_FLAT=0"
+fi
+if [[ $what == *timing* ]]; then
+  timeout 300 python scripts/time_conv.py all ${TPGSR_DESC_MODE:-0} > gpurun_out/time_conv.log 2>&1; echo "timing rc=$?"; cat gpurun_out/time_conv.log
+fi
 if [[ $what == *tests* ]]; then
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-  tail -5 gpurun_out/pytest_gpu.log
+  tail -15 gpurun_out/pytest_gpu.log
 fi
 if [[ $what == *smoke* ]]; then
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
 fi
 if [[ $what == *bench* ]]; then
   timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-  cat gpurun_out/bench.json
+  cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
   TPGSR_CONV_MODE=bf16 TPGSR_BENCH_NO_CPU=1 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
   cat gpurun_out/bench_bf16.json
 fi
@@ -24,14 +40,14 @@ if [[ $what == *refarm* ]]; then
   cat gpurun_out/bench_ref.json
 fi
 if [[ $what == *launches* ]]; then
-  # eager (non-graphed) step so every launch is listed; skip the warm-up/accounting passes (first ~3 steps)
+  # eager (non-graphed) step so every launch is listed
   TPGSR_BENCH_NO_CPU=1 TPGSR_BENCH_NO_ROOFLINE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-e2e > gpurun_out/launches.log 2>&1
   echo "launches rc=$?"; wc -l gpurun_out/launches.csv
 fi
 if [[ $what == *full* ]]; then
   TPGSR_BENCH_NO_CPU=1 TPGSR_BENCH_NO_ROOFLINE=1 timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:'conv_tc_kernel|conv_wgrad_tc_kernel|gru_fwd_kernel|gru_bwd_kernel' -s 40 -c 12 -o gpurun_out/prof_top -f \
+      -k regex:'conv_flat_kernel|conv_wgrad_flat_kernel|gru_fwd_kernel|gru_bwd_kernel|gru_dwhh_kernel' -s 60 -c 14 -o gpurun_out/prof_top -f \
       python bench.py --steps 1 --warmup 3 --no-graph --no-e2e > gpurun_out/full.log 2>&1
   echo "full rc=$?"; ls -la gpurun_out/
 fi

@@ -1,0 +1,162 @@
+"""GPU parity: padded-flat tcgen05 convolutions (conv_flat.cu: forward / data gradient / weight gradient) vs fp32 F.conv2d autograd.
+
+The flat kernels address every tap as a ROW OFFSET into one shared-memory halo buffer (UMMA descriptor start address not aligned to the
+1024-byte swizzle atom).  `desc_mode` probes which descriptor flavour the hardware wants (0: base_offset = 0, 1: base_offset from the
+address) on a small 3x3 case and fails loudly if neither reproduces F.conv2d; every other test runs in the probed mode.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.from_numpy(np.random.RandomState(seed).randn(*shape).astype(np.float32) * scale)
+
+
+def _conv_case(B, Ci, Co, H, W, k, seed=0):
+    pad = k // 2
+    x = rnd(B, Ci, H, W, seed=41 + seed).requires_grad_(True)
+    w = (rnd(Co, Ci, k, k, seed=42 + seed) / np.sqrt(Ci * k * k)).requires_grad_(True)
+    b = rnd(Co, seed=43 + seed, scale=0.1)
+    y = F.conv2d(x, w, b, padding=pad)
+    gy = rnd(*y.shape, seed=44 + seed)
+    (y * gy).sum().backward()
+    return x, w, b, y, gy, pad
+
+
+def _flat_fwd(ops, xd, w, b, Co, k, pad, lo, **kw):
+    d = xd.device
+    (wf, wdg) = ops.pack_conv_weights_bf16(w.detach().to(d), True, lo)
+    xp = ops.split_bf16_flat(xd, pad, lo)
+    return ops.conv_flat(xp, wf, None if b is None else b.to(d), Co, k, k, pad, pad, **kw), wdg
+
+
+@pytest.fixture(scope='module')
+def desc_mode():
+    from tpgsr_b200 import ops
+    from tpgsr_b200._lib import LIB
+    d = torch.device('cuda:0')
+    x, w, b, y, gy, pad = _conv_case(2, 64, 64, 16, 64, 3)
+    errs = {}
+    for mode in (0, 1):
+        assert LIB.tpgsr_tc_set_desc_mode(mode) == 0
+        yd, _ = _flat_fwd(ops, nhwc(x.detach()).to(d), w, b, 64, 3, pad, True)
+        torch.cuda.synchronize()
+        errs[mode] = rel_err(nchw(yd), y)
+        if errs[mode] < 3e-5:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', 'desc_mode.txt'), 'w') as f:
+                f.write(f'desc_mode={mode} errs={errs}\n')
+            return mode
+    LIB.tpgsr_tc_set_desc_mode(0)
+    pytest.fail(f'row-shifted UMMA descriptors do not reproduce F.conv2d in either mode: {errs}')
+
+
+@pytest.mark.parametrize('B,Ci,Co,H,W,k', [
+    (3, 64, 64, 16, 64, 3),       # SRB conv (whole 3x3 halo resident, 3 tiles per CTA)
+    (2, 64, 64, 16, 64, 1),       # GruBlock 1x1 conv (P = 0: flat == dense)
+    (2, 64, 192, 16, 64, 1),      # GRU input projection (two N tiles of 96)
+    (2, 64, 256, 16, 64, 3),      # upsample conv (two N tiles of 128)
+    (1, 64, 4, 32, 128, 9),       # final conv: N = 16, one kernel row per A stage, 9 taps per B stage
+    (2, 192, 64, 16, 64, 1),      # pointwise with three channel blocks (data gradient of the GRU input projection)
+    (3, 64, 64, 5, 17, 3),        # ragged map (rows / columns that are no multiple of anything)
+    (5, 64, 128, 16, 50, 3),      # CRNN conv1 geometry
+    (7, 512, 37, 1, 1, 1),        # linear layer as a pointwise conv (8 channel blocks, ragged N)
+    (24, 64, 4, 32, 128, 9),      # final conv at a batch large enough for 2 tiles per CTA
+])
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
+def test_conv_flat_fwd_dgrad(desc_mode, B, Ci, Co, H, W, k, mode):
+    from tpgsr_b200 import ops
+    x, w, b, y, gy, pad = _conv_case(B, Ci, Co, H, W, k)
+    d = torch.device('cuda:0')
+    old = ops.CONV_MODE
+    ops.CONV_MODE = mode
+    lo = mode == 'bf16x3'
+    tol = 3e-5 if lo else 8e-3
+    try:
+        assert ops.flat_supported(B, H, W, pad, Ci, Co, k, k, pad, pad)
+        xd, gyd = nhwc(x.detach()).to(d), nhwc(gy).to(d)
+        yd, wdg = _flat_fwd(ops, xd, w, b, Co, k, pad, lo)
+        assert rel_err(nchw(yd), y) < tol, rel_err(nchw(yd), y)
+        y2, _ = _flat_fwd(ops, xd, w, b, Co, k, pad, lo, act=ops.ACT_TANH, out_nchw=True)
+        assert rel_err(y2, torch.tanh(y)) < tol
+        if ops.flat_supported(B, H, W, pad, Co, Ci, k, k, k - 1 - pad, k - 1 - pad):
+            gp = ops.split_bf16_flat(gyd, pad, lo)
+            dx = ops.conv_flat(gp, wdg, None, Ci, k, k, k - 1 - pad, k - 1 - pad)
+            assert rel_err(nchw(dx), x.grad) < tol, rel_err(nchw(dx), x.grad)
+            base = torch.ones_like(dx)
+            ops.conv_flat(gp, wdg, None, Ci, k, k, k - 1 - pad, k - 1 - pad, out=base, accumulate=True)
+            assert rel_err(base - 1, nhwc(x.grad)) < 10 * tol
+    finally:
+        ops.CONV_MODE = old
+
+
+@pytest.mark.parametrize('B,Co,H,W,k', [
+    (3, 64, 16, 64, 3),       # SRB conv
+    (2, 64, 16, 64, 1),       # GruBlock 1x1 conv
+    (2, 192, 16, 64, 1),      # GRU input projection (three N tiles of 64)
+    (2, 256, 16, 64, 3),      # upsample conv
+    (1, 4, 32, 128, 9),       # final conv: Co = 4 padded to 64, 9 kw taps in two groups
+    (3, 64, 5, 17, 3),        # ragged map
+    (48, 64, 16, 64, 3),      # full batch: 47 pixel splits
+    (16, 4, 32, 128, 9),      # final conv, many K blocks per split
+])
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
+def test_wgrad_flat(desc_mode, B, Co, H, W, k, mode):
+    from tpgsr_b200 import ops
+    Ci, pad = 64, k // 2
+    x = rnd(B, Ci, H, W, seed=51)
+    w = (rnd(Co, Ci, k, k, seed=52) / np.sqrt(Ci * k * k)).requires_grad_(True)
+    y = F.conv2d(x, w, None, padding=pad)
+    gy = rnd(*y.shape, seed=53)
+    (y * gy).sum().backward()
+    d = torch.device('cuda:0')
+    old = ops.CONV_MODE
+    ops.CONV_MODE = mode
+    try:
+        assert ops.wgrad_flat_supported(B, H, W, pad, Ci, Co, k, k)
+        lo = mode == 'bf16x3'
+        xp = ops.split_bf16_flat(nhwc(x).to(d), pad, lo)
+        dyp = ops.split_bf16_flat(nhwc(gy).to(d), pad, lo, (Co + 63) // 64 * 64)
+        dw = torch.full((Co, Ci, k, k), 3.0, device=d)
+        ops.conv_wgrad_flat(xp, dyp, dw, Co, k, k, pad, pad, False)
+        tol = 3e-5 if lo else 8e-3
+        assert rel_err(dw, w.grad) < tol, rel_err(dw, w.grad)
+        ops.conv_wgrad_flat(xp, dyp, dw, Co, k, k, pad, pad, True)
+        assert rel_err(dw, 2 * w.grad) < tol
+    finally:
+        ops.CONV_MODE = old
+
+
+def test_flat_full_batch_properties(desc_mode):
+    """BASELINE batch (B=48): linearity in the input and agreement with the per-tap TMA kernel (conv_tc) on the same planes' source."""
+    from tpgsr_b200 import ops
+    d = torch.device('cuda:0')
+    B, C, H, W = 48, 64, 16, 64
+    g = torch.Generator(device='cpu').manual_seed(7)
+    x1 = torch.randn(B, H, W, C, generator=g).to(d)
+    x2 = torch.randn(B, H, W, C, generator=g).to(d)
+    w = (torch.randn(C, C, 3, 3, generator=g) / 24.0).to(d)
+    (wf, _) = ops.pack_conv_weights_bf16(w, False, True)
+    f = lambda t: ops.conv_flat(ops.split_bf16_flat(t, 1, True), wf, None, C, 3, 3, 1, 1)
+    y1, y2, y12 = f(x1), f(x2), f(x1 + x2)
+    assert rel_err(y1 + y2, y12) < 2e-5
+    y_tc = ops.conv_tc(ops.split_bf16(x1, True), wf, None, B, H, W, C, C, 3, 3, 1, 1)
+    assert rel_err(y1, y_tc) < 2e-6
+    ref = nhwc(F.conv2d(nchw(x1).cpu(), w.cpu(), None, padding=1))
+    assert rel_err(y1, ref) < 3e-5

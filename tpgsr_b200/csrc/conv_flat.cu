@@ -1,0 +1,768 @@
+// "Padded-flat" tensor-core convolution family for sm_100a: forward / data-gradient / weight-gradient of the 'same' convolutions
+// with 64 input channels that carry ~90% of the TSRN FLOPs (model/tsrn.py:37,376,381,467,495,43; cuDNN in the reference).
+//
+// Why a second tcgen05 conv.  conv_tc.cu fetches one shifted [128 px x 64 ch] A tile per tap through a 4-D TMA: 9 fetches of the
+// same pixels for a 3x3, 81 for the 9x9.  ncu (profiles/r01) shows that kernel pinned at ~43 B/cycle/SM = the L2->SM ceiling with the
+// tensor pipe 22% busy.  Here the bf16 operand planes are stored PADDED-FLAT in HBM:
+//
+//     plane[q][c],  q = (b*(H+P) + r)*(W+P) + col,   rows r >= H and columns col >= W are zero   (P = conv padding)
+//
+// so that the neighbour of pixel q for tap (kh,kw) is simply row  q + (kh-ph)*(W+P) + (kw-pw)  of the same 2-D matrix — the
+// shared zero row/column plays the role of the left/right/top/bottom padding (and TMA zero-fills rows before the first / after the
+// last image).  A CTA loads the halo rows of MT consecutive 128-row tiles ONCE into shared memory (SWIZZLE_128B, one pixel = one
+// 128-byte row) and every tap's A operand is the same buffer at a row offset: the UMMA descriptor start address moves by
+// (kh*(W+P)+kw)*128 bytes.  A traffic drops from KH*KW x to (1 + halo/tile) x, weights are fetched once per MT tiles.
+// Outputs at pad positions are computed and dropped (8% for 16x64 maps with P=1).
+//
+// The weight gradient uses the same planes: dW_tap[ci][co] = sum_q X[q + shift(tap)][ci] * dY[q][co] is a plain GEMM over ALL rows
+// (pads contribute zeros), both operands MN-major straight from the planes, the X window shared by the KW taps of one kernel row.
+//
+// Precision modes as in conv_tc.cu: NPROD = 3 (hi*hi + hi*lo + lo*hi, fp32-class) or 1 (bf16).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int ROW_BYTES = 128;      // one pixel row of a plane: 64 bf16 channels
+constexpr int TILE_M = 128;
+
+// mbarrier wait that traps instead of hanging the GPU if a pipeline bug ever deadlocks (try_wait suspends up to ~10 ms per poll)
+__device__ __forceinline__ void mbar_wait_safe(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = tc::smem_u32(bar);
+    for (int it = 0; it < 400; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {             // 32 lanes x 16 consecutive columns
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// descriptor flavour for row-shifted operand windows (set by tpgsr_tc_set_desc_mode; validated by tests/test_gpu_flat.py):
+//   0: base_offset = 0 (swizzle is a function of the absolute shared-memory address; buffers are 1024-byte aligned)
+//   1: base_offset = (start_address >> 7) & 7
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int mode) {
+    uint64_t d = tc::smem_desc_sw128(saddr, lbo_bytes, sbo_bytes);
+    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+    return d;
+}
+
+// ============================================================================================================ forward / dgrad
+struct FlatConvParams {
+    int B, H, W, Hp, Wp;
+    long long Qtot;            // B*Hp*Wp rows in the planes
+    int Co, KH, KW, ph, pw;
+    int MT;                    // 128-row output tiles per CTA
+    int n_tile;                // output channels per CTA (multiple of 16, <= 128)
+    int tm_stride;             // TMEM columns between the accumulators of consecutive tiles (n_tile rounded up to 32)
+    int pointwise;             // 1x1 conv with Ci = 64*n_groups: the A "groups" are channel blocks instead of kernel rows
+    int G, n_groups;           // kernel rows per A stage; KH / G   (pointwise: G = 1, n_groups = Ci / 64)
+    int a_stages;              // A ring depth (1 when n_groups == 1)
+    int box_rows, n_box;       // one A stage = n_box TMA boxes of box_rows rows (box_rows % 8 == 0)
+    int tb, b_stages;          // taps per B stage; B ring depth
+    int ldy, act, out_mode, accumulate;
+    int desc_mode;
+    const float* bias;
+    const float* act_param;
+    float* y;
+};
+
+template <int NPROD>
+__global__ void __launch_bounds__(192, 1)
+conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, FlatConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int planes = NPROD == 3 ? 2 : 1;
+    const int a_plane_bytes = p.n_box * p.box_rows * ROW_BYTES;
+    const int a_stage_bytes = planes * a_plane_bytes;
+    const int b_tap_bytes = p.n_tile * ROW_BYTES;                 // one tap, one plane: [n_tile co][64 ci] K-major
+    const int b_plane_bytes = p.tb * b_tap_bytes;
+    const int b_stage_bytes = planes * b_plane_bytes;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + (size_t)p.a_stages * a_stage_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_stages * b_stage_bytes);
+    uint64_t* a_empty = a_full + p.a_stages;
+    uint64_t* b_full = a_empty + p.a_stages;
+    uint64_t* b_empty = b_full + p.b_stages;
+    uint64_t* tmem_full = b_empty + p.b_stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);      // [n_tile]
+
+    const long long q0 = (long long)blockIdx.x * p.MT * TILE_M;   // first output row of this CTA
+    const int n0 = blockIdx.y * p.n_tile;
+    const int b_per_group = (p.G * p.KW) / p.tb;                  // B stages consumed per A group
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.MT * p.tm_stride) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmA_hi);
+        tc::prefetch_tmap(&tmB_hi);
+        if (NPROD == 3) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
+        for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, tmem_cols);
+        tc::tmem_relinquish();
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < p.n_tile; i += 128)
+            bias_s[i] = (p.bias && n0 + i < p.Co) ? __ldg(p.bias + n0 + i) : 0.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            uint32_t b_it = 0;
+            for (int g = 0; g < p.n_groups; ++g) {
+                const int as = g % p.a_stages;
+                mbar_wait_safe(&a_empty[as], ((g / p.a_stages) & 1) ^ 1);
+                uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
+                tc::mbar_expect_tx(&a_full[as], (uint32_t)a_stage_bytes);
+                // first halo row of this group of kernel rows (pointwise: same rows, next 64-channel block)
+                const long long row0 = p.pointwise ? q0 : q0 + (long long)(g * p.G - p.ph) * p.Wp - p.pw;
+                const int ch0 = p.pointwise ? g * 64 : 0;
+                for (int bx = 0; bx < p.n_box; ++bx) {
+                    const int r = (int)(row0 + (long long)bx * p.box_rows);
+                    tc::tma_load_2d(ast + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_hi, &a_full[as], ch0, r);
+                    if (NPROD == 3)
+                        tc::tma_load_2d(ast + a_plane_bytes + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_lo, &a_full[as], ch0, r);
+                }
+                for (int j = 0; j < b_per_group; ++j, ++b_it) {
+                    const int bs = b_it % p.b_stages;
+                    mbar_wait_safe(&b_empty[bs], ((b_it / p.b_stages) & 1) ^ 1);
+                    uint8_t* bst = b_ring + (size_t)bs * b_stage_bytes;
+                    tc::mbar_expect_tx(&b_full[bs], (uint32_t)b_stage_bytes);
+                    for (int tt = 0; tt < p.tb; ++tt) {
+                        const int tap = g * p.G * p.KW + j * p.tb + tt;
+                        tc::tma_load_2d(bst + (size_t)tt * b_tap_bytes, &tmB_hi, &b_full[bs], tap * 64, n0);
+                        if (NPROD == 3)
+                            tc::tma_load_2d(bst + b_plane_bytes + (size_t)tt * b_tap_bytes, &tmB_lo, &b_full[bs], tap * 64, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = tc::idesc_bf16(TILE_M, p.n_tile, 0, 0);
+            const int dm = p.desc_mode;
+            uint32_t b_it = 0;
+            for (int g = 0; g < p.n_groups; ++g) {
+                const int as = g % p.a_stages;
+                mbar_wait_safe(&a_full[as], (g / p.a_stages) & 1);
+                tc::tc_fence_after();
+                const uint32_t a_hi0 = tc::smem_u32(a_ring + (size_t)as * a_stage_bytes);
+                const uint32_t a_lo0 = a_hi0 + a_plane_bytes;
+                for (int j = 0; j < b_per_group; ++j, ++b_it) {
+                    const int bs = b_it % p.b_stages;
+                    mbar_wait_safe(&b_full[bs], (b_it / p.b_stages) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t b_hi0 = tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes);
+                    const uint32_t b_lo0 = b_hi0 + b_plane_bytes;
+                    for (int tt = 0; tt < p.tb; ++tt) {
+                        const int tl = j * p.tb + tt;                  // tap index inside the group
+                        const int khl = tl / p.KW, kw = tl - khl * p.KW;
+                        const uint32_t row_off = (uint32_t)(khl * p.Wp + kw) * ROW_BYTES;
+                        const bool first_tap = (g == 0 && tl == 0);
+                        const uint32_t bh = b_hi0 + tt * b_tap_bytes, bl = b_lo0 + tt * b_tap_bytes;
+                        for (int t = 0; t < p.MT; ++t) {
+                            const uint32_t ah = a_hi0 + row_off + (uint32_t)t * TILE_M * ROW_BYTES;
+                            const uint32_t al = a_lo0 + row_off + (uint32_t)t * TILE_M * ROW_BYTES;
+                            const uint32_t d = tmem_base + (uint32_t)(t * p.tm_stride);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t koff = k * 32;          // 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                                const uint64_t da_hi = desc_sw128(ah + koff, 16, 1024, dm);
+                                const uint64_t db_hi = tc::smem_desc_sw128(bh + koff, 16, 1024);
+                                tc::umma_bf16(d, da_hi, db_hi, idesc, (first_tap && k == 0) ? 0u : 1u);
+                                if (NPROD == 3) {
+                                    const uint64_t da_lo = desc_sw128(al + koff, 16, 1024, dm);
+                                    const uint64_t db_lo = tc::smem_desc_sw128(bl + koff, 16, 1024);
+                                    tc::umma_bf16(d, da_hi, db_lo, idesc, 1);
+                                    tc::umma_bf16(d, da_lo, db_hi, idesc, 1);
+                                }
+                            }
+                        }
+                    }
+                    tc::tc_commit(&b_empty[bs]);
+                }
+                tc::tc_commit(&a_empty[as]);
+            }
+            tc::tc_commit(tmem_full);
+        }
+    } else {
+        // ================= epilogue: warps 2..5; warp w owns TMEM lanes 32*(w%4).. = rows 32*(w%4).. of every tile =================
+        const int q = warp & 3;
+        mbar_wait_safe(tmem_full, 0);
+        tc::tc_fence_after();
+        // every MMA (hence every TMA load) has completed: the rings are free and serve as per-warp staging [32 rows][n_tile+4]
+        const int pitch = p.n_tile + 4;
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * pitch;
+        const float slope = (p.act == TPGSR_ACT_PRELU && p.act_param) ? __ldg(p.act_param) : 0.f;
+        const int ncols = (p.Co - n0) < p.n_tile ? (p.Co - n0) : p.n_tile;
+        const long long img = (long long)p.Hp * p.Wp;
+        for (int t = 0; t < p.MT; ++t) {
+            const long long qrow = q0 + (long long)t * TILE_M + q * 32 + lane;      // this lane's output row
+            const int bi = (int)(qrow / img);
+            const int rem = (int)(qrow - (long long)bi * img);
+            const int r = rem / p.Wp, c = rem - r * p.Wp;
+            const bool valid = qrow < p.Qtot && r < p.H && c < p.W;
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                float v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.tm_stride + c0);
+                const int nv = (p.n_tile - c0) >= 32 ? 32 : 16;
+                if (nv == 32) tc::tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
+                tc::tmem_ld_wait();
+                if (p.out_mode == TPGSR_OUT_NHWC) {
+                    float* d = stg + (size_t)lane * pitch + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (j < nv) {
+                            float o[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) o[u] = apply_act(v[j + u] + bias_s[c0 + j + u], p.act, slope);
+                            *reinterpret_cast<float4*>(d + j) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                } else if (valid) {
+                    // NCHW: for a fixed channel the 32 lanes hold 32 consecutive flat positions = (mostly) consecutive columns
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < nv && c0 + j < ncols) {
+                            float o = apply_act(v[j] + bias_s[c0 + j], p.act, slope);
+                            float* dst = p.y + (((size_t)bi * p.Co + n0 + c0 + j) * p.H + r) * p.W + c;
+                            *dst = p.accumulate ? *dst + o : o;
+                        }
+                    }
+                }
+            }
+            if (p.out_mode == TPGSR_OUT_NHWC) {
+                __syncwarp();
+                // coalesced stores of this warp's 32 rows: the row -> pixel mapping is recomputed per row (rows may be pads)
+                const long long qbase = q0 + (long long)t * TILE_M + q * 32;
+                if ((ncols & 3) == 0 && (p.ldy & 3) == 0 && (n0 & 3) == 0) {
+                    const int c4n = ncols >> 2;
+                    for (int i = lane; i < 32 * c4n; i += 32) {
+                        const int row = i / c4n, c4 = i - row * c4n;
+                        const long long qq = qbase + row;
+                        const int b2 = (int)(qq / img);
+                        const int rem2 = (int)(qq - (long long)b2 * img);
+                        const int r2 = rem2 / p.Wp, cc2 = rem2 - r2 * p.Wp;
+                        if (qq < p.Qtot && r2 < p.H && cc2 < p.W) {
+                            float4 val = *reinterpret_cast<const float4*>(stg + (size_t)row * pitch + c4 * 4);
+                            float4* dst = reinterpret_cast<float4*>(p.y + ((size_t)(b2 * p.H + r2) * p.W + cc2) * p.ldy + n0 + c4 * 4);
+                            if (p.accumulate) {
+                                float4 o = *dst;
+                                val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                            }
+                            *dst = val;
+                        }
+                    }
+                } else {
+                    for (int i = lane; i < 32 * ncols; i += 32) {
+                        const int row = i / ncols, cc = i - row * ncols;
+                        const long long qq = qbase + row;
+                        const int b2 = (int)(qq / img);
+                        const int rem2 = (int)(qq - (long long)b2 * img);
+                        const int r2 = rem2 / p.Wp, cc2 = rem2 - r2 * p.Wp;
+                        if (qq < p.Qtot && r2 < p.H && cc2 < p.W) {
+                            float val = stg[(size_t)row * pitch + cc];
+                            float* dst = p.y + ((size_t)(b2 * p.H + r2) * p.W + cc2) * p.ldy + n0 + cc;
+                            *dst = p.accumulate ? *dst + val : val;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// fp32 dense NHWC [B,H,W,C] (pixel pitch ldx) -> padded-flat bf16 hi/lo planes [B][H+P][W+P][Cout] (pads and channels >= C zero)
+__global__ void __launch_bounds__(256)
+split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int B,
+                       int H, int W, int C, int Cout, int P) {
+    const int Hp = H + P, Wp = W + P;
+    const int cq = Cout >> 2;
+    const long long total = (long long)B * Hp * Wp * cq;
+    const bool vec = ((ldx & 3) == 0) && ((C & 3) == 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i / cq;
+        const int c = (int)(i - q * cq) * 4;
+        const int col = (int)(q % Wp);
+        const long long t = q / Wp;
+        const int r = (int)(t % Hp);
+        const int b = (int)(t / Hp);
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < H && col < W) {
+            const float* src = x + ((size_t)(b * H + r) * W + col) * ldx + c;
+            if (vec && c + 3 < C) {
+                float4 v = *reinterpret_cast<const float4*>(src);
+                f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (c + j < C) f[j] = src[j];
+            }
+        }
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2bfloat16_rn(f[j]);
+            l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+        }
+        *reinterpret_cast<uint2*>(hi + (size_t)q * Cout + c) = *reinterpret_cast<uint2*>(h);
+        if (lo) *reinterpret_cast<uint2*>(lo + (size_t)q * Cout + c) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+struct FlatPlan {
+    int MT, n_tile, n_tiles, tm_stride, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages;
+    size_t smem;
+    int grid_x;
+};
+
+int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
+    if (Co < 1 || B < 1 || H < 1 || W < 1 || Ci < 64 || Ci % 64 != 0) return TPGSR_ERR_UNSUPPORTED;
+    const int pointwise = (KH == 1 && KW == 1) ? 1 : 0;
+    if (!pointwise && Ci != 64) return TPGSR_ERR_UNSUPPORTED;
+    if (2 * ph != KH - 1 || 2 * pw != KW - 1 || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
+    const int planes = nprod == 3 ? 2 : 1;
+    const int Wp = W + P;
+    const int co16 = (Co + 15) / 16 * 16;
+    pl.n_tiles = (co16 + 127) / 128;
+    pl.n_tile = ((co16 + pl.n_tiles - 1) / pl.n_tiles + 15) / 16 * 16;
+    pl.tm_stride = (pl.n_tile + 31) / 32 * 32;
+    pl.pointwise = pointwise;
+    const long long Qtot = (long long)B * (H + P) * Wp;
+    if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
+    const size_t budget = 220 * 1024;
+    // candidate configurations, best first: whole kernel resident (G = KH) with MT = 3, 2, 1; then one kernel row per stage
+    // among the feasible MT the one with the fewest (waves x tiles per CTA) wins; near-ties go to the larger MT (less weight traffic)
+    const long long tiles = (Qtot + TILE_M - 1) / TILE_M;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && (KH == 1 || pointwise)) break;
+        long long best_cost = -1;
+        for (int MT = 3; MT >= 1; --MT) {
+            if (MT * pl.tm_stride > 512) continue;
+            const int G = pointwise ? 1 : (pass == 0 ? KH : 1);
+            const int n_groups = pointwise ? Ci / 64 : KH / G;
+            const int a_stages = n_groups > 1 ? 2 : 1;
+            const int rows = TILE_M * MT + (G - 1) * Wp + (KW - 1);
+            int n_box = (rows + 255) / 256;
+            int box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8;
+            if (box_rows > 256) { ++n_box; box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8; }
+            const size_t a_bytes = (size_t)a_stages * planes * n_box * box_rows * ROW_BYTES;
+            // B ring: one tap per stage, 4..2 deep (deepest that fits) — or one kernel row of taps per stage, 2 deep, when the
+            // tap tile is small and the kernel rows are streamed
+            const int taps_per_group = G * KW;
+            const size_t tap_bytes = (size_t)planes * pl.n_tile * ROW_BYTES;
+            const size_t stg_bytes = (size_t)4 * 32 * (pl.n_tile + 4) * sizeof(float);
+            int tb = 1, b_stages = 0;
+            size_t smem = 0;
+            const bool row_stage = n_groups > 1 && KW > 1 && tap_bytes * KW <= 40 * 1024;
+            for (int want = row_stage ? 2 : 4; want >= (row_stage ? 2 : 2); --want) {
+                tb = row_stage ? KW : 1;
+                int bs = want;
+                const int total_b = n_groups * (taps_per_group / tb);
+                if (bs > total_b) bs = total_b;
+                size_t ring = a_bytes + (size_t)bs * tb * tap_bytes;
+                if (ring < stg_bytes) ring = stg_bytes;
+                const size_t need = ring + 1024 /*align*/ + 8 * (2 * a_stages + 2 * bs + 1) + 16 + pl.n_tile * 4 + 64;
+                if (need <= budget) { b_stages = bs; smem = need; break; }
+            }
+            if (b_stages == 0) continue;
+            const long long ctas = (tiles + MT - 1) / MT * pl.n_tiles;
+            const long long cost = ((ctas + 147) / 148) * MT;
+            if (best_cost >= 0 && cost * 23 >= best_cost * 20) continue;       // a smaller MT must win by > 15%
+            best_cost = cost;
+            pl.MT = MT; pl.G = G; pl.n_groups = n_groups; pl.a_stages = a_stages; pl.box_rows = box_rows; pl.n_box = n_box;
+            pl.tb = tb; pl.b_stages = b_stages; pl.smem = smem;
+            pl.grid_x = (int)((tiles + MT - 1) / MT);
+        }
+        if (best_cost >= 0) return TPGSR_OK;
+    }
+    return TPGSR_ERR_UNSUPPORTED;
+}
+
+// ============================================================================================================ weight gradient
+constexpr int WG_KB = 128;            // flat rows (pixels) per K block
+
+struct FlatWgradParams {
+    int Wp, Co, Ci, KH, KW, ph, pw;
+    int kw_groups, taps_per_group;   // the KW taps of a kernel row are split into groups that fit TMEM
+    int n_tile;                      // co per CTA (multiple of 64)
+    int x_rows;                      // rows of the X window per K block (WG_KB + taps_per_group - 1, rounded up to 8)
+    int total_kb, kb_per_split;
+    int stages, desc_mode;
+    float* ws;                       // [splits][K = KH*KW*Ci][Co]
+};
+
+template <int NPROD>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                       const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo, FlatWgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int planes = NPROD == 3 ? 2 : 1;
+    const int kh = blockIdx.y / p.kw_groups, kwg = blockIdx.y % p.kw_groups;
+    const int kw0 = kwg * p.taps_per_group;
+    const int ntaps = (p.KW - kw0) < p.taps_per_group ? (p.KW - kw0) : p.taps_per_group;
+    const int n0 = blockIdx.z * p.n_tile;
+    const int ngroups = p.n_tile / 64;
+    const int dy_tile_bytes = WG_KB * ROW_BYTES;                  // one 64-channel group of dY rows
+    const int dy_plane_bytes = ngroups * dy_tile_bytes;
+    const int x_plane_bytes = p.x_rows * ROW_BYTES;
+    const int stage_bytes = planes * (dy_plane_bytes + x_plane_bytes);
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tmem_full = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int kb_begin = blockIdx.x * p.kb_per_split;
+    int kb_end = kb_begin + p.kb_per_split;
+    if (kb_end > p.total_kb) kb_end = p.total_kb;
+    const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.taps_per_group * p.n_tile) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmX_hi);
+        tc::prefetch_tmap(&tmD_hi);
+        if (NPROD == 3) { tc::prefetch_tmap(&tmX_lo); tc::prefetch_tmap(&tmD_lo); }
+        for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, tmem_cols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // stage layout: [dY hi groups][dY lo groups][X hi window][X lo window]
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                mbar_wait_safe(&empty[s], ((i / p.stages) & 1) ^ 1);
+                const int qk = (kb_begin + i) * WG_KB;
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                tc::mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                for (int gI = 0; gI < ngroups; ++gI) {
+                    tc::tma_load_2d(st + gI * dy_tile_bytes, &tmD_hi, &full[s], n0 + gI * 64, qk);
+                    if (NPROD == 3) tc::tma_load_2d(st + dy_plane_bytes + gI * dy_tile_bytes, &tmD_lo, &full[s], n0 + gI * 64, qk);
+                }
+                uint8_t* xs = st + planes * dy_plane_bytes;
+                const int xr = qk + (kh - p.ph) * p.Wp + (kw0 - p.pw);
+                tc::tma_load_2d(xs, &tmX_hi, &full[s], 0, xr);
+                if (NPROD == 3) tc::tma_load_2d(xs + x_plane_bytes, &tmX_lo, &full[s], 0, xr);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_bf16(64, p.n_tile, 1, 1);      // both operands MN-major
+            const int dm = p.desc_mode;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                mbar_wait_safe(&full[s], (i / p.stages) & 1);
+                tc::tc_fence_after();
+                const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t dy_hi = st, dy_lo = st + dy_plane_bytes;
+                const uint32_t x_hi = st + planes * dy_plane_bytes, x_lo = x_hi + x_plane_bytes;
+                for (int t = 0; t < ntaps; ++t) {
+                    const uint32_t d = tmem_base + (uint32_t)(t * p.n_tile);
+#pragma unroll
+                    for (int k = 0; k < WG_KB / 16; ++k) {
+                        const uint32_t koff = k * 2048;          // 16 K rows = two 1024-byte swizzle atoms
+                        const uint32_t xoff = koff + (uint32_t)t * ROW_BYTES;      // tap t = window shifted by t rows
+                        const uint64_t a_hi = desc_sw128(x_hi + xoff, 1024, 1024, dm);
+                        const uint64_t b_hi = tc::smem_desc_sw128(dy_hi + koff, dy_tile_bytes, 1024);
+                        tc::umma_bf16(d, a_hi, b_hi, idesc, (i | k) != 0);
+                        if (NPROD == 3) {
+                            const uint64_t a_lo = desc_sw128(x_lo + xoff, 1024, 1024, dm);
+                            const uint64_t b_lo = tc::smem_desc_sw128(dy_lo + koff, dy_tile_bytes, 1024);
+                            tc::umma_bf16(d, a_hi, b_lo, idesc, 1);
+                            tc::umma_bf16(d, a_lo, b_hi, idesc, 1);
+                        }
+                    }
+                }
+                tc::tc_commit(&empty[s]);
+            }
+            tc::tc_commit(tmem_full);
+        }
+    } else {
+        // epilogue.  M = 64 accumulators use the half-subpartition layout: row ci = 16*q + l lives in TMEM lane 32*q + l (l < 16)
+        const int q = warp & 3;
+        mbar_wait_safe(tmem_full, 0);
+        tc::tc_fence_after();
+        const int ci = 16 * q + lane;
+        const int K = p.KH * p.KW * p.Ci;
+        for (int t = 0; t < ntaps; ++t) {
+            const int tap = kh * p.KW + kw0 + t;
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                float v[32];
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.n_tile + c0), v);
+                tc::tmem_ld_wait();
+                if (lane < 16) {
+                    float* dst = p.ws + ((size_t)blockIdx.x * K + (size_t)tap * p.Ci + ci) * p.Co + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c0 + j < p.Co) dst[j] = nkb > 0 ? v[j] : 0.f;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+struct FlatWgradPlan {
+    int n_tile, n_tiles, kw_groups, taps_per_group, x_rows, stages, stage_bytes, total_kb, kb_per_split, splits;
+};
+
+int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, FlatWgradPlan& pl) {
+    if (Ci != 64 || Cpad % 64 != 0 || Cpad < Co || 2 * P < KH - 1 || 2 * P < KW - 1) return TPGSR_ERR_UNSUPPORTED;
+    const int planes = nprod == 3 ? 2 : 1;
+    // co tile: the candidate (multiple of 64 dividing Cpad, <= 256) with the fewest CTAs per pixel split whose ring is >= 2 deep
+    int best = -1, best_cost = 1 << 30;
+    for (int nt = 64; nt <= 256 && nt <= Cpad; nt += 64) {
+        if (Cpad % nt != 0) continue;
+        int max_taps = 512 / nt;
+        int kwg = (KW + max_taps - 1) / max_taps;
+        int tpg = (KW + kwg - 1) / kwg;
+        int xr = (WG_KB + tpg - 1 + 7) / 8 * 8;
+        int sb = planes * ((nt / 64) * WG_KB + xr) * ROW_BYTES;
+        if ((212 * 1024) / sb < 2) continue;
+        int cost = kwg * (Cpad / nt);
+        if (cost < best_cost || (cost == best_cost && nt < best)) { best = nt; best_cost = cost; }
+    }
+    if (best < 0) return TPGSR_ERR_UNSUPPORTED;
+    pl.n_tile = best;
+    pl.n_tiles = Cpad / pl.n_tile;
+    const int max_taps = 512 / pl.n_tile;
+    pl.kw_groups = (KW + max_taps - 1) / max_taps;
+    pl.taps_per_group = (KW + pl.kw_groups - 1) / pl.kw_groups;
+    pl.x_rows = (WG_KB + pl.taps_per_group - 1 + 7) / 8 * 8;
+    pl.stage_bytes = planes * ((pl.n_tile / 64) * WG_KB + pl.x_rows) * ROW_BYTES;
+    pl.stages = (212 * 1024) / pl.stage_bytes;
+    if (pl.stages > 4) pl.stages = 4;
+    const long long Qtot = (long long)B * (H + P) * (W + P);
+    if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
+    pl.total_kb = (int)((Qtot + WG_KB - 1) / WG_KB);
+    const int ctas_per_split = KH * pl.kw_groups * pl.n_tiles;
+    int want = 148 / ctas_per_split;                      // one wave of CTAs (1 CTA per SM: the ring takes the whole shared memory)
+    if (want < 1) want = 1;
+    if (want > pl.total_kb) want = pl.total_kb;
+    pl.kb_per_split = (pl.total_kb + want - 1) / want;
+    pl.splits = (pl.total_kb + pl.kb_per_split - 1) / pl.kb_per_split;
+    return TPGSR_OK;
+}
+
+int g_desc_mode = 0;
+
+}  // namespace
+
+// defined in conv_simt.cu
+extern "C" int tpgsr_conv2d_wgrad_reduce(const float* ws, float* dw_oihw, int splits, int K, int N, int Ci, int KH, int KW,
+                                         int accumulate, cudaStream_t stream);
+
+extern "C" {
+
+int tpgsr_tc_set_desc_mode(int mode) {
+    if (mode != 0 && mode != 1) return TPGSR_ERR_BAD_ARG;
+    g_desc_mode = mode;
+    return TPGSR_OK;
+}
+
+int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, int H, int W, int C, int Cout, int P,
+                          cudaStream_t stream) {
+    if (!x || !hi || (Cout & 3) || Cout < C || B < 1 || H < 1 || W < 1 || P < 0) return TPGSR_ERR_BAD_ARG;
+    long long blocks = ((long long)B * (H + P) * (W + P) * (Cout / 4) + 255) / 256;
+    split_bf16_flat_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, stream>>>(
+        x, ldx, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, H, W, C, Cout, P);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod) {
+    FlatPlan pl;
+    return plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl) == TPGSR_OK ? 1 : 0;
+}
+
+// tiling decided for a geometry (host-only; lets tests / docs inspect the plan without a GPU):
+// out[12] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x}; returns smem bytes (0 = unsupported)
+size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, int* out) {
+    FlatPlan pl;
+    if (plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl)) return 0;
+    if (out) {
+        const int v[12] = {pl.MT, pl.n_tile, pl.n_tiles, pl.tm_stride, pl.G, pl.n_groups, pl.a_stages, pl.box_rows, pl.n_box, pl.tb,
+                           pl.b_stages, pl.grid_x};
+        for (int i = 0; i < 12; ++i) out[i] = v[i];
+    }
+    return pl.smem;
+}
+
+// out[9] = {n_tile, n_tiles, kw_groups, taps_per_group, x_rows, stages, total_kb, kb_per_split, splits}; returns stage bytes (0 = unsupported)
+size_t tpgsr_conv2d_wgrad_flat_plan(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, int* out) {
+    FlatWgradPlan pl;
+    if (plan_wgrad_flat(B, H, W, P, Ci, Co, Cpad, KH, KW, nprod, pl)) return 0;
+    if (out) {
+        const int v[9] = {pl.n_tile, pl.n_tiles, pl.kw_groups, pl.taps_per_group, pl.x_rows, pl.stages, pl.total_kb, pl.kb_per_split,
+                          pl.splits};
+        for (int i = 0; i < 9; ++i) out[i] = v[i];
+    }
+    return (size_t)pl.stage_bytes;
+}
+
+// y = act(conv(x) + bias) for a 'same' convolution with 64 input channels.  x_hi/x_lo: padded-flat bf16 planes of the input
+// ([B][H+P][W+P][64], tpgsr_split_bf16_flat); w_hi/w_lo: K-major packed weights [Co][KH*KW*64] (tpgsr_pack_conv_weights_bf16);
+// y: fp32 dense NHWC (pixel pitch ldy) or NCHW.  Data gradient: pass dY planes, the dgrad packing, Co := conv Ci.
+int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, int B,
+                      int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
+                      const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream) {
+    if (!x_hi || !w_hi || !y || (nprod != 1 && nprod != 3) || (nprod == 3 && (!x_lo || !w_lo))) return TPGSR_ERR_BAD_ARG;
+    FlatPlan pl;
+    int rc = plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl);
+    if (rc) return rc;
+    FlatConvParams p;
+    p.B = B; p.H = H; p.W = W; p.Hp = H + P; p.Wp = W + P; p.Qtot = (long long)B * p.Hp * p.Wp;
+    p.Co = Co; p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw;
+    p.MT = pl.MT; p.n_tile = pl.n_tile; p.tm_stride = pl.tm_stride; p.pointwise = pl.pointwise; p.G = pl.G; p.n_groups = pl.n_groups;
+    p.a_stages = pl.a_stages;
+    p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages;
+    p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate; p.desc_mode = g_desc_mode;
+    p.bias = bias; p.act_param = act_param; p.y = y;
+
+    const uint64_t K = (uint64_t)KH * KW * Ci;
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+    uint64_t adims[2] = {(uint64_t)Ci, (uint64_t)p.Qtot};
+    uint64_t astr[1] = {(uint64_t)Ci * 2};
+    uint32_t abox[2] = {64, (uint32_t)pl.box_rows};
+    uint64_t bdims[2] = {K, (uint64_t)Co};
+    uint64_t bstr[1] = {K * 2};
+    uint32_t bbox[2] = {64, (uint32_t)pl.n_tile};
+    if (tpgsr_make_tmap_bf16(&tmA_hi, x_hi, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
+    if (tpgsr_make_tmap_bf16(&tmB_hi, w_hi, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
+    if (nprod == 3) {
+        if (tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
+        if (tpgsr_make_tmap_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
+    } else {
+        tmA_lo = tmA_hi;
+        tmB_lo = tmB_hi;
+    }
+    dim3 grid(pl.grid_x, pl.n_tiles);
+    if (nprod == 3) {
+        if (cudaFuncSetAttribute(conv_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        conv_flat_kernel<3><<<grid, 192, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    } else {
+        if (cudaFuncSetAttribute(conv_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        conv_flat_kernel<1><<<grid, 192, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    }
+    return tpgsr_launch_status();
+}
+
+int tpgsr_conv2d_wgrad_flat_supported(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod) {
+    FlatWgradPlan pl;
+    return plan_wgrad_flat(B, H, W, P, Ci, Co, Cpad, KH, KW, nprod, pl) == TPGSR_OK ? 1 : 0;
+}
+
+size_t tpgsr_conv2d_wgrad_flat_workspace_bytes(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod) {
+    FlatWgradPlan pl;
+    if (plan_wgrad_flat(B, H, W, P, Ci, Co, Cpad, KH, KW, nprod, pl)) return 0;
+    return (size_t)pl.splits * KH * KW * Ci * Co * sizeof(float);
+}
+
+// dW (OIHW) (+)= weight gradient of a 'same' conv.  x planes: padded-flat [B][H+P][W+P][64]; dy planes: padded-flat
+// [B][H+P][W+P][Cpad] (channels >= Co zero), same P.
+int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw_oihw, int B, int H,
+                            int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int ph, int pw, int accumulate, int nprod,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!x_hi || !dy_hi || !dw_oihw || !workspace || (nprod != 1 && nprod != 3) || (nprod == 3 && (!x_lo || !dy_lo)))
+        return TPGSR_ERR_BAD_ARG;
+    if (2 * ph != KH - 1 || 2 * pw != KW - 1 || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
+    FlatWgradPlan pl;
+    int rc = plan_wgrad_flat(B, H, W, P, Ci, Co, Cpad, KH, KW, nprod, pl);
+    if (rc) return rc;
+    if (workspace_bytes < (size_t)pl.splits * KH * KW * Ci * Co * sizeof(float)) return TPGSR_ERR_WORKSPACE;
+    const long long Qtot = (long long)B * (H + P) * (W + P);
+    FlatWgradParams p;
+    p.Wp = W + P; p.Co = Co; p.Ci = Ci; p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw;
+    p.kw_groups = pl.kw_groups; p.taps_per_group = pl.taps_per_group; p.n_tile = pl.n_tile; p.x_rows = pl.x_rows;
+    p.total_kb = pl.total_kb; p.kb_per_split = pl.kb_per_split; p.stages = pl.stages; p.desc_mode = g_desc_mode;
+    p.ws = static_cast<float*>(workspace);
+
+    CUtensorMap tmX_hi, tmX_lo, tmD_hi, tmD_lo;
+    uint64_t xd[2] = {(uint64_t)Ci, (uint64_t)Qtot};
+    uint64_t xs[1] = {(uint64_t)Ci * 2};
+    uint32_t xbox[2] = {64, (uint32_t)pl.x_rows};
+    uint64_t dd[2] = {(uint64_t)Cpad, (uint64_t)Qtot};
+    uint64_t ds[1] = {(uint64_t)Cpad * 2};
+    uint32_t dbox[2] = {64, (uint32_t)WG_KB};
+    if (tpgsr_make_tmap_bf16(&tmX_hi, x_hi, 2, xd, xs, xbox)) return TPGSR_ERR_DRIVER;
+    if (tpgsr_make_tmap_bf16(&tmD_hi, dy_hi, 2, dd, ds, dbox)) return TPGSR_ERR_DRIVER;
+    if (nprod == 3) {
+        if (tpgsr_make_tmap_bf16(&tmX_lo, x_lo, 2, xd, xs, xbox)) return TPGSR_ERR_DRIVER;
+        if (tpgsr_make_tmap_bf16(&tmD_lo, dy_lo, 2, dd, ds, dbox)) return TPGSR_ERR_DRIVER;
+    } else {
+        tmX_lo = tmX_hi;
+        tmD_lo = tmD_hi;
+    }
+    const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + 256;
+    dim3 grid(pl.splits, KH * pl.kw_groups, pl.n_tiles);
+    if (nprod == 3) {
+        if (cudaFuncSetAttribute(conv_wgrad_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        conv_wgrad_flat_kernel<3><<<grid, 192, smem, stream>>>(tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
+    } else {
+        if (cudaFuncSetAttribute(conv_wgrad_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        conv_wgrad_flat_kernel<1><<<grid, 192, smem, stream>>>(tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
+    }
+    rc = tpgsr_launch_status();
+    if (rc) return rc;
+    return tpgsr_conv2d_wgrad_reduce(static_cast<float*>(workspace), dw_oihw, pl.splits, KH * KW * Ci, Co, Ci, KH, KW, accumulate, stream);
+}
+
+}  // extern "C"

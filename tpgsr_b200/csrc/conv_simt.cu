@@ -360,8 +360,19 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __
     const int total = K * N;
     const int idx = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    if (idx < total)
-        for (int z = threadIdx.y; z < splits; z += 8) s += ws[(size_t)z * total + idx];
+    if (idx < total) {
+        // independent partial sums keep 4 loads in flight per thread (fixed association order: deterministic)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int z = threadIdx.y;
+        for (; z + 24 < splits; z += 32) {
+            s0 += __ldg(ws + (size_t)z * total + idx);
+            s1 += __ldg(ws + (size_t)(z + 8) * total + idx);
+            s2 += __ldg(ws + (size_t)(z + 16) * total + idx);
+            s3 += __ldg(ws + (size_t)(z + 24) * total + idx);
+        }
+        for (; z < splits; z += 8) s0 += __ldg(ws + (size_t)z * total + idx);
+        s = (s0 + s1) + (s2 + s3);
+    }
     __shared__ float sh[8][33];
     sh[threadIdx.y][threadIdx.x] = s;
     __syncthreads();

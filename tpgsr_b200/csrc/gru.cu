@@ -2,15 +2,19 @@
 //
 // Reference op replaced: nn.GRU(64, 32, bidirectional=True, batch_first=True) inside GruBlock
 // (model/tsrn.py:491-508; cuDNN RNN in the reference).  The input projection W_ih x + b_ih is a plain GEMM done by the
-// conv/GEMM kernels; this file is the serial part: one warp per (sequence, direction), lane = hidden unit, the 96x32
-// recurrent matrix held in registers (forward) / shared memory (backward), h broadcast through shared memory.
+// conv/GEMM kernels; this file is the serial part: one warp per (sequence, direction), lane = hidden unit, the recurrent
+// matrix held in registers (rows of W_hh forward, columns backward), h / gate gradients broadcast through shared memory.
 // Gate order r,z,n;  n = tanh(gx_n + r * (W_hn h + b_hn));  h' = (1-z) n + z h   (SURVEY Appendix B).
 //
 // Sequences are addressed on the pixel-row index m of the NHWC map so that the column-wise GRU (gru1, which the reference
 // runs on a transposed copy) needs no transpose:  m(s,t) = (s / inner) * outer_stride + (s % inner) * inner_stride + t * t_stride.
 //
-// Latency-bound (serial T); traffic per (pixel, direction): read 96 gate pre-activations + write 32 outputs + 128 stash
-// floats.  Reported in DESIGN.md as achieved bytes/s and steps/us, not against the tensor roofline.
+// Round-1 profile (profiles/r01): the first version prefetched one step ahead (forward) / not at all (backward) and ran at
+// ~1 700 cycles per serial step = DRAM latency.  This version keeps a PF-deep register ring of every per-step operand, sizes
+// the grid to one resident wave, issues the 32x96 mat-vec as packed fp32 FMAs (FFMA2, sm_100) and moves the dW_hh outer products
+// out of the serial loop into their own reduction kernel, so the recurrences are issue/HBM bound instead of latency bound.
+// Traffic per (pixel, direction): forward reads 96 gate pre-activations, writes 32 outputs (+32 fused residual sum) + 128 stash
+// floats; backward reads 32 dy + 32 h + 128 stash, writes 96.
 #include "common.cuh"
 
 namespace {
@@ -26,11 +30,14 @@ __device__ __forceinline__ long seq_base(const SeqGeom& g, int s) {
 
 constexpr int H = 32;          // hidden units per direction
 constexpr int WARPS = 4;
+constexpr int PF = 4;          // prefetch depth (steps) of the register rings
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
 // gx: [M, 192] = [dir][gate r,z,n][32] pre-activations from the input side (bias_ih included)
 // y:  [M, ldy] GRU output (dir0 -> cols 0..31, dir1 -> cols 32..63); ysum = y + residual (optional)
 // stash: [M][2][4][32] = r, z, n, (W_hn h + b_hn)   (training only; may be NULL)
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 3)
 gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, const float* __restrict__ bhh,
                float* __restrict__ y, int ldy, const float* __restrict__ residual, int ldr, float* __restrict__ ysum,
                int ldys, float* __restrict__ stash, SeqGeom g) {
@@ -38,167 +45,271 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, cons
     const int dir = blockIdx.y;
     __shared__ __align__(16) float hbuf[WARPS][H];
 
-    float wr[H], wz[H], wn[H];
+    // row `lane` of W_hr / W_hz / W_hn as 16 (even, odd) pairs: one FFMA2 covers two recurrent inputs
+    float2 wr[H / 2], wz[H / 2], wn[H / 2];
     const float* W = whh + (size_t)dir * 3 * H * H;
 #pragma unroll
-    for (int i = 0; i < H; ++i) {
-        wr[i] = __ldg(W + (0 * H + lane) * H + i);
-        wz[i] = __ldg(W + (1 * H + lane) * H + i);
-        wn[i] = __ldg(W + (2 * H + lane) * H + i);
+    for (int i = 0; i < H / 2; ++i) {
+        wr[i] = __ldg(reinterpret_cast<const float2*>(W + (0 * H + lane) * H) + i);
+        wz[i] = __ldg(reinterpret_cast<const float2*>(W + (1 * H + lane) * H) + i);
+        wn[i] = __ldg(reinterpret_cast<const float2*>(W + (2 * H + lane) * H) + i);
     }
     const float bhr = __ldg(bhh + dir * 3 * H + lane), bhz = __ldg(bhh + dir * 3 * H + H + lane),
                 bhn = __ldg(bhh + dir * 3 * H + 2 * H + lane);
+    const bool has_res = ysum != nullptr;
 
     for (int s = blockIdx.x * WARPS + warp; s < g.S; s += gridDim.x * WARPS) {
-        const long base = seq_base(g, s);
+        const long m0 = seq_base(g, s) + (dir ? (long)(g.T - 1) * g.t_stride : 0);
+        const long step = dir ? -g.t_stride : g.t_stride;
+        float pr[PF], pz[PF], pn[PF], pres[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            pr[u] = pz[u] = pn[u] = pres[u] = 0.f;
+            if (u < g.T) {
+                const long m = m0 + u * step;
+                const float* gp = gx + (size_t)m * 6 * H + dir * 3 * H + lane;
+                pr[u] = __ldg(gp); pz[u] = __ldg(gp + H); pn[u] = __ldg(gp + 2 * H);
+                if (has_res) pres[u] = __ldg(residual + (size_t)m * ldr + dir * H + lane);
+            }
+        }
         float h = 0.f;
+        __syncwarp();
         hbuf[warp][lane] = 0.f;
         __syncwarp();
-        long m = base + (dir ? (long)(g.T - 1) * g.t_stride : 0);
-        const long step = dir ? -g.t_stride : g.t_stride;
-        const float* gp = gx + (size_t)m * 6 * H + dir * 3 * H + lane;
-        float gxr = __ldg(gp), gxz = __ldg(gp + H), gxn = __ldg(gp + 2 * H);
-        for (int t = 0; t < g.T; ++t) {
-            float nr = 0.f, nz = 0.f, nn = 0.f;
-            if (t + 1 < g.T) {   // prefetch next step's pre-activations
-                const float* np = gx + (size_t)(m + step) * 6 * H + dir * 3 * H + lane;
-                nr = __ldg(np); nz = __ldg(np + H); nn = __ldg(np + 2 * H);
-            }
-            float ar = bhr, az = bhz, an = bhn;
+        for (int t0 = 0; t0 < g.T; t0 += PF) {
 #pragma unroll
-            for (int q = 0; q < H / 4; ++q) {
-                float4 hv = *reinterpret_cast<const float4*>(&hbuf[warp][q * 4]);
-                ar = fmaf(wr[q * 4 + 0], hv.x, ar); az = fmaf(wz[q * 4 + 0], hv.x, az); an = fmaf(wn[q * 4 + 0], hv.x, an);
-                ar = fmaf(wr[q * 4 + 1], hv.y, ar); az = fmaf(wz[q * 4 + 1], hv.y, az); an = fmaf(wn[q * 4 + 1], hv.y, an);
-                ar = fmaf(wr[q * 4 + 2], hv.z, ar); az = fmaf(wz[q * 4 + 2], hv.z, az); an = fmaf(wn[q * 4 + 2], hv.z, an);
-                ar = fmaf(wr[q * 4 + 3], hv.w, ar); az = fmaf(wz[q * 4 + 3], hv.w, az); an = fmaf(wn[q * 4 + 3], hv.w, an);
+            for (int u = 0; u < PF; ++u) {
+                const int t = t0 + u;
+                if (t < g.T) {
+                    const long m = m0 + t * step;
+                    const float gxr = pr[u], gxz = pz[u], gxn = pn[u], res = pres[u];
+                    if (t + PF < g.T) {   // refill this ring slot with the operands of step t + PF
+                        const long mn = m + PF * step;
+                        const float* np = gx + (size_t)mn * 6 * H + dir * 3 * H + lane;
+                        pr[u] = __ldg(np); pz[u] = __ldg(np + H); pn[u] = __ldg(np + 2 * H);
+                        if (has_res) pres[u] = __ldg(residual + (size_t)mn * ldr + dir * H + lane);
+                    }
+                    float2 ar = make_float2(bhr, 0.f), az = make_float2(bhz, 0.f), an = make_float2(bhn, 0.f);
+#pragma unroll
+                    for (int q = 0; q < H / 4; ++q) {
+                        const float4 hv = *reinterpret_cast<const float4*>(&hbuf[warp][q * 4]);
+                        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+                        ar = ffma2(wr[2 * q], h01, ar); az = ffma2(wz[2 * q], h01, az); an = ffma2(wn[2 * q], h01, an);
+                        ar = ffma2(wr[2 * q + 1], h23, ar); az = ffma2(wz[2 * q + 1], h23, az); an = ffma2(wn[2 * q + 1], h23, an);
+                    }
+                    const float hn = an.x + an.y;
+                    const float r = sigmoid_f(gxr + (ar.x + ar.y));
+                    const float z = sigmoid_f(gxz + (az.x + az.y));
+                    const float n = tanhf(gxn + r * hn);
+                    h = (1.f - z) * n + z * h;
+                    y[(size_t)m * ldy + dir * H + lane] = h;
+                    if (has_res) ysum[(size_t)m * ldys + dir * H + lane] = h + res;
+                    if (stash) {
+                        float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
+                        sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = hn;
+                    }
+                    __syncwarp();
+                    hbuf[warp][lane] = h;
+                    __syncwarp();
+                }
             }
-            float r = sigmoid_f(gxr + ar);
-            float z = sigmoid_f(gxz + az);
-            float n = tanhf(gxn + r * an);
-            h = (1.f - z) * n + z * h;
-            y[(size_t)m * ldy + dir * H + lane] = h;
-            if (ysum) ysum[(size_t)m * ldys + dir * H + lane] = h + residual[(size_t)m * ldr + dir * H + lane];
-            if (stash) {
-                float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
-                sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = an;
-            }
-            __syncwarp();
-            hbuf[warp][lane] = h;
-            __syncwarp();
-            gxr = nr; gxz = nz; gxn = nn;
-            m += step;
         }
     }
 }
 
-// BPTT.  dy: grad wrt GRU output [M, lddy]; y: forward output (h values); stash from forward.
-// Writes dgx [M,192] and per-block partials of dW_hh [2][96][32], db_hh [2][96]; db_ih partials [2][96].
-// partial layout: part[block][dir][ 3072 (dWhh) + 96 (dbhh) + 96 (dbih) ]
+// workspace layout shared by the two backward kernels and the reduction: part[block][dir][PART]
+//   [0, 3072)      dW_hh partial  [g*32 + j][i]          (gru_dwhh_kernel)
+//   [3072, 3168)   db_hh partial  [g*32 + j]             (gru_bwd_kernel)
+//   [3168, 3264)   db_ih partial  [g*32 + j]             (gru_bwd_kernel)
 constexpr int PART = 3 * H * H + 6 * H;
 
-__global__ void __launch_bounds__(WARPS * 32)
+// BPTT, serial part.  dy: grad wrt GRU output [M, lddy]; y: forward output (h values); stash from forward.
+// Writes dgx [M,192] = (dr_pre, dz_pre, dn_pre) and per-block bias-gradient partials.
+__global__ void __launch_bounds__(WARPS * 32, 3)
 gru_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
                const float* __restrict__ stash, const float* __restrict__ whh, float* __restrict__ dgx,
                float* __restrict__ part, SeqGeom g) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    __shared__ __align__(16) float Wsm[3 * H * H];          // [g*32+j][i]
-    __shared__ __align__(16) float dg[WARPS][3][H];          // broadcast of dgh = (dr_pre, dz_pre, d_hn)
-    __shared__ float red[3 * H * H];
-    for (int i = threadIdx.x; i < 3 * H * H; i += blockDim.x) Wsm[i] = __ldg(whh + (size_t)dir * 3 * H * H + i);
-    __syncthreads();
+    __shared__ __align__(16) float dg[WARPS][3][H];          // broadcast of (dr_pre, dz_pre, d_hn)
+    __shared__ float red[WARPS][6][H];
 
-    float acc[3][H];   // dW_hh[g*32+j][lane]
+    // column `lane` of W_hr / W_hz / W_hn as (j, j+1) pairs:  dh_prev[lane] += sum_j W[g*32+j][lane] * dgate_g[j]
+    float2 wr[H / 2], wz[H / 2], wn[H / 2];
+    const float* W = whh + (size_t)dir * 3 * H * H;
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int j = 0; j < H; ++j) acc[a][j] = 0.f;
+    for (int j = 0; j < H / 2; ++j) {
+        wr[j] = make_float2(__ldg(W + (0 * H + 2 * j) * H + lane), __ldg(W + (0 * H + 2 * j + 1) * H + lane));
+        wz[j] = make_float2(__ldg(W + (1 * H + 2 * j) * H + lane), __ldg(W + (1 * H + 2 * j + 1) * H + lane));
+        wn[j] = make_float2(__ldg(W + (2 * H + 2 * j) * H + lane), __ldg(W + (2 * H + 2 * j + 1) * H + lane));
+    }
     float dbh[3] = {0.f, 0.f, 0.f}, dbi[3] = {0.f, 0.f, 0.f};
 
     for (int s = blockIdx.x * WARPS + warp; s < g.S; s += gridDim.x * WARPS) {
-        const long base = seq_base(g, s);
         // BPTT walks the processing order backwards: dir0 processed t=0..T-1 -> walk T-1..0; dir1 processed T-1..0 -> walk 0..T-1
-        long m = base + (dir ? 0 : (long)(g.T - 1) * g.t_stride);
+        const long m0 = seq_base(g, s) + (dir ? 0 : (long)(g.T - 1) * g.t_stride);
         const long step = dir ? g.t_stride : -g.t_stride;      // towards the previously processed element
+        float p_dy[PF], p_hp[PF], p_r[PF], p_z[PF], p_n[PF], p_hn[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            p_dy[u] = p_hp[u] = p_r[u] = p_z[u] = p_n[u] = p_hn[u] = 0.f;
+            if (u < g.T) {
+                const long m = m0 + u * step;
+                const float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
+                p_r[u] = __ldg(sp); p_z[u] = __ldg(sp + H); p_n[u] = __ldg(sp + 2 * H); p_hn[u] = __ldg(sp + 3 * H);
+                p_dy[u] = __ldg(dy + (size_t)m * lddy + dir * H + lane);
+                if (u + 1 < g.T) p_hp[u] = __ldg(y + (size_t)(m + step) * ldy + dir * H + lane);
+            }
+        }
         float dh = 0.f;
-        for (int t = 0; t < g.T; ++t) {
-            const bool has_prev = t + 1 < g.T;
-            float hprev = has_prev ? __ldg(y + (size_t)(m + step) * ldy + dir * H + lane) : 0.f;
-            const float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
-            float r = __ldg(sp), z = __ldg(sp + H), n = __ldg(sp + 2 * H), hn = __ldg(sp + 3 * H);
-            dh += __ldg(dy + (size_t)m * lddy + dir * H + lane);
-            float dn = dh * (1.f - z);
-            float dz = dh * (hprev - n);
-            float dn_pre = dn * (1.f - n * n);
-            float dr_pre = dn_pre * hn * r * (1.f - r);
-            float dz_pre = dz * z * (1.f - z);
-            float dhn = dn_pre * r;
-            float* gp = dgx + (size_t)m * 6 * H + dir * 3 * H + lane;
-            gp[0] = dr_pre; gp[H] = dz_pre; gp[2 * H] = dn_pre;
-            dbi[0] += dr_pre; dbi[1] += dz_pre; dbi[2] += dn_pre;
-            dbh[0] += dr_pre; dbh[1] += dz_pre; dbh[2] += dhn;
-            __syncwarp();
-            dg[warp][0][lane] = dr_pre; dg[warp][1][lane] = dz_pre; dg[warp][2][lane] = dhn;
-            __syncwarp();
-            float carry = dh * z;
+        for (int t0 = 0; t0 < g.T; t0 += PF) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int u = 0; u < PF; ++u) {
+                const int t = t0 + u;
+                if (t < g.T) {
+                    const long m = m0 + t * step;
+                    const float r = p_r[u], z = p_z[u], n = p_n[u], hn = p_hn[u], hprev = p_hp[u];
+                    dh += p_dy[u];
+                    if (t + PF < g.T) {
+                        const long mn = m + PF * step;
+                        const float* sp = stash + ((size_t)mn * 2 + dir) * 4 * H + lane;
+                        p_r[u] = __ldg(sp); p_z[u] = __ldg(sp + H); p_n[u] = __ldg(sp + 2 * H); p_hn[u] = __ldg(sp + 3 * H);
+                        p_dy[u] = __ldg(dy + (size_t)mn * lddy + dir * H + lane);
+                        p_hp[u] = (t + PF + 1 < g.T) ? __ldg(y + (size_t)(mn + step) * ldy + dir * H + lane) : 0.f;
+                    }
+                    const float dn = dh * (1.f - z);
+                    const float dz = dh * (hprev - n);
+                    const float dn_pre = dn * (1.f - n * n);
+                    const float dr_pre = dn_pre * hn * r * (1.f - r);
+                    const float dz_pre = dz * z * (1.f - z);
+                    const float dhn = dn_pre * r;
+                    float* gp = dgx + (size_t)m * 6 * H + dir * 3 * H + lane;
+                    gp[0] = dr_pre; gp[H] = dz_pre; gp[2 * H] = dn_pre;
+                    dbi[0] += dr_pre; dbi[1] += dz_pre; dbi[2] += dn_pre;
+                    dbh[0] += dr_pre; dbh[1] += dz_pre; dbh[2] += dhn;
+                    __syncwarp();
+                    dg[warp][0][lane] = dr_pre; dg[warp][1][lane] = dz_pre; dg[warp][2][lane] = dhn;
+                    __syncwarp();
+                    float2 c0 = make_float2(dh * z, 0.f), c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int q = 0; q < H / 4; ++q) {
-                    float4 v = *reinterpret_cast<const float4*>(&dg[warp][a][q * 4]);
-                    const float* wp = &Wsm[(a * H + q * 4) * H + lane];
-                    carry = fmaf(wp[0], v.x, carry);
-                    carry = fmaf(wp[H], v.y, carry);
-                    carry = fmaf(wp[2 * H], v.z, carry);
-                    carry = fmaf(wp[3 * H], v.w, carry);
-                    acc[a][q * 4 + 0] = fmaf(v.x, hprev, acc[a][q * 4 + 0]);
-                    acc[a][q * 4 + 1] = fmaf(v.y, hprev, acc[a][q * 4 + 1]);
-                    acc[a][q * 4 + 2] = fmaf(v.z, hprev, acc[a][q * 4 + 2]);
-                    acc[a][q * 4 + 3] = fmaf(v.w, hprev, acc[a][q * 4 + 3]);
+                    for (int q = 0; q < H / 4; ++q) {
+                        const float4 vr = *reinterpret_cast<const float4*>(&dg[warp][0][q * 4]);
+                        const float4 vz = *reinterpret_cast<const float4*>(&dg[warp][1][q * 4]);
+                        const float4 vn = *reinterpret_cast<const float4*>(&dg[warp][2][q * 4]);
+                        c0 = ffma2(wr[2 * q], make_float2(vr.x, vr.y), c0); c0 = ffma2(wr[2 * q + 1], make_float2(vr.z, vr.w), c0);
+                        c1 = ffma2(wz[2 * q], make_float2(vz.x, vz.y), c1); c1 = ffma2(wz[2 * q + 1], make_float2(vz.z, vz.w), c1);
+                        c2 = ffma2(wn[2 * q], make_float2(vn.x, vn.y), c2); c2 = ffma2(wn[2 * q + 1], make_float2(vn.z, vn.w), c2);
+                    }
+                    dh = (c0.x + c0.y) + (c1.x + c1.y) + (c2.x + c2.y);
                 }
             }
-            dh = carry;
-            m += step;
         }
     }
-    // deterministic block reduction: warps add their accumulators one after another
-    for (int wsel = 0; wsel < WARPS; ++wsel) {
-        if (warp == wsel) {
+    // deterministic block reduction of the bias partials (fixed warp order)
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 3; ++a) { red[warp][a][lane] = dbh[a]; red[warp][3 + a][lane] = dbi[a]; }
+    __syncthreads();
+    float* out = part + ((size_t)blockIdx.x * 2 + dir) * PART + 3 * H * H;
+    for (int i = threadIdx.x; i < 6 * H; i += blockDim.x) {
+        const int a = i / H, l = i % H;
+        float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    int idx = (a * H + j) * H + lane;
-                    red[idx] = (wsel == 0 ? 0.f : red[idx]) + acc[a][j];
-                }
+        for (int w = 0; w < WARPS; ++w) sum += red[w][a][l];
+        out[i] = sum;
+    }
+}
+
+// dW_hh[dir][g*32+j][i] = sum over (sequence, step) of G_g[j] * h_prev[i],  G = (dr_pre, dz_pre, dn_pre * r), h_prev = the
+// output of the previously processed step (0 at the first).  256 threads: thread (i = tid % 32, jg = tid / 32) owns the 12 rows
+// jg*12 .. jg*12+11 of column i; 32 (sequence, step) rows are staged per iteration.
+constexpr int DW_ROWS = 32;
+__global__ void __launch_bounds__(256)
+gru_dwhh_kernel(const float* __restrict__ dgx, const float* __restrict__ stash, const float* __restrict__ y, int ldy,
+                float* __restrict__ part, SeqGeom g) {
+    const int dir = blockIdx.y;
+    const int tid = threadIdx.x, i = tid & 31, jg = tid >> 5;
+    __shared__ __align__(16) float Gs[DW_ROWS][3 * H];
+    __shared__ float Hs[DW_ROWS][H];
+    __shared__ long rowM[DW_ROWS], rowP[DW_ROWS];
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+    const long total = (long)g.S * g.T;
+    const long chunks = (total + DW_ROWS - 1) / DW_ROWS;
+    for (long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        // row -> pixel-row index of the step (rowM) and of the previously processed step (rowP), -1 = none
+        if (tid < DW_ROWS) {
+            const long rho = ch * DW_ROWS + tid;
+            long m = -1, mp = -1;
+            if (rho < total) {
+                const int s = (int)(rho / g.T), t = (int)(rho - (long)s * g.T);
+                const long base = seq_base(g, s);
+                m = base + (long)t * g.t_stride;
+                const int tp = dir ? t + 1 : t - 1;           // previously processed position
+                if (tp >= 0 && tp < g.T) mp = base + (long)tp * g.t_stride;
+            }
+            rowM[tid] = m; rowP[tid] = mp;
+        }
+        __syncthreads();
+        // stage: G rows (96 floats, third gate scaled by r) and h_prev rows (32 floats)
+        for (int e = tid; e < DW_ROWS * 3 * H; e += 256) {
+            const int row = e / (3 * H), c = e - row * (3 * H);
+            const long m = rowM[row];
+            float v = 0.f;
+            if (m >= 0) {
+                v = __ldg(dgx + (size_t)m * 6 * H + dir * 3 * H + c);
+                if (c >= 2 * H) v *= __ldg(stash + ((size_t)m * 2 + dir) * 4 * H + (c - 2 * H));      // dn_pre * r
+            }
+            Gs[row][c] = v;
+        }
+        for (int e = tid; e < DW_ROWS * H; e += 256) {
+            const int row = e / H, c = e - row * H;
+            const long mp = rowP[row];
+            Hs[row][c] = mp >= 0 ? __ldg(y + (size_t)mp * ldy + dir * H + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int row = 0; row < DW_ROWS; ++row) {
+            const float hv = Hs[row][i];
+            const float4 g0 = *reinterpret_cast<const float4*>(&Gs[row][jg * 12]);
+            const float4 g1 = *reinterpret_cast<const float4*>(&Gs[row][jg * 12 + 4]);
+            const float4 g2 = *reinterpret_cast<const float4*>(&Gs[row][jg * 12 + 8]);
+            acc[0] = fmaf(g0.x, hv, acc[0]); acc[1] = fmaf(g0.y, hv, acc[1]); acc[2] = fmaf(g0.z, hv, acc[2]); acc[3] = fmaf(g0.w, hv, acc[3]);
+            acc[4] = fmaf(g1.x, hv, acc[4]); acc[5] = fmaf(g1.y, hv, acc[5]); acc[6] = fmaf(g1.z, hv, acc[6]); acc[7] = fmaf(g1.w, hv, acc[7]);
+            acc[8] = fmaf(g2.x, hv, acc[8]); acc[9] = fmaf(g2.y, hv, acc[9]); acc[10] = fmaf(g2.z, hv, acc[10]); acc[11] = fmaf(g2.w, hv, acc[11]);
         }
         __syncthreads();
     }
     float* out = part + ((size_t)blockIdx.x * 2 + dir) * PART;
-    for (int i = threadIdx.x; i < 3 * H * H; i += blockDim.x) out[i] = red[i];
-    __syncthreads();
-    // bias partials through the same buffer
-    for (int wsel = 0; wsel < WARPS; ++wsel) {
-        if (warp == wsel) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                red[a * H + lane] = (wsel == 0 ? 0.f : red[a * H + lane]) + dbh[a];
-                red[3 * H + a * H + lane] = (wsel == 0 ? 0.f : red[3 * H + a * H + lane]) + dbi[a];
-            }
-        }
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < 6 * H; i += blockDim.x) out[3 * H * H + i] = red[i];
+    for (int k = 0; k < 12; ++k) out[(jg * 12 + k) * H + i] = acc[k];
 }
 
-__global__ void gru_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, float* __restrict__ dwhh,
+// sums the per-block partials in a fixed order.  blockDim (32, 8): 32 consecutive elements x 8 lanes over the blocks.
+__global__ void gru_bwd_reduce_kernel(const float* __restrict__ part, int nb_w, int nb_b, float* __restrict__ dwhh,
                                       float* __restrict__ dbhh, float* __restrict__ dbih, int accumulate) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 2 * PART
-    if (idx >= 2 * PART) return;
-    int dir = idx / PART, e = idx % PART;
+    const int idx = blockIdx.x * 32 + threadIdx.x;   // over 2 * PART
+    __shared__ float sh[8][33];
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += part[((size_t)b * 2 + dir) * PART + e];
+    int dir = 0, e = 0;
+    if (idx < 2 * PART) {
+        dir = idx / PART; e = idx % PART;
+        const int nb = e < 3 * H * H ? nb_w : nb_b;
+        float s0 = 0.f, s1 = 0.f;
+        int b = threadIdx.y;
+        for (; b + 8 < nb; b += 16) {
+            s0 += part[((size_t)b * 2 + dir) * PART + e];
+            s1 += part[((size_t)(b + 8) * 2 + dir) * PART + e];
+        }
+        if (b < nb) s0 += part[((size_t)b * 2 + dir) * PART + e];
+        s = s0 + s1;
+    }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y != 0 || idx >= 2 * PART) return;
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sh[k][threadIdx.x];
     float* dst;
     if (e < 3 * H * H) dst = dwhh + (size_t)dir * 3 * H * H + e;
     else if (e < 3 * H * H + 3 * H) dst = dbhh + dir * 3 * H + (e - 3 * H * H);
@@ -206,17 +317,26 @@ __global__ void gru_bwd_reduce_kernel(const float* __restrict__ part, int nblock
     *dst = accumulate ? *dst + s : s;
 }
 
+// one resident wave: 3 CTAs of 4 warps per SM, two directions
 int gru_blocks(int S) {
     int b = (S + WARPS - 1) / WARPS;
-    int cap = 148 * 3;
+    int cap = 148 * 3 / 2;
     return b < cap ? b : cap;
+}
+int dw_blocks(int S, int T) {
+    long chunks = ((long)S * T + DW_ROWS - 1) / DW_ROWS;
+    return (int)(chunks < 148 ? chunks : 148);
 }
 
 }  // namespace
 
 extern "C" {
 
-size_t tpgsr_gru_bwd_workspace_bytes(int S) { return (size_t)gru_blocks(S) * 2 * PART * sizeof(float); }
+size_t tpgsr_gru_bwd_workspace_bytes(int S) {
+    // the second kernel's block count depends on T too; 148 is its cap
+    int nb = gru_blocks(S) > 148 ? gru_blocks(S) : 148;
+    return (size_t)nb * 2 * PART * sizeof(float);
+}
 
 // whh: [2][96][32] (weight_hh_l0, weight_hh_l0_reverse), bhh: [2][96].
 int tpgsr_gru_fwd(const float* gx, const float* whh, const float* bhh, float* y, int ldy, const float* residual, int ldr,
@@ -235,14 +355,18 @@ int tpgsr_gru_bwd(const float* dy, int lddy, const float* y, int ldy, const floa
                   float* dwhh, float* dbhh, float* dbih, int accumulate, int S, int T, int inner, long outer_stride,
                   long inner_stride, long t_stride, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (!dy || !y || !stash || !whh || !dgx || !dwhh || !dbhh || !dbih || !workspace) return TPGSR_ERR_BAD_ARG;
+    if (S <= 0 || T <= 0 || inner <= 0) return TPGSR_ERR_BAD_ARG;
     if (workspace_bytes < tpgsr_gru_bwd_workspace_bytes(S)) return TPGSR_ERR_WORKSPACE;
     SeqGeom g{S, T, inner, outer_stride, inner_stride, t_stride};
-    int nb = gru_blocks(S);
-    dim3 grid(nb, 2);
-    gru_bwd_kernel<<<grid, WARPS * 32, 0, stream>>>(dy, lddy, y, ldy, stash, whh, dgx, static_cast<float*>(workspace), g);
+    float* part = static_cast<float*>(workspace);
+    const int nb = gru_blocks(S), nbw = dw_blocks(S, T);
+    gru_bwd_kernel<<<dim3(nb, 2), WARPS * 32, 0, stream>>>(dy, lddy, y, ldy, stash, whh, dgx, part, g);
     int rc = tpgsr_launch_status();
     if (rc) return rc;
-    gru_bwd_reduce_kernel<<<ceil_div(2 * PART, 256), 256, 0, stream>>>(static_cast<float*>(workspace), nb, dwhh, dbhh, dbih, accumulate);
+    gru_dwhh_kernel<<<dim3(nbw, 2), 256, 0, stream>>>(dgx, stash, y, ldy, part, g);
+    rc = tpgsr_launch_status();
+    if (rc) return rc;
+    gru_bwd_reduce_kernel<<<ceil_div(2 * PART, 32), dim3(32, 8), 0, stream>>>(part, nbw, nb, dwhh, dbhh, dbih, accumulate);
     return tpgsr_launch_status();
 }
 

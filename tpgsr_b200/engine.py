@@ -52,6 +52,15 @@ class Ctx:
             self._planes[key] = hit
         return hit[1]
 
+    def flat(self, x: Tensor, P: int, c_out: int = 0):
+        """padded-flat bf16 planes of an activation (cached per (activation, padding, channel count))."""
+        key = (id(x), 'flat', P, c_out or x.shape[-1])
+        hit = self._planes.get(key)
+        if hit is None:
+            hit = (x, ops.split_bf16_flat(x, P, ops.CONV_MODE == 'bf16x3', c_out))
+            self._planes[key] = hit
+        return hit[1]
+
     def planes_padded(self, x: Tensor, c_out: int):
         key = (id(x), c_out)
         hit = self._planes.get(key)
@@ -93,6 +102,12 @@ def _tc_ok(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: int, ldx:
             and ops.tc_supported(B, H, W, Ci, H, W, Co, kh, kw))
 
 
+def _flat_ok(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: int, ldx: int) -> bool:
+    B, H, W, Cx = x.shape
+    return (ldx in (0, Cx) and Cx == Ci and 2 * ph == kh - 1 and 2 * pw == kw - 1 and x.is_contiguous()
+            and ops.flat_supported(B, H, W, max(ph, pw), Ci, Co, kh, kw, ph, pw))
+
+
 def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=ACT_NONE, act_param: Optional[Tensor] = None,
              out_nchw: bool = False, need_dgrad: bool = True, as4d=None, ldx: int = 0, out: Optional[Tensor] = None):
     w = ctx.P(wname)
@@ -102,6 +117,10 @@ def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=
     Ci = (w.numel() // Co) // (kh * kw)
     saved = (x, wname, bname, kh, kw, ph, pw, as4d, ldx)
     bias = ctx.P(bname) if bname else None
+    if out is None and _flat_ok(x, Ci, Co, kh, kw, ph, pw, ldx):
+        wf, _ = ctx.packed_bf16(wname, as4d)
+        y = ops.conv_flat(ctx.flat(x, max(ph, pw)), wf, bias, Co, kh, kw, ph, pw, act, act_param, out_nchw)
+        return y, saved
     if out is None and _tc_ok(x, Ci, Co, kh, kw, ph, pw, ldx):
         B, H, W, _ = x.shape
         wf, _ = ctx.packed_bf16(wname, as4d)
@@ -120,8 +139,11 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     Ci = (w.numel() // Co) // (kh * kw)
     gw, acc = ctx.G(wname)
     B, H, W, Cx = x.shape
-    if (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 2 * ph == kh - 1 and 2 * pw == kw - 1
-            and ops.wgrad_tc_supported(B, H, W, Ci, Co, kh, kw)):
+    P = max(ph, pw)
+    same = (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 2 * ph == kh - 1 and 2 * pw == kw - 1)
+    if same and ops.wgrad_flat_supported(B, H, W, P, Ci, Co, kh, kw):
+        ops.conv_wgrad_flat(ctx.flat(x, P), ctx.flat(dy, P, (Co + 63) // 64 * 64), gw, Co, kh, kw, ph, pw, acc)
+    elif (same and ops.wgrad_tc_supported(B, H, W, Ci, Co, kh, kw)):
         dyp = ctx.planes(dy) if Co % 64 == 0 else ctx.planes_padded(dy, (Co + 63) // 64 * 64)
         ops.conv_wgrad_tc(ctx.planes(x), dyp, gw, B, H, W, Ci, Co, kh, kw, ph, pw, acc)
     else:
@@ -132,6 +154,9 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     if not need_dx:
         return None
     dense_out = dx_out is None or dx_out.shape[-1] == Ci
+    if dense_out and _flat_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
+        _, wd = ctx.packed_bf16(wname, as4d)
+        return ops.conv_flat(ctx.flat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out, accumulate=dx_accumulate)
     if dense_out and _tc_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)
         return ops.conv_tc(ctx.planes(dy), wd, None, B, H, W, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out,

@@ -18,9 +18,9 @@ OUT_NHWC, OUT_NCHW = 0, 1
 # number of kernel launches issued by this process through the C ABI (bench.py reports it as `gpu_launches`)
 LAUNCHES = 0
 _KERNELS_PER_CALL = {
-    'tpgsr_conv2d_wgrad': 2, 'tpgsr_bn_stats': 2, 'tpgsr_bn_bwd': 3, 'tpgsr_colsum': 2, 'tpgsr_gru_bwd': 2,
+    'tpgsr_conv2d_wgrad': 2, 'tpgsr_bn_stats': 2, 'tpgsr_bn_bwd': 3, 'tpgsr_colsum': 2, 'tpgsr_gru_bwd': 3,
     'tpgsr_image_loss_fwd': 2, 'tpgsr_semantic_loss_fwd': 2, 'tpgsr_optim_prepare': 2, 'tpgsr_lstm_bwd': 2,
-    'tpgsr_conv2d_tc': 1, 'tpgsr_conv2d_wgrad_tc': 2,
+    'tpgsr_conv2d_tc': 1, 'tpgsr_conv2d_wgrad_tc': 2, 'tpgsr_conv2d_flat': 1, 'tpgsr_conv2d_wgrad_flat': 2,
 }
 
 
@@ -198,6 +198,69 @@ def conv_wgrad_tc(x_planes, dy_planes, dw: torch.Tensor, B, H, W, Ci, Co, KH, KW
     wp, wn = workspace(nbytes, dw.device)
     _call('tpgsr_conv2d_wgrad_tc', ptr(x_planes[0]), ptr(x_planes[1]), ptr(dy_planes[0]), ptr(dy_planes[1]), ptr(dw), B, H, W, Ci,
           Co, cpad, KH, KW, ph, pw, int(accumulate), nprod, wp, wn, stream())
+
+
+# ---- padded-flat tensor-core path (conv_flat.cu): operand planes [B][H+P][W+P][C] with zero pad rows / columns ------------------
+# TPGSR_FLAT=0 falls back to the per-tap TMA kernels above (kept for the shapes the flat kernels do not take).
+FLAT = os.environ.get('TPGSR_FLAT', '1') != '0'
+LIB.tpgsr_tc_set_desc_mode(int(os.environ.get('TPGSR_DESC_MODE', '0')))
+
+
+class FlatPlanes:
+    """bf16 hi/lo planes of an NHWC activation in the padded-flat layout."""
+    __slots__ = ('hi', 'lo', 'B', 'H', 'W', 'C', 'P')
+
+    def __init__(self, hi, lo, B, H, W, C, P):
+        self.hi, self.lo, self.B, self.H, self.W, self.C, self.P = hi, lo, B, H, W, C, P
+
+
+def nprod() -> int:
+    return 3 if CONV_MODE == 'bf16x3' else 1
+
+
+def split_bf16_flat(x: torch.Tensor, P: int, need_lo: bool = True, c_out: int = 0) -> FlatPlanes:
+    """fp32 NHWC [B,H,W,C] (dense) -> padded-flat bf16 planes with c_out >= C channels (extra channels zero)."""
+    B, H, W, C = x.shape
+    c_out = c_out or C
+    rows = B * (H + P) * (W + P)
+    hi = torch.empty((rows, c_out), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((rows, c_out), dtype=torch.bfloat16, device=x.device) if need_lo else None
+    _call('tpgsr_split_bf16_flat', ptr(x), C, ptr(hi), ptr(lo), B, H, W, C, c_out, P, stream())
+    return FlatPlanes(hi, lo, B, H, W, c_out, P)
+
+
+def flat_supported(B, H, W, P, Ci, Co, KH, KW, ph, pw) -> bool:
+    return (FLAT and CONV_MODE != 'fp32'
+            and bool(LIB.tpgsr_conv2d_flat_supported(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod())))
+
+
+def conv_flat(xp: FlatPlanes, w_planes, bias, Co, KH, KW, ph, pw, act=ACT_NONE, act_param=None, out_nchw=False,
+              out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """'same' conv on padded-flat planes -> dense fp32 NHWC [B,H,W,Co] (or NCHW)."""
+    B, H, W = xp.B, xp.H, xp.W
+    if out is None:
+        out = torch.empty((B, Co, H, W) if out_nchw else (B, H, W, Co), dtype=torch.float32, device=xp.hi.device)
+        accumulate = False
+    n = 3 if (nprod() == 3 and xp.lo is not None and w_planes[1] is not None) else 1
+    _call('tpgsr_conv2d_flat', ptr(xp.hi), ptr(xp.lo), ptr(w_planes[0]), ptr(w_planes[1]), ptr(bias), ptr(out), B, H, W, xp.P,
+          xp.C, Co, KH, KW, ph, pw, out.shape[-1] if not out_nchw else Co, act, ptr(act_param),
+          OUT_NCHW if out_nchw else OUT_NHWC, int(accumulate), n, stream())
+    return out
+
+
+def wgrad_flat_supported(B, H, W, P, Ci, Co, KH, KW) -> bool:
+    cpad = (Co + 63) // 64 * 64
+    return (FLAT and CONV_MODE != 'fp32'
+            and bool(LIB.tpgsr_conv2d_wgrad_flat_supported(B, H, W, P, Ci, Co, cpad, KH, KW, nprod())))
+
+
+def conv_wgrad_flat(xp: FlatPlanes, dyp: FlatPlanes, dw: torch.Tensor, Co, KH, KW, ph, pw, accumulate: bool) -> None:
+    assert (xp.B, xp.H, xp.W, xp.P) == (dyp.B, dyp.H, dyp.W, dyp.P)
+    n = 3 if (nprod() == 3 and xp.lo is not None and dyp.lo is not None) else 1
+    nbytes = query('tpgsr_conv2d_wgrad_flat_workspace_bytes', xp.B, xp.H, xp.W, xp.P, xp.C, Co, dyp.C, KH, KW, n)
+    wp, wn = workspace(nbytes, dw.device)
+    _call('tpgsr_conv2d_wgrad_flat', ptr(xp.hi), ptr(xp.lo), ptr(dyp.hi), ptr(dyp.lo), ptr(dw), xp.B, xp.H, xp.W, xp.P, xp.C, Co,
+          dyp.C, KH, KW, ph, pw, int(accumulate), n, wp, wn, stream())
 
 
 def colsum(x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> None:
