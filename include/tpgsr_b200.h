@@ -82,7 +82,6 @@ int tpgsr_conv2d_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi,
 /* ---- "padded-flat" tensor-core convolutions: halo rows staged ONCE in shared memory, every tap = a row offset of the same buffer ----
  * Same reference ops as tpgsr_conv2d_tc (nn.Conv2d 'same', 64 input channels: model/tsrn.py:37,376,381,467,495,43), but the
  * bf16 planes are stored [B][H+P][W+P][C] with zero pad rows/columns (tpgsr_split_bf16_flat) so shifted taps are row offsets. */
-int tpgsr_tc_set_desc_mode(int mode);
 int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, int H, int W, int C, int Cout, int P,
                           cudaStream_t stream);
 int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod);
@@ -133,6 +132,9 @@ int tpgsr_pixelshuffle_mish_bwd(const float* dy, const float* x, float* dx, int 
 int tpgsr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, long sb, long sc, long sh, long sw,
                        int ldd, const float* tanh_out, cudaStream_t stream);
 int tpgsr_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, int lds, cudaStream_t stream);
+/* F.interpolate(x, scale_factor) nearest (model/srcnn.py:138) fused with the NCHW -> NHWC boundary change */
+int tpgsr_upsample_nearest_nchw_to_nhwc(const float* src, float* dst, int B, int C, int Hi, int Wi, int scale, long sb, long sc,
+                                        long sh, long sw, cudaStream_t stream);
 
 /* ---- resampling / prior formatting of the text-prior branch -------------------------------------------------------------------
  * parse_crnn_data (interfaces/base.py:806-829); F.interpolate bilinear align_corners=True (model/tsrn.py:196); InfoGen's

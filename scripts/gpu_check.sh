@@ -1,26 +1,17 @@
 #!/bin/bash
 # One gpurun call: probes, GPU parity tests, bench (both arms), ncu launch list of one eager step, ncu --set full of the top kernels.
-# Usage (repo root, on the GPU box): bash scripts/gpu_check.sh [probe] [flat] [timing] [tests] [smoke] [bench] [refarm] [launches] [full]
+# Usage (repo root, on the GPU box): bash scripts/gpu_check.sh [flat] [timing] [tests] [smoke] [bench] [refarm] [launches] [full]
 set -u
 mkdir -p gpurun_out
 what="${*:-tests bench launches full}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
-if [[ $what == *probe* ]]; then
-  timeout 300 python scripts/probe_flat.py > gpurun_out/probe_flat.log 2>&1; echo "probe rc=$?"; cat gpurun_out/probe_flat.log | tail -12
-fi
 if [[ $what == *flat* ]]; then
   timeout 600 python -m pytest tests/test_gpu_flat.py -m gpu -q -x > gpurun_out/pytest_flat.log 2>&1; echo "pytest flat rc=$?"
-  tail -15 gpurun_out/pytest_flat.log; cat gpurun_out/desc_mode.txt 2>/dev/null
-fi
-# pick the descriptor flavour the probe validated (default 0); fall back to the per-tap kernels when neither reproduces F.conv2d
-if [[ -f gpurun_out/desc_mode.txt ]]; then
-  export TPGSR_DESC_MODE=$(sed -n 's/^desc_mode=\([01]\).*/\1/p' gpurun_out/desc_mode.txt)
-elif [[ $what == *flat* ]]; then
-  export TPGSR_FLAT=0; echo "flat kernels NOT validated: running the rest with TPGSR_FLAT=0"
+  tail -15 gpurun_out/pytest_flat.log
 fi
 if [[ $what == *timing* ]]; then
-  timeout 300 python scripts/time_conv.py all ${TPGSR_DESC_MODE:-0} > gpurun_out/time_conv.log 2>&1; echo "timing rc=$?"; cat gpurun_out/time_conv.log
+  timeout 300 python scripts/time_conv.py all > gpurun_out/time_conv.log 2>&1; echo "timing rc=$?"; cat gpurun_out/time_conv.log
 fi
 if [[ $what == *tests* ]]; then
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log

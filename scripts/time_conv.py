@@ -4,10 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from tpgsr_b200 import ops
-from tpgsr_b200._lib import LIB
 d = torch.device('cuda:0')
-if len(sys.argv) > 2:
-    LIB.tpgsr_tc_set_desc_mode(int(sys.argv[2]))
 
 def timeit(fn, n=20, flush=None):
     for _ in range(3): fn()

@@ -1,17 +1,14 @@
 """GPU parity: padded-flat tcgen05 convolutions (conv_flat.cu: forward / data gradient / weight gradient) vs fp32 F.conv2d autograd.
 
 The flat kernels address every tap as a ROW OFFSET into one shared-memory halo buffer (UMMA descriptor start address not aligned to the
-1024-byte swizzle atom).  `desc_mode` probes which descriptor flavour the hardware wants (0: base_offset = 0, 1: base_offset from the
-address) on a small 3x3 case and fails loudly if neither reproduces F.conv2d; every other test runs in the probed mode.
+1024-byte swizzle atom, base_offset = 0: the hardware swizzles on the absolute address — probed in profiles/r01/probe_flat.log).
 """
-import os
-
 import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import ROOT, rel_err
+from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -46,27 +43,6 @@ def _flat_fwd(ops, xd, w, b, Co, k, pad, lo, **kw):
     return ops.conv_flat(xp, wf, None if b is None else b.to(d), Co, k, k, pad, pad, **kw), wdg
 
 
-@pytest.fixture(scope='module')
-def desc_mode():
-    from tpgsr_b200 import ops
-    from tpgsr_b200._lib import LIB
-    d = torch.device('cuda:0')
-    x, w, b, y, gy, pad = _conv_case(2, 64, 64, 16, 64, 3)
-    errs = {}
-    for mode in (0, 1):
-        assert LIB.tpgsr_tc_set_desc_mode(mode) == 0
-        yd, _ = _flat_fwd(ops, nhwc(x.detach()).to(d), w, b, 64, 3, pad, True)
-        torch.cuda.synchronize()
-        errs[mode] = rel_err(nchw(yd), y)
-        if errs[mode] < 3e-5:
-            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-            with open(os.path.join(ROOT, 'gpurun_out', 'desc_mode.txt'), 'w') as f:
-                f.write(f'desc_mode={mode} errs={errs}\n')
-            return mode
-    LIB.tpgsr_tc_set_desc_mode(0)
-    pytest.fail(f'row-shifted UMMA descriptors do not reproduce F.conv2d in either mode: {errs}')
-
-
 @pytest.mark.parametrize('B,Ci,Co,H,W,k', [
     (3, 64, 64, 16, 64, 3),       # SRB conv (whole 3x3 halo resident, 3 tiles per CTA)
     (2, 64, 64, 16, 64, 1),       # GruBlock 1x1 conv (P = 0: flat == dense)
@@ -80,7 +56,7 @@ def desc_mode():
     (24, 64, 4, 32, 128, 9),      # final conv at a batch large enough for 2 tiles per CTA
 ])
 @pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
-def test_conv_flat_fwd_dgrad(desc_mode, B, Ci, Co, H, W, k, mode):
+def test_conv_flat_fwd_dgrad(B, Ci, Co, H, W, k, mode):
     from tpgsr_b200 import ops
     x, w, b, y, gy, pad = _conv_case(B, Ci, Co, H, W, k)
     d = torch.device('cuda:0')
@@ -117,7 +93,7 @@ def test_conv_flat_fwd_dgrad(desc_mode, B, Ci, Co, H, W, k, mode):
     (16, 4, 32, 128, 9),      # final conv, many K blocks per split
 ])
 @pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
-def test_wgrad_flat(desc_mode, B, Co, H, W, k, mode):
+def test_wgrad_flat(B, Co, H, W, k, mode):
     from tpgsr_b200 import ops
     Ci, pad = 64, k // 2
     x = rnd(B, Ci, H, W, seed=51)
@@ -143,7 +119,7 @@ def test_wgrad_flat(desc_mode, B, Co, H, W, k, mode):
         ops.CONV_MODE = old
 
 
-def test_flat_full_batch_properties(desc_mode):
+def test_flat_full_batch_properties():
     """BASELINE batch (B=48): linearity in the input and agreement with the per-tap TMA kernel (conv_tc) on the same planes' source."""
     from tpgsr_b200 import ops
     d = torch.device('cuda:0')

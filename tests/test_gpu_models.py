@@ -203,3 +203,29 @@ def test_stn_head_forward_backward_vs_oracle_and_golden(shapes):
     for k, v in p.items():
         if 'running_' in k:
             assert rel_err(st.views[k], v) < 1e-4, k
+
+
+def test_srcnn_config1_vs_golden_and_oracle(shapes):
+    """BASELINE config 1 (SRCNN, B=4, `images[:, :3]`, MSE*100): forward, loss, every parameter gradient vs the fixture recorded
+    from the reference module, and the full output vs the oracle."""
+    from oracle import models
+    from oracle.weights import synth_state_dict
+    from tpgsr_b200.model.srcnn import SRCNN
+    g = load_golden('srcnn_train')
+    sd = synth_state_dict(shapes['srcnn'], 8)
+    net = SRCNN(scale_factor=2, width=128, height=32, STN=False)
+    net.load_state_dict(sd)
+    net = net.to(_dev()).train()
+    lr, hr = torch.from_numpy(g['lr']).to(_dev()), torch.from_numpy(g['hr']).to(_dev())
+    sr = net(lr[:, :3])
+    loss = torch.nn.MSELoss()(sr, hr[:, :3]) * 100
+    loss.backward()
+    assert rel_err(sr, g['sr']) < 1e-4, rel_err(sr, g['sr'])
+    assert rel_err(sr, models.srcnn(torch.from_numpy(g['lr'])[:, :3], sd)) < 1e-4
+    assert abs(float(loss) - float(g['loss'])) < 1e-3 * float(g['loss'])
+    for k, p in net.named_parameters():
+        assert_fp_close(fingerprint(p.grad), g['g/' + k], k, rtol=2e-3)
+    with torch.no_grad():
+        net.eval()
+        sr2 = net(lr[:, :3])
+    assert rel_err(sr2, g['sr']) < 1e-4

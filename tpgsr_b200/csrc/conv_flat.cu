@@ -30,6 +30,7 @@ constexpr int TILE_M = 128;
 // mbarrier wait that traps instead of hanging the GPU if a pipeline bug ever deadlocks (try_wait suspends up to ~10 ms per poll)
 __device__ __forceinline__ void mbar_wait_safe(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = tc::smem_u32(bar);
+#pragma unroll 1
     for (int it = 0; it < 400; ++it) {
         uint32_t ok;
         asm volatile(
@@ -56,15 +57,36 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {       
         : "r"(taddr));
 }
 
-// descriptor flavour for row-shifted operand windows (set by tpgsr_tc_set_desc_mode; validated by tests/test_gpu_flat.py):
-//   0: base_offset = 0 (swizzle is a function of the absolute shared-memory address; buffers are 1024-byte aligned)
-//   1: base_offset = (start_address >> 7) & 7
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int mode) {
-    uint64_t d = tc::smem_desc_sw128(saddr, lbo_bytes, sbo_bytes);
-    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7) << 49;
-    return d;
+// UMMA shared-memory descriptors, SWIZZLE_128B, SBO = 1024 bytes (8 rows of 128 bytes).  Row-shifted operand windows (start address a
+// multiple of 128 but not of 1024 bytes) need NO base_offset: the hardware applies the swizzle to the absolute shared-memory address
+// (probed on B200: scripts/probe_flat.py, profiles/r01/probe_flat.log — base_offset = (addr >> 7) & 7 gives garbage).
+// The descriptor is split in two 32-bit words so that the issue loop only ever adds small constants to the low word:
+//   lo = (addr >> 4) | (LBO >> 4) << 16        hi = (SBO >> 4) | version 1 << 14 | SWIZZLE_128B << 29 = 0x40004040
+constexpr uint32_t DESC_HI = 0x40004040u;
+// one lane of a converged warp (the MMA warp runs its loops warp-uniformly and only the tcgen05 instructions are predicated on the
+// elected lane: ptxas then keeps descriptors / TMEM addresses in uniform registers and emits straight UTCHMMA sequences instead of
+// one ELECT + R2UR + branch loop per instruction — measured 3x fewer issue slots per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
 
+// D[tmem] (+)= A * B with descriptors given as (lo word, shared hi word); ACC is a compile-time accumulate flag
+template <int ACC>
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC), "r"(DESC_HI)
+        : "memory");
+}
 // ============================================================================================================ forward / dgrad
 struct FlatConvParams {
     int B, H, W, Hp, Wp;
@@ -78,8 +100,8 @@ struct FlatConvParams {
     int a_stages;              // A ring depth (1 when n_groups == 1)
     int box_rows, n_box;       // one A stage = n_box TMA boxes of box_rows rows (box_rows % 8 == 0)
     int tb, b_stages;          // taps per B stage; B ring depth
+    int ring_bytes;            // bytes reserved for the A+B rings (>= the epilogue staging area that aliases them)
     int ldy, act, out_mode, accumulate;
-    int desc_mode;
     const float* bias;
     const float* act_param;
     float* y;
@@ -100,7 +122,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)p.a_stages * a_stage_bytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_stages * b_stage_bytes);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + p.ring_bytes);
     uint64_t* a_empty = a_full + p.a_stages;
     uint64_t* b_full = a_empty + p.a_stages;
     uint64_t* b_empty = b_full + p.b_stages;
@@ -169,53 +191,60 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);      // same value, provably warp-uniform
+        const bool leader = elect_one();
+        {
             // ================= MMA issuer =================
+            // per-MMA issue cost matters here (a 128x64x16 MMA is only 32 tensor-pipe cycles): descriptors are advanced by adding
+            // constants to their low words, the accumulate flag is a compile-time constant everywhere but the very first K step
             const uint32_t idesc = tc::idesc_bf16(TILE_M, p.n_tile, 0, 0);
-            const int dm = p.desc_mode;
+            const uint32_t tile_lo = (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
             uint32_t b_it = 0;
             for (int g = 0; g < p.n_groups; ++g) {
                 const int as = g % p.a_stages;
                 mbar_wait_safe(&a_full[as], (g / p.a_stages) & 1);
                 tc::tc_fence_after();
-                const uint32_t a_hi0 = tc::smem_u32(a_ring + (size_t)as * a_stage_bytes);
-                const uint32_t a_lo0 = a_hi0 + a_plane_bytes;
+                const uint32_t a_hi0 = desc_lo(tc::smem_u32(a_ring + (size_t)as * a_stage_bytes), 16);
+                const uint32_t a_lo0 = a_hi0 + (a_plane_bytes >> 4);
                 for (int j = 0; j < b_per_group; ++j, ++b_it) {
                     const int bs = b_it % p.b_stages;
                     mbar_wait_safe(&b_full[bs], (b_it / p.b_stages) & 1);
                     tc::tc_fence_after();
-                    const uint32_t b_hi0 = tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes);
-                    const uint32_t b_lo0 = b_hi0 + b_plane_bytes;
+                    const uint32_t b_hi0 = desc_lo(tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes), 16);
+                    const uint32_t b_lo0 = b_hi0 + (b_plane_bytes >> 4);
                     for (int tt = 0; tt < p.tb; ++tt) {
                         const int tl = j * p.tb + tt;                  // tap index inside the group
                         const int khl = tl / p.KW, kw = tl - khl * p.KW;
-                        const uint32_t row_off = (uint32_t)(khl * p.Wp + kw) * ROW_BYTES;
-                        const bool first_tap = (g == 0 && tl == 0);
-                        const uint32_t bh = b_hi0 + tt * b_tap_bytes, bl = b_lo0 + tt * b_tap_bytes;
-                        for (int t = 0; t < p.MT; ++t) {
-                            const uint32_t ah = a_hi0 + row_off + (uint32_t)t * TILE_M * ROW_BYTES;
-                            const uint32_t al = a_lo0 + row_off + (uint32_t)t * TILE_M * ROW_BYTES;
-                            const uint32_t d = tmem_base + (uint32_t)(t * p.tm_stride);
+                        const uint32_t row_off = (uint32_t)(khl * p.Wp + kw) * (ROW_BYTES >> 4);
+                        const uint32_t bh = b_hi0 + tt * (b_tap_bytes >> 4), bl = b_lo0 + tt * (b_tap_bytes >> 4);
+                        uint32_t ah = a_hi0 + row_off, al = a_lo0 + row_off;
+                        uint32_t d = tmem_u;
+                        if (!leader) continue;
+                        if (g == 0 && tl == 0) {
+                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) {
+                                umma_lo<0>(d, ah, bh, idesc);
+                                if (NPROD == 3) { umma_lo<1>(d, ah, bl, idesc); umma_lo<1>(d, al, bh, idesc); }
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t koff = k * 32;          // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-                                const uint64_t da_hi = desc_sw128(ah + koff, 16, 1024, dm);
-                                const uint64_t db_hi = tc::smem_desc_sw128(bh + koff, 16, 1024);
-                                tc::umma_bf16(d, da_hi, db_hi, idesc, (first_tap && k == 0) ? 0u : 1u);
-                                if (NPROD == 3) {
-                                    const uint64_t da_lo = desc_sw128(al + koff, 16, 1024, dm);
-                                    const uint64_t db_lo = tc::smem_desc_sw128(bl + koff, 16, 1024);
-                                    tc::umma_bf16(d, da_hi, db_lo, idesc, 1);
-                                    tc::umma_bf16(d, da_lo, db_hi, idesc, 1);
+                                for (int k = 1; k < 4; ++k) {
+                                    umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
+                                    if (NPROD == 3) { umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc); umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc); }
+                                }
+                            }
+                        } else {
+                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {      // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle row
+                                    umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
+                                    if (NPROD == 3) { umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc); umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc); }
                                 }
                             }
                         }
                     }
-                    tc::tc_commit(&b_empty[bs]);
+                    if (leader) tc::tc_commit(&b_empty[bs]);
                 }
-                tc::tc_commit(&a_empty[as]);
+                if (leader) tc::tc_commit(&a_empty[as]);
             }
-            tc::tc_commit(tmem_full);
+            if (leader) tc::tc_commit(tmem_full);
         }
     } else {
         // ================= epilogue: warps 2..5; warp w owns TMEM lanes 32*(w%4).. = rows 32*(w%4).. of every tile =================
@@ -227,57 +256,48 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * pitch;
         const float slope = (p.act == TPGSR_ACT_PRELU && p.act_param) ? __ldg(p.act_param) : 0.f;
         const int ncols = (p.Co - n0) < p.n_tile ? (p.Co - n0) : p.n_tile;
-        const long long img = (long long)p.Hp * p.Wp;
+        const unsigned img = (unsigned)(p.Hp * p.Wp);
+        const unsigned qtot = (unsigned)p.Qtot;               // < 2^31 (checked by the plan)
         for (int t = 0; t < p.MT; ++t) {
-            const long long qrow = q0 + (long long)t * TILE_M + q * 32 + lane;      // this lane's output row
-            const int bi = (int)(qrow / img);
-            const int rem = (int)(qrow - (long long)bi * img);
-            const int r = rem / p.Wp, c = rem - r * p.Wp;
-            const bool valid = qrow < p.Qtot && r < p.H && c < p.W;
+            // dense pixel index of this lane's output row (-1: pad position or beyond the last image)
+            const unsigned qrow = (unsigned)q0 + (unsigned)(t * TILE_M + q * 32 + lane);
+            const unsigned bi = qrow / img;
+            const unsigned rem = qrow - bi * img;
+            const unsigned r = rem / (unsigned)p.Wp, c = rem - r * (unsigned)p.Wp;
+            const bool valid = qrow < qtot && r < (unsigned)p.H && c < (unsigned)p.W;
+            const int pix = valid ? (int)((bi * p.H + r) * p.W + c) : -1;
+            // TMEM -> registers -> (+bias) -> this warp's staging rows.  The activation is applied once, in the store loops below
+            // (keeping it out of the unrolled register loop keeps the kernel's code small).
             for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
                 float v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.tm_stride + c0);
                 const int nv = (p.n_tile - c0) >= 32 ? 32 : 16;
                 if (nv == 32) tc::tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
                 tc::tmem_ld_wait();
-                if (p.out_mode == TPGSR_OUT_NHWC) {
-                    float* d = stg + (size_t)lane * pitch + c0;
+                float* d = stg + (size_t)lane * pitch + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (j < nv) {
-                            float o[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) o[u] = apply_act(v[j + u] + bias_s[c0 + j + u], p.act, slope);
-                            *reinterpret_cast<float4*>(d + j) = make_float4(o[0], o[1], o[2], o[3]);
-                        }
-                    }
-                } else if (valid) {
-                    // NCHW: for a fixed channel the 32 lanes hold 32 consecutive flat positions = (mostly) consecutive columns
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j < nv && c0 + j < ncols) {
-                            float o = apply_act(v[j] + bias_s[c0 + j], p.act, slope);
-                            float* dst = p.y + (((size_t)bi * p.Co + n0 + c0 + j) * p.H + r) * p.W + c;
-                            *dst = p.accumulate ? *dst + o : o;
-                        }
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < nv)
+                        *reinterpret_cast<float4*>(d + j) = make_float4(v[j] + bias_s[c0 + j], v[j + 1] + bias_s[c0 + j + 1],
+                                                                        v[j + 2] + bias_s[c0 + j + 2], v[j + 3] + bias_s[c0 + j + 3]);
                 }
             }
+            __syncwarp();
             if (p.out_mode == TPGSR_OUT_NHWC) {
-                __syncwarp();
-                // coalesced stores of this warp's 32 rows: the row -> pixel mapping is recomputed per row (rows may be pads)
-                const long long qbase = q0 + (long long)t * TILE_M + q * 32;
+                // coalesced stores of this warp's 32 rows; the pixel index of row j lives in lane j
                 if ((ncols & 3) == 0 && (p.ldy & 3) == 0 && (n0 & 3) == 0) {
                     const int c4n = ncols >> 2;
-                    for (int i = lane; i < 32 * c4n; i += 32) {
+                    for (int i0 = 0; i0 < 32 * c4n; i0 += 32) {
+                        const int i = i0 + lane;
                         const int row = i / c4n, c4 = i - row * c4n;
-                        const long long qq = qbase + row;
-                        const int b2 = (int)(qq / img);
-                        const int rem2 = (int)(qq - (long long)b2 * img);
-                        const int r2 = rem2 / p.Wp, cc2 = rem2 - r2 * p.Wp;
-                        if (qq < p.Qtot && r2 < p.H && cc2 < p.W) {
+                        const int px = __shfl_sync(0xffffffffu, pix, row);
+                        if (px >= 0) {
                             float4 val = *reinterpret_cast<const float4*>(stg + (size_t)row * pitch + c4 * 4);
-                            float4* dst = reinterpret_cast<float4*>(p.y + ((size_t)(b2 * p.H + r2) * p.W + cc2) * p.ldy + n0 + c4 * 4);
+                            if (p.act != TPGSR_ACT_NONE) {
+                                val.x = apply_act(val.x, p.act, slope); val.y = apply_act(val.y, p.act, slope);
+                                val.z = apply_act(val.z, p.act, slope); val.w = apply_act(val.w, p.act, slope);
+                            }
+                            float4* dst = reinterpret_cast<float4*>(p.y + (size_t)px * p.ldy + n0 + c4 * 4);
                             if (p.accumulate) {
                                 float4 o = *dst;
                                 val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
@@ -286,21 +306,26 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         }
                     }
                 } else {
-                    for (int i = lane; i < 32 * ncols; i += 32) {
+                    for (int i0 = 0; i0 < 32 * ncols; i0 += 32) {
+                        const int i = i0 + lane;
                         const int row = i / ncols, cc = i - row * ncols;
-                        const long long qq = qbase + row;
-                        const int b2 = (int)(qq / img);
-                        const int rem2 = (int)(qq - (long long)b2 * img);
-                        const int r2 = rem2 / p.Wp, cc2 = rem2 - r2 * p.Wp;
-                        if (qq < p.Qtot && r2 < p.H && cc2 < p.W) {
-                            float val = stg[(size_t)row * pitch + cc];
-                            float* dst = p.y + ((size_t)(b2 * p.H + r2) * p.W + cc2) * p.ldy + n0 + cc;
+                        const int px = __shfl_sync(0xffffffffu, pix, row);
+                        if (px >= 0) {
+                            float val = apply_act(stg[(size_t)row * pitch + cc], p.act, slope);
+                            float* dst = p.y + (size_t)px * p.ldy + n0 + cc;
                             *dst = p.accumulate ? *dst + val : val;
                         }
                     }
                 }
-                __syncwarp();
+            } else if (valid) {
+                // NCHW: for a fixed channel the 32 lanes hold 32 consecutive flat positions = (mostly) consecutive columns
+                for (int n = 0; n < ncols; ++n) {
+                    const float val = apply_act(stg[(size_t)lane * pitch + n], p.act, slope);
+                    float* dst = p.y + (((size_t)bi * p.Co + n0 + n) * p.H + r) * p.W + c;
+                    *dst = p.accumulate ? *dst + val : val;
+                }
             }
+            __syncwarp();
         }
     }
     tc::tc_fence_before();
@@ -349,7 +374,7 @@ split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __re
 }
 
 struct FlatPlan {
-    int MT, n_tile, n_tiles, tm_stride, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages;
+    int MT, n_tile, n_tiles, tm_stride, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, ring_bytes;
     size_t smem;
     int grid_x;
 };
@@ -390,7 +415,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             const int taps_per_group = G * KW;
             const size_t tap_bytes = (size_t)planes * pl.n_tile * ROW_BYTES;
             const size_t stg_bytes = (size_t)4 * 32 * (pl.n_tile + 4) * sizeof(float);
-            int tb = 1, b_stages = 0;
+            int tb = 1, b_stages = 0, ring_bytes = 0;
             size_t smem = 0;
             const bool row_stage = n_groups > 1 && KW > 1 && tap_bytes * KW <= 40 * 1024;
             for (int want = row_stage ? 2 : 4; want >= (row_stage ? 2 : 2); --want) {
@@ -401,7 +426,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
                 size_t ring = a_bytes + (size_t)bs * tb * tap_bytes;
                 if (ring < stg_bytes) ring = stg_bytes;
                 const size_t need = ring + 1024 /*align*/ + 8 * (2 * a_stages + 2 * bs + 1) + 16 + pl.n_tile * 4 + 64;
-                if (need <= budget) { b_stages = bs; smem = need; break; }
+                if (need <= budget) { b_stages = bs; smem = need; ring_bytes = (int)ring; break; }
             }
             if (b_stages == 0) continue;
             const long long ctas = (tiles + MT - 1) / MT * pl.n_tiles;
@@ -409,7 +434,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             if (best_cost >= 0 && cost * 23 >= best_cost * 20) continue;       // a smaller MT must win by > 15%
             best_cost = cost;
             pl.MT = MT; pl.G = G; pl.n_groups = n_groups; pl.a_stages = a_stages; pl.box_rows = box_rows; pl.n_box = n_box;
-            pl.tb = tb; pl.b_stages = b_stages; pl.smem = smem;
+            pl.tb = tb; pl.b_stages = b_stages; pl.smem = smem; pl.ring_bytes = ring_bytes;
             pl.grid_x = (int)((tiles + MT - 1) / MT);
         }
         if (best_cost >= 0) return TPGSR_OK;
@@ -426,7 +451,7 @@ struct FlatWgradParams {
     int n_tile;                      // co per CTA (multiple of 64)
     int x_rows;                      // rows of the X window per K block (WG_KB + taps_per_group - 1, rounded up to 8)
     int total_kb, kb_per_split;
-    int stages, desc_mode;
+    int stages;
     float* ws;                       // [splits][K = KH*KW*Ci][Co]
 };
 
@@ -496,36 +521,41 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);      // same value, provably warp-uniform
+        const bool leader = elect_one();
+        {
             const uint32_t idesc = tc::idesc_bf16(64, p.n_tile, 1, 1);      // both operands MN-major
-            const int dm = p.desc_mode;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % p.stages;
                 mbar_wait_safe(&full[s], (i / p.stages) & 1);
                 tc::tc_fence_after();
                 const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t dy_hi = st, dy_lo = st + dy_plane_bytes;
-                const uint32_t x_hi = st + planes * dy_plane_bytes, x_lo = x_hi + x_plane_bytes;
+                // MN-major SWIZZLE_128B: LBO = bytes between 64-element M/N chunks (one chunk for A; dY groups for B), SBO = 1024
+                const uint32_t dy_hi = desc_lo(st, dy_tile_bytes), dy_lo = dy_hi + (dy_plane_bytes >> 4);
+                const uint32_t x_hi = desc_lo(st + planes * dy_plane_bytes, 1024), x_lo = x_hi + (x_plane_bytes >> 4);
                 for (int t = 0; t < ntaps; ++t) {
-                    const uint32_t d = tmem_base + (uint32_t)(t * p.n_tile);
+                    if (!leader) continue;
+                    const uint32_t d = tmem_u + (uint32_t)(t * p.n_tile);
+                    const uint32_t xh = x_hi + (uint32_t)t * (ROW_BYTES >> 4), xl = x_lo + (uint32_t)t * (ROW_BYTES >> 4);   // tap t = window shifted by t rows
+                    if (i == 0) {
+                        umma_lo<0>(d, xh, dy_hi, idesc);
+                        if (NPROD == 3) { umma_lo<1>(d, xh, dy_lo, idesc); umma_lo<1>(d, xl, dy_hi, idesc); }
 #pragma unroll
-                    for (int k = 0; k < WG_KB / 16; ++k) {
-                        const uint32_t koff = k * 2048;          // 16 K rows = two 1024-byte swizzle atoms
-                        const uint32_t xoff = koff + (uint32_t)t * ROW_BYTES;      // tap t = window shifted by t rows
-                        const uint64_t a_hi = desc_sw128(x_hi + xoff, 1024, 1024, dm);
-                        const uint64_t b_hi = tc::smem_desc_sw128(dy_hi + koff, dy_tile_bytes, 1024);
-                        tc::umma_bf16(d, a_hi, b_hi, idesc, (i | k) != 0);
-                        if (NPROD == 3) {
-                            const uint64_t a_lo = desc_sw128(x_lo + xoff, 1024, 1024, dm);
-                            const uint64_t b_lo = tc::smem_desc_sw128(dy_lo + koff, dy_tile_bytes, 1024);
-                            tc::umma_bf16(d, a_hi, b_lo, idesc, 1);
-                            tc::umma_bf16(d, a_lo, b_hi, idesc, 1);
+                        for (int k = 1; k < WG_KB / 16; ++k) {      // 16 K rows = 2048 bytes = 128 descriptor units
+                            umma_lo<1>(d, xh + 128 * k, dy_hi + 128 * k, idesc);
+                            if (NPROD == 3) { umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc); umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc); }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < WG_KB / 16; ++k) {
+                            umma_lo<1>(d, xh + 128 * k, dy_hi + 128 * k, idesc);
+                            if (NPROD == 3) { umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc); umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc); }
                         }
                     }
                 }
-                tc::tc_commit(&empty[s]);
+                if (leader) tc::tc_commit(&empty[s]);
             }
-            tc::tc_commit(tmem_full);
+            if (leader) tc::tc_commit(tmem_full);
         }
     } else {
         // epilogue.  M = 64 accumulators use the half-subpartition layout: row ci = 16*q + l lives in TMEM lane 32*q + l (l < 16)
@@ -599,8 +629,6 @@ int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH
     return TPGSR_OK;
 }
 
-int g_desc_mode = 0;
-
 }  // namespace
 
 // defined in conv_simt.cu
@@ -608,12 +636,6 @@ extern "C" int tpgsr_conv2d_wgrad_reduce(const float* ws, float* dw_oihw, int sp
                                          int accumulate, cudaStream_t stream);
 
 extern "C" {
-
-int tpgsr_tc_set_desc_mode(int mode) {
-    if (mode != 0 && mode != 1) return TPGSR_ERR_BAD_ARG;
-    g_desc_mode = mode;
-    return TPGSR_OK;
-}
 
 int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, int H, int W, int C, int Cout, int P,
                           cudaStream_t stream) {
@@ -669,8 +691,8 @@ int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, cons
     p.Co = Co; p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw;
     p.MT = pl.MT; p.n_tile = pl.n_tile; p.tm_stride = pl.tm_stride; p.pointwise = pl.pointwise; p.G = pl.G; p.n_groups = pl.n_groups;
     p.a_stages = pl.a_stages;
-    p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages;
-    p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate; p.desc_mode = g_desc_mode;
+    p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
+    p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
     p.bias = bias; p.act_param = act_param; p.y = y;
 
     const uint64_t K = (uint64_t)KH * KW * Ci;
@@ -730,7 +752,7 @@ int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_h
     FlatWgradParams p;
     p.Wp = W + P; p.Co = Co; p.Ci = Ci; p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw;
     p.kw_groups = pl.kw_groups; p.taps_per_group = pl.taps_per_group; p.n_tile = pl.n_tile; p.x_rows = pl.x_rows;
-    p.total_kb = pl.total_kb; p.kb_per_split = pl.kb_per_split; p.stages = pl.stages; p.desc_mode = g_desc_mode;
+    p.total_kb = pl.total_kb; p.kb_per_split = pl.kb_per_split; p.stages = pl.stages;
     p.ws = static_cast<float*>(workspace);
 
     CUtensorMap tmX_hi, tmX_lo, tmD_hi, tmD_lo;

@@ -388,6 +388,22 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
     }
 }
 
+// F.interpolate(x, scale_factor=s) (mode 'nearest', model/srcnn.py:138) fused with the NCHW -> NHWC boundary change:
+// dst[b][h][w][c] = src[b][c][h / s][w / s]   (src addressed through its strides: callers pass channel-sliced views)
+__global__ void upsample_nearest_nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int Ho,
+                                                     int Wo, int scale, long sb, long sc, long sh, long sw) {
+    const long total = (long)B * Ho * Wo * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long p = i / C;
+        int w = (int)(p % Wo);
+        long q = p / Wo;
+        int h = (int)(q % Ho);
+        int b = (int)(q / Ho);
+        dst[i] = src[(size_t)(b * sb + c * sc + (h / scale) * sh + (w / scale) * sw)];
+    }
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W, int lds) {
     const long total = (long)B * C * H * W;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -576,6 +592,14 @@ int tpgsr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W,
                        const float* tanh_out, cudaStream_t stream) {
     if (!src || !dst) return TPGSR_ERR_BAD_ARG;
     nchw_to_nhwc_kernel<<<ew_grid((long)B * C * H * W), 256, 0, stream>>>(src, dst, B, C, H, W, sb, sc, sh, sw, ldd > 0 ? ldd : C, tanh_out);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_upsample_nearest_nchw_to_nhwc(const float* src, float* dst, int B, int C, int Hi, int Wi, int scale, long sb, long sc,
+                                        long sh, long sw, cudaStream_t stream) {
+    if (!src || !dst || scale < 1 || B < 1 || C < 1 || Hi < 1 || Wi < 1) return TPGSR_ERR_BAD_ARG;
+    upsample_nearest_nchw_to_nhwc_kernel<<<ew_grid((long)B * C * Hi * Wi * scale * scale), 256, 0, stream>>>(
+        src, dst, B, C, Hi * scale, Wi * scale, scale, sb, sc, sh, sw);
     return tpgsr_launch_status();
 }
 

@@ -72,6 +72,15 @@ def nchw_to_nhwc(x: torch.Tensor, tanh_out: Optional[torch.Tensor] = None) -> to
     return y
 
 
+def upsample_nearest_to_nhwc(x: torch.Tensor, scale: int) -> torch.Tensor:
+    """Strided NCHW view -> dense NHWC [B, H*scale, W*scale, C] with nearest-neighbour replication."""
+    B, C, H, W = x.shape
+    y = new((B, H * scale, W * scale, C), x)
+    sb, sc, sh, sw = x.stride()
+    _call('tpgsr_upsample_nearest_nchw_to_nhwc', ptr(x), ptr(y), B, C, H, W, scale, sb, sc, sh, sw, stream())
+    return y
+
+
 def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
     B, H, W, C = x.shape
     y = new((B, C, H, W), x)
@@ -203,7 +212,6 @@ def conv_wgrad_tc(x_planes, dy_planes, dw: torch.Tensor, B, H, W, Ci, Co, KH, KW
 # ---- padded-flat tensor-core path (conv_flat.cu): operand planes [B][H+P][W+P][C] with zero pad rows / columns ------------------
 # TPGSR_FLAT=0 falls back to the per-tap TMA kernels above (kept for the shapes the flat kernels do not take).
 FLAT = os.environ.get('TPGSR_FLAT', '1') != '0'
-LIB.tpgsr_tc_set_desc_mode(int(os.environ.get('TPGSR_DESC_MODE', '0')))
 
 
 class FlatPlanes:
