@@ -85,6 +85,7 @@ int tpgsr_conv2d_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi,
 int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, int H, int W, int C, int Cout, int P,
                           cudaStream_t stream);
 int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod);
+int tpgsr_conv2d_flat_set_debug(long long* dbg);
 size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, int* out);
 size_t tpgsr_conv2d_wgrad_flat_plan(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, int* out);
 int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, int B,

@@ -105,6 +105,7 @@ struct FlatConvParams {
     const float* bias;
     const float* act_param;
     float* y;
+    long long* dbg;            // optional [grid][8] clock64 timestamps (developer instrumentation, scripts/flat_timeline.py)
 };
 
 template <int NPROD>
@@ -135,6 +136,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int b_per_group = (p.G * p.KW) / p.tb;                  // B stages consumed per A group
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.MT * p.tm_stride) tmem_cols <<= 1;
+    long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmA_hi);
@@ -157,6 +160,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -204,12 +208,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const int as = g % p.a_stages;
                 mbar_wait_safe(&a_full[as], (g / p.a_stages) & 1);
                 tc::tc_fence_after();
+                if (dbg && g == 0 && leader) dbg[2] = clock64();
                 const uint32_t a_hi0 = desc_lo(tc::smem_u32(a_ring + (size_t)as * a_stage_bytes), 16);
                 const uint32_t a_lo0 = a_hi0 + (a_plane_bytes >> 4);
                 for (int j = 0; j < b_per_group; ++j, ++b_it) {
                     const int bs = b_it % p.b_stages;
                     mbar_wait_safe(&b_full[bs], (b_it / p.b_stages) & 1);
                     tc::tc_fence_after();
+                    if (dbg && b_it == 0 && leader) dbg[3] = clock64();
                     const uint32_t b_hi0 = desc_lo(tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes), 16);
                     const uint32_t b_lo0 = b_hi0 + (b_plane_bytes >> 4);
                     for (int tt = 0; tt < p.tb; ++tt) {
@@ -244,6 +250,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
                 if (leader) tc::tc_commit(&a_empty[as]);
             }
+            if (dbg && leader) dbg[4] = clock64();
             if (leader) tc::tc_commit(tmem_full);
         }
     } else {
@@ -251,6 +258,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int q = warp & 3;
         mbar_wait_safe(tmem_full, 0);
         tc::tc_fence_after();
+        if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
         // every MMA (hence every TMA load) has completed: the rings are free and serve as per-warp staging [32 rows][n_tile+4]
         const int pitch = p.n_tile + 4;
         float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * pitch;
@@ -326,7 +334,9 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
             }
             __syncwarp();
+            if (dbg && warp == 2 && lane == 0 && t == 0) dbg[6] = clock64();
         }
+        if (dbg && warp == 2 && lane == 0) dbg[7] = clock64();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -378,6 +388,8 @@ struct FlatPlan {
     size_t smem;
     int grid_x;
 };
+
+long long* g_flat_dbg = nullptr;
 
 int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
     if (Co < 1 || B < 1 || H < 1 || W < 1 || Ci < 64 || Ci % 64 != 0) return TPGSR_ERR_UNSUPPORTED;
@@ -651,6 +663,9 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
     return plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl) == TPGSR_OK ? 1 : 0;
 }
 
+// developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][8]
+int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
+
 // tiling decided for a geometry (host-only; lets tests / docs inspect the plan without a GPU):
 // out[12] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x}; returns smem bytes (0 = unsupported)
 size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, int* out) {
@@ -693,7 +708,7 @@ int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, cons
     p.a_stages = pl.a_stages;
     p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
-    p.bias = bias; p.act_param = act_param; p.y = y;
+    p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg;
 
     const uint64_t K = (uint64_t)KH * KW * Ci;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;

@@ -30,9 +30,19 @@ __device__ __forceinline__ long seq_base(const SeqGeom& g, int s) {
 
 constexpr int H = 32;          // hidden units per direction
 constexpr int WARPS = 4;
-constexpr int PF = 4;          // prefetch depth (steps) of the register rings
+constexpr int PF = 8;          // prefetch depth (steps) of the per-warp cp.async rings in shared memory
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): the per-step operands of step t + PF are in flight while step t computes.
+// (A register ring did not work: ptxas loaded into one temporary and moved it into the ring slot right away, so every step
+// still waited for its own load — profiles/r01 source view.)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // gx: [M, 192] = [dir][gate r,z,n][32] pre-activations from the input side (bias_ih included)
 // y:  [M, ldy] GRU output (dir0 -> cols 0..31, dir1 -> cols 32..63); ysum = y + residual (optional)
@@ -57,63 +67,67 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, cons
     const float bhr = __ldg(bhh + dir * 3 * H + lane), bhz = __ldg(bhh + dir * 3 * H + H + lane),
                 bhn = __ldg(bhh + dir * 3 * H + 2 * H + lane);
     const bool has_res = ysum != nullptr;
+    __shared__ float ring[WARPS][PF][4][H];       // [step slot][gx_r, gx_z, gx_n, residual][lane]
 
     for (int s = blockIdx.x * WARPS + warp; s < g.S; s += gridDim.x * WARPS) {
         const long m0 = seq_base(g, s) + (dir ? (long)(g.T - 1) * g.t_stride : 0);
         const long step = dir ? -g.t_stride : g.t_stride;
-        float pr[PF], pz[PF], pn[PF], pres[PF];
+        // one commit group per step (empty beyond the end) keeps the wait_group arithmetic uniform
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-            pr[u] = pz[u] = pn[u] = pres[u] = 0.f;
             if (u < g.T) {
                 const long m = m0 + u * step;
                 const float* gp = gx + (size_t)m * 6 * H + dir * 3 * H + lane;
-                pr[u] = __ldg(gp); pz[u] = __ldg(gp + H); pn[u] = __ldg(gp + 2 * H);
-                if (has_res) pres[u] = __ldg(residual + (size_t)m * ldr + dir * H + lane);
+                cp_async4(&ring[warp][u][0][lane], gp);
+                cp_async4(&ring[warp][u][1][lane], gp + H);
+                cp_async4(&ring[warp][u][2][lane], gp + 2 * H);
+                if (has_res) cp_async4(&ring[warp][u][3][lane], residual + (size_t)m * ldr + dir * H + lane);
             }
+            cp_async_commit();
         }
         float h = 0.f;
         __syncwarp();
         hbuf[warp][lane] = 0.f;
         __syncwarp();
-        for (int t0 = 0; t0 < g.T; t0 += PF) {
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int t = t0 + u;
-                if (t < g.T) {
-                    const long m = m0 + t * step;
-                    const float gxr = pr[u], gxz = pz[u], gxn = pn[u], res = pres[u];
-                    if (t + PF < g.T) {   // refill this ring slot with the operands of step t + PF
-                        const long mn = m + PF * step;
-                        const float* np = gx + (size_t)mn * 6 * H + dir * 3 * H + lane;
-                        pr[u] = __ldg(np); pz[u] = __ldg(np + H); pn[u] = __ldg(np + 2 * H);
-                        if (has_res) pres[u] = __ldg(residual + (size_t)mn * ldr + dir * H + lane);
-                    }
-                    float2 ar = make_float2(bhr, 0.f), az = make_float2(bhz, 0.f), an = make_float2(bhn, 0.f);
-#pragma unroll
-                    for (int q = 0; q < H / 4; ++q) {
-                        const float4 hv = *reinterpret_cast<const float4*>(&hbuf[warp][q * 4]);
-                        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
-                        ar = ffma2(wr[2 * q], h01, ar); az = ffma2(wz[2 * q], h01, az); an = ffma2(wn[2 * q], h01, an);
-                        ar = ffma2(wr[2 * q + 1], h23, ar); az = ffma2(wz[2 * q + 1], h23, az); an = ffma2(wn[2 * q + 1], h23, an);
-                    }
-                    const float hn = an.x + an.y;
-                    const float r = sigmoid_f(gxr + (ar.x + ar.y));
-                    const float z = sigmoid_f(gxz + (az.x + az.y));
-                    const float n = tanhf(gxn + r * hn);
-                    h = (1.f - z) * n + z * h;
-                    y[(size_t)m * ldy + dir * H + lane] = h;
-                    if (has_res) ysum[(size_t)m * ldys + dir * H + lane] = h + res;
-                    if (stash) {
-                        float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
-                        sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = hn;
-                    }
-                    __syncwarp();
-                    hbuf[warp][lane] = h;
-                    __syncwarp();
-                }
+        for (int t = 0; t < g.T; ++t) {
+            const long m = m0 + t * step;
+            const int slot = t % PF;
+            cp_async_wait<PF - 1>();               // this lane's copies for step t have landed (each lane reads only its own)
+            const float gxr = ring[warp][slot][0][lane], gxz = ring[warp][slot][1][lane], gxn = ring[warp][slot][2][lane];
+            const float res = has_res ? ring[warp][slot][3][lane] : 0.f;
+            if (t + PF < g.T) {                    // refill the slot just consumed with the operands of step t + PF
+                const long mn = m + PF * step;
+                const float* np = gx + (size_t)mn * 6 * H + dir * 3 * H + lane;
+                cp_async4(&ring[warp][slot][0][lane], np);
+                cp_async4(&ring[warp][slot][1][lane], np + H);
+                cp_async4(&ring[warp][slot][2][lane], np + 2 * H);
+                if (has_res) cp_async4(&ring[warp][slot][3][lane], residual + (size_t)mn * ldr + dir * H + lane);
             }
+            cp_async_commit();
+            float2 ar = make_float2(bhr, 0.f), az = make_float2(bhz, 0.f), an = make_float2(bhn, 0.f);
+#pragma unroll
+            for (int q = 0; q < H / 4; ++q) {
+                const float4 hv = *reinterpret_cast<const float4*>(&hbuf[warp][q * 4]);
+                const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+                ar = ffma2(wr[2 * q], h01, ar); az = ffma2(wz[2 * q], h01, az); an = ffma2(wn[2 * q], h01, an);
+                ar = ffma2(wr[2 * q + 1], h23, ar); az = ffma2(wz[2 * q + 1], h23, az); an = ffma2(wn[2 * q + 1], h23, an);
+            }
+            const float hn = an.x + an.y;
+            const float r = sigmoid_f(gxr + (ar.x + ar.y));
+            const float z = sigmoid_f(gxz + (az.x + az.y));
+            const float n = tanhf(gxn + r * hn);
+            h = (1.f - z) * n + z * h;
+            y[(size_t)m * ldy + dir * H + lane] = h;
+            if (has_res) ysum[(size_t)m * ldys + dir * H + lane] = h + res;
+            if (stash) {
+                float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
+                sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = hn;
+            }
+            __syncwarp();
+            hbuf[warp][lane] = h;
+            __syncwarp();
         }
+        cp_async_wait<0>();
     }
 }
 
@@ -144,66 +158,72 @@ gru_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__
         wn[j] = make_float2(__ldg(W + (2 * H + 2 * j) * H + lane), __ldg(W + (2 * H + 2 * j + 1) * H + lane));
     }
     float dbh[3] = {0.f, 0.f, 0.f}, dbi[3] = {0.f, 0.f, 0.f};
+    __shared__ float ring[WARPS][PF][6][H];       // [step slot][r, z, n, hn, dy, h_prev][lane]
 
     for (int s = blockIdx.x * WARPS + warp; s < g.S; s += gridDim.x * WARPS) {
         // BPTT walks the processing order backwards: dir0 processed t=0..T-1 -> walk T-1..0; dir1 processed T-1..0 -> walk 0..T-1
         const long m0 = seq_base(g, s) + (dir ? 0 : (long)(g.T - 1) * g.t_stride);
         const long step = dir ? g.t_stride : -g.t_stride;      // towards the previously processed element
-        float p_dy[PF], p_hp[PF], p_r[PF], p_z[PF], p_n[PF], p_hn[PF];
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-            p_dy[u] = p_hp[u] = p_r[u] = p_z[u] = p_n[u] = p_hn[u] = 0.f;
             if (u < g.T) {
                 const long m = m0 + u * step;
                 const float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
-                p_r[u] = __ldg(sp); p_z[u] = __ldg(sp + H); p_n[u] = __ldg(sp + 2 * H); p_hn[u] = __ldg(sp + 3 * H);
-                p_dy[u] = __ldg(dy + (size_t)m * lddy + dir * H + lane);
-                if (u + 1 < g.T) p_hp[u] = __ldg(y + (size_t)(m + step) * ldy + dir * H + lane);
+                cp_async4(&ring[warp][u][0][lane], sp);
+                cp_async4(&ring[warp][u][1][lane], sp + H);
+                cp_async4(&ring[warp][u][2][lane], sp + 2 * H);
+                cp_async4(&ring[warp][u][3][lane], sp + 3 * H);
+                cp_async4(&ring[warp][u][4][lane], dy + (size_t)m * lddy + dir * H + lane);
+                if (u + 1 < g.T) cp_async4(&ring[warp][u][5][lane], y + (size_t)(m + step) * ldy + dir * H + lane);
             }
+            cp_async_commit();
         }
         float dh = 0.f;
-        for (int t0 = 0; t0 < g.T; t0 += PF) {
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int t = t0 + u;
-                if (t < g.T) {
-                    const long m = m0 + t * step;
-                    const float r = p_r[u], z = p_z[u], n = p_n[u], hn = p_hn[u], hprev = p_hp[u];
-                    dh += p_dy[u];
-                    if (t + PF < g.T) {
-                        const long mn = m + PF * step;
-                        const float* sp = stash + ((size_t)mn * 2 + dir) * 4 * H + lane;
-                        p_r[u] = __ldg(sp); p_z[u] = __ldg(sp + H); p_n[u] = __ldg(sp + 2 * H); p_hn[u] = __ldg(sp + 3 * H);
-                        p_dy[u] = __ldg(dy + (size_t)mn * lddy + dir * H + lane);
-                        p_hp[u] = (t + PF + 1 < g.T) ? __ldg(y + (size_t)(mn + step) * ldy + dir * H + lane) : 0.f;
-                    }
-                    const float dn = dh * (1.f - z);
-                    const float dz = dh * (hprev - n);
-                    const float dn_pre = dn * (1.f - n * n);
-                    const float dr_pre = dn_pre * hn * r * (1.f - r);
-                    const float dz_pre = dz * z * (1.f - z);
-                    const float dhn = dn_pre * r;
-                    float* gp = dgx + (size_t)m * 6 * H + dir * 3 * H + lane;
-                    gp[0] = dr_pre; gp[H] = dz_pre; gp[2 * H] = dn_pre;
-                    dbi[0] += dr_pre; dbi[1] += dz_pre; dbi[2] += dn_pre;
-                    dbh[0] += dr_pre; dbh[1] += dz_pre; dbh[2] += dhn;
-                    __syncwarp();
-                    dg[warp][0][lane] = dr_pre; dg[warp][1][lane] = dz_pre; dg[warp][2][lane] = dhn;
-                    __syncwarp();
-                    float2 c0 = make_float2(dh * z, 0.f), c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < H / 4; ++q) {
-                        const float4 vr = *reinterpret_cast<const float4*>(&dg[warp][0][q * 4]);
-                        const float4 vz = *reinterpret_cast<const float4*>(&dg[warp][1][q * 4]);
-                        const float4 vn = *reinterpret_cast<const float4*>(&dg[warp][2][q * 4]);
-                        c0 = ffma2(wr[2 * q], make_float2(vr.x, vr.y), c0); c0 = ffma2(wr[2 * q + 1], make_float2(vr.z, vr.w), c0);
-                        c1 = ffma2(wz[2 * q], make_float2(vz.x, vz.y), c1); c1 = ffma2(wz[2 * q + 1], make_float2(vz.z, vz.w), c1);
-                        c2 = ffma2(wn[2 * q], make_float2(vn.x, vn.y), c2); c2 = ffma2(wn[2 * q + 1], make_float2(vn.z, vn.w), c2);
-                    }
-                    dh = (c0.x + c0.y) + (c1.x + c1.y) + (c2.x + c2.y);
-                }
+        for (int t = 0; t < g.T; ++t) {
+            const long m = m0 + t * step;
+            const int slot = t % PF;
+            cp_async_wait<PF - 1>();
+            const float r = ring[warp][slot][0][lane], z = ring[warp][slot][1][lane], n = ring[warp][slot][2][lane],
+                        hn = ring[warp][slot][3][lane];
+            dh += ring[warp][slot][4][lane];
+            const float hprev = (t + 1 < g.T) ? ring[warp][slot][5][lane] : 0.f;
+            if (t + PF < g.T) {
+                const long mn = m + PF * step;
+                const float* sp = stash + ((size_t)mn * 2 + dir) * 4 * H + lane;
+                cp_async4(&ring[warp][slot][0][lane], sp);
+                cp_async4(&ring[warp][slot][1][lane], sp + H);
+                cp_async4(&ring[warp][slot][2][lane], sp + 2 * H);
+                cp_async4(&ring[warp][slot][3][lane], sp + 3 * H);
+                cp_async4(&ring[warp][slot][4][lane], dy + (size_t)mn * lddy + dir * H + lane);
+                if (t + PF + 1 < g.T) cp_async4(&ring[warp][slot][5][lane], y + (size_t)(mn + step) * ldy + dir * H + lane);
             }
+            cp_async_commit();
+            const float dn = dh * (1.f - z);
+            const float dz = dh * (hprev - n);
+            const float dn_pre = dn * (1.f - n * n);
+            const float dr_pre = dn_pre * hn * r * (1.f - r);
+            const float dz_pre = dz * z * (1.f - z);
+            const float dhn = dn_pre * r;
+            float* gp = dgx + (size_t)m * 6 * H + dir * 3 * H + lane;
+            gp[0] = dr_pre; gp[H] = dz_pre; gp[2 * H] = dn_pre;
+            dbi[0] += dr_pre; dbi[1] += dz_pre; dbi[2] += dn_pre;
+            dbh[0] += dr_pre; dbh[1] += dz_pre; dbh[2] += dhn;
+            __syncwarp();
+            dg[warp][0][lane] = dr_pre; dg[warp][1][lane] = dz_pre; dg[warp][2][lane] = dhn;
+            __syncwarp();
+            float2 c0 = make_float2(dh * z, 0.f), c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < H / 4; ++q) {
+                const float4 vr = *reinterpret_cast<const float4*>(&dg[warp][0][q * 4]);
+                const float4 vz = *reinterpret_cast<const float4*>(&dg[warp][1][q * 4]);
+                const float4 vn = *reinterpret_cast<const float4*>(&dg[warp][2][q * 4]);
+                c0 = ffma2(wr[2 * q], make_float2(vr.x, vr.y), c0); c0 = ffma2(wr[2 * q + 1], make_float2(vr.z, vr.w), c0);
+                c1 = ffma2(wz[2 * q], make_float2(vz.x, vz.y), c1); c1 = ffma2(wz[2 * q + 1], make_float2(vz.z, vz.w), c1);
+                c2 = ffma2(wn[2 * q], make_float2(vn.x, vn.y), c2); c2 = ffma2(wn[2 * q + 1], make_float2(vn.z, vn.w), c2);
+            }
+            dh = (c0.x + c0.y) + (c1.x + c1.y) + (c2.x + c2.y);
         }
+        cp_async_wait<0>();
     }
     // deterministic block reduction of the bias partials (fixed warp order)
 #pragma unroll
@@ -230,44 +250,53 @@ gru_dwhh_kernel(const float* __restrict__ dgx, const float* __restrict__ stash, 
     const int tid = threadIdx.x, i = tid & 31, jg = tid >> 5;
     __shared__ __align__(16) float Gs[DW_ROWS][3 * H];
     __shared__ float Hs[DW_ROWS][H];
-    __shared__ long rowM[DW_ROWS], rowP[DW_ROWS];
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.f;
     const long total = (long)g.S * g.T;
     const long chunks = (total + DW_ROWS - 1) / DW_ROWS;
-    for (long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
-        // row -> pixel-row index of the step (rowM) and of the previously processed step (rowP), -1 = none
-        if (tid < DW_ROWS) {
-            const long rho = ch * DW_ROWS + tid;
-            long m = -1, mp = -1;
-            if (rho < total) {
-                const int s = (int)(rho / g.T), t = (int)(rho - (long)s * g.T);
-                const long base = seq_base(g, s);
-                m = base + (long)t * g.t_stride;
-                const int tp = dir ? t + 1 : t - 1;           // previously processed position
-                if (tp >= 0 && tp < g.T) mp = base + (long)tp * g.t_stride;
-            }
-            rowM[tid] = m; rowP[tid] = mp;
-        }
-        __syncthreads();
-        // stage: G rows (96 floats, third gate scaled by r) and h_prev rows (32 floats)
-        for (int e = tid; e < DW_ROWS * 3 * H; e += 256) {
+    // Software pipeline: the 12 + 4 global loads of chunk i+1 are issued into registers (all independent, all in flight) before the
+    // outer products of chunk i run from shared memory.  (The first version loaded inside the staging loop: one DRAM latency per
+    // element, 123 us per launch.)
+    float gv[12], hv4[4];
+    auto load_chunk = [&](long ch) {
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+            const int e = tid + u * 256;
             const int row = e / (3 * H), c = e - row * (3 * H);
-            const long m = rowM[row];
+            const long rho = ch * DW_ROWS + row;
             float v = 0.f;
-            if (m >= 0) {
+            if (rho < total) {
+                const int sq = (int)(rho / g.T), t = (int)(rho - (long)sq * g.T);
+                const long m = seq_base(g, sq) + (long)t * g.t_stride;
                 v = __ldg(dgx + (size_t)m * 6 * H + dir * 3 * H + c);
                 if (c >= 2 * H) v *= __ldg(stash + ((size_t)m * 2 + dir) * 4 * H + (c - 2 * H));      // dn_pre * r
             }
-            Gs[row][c] = v;
+            gv[u] = v;
         }
-        for (int e = tid; e < DW_ROWS * H; e += 256) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * 256;
             const int row = e / H, c = e - row * H;
-            const long mp = rowP[row];
-            Hs[row][c] = mp >= 0 ? __ldg(y + (size_t)mp * ldy + dir * H + c) : 0.f;
+            const long rho = ch * DW_ROWS + row;
+            float v = 0.f;
+            if (rho < total) {
+                const int sq = (int)(rho / g.T), t = (int)(rho - (long)sq * g.T);
+                const int tp = dir ? t + 1 : t - 1;           // previously processed position
+                if (tp >= 0 && tp < g.T) v = __ldg(y + (size_t)(seq_base(g, sq) + (long)tp * g.t_stride) * ldy + dir * H + c);
+            }
+            hv4[u] = v;
         }
+    };
+    long ch = blockIdx.x;
+    if (ch < chunks) load_chunk(ch);
+    for (; ch < chunks; ch += gridDim.x) {
+#pragma unroll
+        for (int u = 0; u < 12; ++u) { const int e = tid + u * 256; Gs[e / (3 * H)][e % (3 * H)] = gv[u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = tid + u * 256; Hs[e / H][e % H] = hv4[u]; }
         __syncthreads();
+        if (ch + gridDim.x < chunks) load_chunk(ch + gridDim.x);
 #pragma unroll 4
         for (int row = 0; row < DW_ROWS; ++row) {
             const float hv = Hs[row][i];
