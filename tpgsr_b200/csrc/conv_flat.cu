@@ -88,6 +88,11 @@ __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t
         : "memory");
 }
 // ============================================================================================================ forward / dgrad
+constexpr int EPI_WARPS = 8;        // warps 2..9: two per TMEM lane quarter, alternating over the (tile, 32-column chunk) work items
+constexpr int FWD_THREADS = (2 + EPI_WARPS) * 32;
+constexpr int STG_PITCH = 36;       // floats per staged row: 32 columns + 4 (keeps 16-byte alignment, spreads banks)
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;
+
 struct FlatConvParams {
     int B, H, W, Hp, Wp;
     long long Qtot;            // B*Hp*Wp rows in the planes
@@ -100,7 +105,11 @@ struct FlatConvParams {
     int a_stages;              // A ring depth (1 when n_groups == 1)
     int box_rows, n_box;       // one A stage = n_box TMA boxes of box_rows rows (box_rows % 8 == 0)
     int tb, b_stages;          // taps per B stage; B ring depth
-    int ring_bytes;            // bytes reserved for the A+B rings (>= the epilogue staging area that aliases them)
+    int tile_outer;            // 1: whole halo resident (n_groups == 1) -> finish tile after tile (weights re-streamed per tile from L2) so
+                               //    that the epilogue of tile t overlaps the MMAs of tile t+1;  0: streamed A groups, taps outermost
+    int ring_bytes;            // bytes of the A+B rings
+    int stg_off;               // byte offset of the epilogue staging area (== 0: aliases the rings, only legal when !tile_outer)
+    int bar_off;               // byte offset of the barrier block
     int ldy, act, out_mode, accumulate;
     const float* bias;
     const float* act_param;
@@ -108,8 +117,20 @@ struct FlatConvParams {
     long long* dbg;            // optional [grid][8] clock64 timestamps (developer instrumentation, scripts/flat_timeline.py)
 };
 
+// the 4 K steps (x 1 or 3 products) of one (tile, tap): 128 x n_tile x 64 MACs.  FIRST: the first MMA overwrites the accumulator.
+template <int NPROD, int FIRST>
+__device__ __forceinline__ void mma_tap(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc) {
+    if (FIRST) umma_lo<0>(d, ah, bh, idesc); else umma_lo<1>(d, ah, bh, idesc);
+    if (NPROD == 3) { umma_lo<1>(d, ah, bl, idesc); umma_lo<1>(d, al, bh, idesc); }
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {          // 16 bf16 = 32 bytes = 2 descriptor units inside the 128-byte swizzle row
+        umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
+        if (NPROD == 3) { umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc); umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc); }
+    }
+}
+
 template <int NPROD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, FlatConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -123,17 +144,18 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)p.a_stages * a_stage_bytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + p.ring_bytes);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + p.bar_off);
     uint64_t* a_empty = a_full + p.a_stages;
     uint64_t* b_full = a_empty + p.a_stages;
     uint64_t* b_empty = b_full + p.b_stages;
-    uint64_t* tmem_full = b_empty + p.b_stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = b_empty + p.b_stages;                   // [MT] one per tile (tile_outer) / only [0] used otherwise
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 4);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);      // [n_tile]
 
     const long long q0 = (long long)blockIdx.x * p.MT * TILE_M;   // first output row of this CTA
     const int n0 = blockIdx.y * p.n_tile;
-    const int b_per_group = (p.G * p.KW) / p.tb;                  // B stages consumed per A group
+    const int taps_per_group = p.G * p.KW;
+    const int b_per_group = taps_per_group / p.tb;                // B stages consumed per A group (per tile when tile_outer)
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.MT * p.tm_stride) tmem_cols <<= 1;
     long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 : nullptr;
@@ -145,7 +167,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (NPROD == 3) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
         for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-        tc::mbar_init(tmem_full, 1);
+        for (int t = 0; t < 4; ++t) tc::mbar_init(&tmem_full[t], 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) {
@@ -153,7 +175,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tc::tmem_relinquish();
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < p.n_tile; i += 128)
+        for (int i = threadIdx.x - 64; i < p.n_tile; i += EPI_WARPS * 32)
             bias_s[i] = (p.bias && n0 + i < p.Co) ? __ldg(p.bias + n0 + i) : 0.f;
     }
     tc::tc_fence_before();
@@ -180,30 +202,59 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (NPROD == 3)
                         tc::tma_load_2d(ast + a_plane_bytes + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_lo, &a_full[as], ch0, r);
                 }
-                for (int j = 0; j < b_per_group; ++j, ++b_it) {
-                    const int bs = b_it % p.b_stages;
-                    mbar_wait_safe(&b_empty[bs], ((b_it / p.b_stages) & 1) ^ 1);
-                    uint8_t* bst = b_ring + (size_t)bs * b_stage_bytes;
-                    tc::mbar_expect_tx(&b_full[bs], (uint32_t)b_stage_bytes);
-                    for (int tt = 0; tt < p.tb; ++tt) {
-                        const int tap = g * p.G * p.KW + j * p.tb + tt;
-                        tc::tma_load_2d(bst + (size_t)tt * b_tap_bytes, &tmB_hi, &b_full[bs], tap * 64, n0);
-                        if (NPROD == 3)
-                            tc::tma_load_2d(bst + b_plane_bytes + (size_t)tt * b_tap_bytes, &tmB_lo, &b_full[bs], tap * 64, n0);
+                const int reps = p.tile_outer ? p.MT : 1;             // tile_outer: the taps are streamed once per tile
+                for (int rep = 0; rep < reps; ++rep) {
+                    for (int j = 0; j < b_per_group; ++j, ++b_it) {
+                        const int bs = b_it % p.b_stages;
+                        mbar_wait_safe(&b_empty[bs], ((b_it / p.b_stages) & 1) ^ 1);
+                        uint8_t* bst = b_ring + (size_t)bs * b_stage_bytes;
+                        tc::mbar_expect_tx(&b_full[bs], (uint32_t)b_stage_bytes);
+                        for (int tt = 0; tt < p.tb; ++tt) {
+                            const int tap = g * taps_per_group + j * p.tb + tt;
+                            tc::tma_load_2d(bst + (size_t)tt * b_tap_bytes, &tmB_hi, &b_full[bs], tap * 64, n0);
+                            if (NPROD == 3)
+                                tc::tma_load_2d(bst + b_plane_bytes + (size_t)tt * b_tap_bytes, &tmB_lo, &b_full[bs], tap * 64, n0);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
+        // ================= MMA issuer =================
+        // The warp runs the loops converged; only the tcgen05 instructions are predicated on the elected lane.  Per-MMA issue cost matters
+        // (a 128x64x16 MMA is 32 tensor-pipe cycles): descriptors advance by adding constants to their low words.
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);      // same value, provably warp-uniform
         const bool leader = elect_one();
-        {
-            // ================= MMA issuer =================
-            // per-MMA issue cost matters here (a 128x64x16 MMA is only 32 tensor-pipe cycles): descriptors are advanced by adding
-            // constants to their low words, the accumulate flag is a compile-time constant everywhere but the very first K step
-            const uint32_t idesc = tc::idesc_bf16(TILE_M, p.n_tile, 0, 0);
-            const uint32_t tile_lo = (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
-            uint32_t b_it = 0;
+        const uint32_t idesc = tc::idesc_bf16(TILE_M, p.n_tile, 0, 0);
+        const uint32_t tile_lo = (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
+        uint32_t b_it = 0;
+        if (p.tile_outer) {
+            mbar_wait_safe(&a_full[0], 0);
+            tc::tc_fence_after();
+            if (dbg && leader) dbg[2] = clock64();
+            const uint32_t a_hi0 = desc_lo(tc::smem_u32(a_ring), 16);
+            const uint32_t a_lo0 = a_hi0 + (a_plane_bytes >> 4);
+            for (int t = 0; t < p.MT; ++t) {
+                const uint32_t d = tmem_u + (uint32_t)(t * p.tm_stride);
+                for (int j = 0; j < taps_per_group; ++j, ++b_it) {            // tb == 1 in this mode
+                    const int bs = b_it % p.b_stages;
+                    mbar_wait_safe(&b_full[bs], (b_it / p.b_stages) & 1);
+                    tc::tc_fence_after();
+                    if (dbg && b_it == 0 && leader) dbg[3] = clock64();
+                    const int khl = j / p.KW, kw = j - khl * p.KW;
+                    const uint32_t off = (uint32_t)(khl * p.Wp + kw) * (ROW_BYTES >> 4) + (uint32_t)t * tile_lo;
+                    const uint32_t bh = desc_lo(tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes), 16);
+                    const uint32_t bl = bh + (b_plane_bytes >> 4);
+                    if (leader) {
+                        if (j == 0) mma_tap<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
+                        else mma_tap<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
+                        tc::tc_commit(&b_empty[bs]);
+                    }
+                }
+                if (leader) tc::tc_commit(&tmem_full[t]);             // tile t complete: its epilogue overlaps the next tile's MMAs
+            }
+            if (dbg && leader) dbg[4] = clock64();
+        } else {
             for (int g = 0; g < p.n_groups; ++g) {
                 const int as = g % p.a_stages;
                 mbar_wait_safe(&a_full[as], (g / p.a_stages) & 1);
@@ -223,27 +274,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         const int khl = tl / p.KW, kw = tl - khl * p.KW;
                         const uint32_t row_off = (uint32_t)(khl * p.Wp + kw) * (ROW_BYTES >> 4);
                         const uint32_t bh = b_hi0 + tt * (b_tap_bytes >> 4), bl = b_lo0 + tt * (b_tap_bytes >> 4);
-                        uint32_t ah = a_hi0 + row_off, al = a_lo0 + row_off;
-                        uint32_t d = tmem_u;
                         if (!leader) continue;
+                        uint32_t ah = a_hi0 + row_off, al = a_lo0 + row_off, d = tmem_u;
                         if (g == 0 && tl == 0) {
-                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) {
-                                umma_lo<0>(d, ah, bh, idesc);
-                                if (NPROD == 3) { umma_lo<1>(d, ah, bl, idesc); umma_lo<1>(d, al, bh, idesc); }
-#pragma unroll
-                                for (int k = 1; k < 4; ++k) {
-                                    umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
-                                    if (NPROD == 3) { umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc); umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc); }
-                                }
-                            }
+                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 1>(d, ah, al, bh, bl, idesc);
                         } else {
-                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {      // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle row
-                                    umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
-                                    if (NPROD == 3) { umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc); umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc); }
-                                }
-                            }
+                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 0>(d, ah, al, bh, bl, idesc);
                         }
                     }
                     if (leader) tc::tc_commit(&b_empty[bs]);
@@ -251,92 +287,102 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (leader) tc::tc_commit(&a_empty[as]);
             }
             if (dbg && leader) dbg[4] = clock64();
-            if (leader) tc::tc_commit(tmem_full);
+            if (leader) tc::tc_commit(&tmem_full[0]);
         }
     } else {
-        // ================= epilogue: warps 2..5; warp w owns TMEM lanes 32*(w%4).. = rows 32*(w%4).. of every tile =================
-        const int q = warp & 3;
-        mbar_wait_safe(tmem_full, 0);
-        tc::tc_fence_after();
-        if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
-        // every MMA (hence every TMA load) has completed: the rings are free and serve as per-warp staging [32 rows][n_tile+4]
-        const int pitch = p.n_tile + 4;
-        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * pitch;
+        // ================= epilogue: warps 2..9.  Warp e = warp - 2 owns TMEM lanes 32*(e % 4).. (= rows 32*(e%4).. of every tile) and
+        // takes every second (tile, 32-column chunk) work item: TMEM -> registers -> (+bias) -> private staging rows -> coalesced stores.
+        const int e = warp - 2, q = e & 3, half = e >> 2;
+        float* stg = reinterpret_cast<float*>(smem + p.stg_off) + (size_t)e * 32 * STG_PITCH;
         const float slope = (p.act == TPGSR_ACT_PRELU && p.act_param) ? __ldg(p.act_param) : 0.f;
-        const int ncols = (p.Co - n0) < p.n_tile ? (p.Co - n0) : p.n_tile;
+        const int nchunks = (p.n_tile + 31) / 32;
         const unsigned img = (unsigned)(p.Hp * p.Wp);
         const unsigned qtot = (unsigned)p.Qtot;               // < 2^31 (checked by the plan)
+        int item = 0;
         for (int t = 0; t < p.MT; ++t) {
-            // dense pixel index of this lane's output row (-1: pad position or beyond the last image)
-            const unsigned qrow = (unsigned)q0 + (unsigned)(t * TILE_M + q * 32 + lane);
-            const unsigned bi = qrow / img;
-            const unsigned rem = qrow - bi * img;
-            const unsigned r = rem / (unsigned)p.Wp, c = rem - r * (unsigned)p.Wp;
-            const bool valid = qrow < qtot && r < (unsigned)p.H && c < (unsigned)p.W;
-            const int pix = valid ? (int)((bi * p.H + r) * p.W + c) : -1;
-            // TMEM -> registers -> (+bias) -> this warp's staging rows.  The activation is applied once, in the store loops below
-            // (keeping it out of the unrolled register loop keeps the kernel's code small).
-            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+            bool waited = false;
+            int pix = -1, bi = 0, r = 0, c = 0;
+            for (int ch = 0; ch < nchunks; ++ch, ++item) {
+                if ((item & 1) != half) continue;
+                if (!waited) {
+                    mbar_wait_safe(&tmem_full[p.tile_outer ? t : 0], 0);
+                    tc::tc_fence_after();
+                    waited = true;
+                    if (dbg && e == 0 && lane == 0 && t == 0) dbg[5] = clock64();
+                    // dense pixel index of this lane's output row (-1: pad position or beyond the last image)
+                    const unsigned qrow = (unsigned)q0 + (unsigned)(t * TILE_M + q * 32 + lane);
+                    const unsigned ub = qrow / img, rem = qrow - ub * img;
+                    const unsigned ur = rem / (unsigned)p.Wp, uc = rem - ur * (unsigned)p.Wp;
+                    bi = (int)ub; r = (int)ur; c = (int)uc;
+                    pix = (qrow < qtot && r < p.H && c < p.W) ? (bi * p.H + r) * p.W + c : -1;
+                }
+                const int c0 = ch * 32;
+                const int cw = (p.n_tile - c0) >= 32 ? 32 : (p.n_tile - c0);       // 32 or 16 columns in this chunk
+                int ncols = p.Co - n0 - c0;                                         // valid output channels in this chunk
+                ncols = ncols < 0 ? 0 : (ncols > cw ? cw : ncols);
                 float v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.tm_stride + c0);
-                const int nv = (p.n_tile - c0) >= 32 ? 32 : 16;
-                if (nv == 32) tc::tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
+                if (cw == 32) tc::tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
                 tc::tmem_ld_wait();
-                float* d = stg + (size_t)lane * pitch + c0;
+                float* drow = stg + (size_t)lane * STG_PITCH;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    if (j < nv)
-                        *reinterpret_cast<float4*>(d + j) = make_float4(v[j] + bias_s[c0 + j], v[j + 1] + bias_s[c0 + j + 1],
-                                                                        v[j + 2] + bias_s[c0 + j + 2], v[j + 3] + bias_s[c0 + j + 3]);
+                    if (j < cw)
+                        *reinterpret_cast<float4*>(drow + j) = make_float4(v[j] + bias_s[c0 + j], v[j + 1] + bias_s[c0 + j + 1],
+                                                                           v[j + 2] + bias_s[c0 + j + 2], v[j + 3] + bias_s[c0 + j + 3]);
                 }
-            }
-            __syncwarp();
-            if (p.out_mode == TPGSR_OUT_NHWC) {
-                // coalesced stores of this warp's 32 rows; the pixel index of row j lives in lane j
-                if ((ncols & 3) == 0 && (p.ldy & 3) == 0 && (n0 & 3) == 0) {
-                    const int c4n = ncols >> 2;
-                    for (int i0 = 0; i0 < 32 * c4n; i0 += 32) {
-                        const int i = i0 + lane;
-                        const int row = i / c4n, c4 = i - row * c4n;
-                        const int px = __shfl_sync(0xffffffffu, pix, row);
-                        if (px >= 0) {
-                            float4 val = *reinterpret_cast<const float4*>(stg + (size_t)row * pitch + c4 * 4);
-                            if (p.act != TPGSR_ACT_NONE) {
-                                val.x = apply_act(val.x, p.act, slope); val.y = apply_act(val.y, p.act, slope);
-                                val.z = apply_act(val.z, p.act, slope); val.w = apply_act(val.w, p.act, slope);
+                __syncwarp();
+                if (p.out_mode == TPGSR_OUT_NHWC) {
+                    if (ncols == cw && (p.ldy & 3) == 0 && ((n0 + c0) & 3) == 0) {
+                        // a lane owns one 16-byte column chunk; 4 (cw = 32) or 8 (cw = 16) rows per iteration
+                        const int sh = cw == 32 ? 3 : 2;
+                        const int lr = lane >> sh, c4 = lane & ((1 << sh) - 1);
+                        const int R = 32 >> sh;
+                        const float* src = stg + (size_t)lr * STG_PITCH + c4 * 4;
+                        float* dcol = p.y + n0 + c0 + c4 * 4;
+                        const size_t ldy = (size_t)p.ldy;
+#pragma unroll 4
+                        for (int row = lr; row < 32; row += R, src += (size_t)R * STG_PITCH) {
+                            const int px = __shfl_sync(0xffffffffu, pix, row);
+                            if (px >= 0) {
+                                float4 val = *reinterpret_cast<const float4*>(src);
+                                if (p.act != TPGSR_ACT_NONE) {
+                                    val.x = apply_act(val.x, p.act, slope); val.y = apply_act(val.y, p.act, slope);
+                                    val.z = apply_act(val.z, p.act, slope); val.w = apply_act(val.w, p.act, slope);
+                                }
+                                float4* dst = reinterpret_cast<float4*>(dcol + (size_t)px * ldy);
+                                if (p.accumulate) {
+                                    float4 o = *dst;
+                                    val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                                }
+                                *dst = val;
                             }
-                            float4* dst = reinterpret_cast<float4*>(p.y + (size_t)px * p.ldy + n0 + c4 * 4);
-                            if (p.accumulate) {
-                                float4 o = *dst;
-                                val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                        }
+                    } else if (ncols > 0) {
+                        for (int i0 = 0; i0 < 32 * ncols; i0 += 32) {      // ragged channel counts (e.g. 37): scalar stores
+                            const int i = i0 + lane;
+                            const int row = i / ncols, cc = i - row * ncols;
+                            const int px = __shfl_sync(0xffffffffu, pix, row & 31);
+                            if (row < 32 && px >= 0) {
+                                const float val = apply_act(stg[(size_t)row * STG_PITCH + cc], p.act, slope);
+                                float* dst = p.y + (size_t)px * p.ldy + n0 + c0 + cc;
+                                *dst = p.accumulate ? *dst + val : val;
                             }
-                            *dst = val;
                         }
                     }
-                } else {
-                    for (int i0 = 0; i0 < 32 * ncols; i0 += 32) {
-                        const int i = i0 + lane;
-                        const int row = i / ncols, cc = i - row * ncols;
-                        const int px = __shfl_sync(0xffffffffu, pix, row);
-                        if (px >= 0) {
-                            float val = apply_act(stg[(size_t)row * pitch + cc], p.act, slope);
-                            float* dst = p.y + (size_t)px * p.ldy + n0 + cc;
-                            *dst = p.accumulate ? *dst + val : val;
-                        }
+                } else if (pix >= 0) {
+                    // NCHW: for a fixed channel the 32 lanes hold 32 consecutive flat positions = (mostly) consecutive columns
+                    for (int n = 0; n < ncols; ++n) {
+                        const float val = apply_act(drow[n], p.act, slope);
+                        float* dst = p.y + (((size_t)bi * p.Co + n0 + c0 + n) * p.H + r) * p.W + c;
+                        *dst = p.accumulate ? *dst + val : val;
                     }
                 }
-            } else if (valid) {
-                // NCHW: for a fixed channel the 32 lanes hold 32 consecutive flat positions = (mostly) consecutive columns
-                for (int n = 0; n < ncols; ++n) {
-                    const float val = apply_act(stg[(size_t)lane * pitch + n], p.act, slope);
-                    float* dst = p.y + (((size_t)bi * p.Co + n0 + n) * p.H + r) * p.W + c;
-                    *dst = p.accumulate ? *dst + val : val;
-                }
+                __syncwarp();
             }
-            __syncwarp();
-            if (dbg && warp == 2 && lane == 0 && t == 0) dbg[6] = clock64();
+            if (dbg && e == 0 && lane == 0 && t == 0) dbg[6] = clock64();
         }
-        if (dbg && warp == 2 && lane == 0) dbg[7] = clock64();
+        if (dbg && e == 0 && lane == 0) dbg[7] = clock64();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -384,7 +430,7 @@ split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __re
 }
 
 struct FlatPlan {
-    int MT, n_tile, n_tiles, tm_stride, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, ring_bytes;
+    int MT, n_tile, n_tiles, tm_stride, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, tile_outer, ring_bytes, stg_off, bar_off;
     size_t smem;
     int grid_x;
 };
@@ -405,7 +451,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
     pl.pointwise = pointwise;
     const long long Qtot = (long long)B * (H + P) * Wp;
     if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
-    const size_t budget = 220 * 1024;
+    const size_t budget = 226 * 1024;          // of the 227 KB a CTA may use
     // candidate configurations, best first: whole kernel resident (G = KH) with MT = 3, 2, 1; then one kernel row per stage
     // among the feasible MT the one with the fewest (waves x tiles per CTA) wins; near-ties go to the larger MT (less weight traffic)
     const long long tiles = (Qtot + TILE_M - 1) / TILE_M;
@@ -423,22 +469,25 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             if (box_rows > 256) { ++n_box; box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8; }
             const size_t a_bytes = (size_t)a_stages * planes * n_box * box_rows * ROW_BYTES;
             // B ring: one tap per stage, 4..2 deep (deepest that fits) — or one kernel row of taps per stage, 2 deep, when the
-            // tap tile is small and the kernel rows are streamed
+            // tap tile is small and the kernel rows are streamed.  tile_outer (whole halo resident): the epilogue of one tile runs while
+            // the next tile's MMAs read the rings, so its staging area is separate; otherwise it aliases the (drained) rings.
             const int taps_per_group = G * KW;
+            const int tile_outer = n_groups == 1 ? 1 : 0;
             const size_t tap_bytes = (size_t)planes * pl.n_tile * ROW_BYTES;
-            const size_t stg_bytes = (size_t)4 * 32 * (pl.n_tile + 4) * sizeof(float);
-            int tb = 1, b_stages = 0, ring_bytes = 0;
+            int tb = 1, b_stages = 0, ring_bytes = 0, stg_off = 0, bar_off = 0;
             size_t smem = 0;
-            const bool row_stage = n_groups > 1 && KW > 1 && tap_bytes * KW <= 40 * 1024;
-            for (int want = row_stage ? 2 : 4; want >= (row_stage ? 2 : 2); --want) {
+            const bool row_stage = !tile_outer && KW > 1 && tap_bytes * KW <= 40 * 1024;
+            for (int want = row_stage ? 2 : 4; want >= 2; --want) {
                 tb = row_stage ? KW : 1;
                 int bs = want;
-                const int total_b = n_groups * (taps_per_group / tb);
+                const int total_b = (tile_outer ? MT : n_groups) * (taps_per_group / tb);
                 if (bs > total_b) bs = total_b;
                 size_t ring = a_bytes + (size_t)bs * tb * tap_bytes;
-                if (ring < stg_bytes) ring = stg_bytes;
-                const size_t need = ring + 1024 /*align*/ + 8 * (2 * a_stages + 2 * bs + 1) + 16 + pl.n_tile * 4 + 64;
-                if (need <= budget) { b_stages = bs; smem = need; ring_bytes = (int)ring; break; }
+                if (!tile_outer && ring < (size_t)STG_BYTES) ring = STG_BYTES;
+                const size_t so = tile_outer ? ring : 0;
+                const size_t bo = tile_outer ? ring + STG_BYTES : ring;
+                const size_t need = bo + 8 * (2 * a_stages + 2 * bs + 4) + 16 + pl.n_tile * 4 + 64 + 1024 /*align*/;
+                if (need <= budget) { b_stages = bs; smem = need; ring_bytes = (int)ring; stg_off = (int)so; bar_off = (int)bo; break; }
             }
             if (b_stages == 0) continue;
             const long long ctas = (tiles + MT - 1) / MT * pl.n_tiles;
@@ -446,7 +495,8 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             if (best_cost >= 0 && cost * 23 >= best_cost * 20) continue;       // a smaller MT must win by > 15%
             best_cost = cost;
             pl.MT = MT; pl.G = G; pl.n_groups = n_groups; pl.a_stages = a_stages; pl.box_rows = box_rows; pl.n_box = n_box;
-            pl.tb = tb; pl.b_stages = b_stages; pl.smem = smem; pl.ring_bytes = ring_bytes;
+            pl.tb = tb; pl.b_stages = b_stages; pl.smem = smem; pl.ring_bytes = ring_bytes; pl.stg_off = stg_off; pl.bar_off = bar_off;
+            pl.tile_outer = tile_outer;
             pl.grid_x = (int)((tiles + MT - 1) / MT);
         }
         if (best_cost >= 0) return TPGSR_OK;
@@ -667,14 +717,14 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
 
 // tiling decided for a geometry (host-only; lets tests / docs inspect the plan without a GPU):
-// out[12] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x}; returns smem bytes (0 = unsupported)
+// out[13] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer}; returns smem bytes (0 = unsupported)
 size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, int* out) {
     FlatPlan pl;
     if (plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl)) return 0;
     if (out) {
-        const int v[12] = {pl.MT, pl.n_tile, pl.n_tiles, pl.tm_stride, pl.G, pl.n_groups, pl.a_stages, pl.box_rows, pl.n_box, pl.tb,
-                           pl.b_stages, pl.grid_x};
-        for (int i = 0; i < 12; ++i) out[i] = v[i];
+        const int v[13] = {pl.MT, pl.n_tile, pl.n_tiles, pl.tm_stride, pl.G, pl.n_groups, pl.a_stages, pl.box_rows, pl.n_box, pl.tb,
+                           pl.b_stages, pl.grid_x, pl.tile_outer};
+        for (int i = 0; i < 13; ++i) out[i] = v[i];
     }
     return pl.smem;
 }
@@ -707,6 +757,7 @@ int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, cons
     p.MT = pl.MT; p.n_tile = pl.n_tile; p.tm_stride = pl.tm_stride; p.pointwise = pl.pointwise; p.G = pl.G; p.n_groups = pl.n_groups;
     p.a_stages = pl.a_stages;
     p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
+    p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
     p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg;
 
@@ -731,11 +782,11 @@ int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, cons
     if (nprod == 3) {
         if (cudaFuncSetAttribute(conv_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
-        conv_flat_kernel<3><<<grid, 192, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+        conv_flat_kernel<3><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else {
         if (cudaFuncSetAttribute(conv_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
-        conv_flat_kernel<1><<<grid, 192, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+        conv_flat_kernel<1><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     }
     return tpgsr_launch_status();
 }
