@@ -86,6 +86,7 @@ int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, in
                           cudaStream_t stream);
 int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod);
 int tpgsr_conv2d_flat_set_debug(long long* dbg);
+int tpgsr_conv2d_flat_set_debug_skip(int bits);
 size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, int* out);
 size_t tpgsr_conv2d_wgrad_flat_plan(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, int* out);
 int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, int B,
@@ -96,6 +97,17 @@ size_t tpgsr_conv2d_wgrad_flat_workspace_bytes(int B, int H, int W, int P, int C
 int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw_oihw, int B,
                             int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int ph, int pw, int accumulate,
                             int nprod, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- kw-stacking: 9x9 convs with a 4-channel side (model/tsrn.py:26,43) as 9x1 tensor-core convs on 64-channel operands --------------
+ * (kwstack.cu) weight packing for tpgsr_conv2d_flat, the stacked operand split, the shift-and-add epilogue, the wgrad scatter. */
+int tpgsr_kwstack_pack_weights(const float* w_oihw, void* hi, void* lo, int Co, int Ci, int KH, int KW, int narrow_out, int transposed,
+                               int flip_kh, int flip_kw, int rows, cudaStream_t stream);
+int tpgsr_kwstack_split(const float* x, int ldx, void* hi, void* lo, int B, int H, int W, int C, int KW, int pw, int P, int sign,
+                        cudaStream_t stream);
+int tpgsr_kwsum(const float* p, int ldp, const float* bias, float* y, int B, int H, int W, int C, int KW, int pw, int ldy, int act,
+                const float* act_param, int out_mode, int accumulate, cudaStream_t stream);
+int tpgsr_kwstack_wgrad_scatter(const float* dwp, float* dw_oihw, int Co, int Ci, int KH, int KW, int layout, int accumulate,
+                                cudaStream_t stream);
 
 /* ---- batch norm, activations, pooling, reshuffles -----------------------------------------------------------------
  * nn.BatchNorm2d/1d (model/tsrn.py:377,382,38; model/stn_head.py:19,51; model/crnn/crnn.py:48), mish

@@ -5,7 +5,7 @@ import torch
 from tpgsr_b200 import ops
 from tpgsr_b200._lib import LIB
 d = torch.device('cuda:0')
-names = ['setup_done', 'A_full', 'B0_full', 'mma_issued', 'tmem_full', 'tile0_stored', 'epi_done']
+names = ['setup_done', 'A_full', 'B0_full', 'mma_issued', 'tmem_full0', 'tile0_stored', 'epi_done', 'item0_ldtm', 'item0_staged']
 
 def batch_time(f, n=20, reps=5):
     for _ in range(3): f()
@@ -29,12 +29,12 @@ for (B, Ci, Co, H, W, k) in [(48, 64, 64, 16, 64, 1), (48, 64, 64, 16, 64, 3), (
         y = torch.empty(B, H, W, Co, device=d)
         f = lambda: ops.conv_flat(fp, wf, b, Co, k, k, pad, pad, out=y)
         us = batch_time(f)
-        dbg = torch.zeros(4096, 8, dtype=torch.int64, device=d)
+        dbg = torch.zeros(4096, 16, dtype=torch.int64, device=d)
         LIB.tpgsr_conv2d_flat_set_debug(dbg.data_ptr())
         f(); torch.cuda.synchronize()
         LIB.tpgsr_conv2d_flat_set_debug(None)
         t = dbg.cpu(); t = t[t[:, 0] != 0]
-        rel = (t[:, 1:8] - t[:, 0:1]).float()
+        rel = (t[:, 1:10] - t[:, 0:1]).float()
         print(f'k={k} {Ci}->{Co} {mode}: {us:.1f} us/launch back-to-back (L2-hot); per-CTA cycles since CTA start, median / p90 over {t.shape[0]} CTAs; '
               f'first CTA start spread {(t[:, 0].max() - t[:, 0].min()).item()} cyc', flush=True)
         for i, n in enumerate(names):

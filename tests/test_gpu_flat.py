@@ -136,3 +136,49 @@ def test_flat_full_batch_properties():
     assert rel_err(y1, y_tc) < 2e-6
     ref = nhwc(F.conv2d(nchw(x1).cpu(), w.cpu(), None, padding=1))
     assert rel_err(y1, ref) < 3e-5
+
+
+@pytest.mark.parametrize('B,Ci,Co,H,W,k,nchw_out', [
+    (2, 64, 4, 32, 128, 9, True),     # final conv: narrow output, tanh, NCHW result
+    (24, 64, 4, 32, 128, 9, True),    # ... at a batch with 3 tiles per CTA
+    (3, 4, 64, 16, 64, 9, False),     # block1: narrow input (+ data gradient for the STN branch = narrow output)
+    (2, 3, 64, 8, 24, 5, False),      # 5x5 with 3 input channels, ragged map
+])
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
+def test_kwstack_conv_through_engine(B, Ci, Co, H, W, k, nchw_out, mode):
+    """9x9 / 5x5 convs with a narrow side through engine.conv_fwd / conv_bwd (kw-stacking -> 9x1 tcgen05 convs) vs fp32 autograd."""
+    from tpgsr_b200 import engine, ops
+    pad = k // 2
+    x = rnd(B, Ci, H, W, seed=61).requires_grad_(True)
+    w = (rnd(Co, Ci, k, k, seed=62) / np.sqrt(Ci * k * k)).requires_grad_(True)
+    b = rnd(Co, seed=63, scale=0.1).requires_grad_(True)
+    y = torch.tanh(F.conv2d(x, w, b, padding=pad)) if nchw_out else F.conv2d(x, w, b, padding=pad)
+    gy = rnd(*y.shape, seed=64)
+    (y * gy).sum().backward()
+    d = torch.device('cuda:0')
+    old = ops.CONV_MODE
+    ops.CONV_MODE = mode
+    tol = 5e-5 if mode == 'bf16x3' else 1e-2
+    try:
+        assert ops.kwstack_kind(B, H, W, Ci, Co, k, pad) == ('N' if Ci == 64 else 'I')
+        params = {'w': w.detach().to(d), 'b': b.detach().to(d)}
+        grads = {'w': torch.full_like(params['w'], 7.0), 'b': torch.zeros_like(params['b'])}
+        ctx = engine.Ctx(params, grads, True)
+        xd = nhwc(x.detach()).to(d)
+        if nchw_out:
+            yd, saved = engine.conv_fwd(ctx, xd, 'w', 'b', k, pad, act=ops.ACT_TANH, out_nchw=True)
+            assert rel_err(yd, y) < tol, rel_err(yd, y)
+            dpre = nhwc(gy * (1 - y.detach() ** 2)).to(d)          # gradient w.r.t. the pre-activation
+        else:
+            yd, saved = engine.conv_fwd(ctx, xd, 'w', 'b', k, pad)
+            assert rel_err(nchw(yd), y) < tol, rel_err(nchw(yd), y)
+            dpre = nhwc(gy).to(d)
+        dx = engine.conv_bwd(ctx, saved, dpre, need_dx=True)
+        assert rel_err(grads['w'], w.grad) < tol, rel_err(grads['w'], w.grad)
+        assert rel_err(grads['b'], b.grad) < 1e-4
+        assert rel_err(nchw(dx), x.grad) < tol, rel_err(nchw(dx), x.grad)
+        # second backward accumulates into the same gradient buffers
+        engine.conv_bwd(ctx, saved, dpre, need_dx=False)
+        assert rel_err(grads['w'], 2 * w.grad) < tol
+    finally:
+        ops.CONV_MODE = old

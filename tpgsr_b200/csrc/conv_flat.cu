@@ -114,7 +114,8 @@ struct FlatConvParams {
     const float* bias;
     const float* act_param;
     float* y;
-    long long* dbg;            // optional [grid][8] clock64 timestamps (developer instrumentation, scripts/flat_timeline.py)
+    int dbg_skip;              // developer experiments: bit0 = skip the global stores, bit1 = skip TMEM load + staging
+    long long* dbg;            // optional [grid][16] clock64 timestamps (developer instrumentation, scripts/flat_timeline.py)
 };
 
 // the 4 K steps (x 1 or 3 products) of one (tile, tap): 128 x n_tile x 64 MACs.  FIRST: the first MMA overwrites the accumulator.
@@ -141,7 +142,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int b_tap_bytes = p.n_tile * ROW_BYTES;                 // one tap, one plane: [n_tile co][64 ci] K-major
     const int b_plane_bytes = p.tb * b_tap_bytes;
     const int b_stage_bytes = planes * b_plane_bytes;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared-space provenance (LDS/STS, not generic LD/ST)
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)p.a_stages * a_stage_bytes;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + p.bar_off);
@@ -150,7 +151,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint64_t* b_empty = b_full + p.b_stages;
     uint64_t* tmem_full = b_empty + p.b_stages;                   // [MT] one per tile (tile_outer) / only [0] used otherwise
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 4);
-    float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);      // [n_tile]
+    float* bias_s = reinterpret_cast<float*>(smem + p.bar_off + 256);      // [n_tile], 16-byte aligned (barrier block <= 256 bytes)
 
     const long long q0 = (long long)blockIdx.x * p.MT * TILE_M;   // first output row of this CTA
     const int n0 = blockIdx.y * p.n_tile;
@@ -158,7 +159,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int b_per_group = taps_per_group / p.tb;                // B stages consumed per A group (per tile when tile_outer)
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.MT * p.tm_stride) tmem_cols <<= 1;
-    long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 : nullptr;
+    long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 16 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     if (threadIdx.x == 0) {
@@ -290,9 +291,9 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             if (leader) tc::tc_commit(&tmem_full[0]);
         }
     } else {
-        // ================= epilogue: warps 2..9.  Warp e = warp - 2 owns TMEM lanes 32*(e % 4).. (= rows 32*(e%4).. of every tile) and
+        // ================= epilogue: warps 2..9.  Warp w owns TMEM lanes 32*(w % 4).. (= rows 32*(w%4).. of every tile) and
         // takes every second (tile, 32-column chunk) work item: TMEM -> registers -> (+bias) -> private staging rows -> coalesced stores.
-        const int e = warp - 2, q = e & 3, half = e >> 2;
+        const int e = warp - 2, q = warp & 3, half = e >> 2;      // hardware rule: warp w may only read TMEM lanes 32*(w % 4)..+31
         float* stg = reinterpret_cast<float*>(smem + p.stg_off) + (size_t)e * 32 * STG_PITCH;
         const float slope = (p.act == TPGSR_ACT_PRELU && p.act_param) ? __ldg(p.act_param) : 0.f;
         const int nchunks = (p.n_tile + 31) / 32;
@@ -322,16 +323,27 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 ncols = ncols < 0 ? 0 : (ncols > cw ? cw : ncols);
                 float v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.tm_stride + c0);
+                if (p.dbg_skip & 2) continue;
                 if (cw == 32) tc::tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
                 tc::tmem_ld_wait();
+                if (dbg && e == 0 && lane == 0 && item == 0) dbg[8] = clock64();
                 float* drow = stg + (size_t)lane * STG_PITCH;
+                const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j < cw)
-                        *reinterpret_cast<float4*>(drow + j) = make_float4(v[j] + bias_s[c0 + j], v[j + 1] + bias_s[c0 + j + 1],
-                                                                           v[j + 2] + bias_s[c0 + j + 2], v[j + 3] + bias_s[c0 + j + 3]);
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = b4[j];
+                    *reinterpret_cast<float4*>(drow + 4 * j) = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+                }
+                if (cw == 32) {
+#pragma unroll
+                    for (int j = 4; j < 8; ++j) {
+                        const float4 bb = b4[j];
+                        *reinterpret_cast<float4*>(drow + 4 * j) = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+                    }
                 }
                 __syncwarp();
+                if (dbg && e == 0 && lane == 0 && item == 0) dbg[9] = clock64();
+                if (p.dbg_skip & 1) continue;
                 if (p.out_mode == TPGSR_OUT_NHWC) {
                     if (ncols == cw && (p.ldy & 3) == 0 && ((n0 + c0) & 3) == 0) {
                         // a lane owns one 16-byte column chunk; 4 (cw = 32) or 8 (cw = 16) rows per iteration
@@ -436,6 +448,7 @@ struct FlatPlan {
 };
 
 long long* g_flat_dbg = nullptr;
+int g_flat_dbg_skip = 0;
 
 int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
     if (Co < 1 || B < 1 || H < 1 || W < 1 || Ci < 64 || Ci % 64 != 0) return TPGSR_ERR_UNSUPPORTED;
@@ -472,7 +485,10 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             // tap tile is small and the kernel rows are streamed.  tile_outer (whole halo resident): the epilogue of one tile runs while
             // the next tile's MMAs read the rings, so its staging area is separate; otherwise it aliases the (drained) rings.
             const int taps_per_group = G * KW;
-            const int tile_outer = n_groups == 1 ? 1 : 0;
+            // tile_outer measured slower on B200 (profiles/r01/flat_timeline_v3.log): with the taps re-streamed per tile a B stage feeds
+            // only 12 MMAs and the 3-deep ring cannot cover the L2 round trip (90 cycles/MMA vs 63 with the taps outermost, where a
+            // stage feeds MT x 12 MMAs); the epilogue it would hide is ~2 us.  Kept in the kernel for geometries with many tiles per CTA.
+            const int tile_outer = 0;
             const size_t tap_bytes = (size_t)planes * pl.n_tile * ROW_BYTES;
             int tb = 1, b_stages = 0, ring_bytes = 0, stg_off = 0, bar_off = 0;
             size_t smem = 0;
@@ -486,7 +502,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
                 if (!tile_outer && ring < (size_t)STG_BYTES) ring = STG_BYTES;
                 const size_t so = tile_outer ? ring : 0;
                 const size_t bo = tile_outer ? ring + STG_BYTES : ring;
-                const size_t need = bo + 8 * (2 * a_stages + 2 * bs + 4) + 16 + pl.n_tile * 4 + 64 + 1024 /*align*/;
+                const size_t need = bo + 256 /*barriers*/ + (size_t)(pl.n_tile + 32) * 4 /*bias*/ + 1024 /*align*/;
                 if (need <= budget) { b_stages = bs; smem = need; ring_bytes = (int)ring; stg_off = (int)so; bar_off = (int)bo; break; }
             }
             if (b_stages == 0) continue;
@@ -533,7 +549,7 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
     const int dy_plane_bytes = ngroups * dy_tile_bytes;
     const int x_plane_bytes = p.x_rows * ROW_BYTES;
     const int stage_bytes = planes * (dy_plane_bytes + x_plane_bytes);
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared-space provenance (LDS/STS, not generic LD/ST)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty = full + p.stages;
     uint64_t* tmem_full = empty + p.stages;
@@ -713,8 +729,9 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
     return plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl) == TPGSR_OK ? 1 : 0;
 }
 
-// developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][8]
+// developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][16]
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
+int tpgsr_conv2d_flat_set_debug_skip(int bits) { g_flat_dbg_skip = bits; return TPGSR_OK; }
 
 // tiling decided for a geometry (host-only; lets tests / docs inspect the plan without a GPU):
 // out[13] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer}; returns smem bytes (0 = unsupported)
@@ -759,7 +776,7 @@ int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, cons
     p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
     p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
-    p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg;
+    p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg; p.dbg_skip = g_flat_dbg_skip;
 
     const uint64_t K = (uint64_t)KH * KW * Ci;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;

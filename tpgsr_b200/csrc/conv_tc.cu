@@ -47,7 +47,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int b_plane_bytes = p.n_tile * BLOCK_K * 2;
     const int planes = NPROD == 3 ? 2 : 1;
     const int stage_bytes = planes * (A_PLANE_BYTES + b_plane_bytes);
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared-space provenance (LDS/STS, not generic LD/ST)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty = full + stages;
     uint64_t* tmem_full = empty + stages;

@@ -45,7 +45,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
     const int n0 = blockIdx.z * p.n_tile;
     const int ngroups = p.n_tile / 64;
     const int stage_bytes = planes * (ngroups + p.taps_per_group) * TILE_BYTES;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared-space provenance (LDS/STS, not generic LD/ST)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty = full + stages;
     uint64_t* tmem_full = empty + stages;

@@ -61,6 +61,23 @@ class Ctx:
             self._planes[key] = hit
         return hit[1]
 
+    def stacked(self, x: Tensor, KW: int, pw: int, P: int, sign: int):
+        """kw-stacked padded-flat planes of a narrow activation (cached)."""
+        key = (id(x), 'kwstack', KW, pw, P, sign)
+        hit = self._planes.get(key)
+        if hit is None:
+            hit = (x, ops.kwstack_split(x, KW, pw, P, sign, ops.CONV_MODE == 'bf16x3'))
+            self._planes[key] = hit
+        return hit[1]
+
+    def packed_kwstack(self, name: str, narrow_out: bool, transposed: bool, flip_kh: bool, flip_kw: bool):
+        key = (name, 'kwstack', narrow_out, transposed, flip_kh, flip_kw)
+        hit = self._packed_bf16.get(key)
+        if hit is None:
+            hit = ops.kwstack_pack(self.params[name], narrow_out, transposed, flip_kh, flip_kw, ops.CONV_MODE == 'bf16x3')
+            self._packed_bf16[key] = hit
+        return hit
+
     def planes_padded(self, x: Tensor, c_out: int):
         key = (id(x), c_out)
         hit = self._planes.get(key)
@@ -108,6 +125,13 @@ def _flat_ok(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: int, ld
             and ops.flat_supported(B, H, W, max(ph, pw), Ci, Co, kh, kw, ph, pw))
 
 
+def _kwstack_kind(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: int, ldx: int, as4d):
+    B, H, W, Cx = x.shape
+    if as4d is not None or kh != kw or ph != pw or ldx not in (0, Cx) or Cx != Ci or not x.is_contiguous():
+        return None
+    return ops.kwstack_kind(B, H, W, Ci, Co, kh, ph)
+
+
 def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=ACT_NONE, act_param: Optional[Tensor] = None,
              out_nchw: bool = False, need_dgrad: bool = True, as4d=None, ldx: int = 0, out: Optional[Tensor] = None):
     w = ctx.P(wname)
@@ -117,6 +141,15 @@ def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=
     Ci = (w.numel() // Co) // (kh * kw)
     saved = (x, wname, bname, kh, kw, ph, pw, as4d, ldx)
     bias = ctx.P(bname) if bname else None
+    kind = _kwstack_kind(x, Ci, Co, kh, kw, ph, pw, ldx, as4d) if out is None else None
+    if kind == 'N':        # narrow output (final conv): 9x1 conv to the kw-stacked partial sums, then shift-and-add (+bias, act)
+        wpk = ctx.packed_kwstack(wname, True, False, False, False)
+        part = ops.conv_flat(ctx.flat(x, ph), wpk, None, kw * Co, kh, 1, ph, 0)
+        return ops.kwsum(part, bias, Co, kw, pw, act, act_param, out_nchw), saved
+    if kind == 'I':        # narrow input (block1): 9x1 conv on the kw-stacked input planes
+        wpk = ctx.packed_kwstack(wname, False, False, False, False)
+        y = ops.conv_flat(ctx.stacked(x, kw, pw, ph, 1), wpk, bias, Co, kh, 1, ph, 0, act, act_param, out_nchw)
+        return y, saved
     if out is None and _flat_ok(x, Ci, Co, kh, kw, ph, pw, ldx):
         wf, _ = ctx.packed_bf16(wname, as4d)
         y = ops.conv_flat(ctx.flat(x, max(ph, pw)), wf, bias, Co, kh, kw, ph, pw, act, act_param, out_nchw)
@@ -140,6 +173,27 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     gw, acc = ctx.G(wname)
     B, H, W, Cx = x.shape
     P = max(ph, pw)
+    kind = _kwstack_kind(x, Ci, Co, kh, kw, ph, pw, ldx, as4d) if dy.is_contiguous() else None
+    if kind is not None:
+        dwp = torch.empty(((kw * Co) if kind == 'N' else 64, 64, kh, 1), dtype=torch.float32, device=x.device)
+        if kind == 'N':     # final conv: dY is the narrow side -> stack it (sign -1), shared by the weight and the data gradient
+            dys = ctx.stacked(dy, kw, pw, ph, -1)
+            ops.conv_wgrad_flat(ctx.flat(x, ph), dys, dwp, kw * Co, kh, 1, ph, 0, False)
+            ops.kwstack_wgrad_scatter(dwp, gw, 0, acc)
+        else:               # block1: the stacked input planes of the forward pass against the plain dY planes
+            ops.conv_wgrad_flat(ctx.stacked(x, kw, pw, ph, 1), ctx.flat(dy, ph), dwp, 64, kh, 1, ph, 0, False)
+            ops.kwstack_wgrad_scatter(dwp, gw, 1, acc)
+        if bname:
+            gb, accb = ctx.G(bname)
+            ops.colsum(dy.view(-1, Co), gb, accb)
+        if not need_dx:
+            return None
+        if kind == 'N':     # dX[q][ci] = sum_t sum_j DYS[q + (t-ph)*Wp][j] * W[co(j)][ci][KH-1-t][kw(j)]
+            wpk = ctx.packed_kwstack(wname, False, True, True, False)
+            return ops.conv_flat(ctx.stacked(dy, kw, pw, ph, -1), wpk, None, Ci, kh, 1, ph, 0, out=dx_out, accumulate=dx_accumulate)
+        wpk = ctx.packed_kwstack(wname, True, True, True, True)      # narrow output: dX = shift-and-add of the stacked partial sums
+        part = ops.conv_flat(ctx.flat(dy, ph), wpk, None, kw * Ci, kh, 1, ph, 0)
+        return ops.kwsum(part, None, Ci, kw, pw, out=dx_out, accumulate=dx_accumulate)
     same = (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 2 * ph == kh - 1 and 2 * pw == kw - 1)
     if same and ops.wgrad_flat_supported(B, H, W, P, Ci, Co, kh, kw):
         ops.conv_wgrad_flat(ctx.flat(x, P), ctx.flat(dy, P, (Co + 63) // 64 * 64), gw, Co, kh, kw, ph, pw, acc)

@@ -271,6 +271,66 @@ def conv_wgrad_flat(xp: FlatPlanes, dyp: FlatPlanes, dw: torch.Tensor, Co, KH, K
           dyp.C, KH, KW, ph, pw, int(accumulate), n, wp, wn, stream())
 
 
+# ---- kw-stacking (kwstack.cu): 9x9 convs with a narrow (<= 64/9 channel) side as 9x1 tensor-core convs -----------------------------------
+KWSTACK = os.environ.get('TPGSR_KWSTACK', '1') != '0'
+
+
+def kwstack_kind(B, H, W, Ci, Co, k, pad):
+    """'N' (narrow output: Ci == 64, Co*k <= 64), 'I' (narrow input: Co == 64, Ci*k <= 64) or None."""
+    if not (FLAT and KWSTACK) or CONV_MODE == 'fp32' or k < 5 or 2 * pad != k - 1:
+        return None
+    if Ci == 64 and Co * k <= 64:
+        kind, co_eff = 'N', Co * k
+    elif Co == 64 and Ci * k <= 64:
+        kind, co_eff = 'I', 64
+    else:
+        return None
+    if not LIB.tpgsr_conv2d_flat_supported(B, H, W, pad, 64, co_eff, k, 1, pad, 0, nprod()):
+        return None
+    if not LIB.tpgsr_conv2d_wgrad_flat_supported(B, H, W, pad, 64, co_eff, 64, k, 1, nprod()):
+        return None
+    return kind
+
+
+def kwstack_pack(w: torch.Tensor, narrow_out: bool, transposed: bool, flip_kh: bool, flip_kw: bool, need_lo: bool = True):
+    """OIHW fp32 -> K-major bf16 hi/lo [rows][KH*64] for the KHx1 stacked conv (see kwstack.cu)."""
+    Co, Ci, KH, KW = w.shape
+    narrow = (Ci if transposed else Co) if narrow_out else (Co if transposed else Ci)
+    rows = (KW * narrow + 15) // 16 * 16 if narrow_out else 64
+    hi = torch.empty((rows, KH * 64), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty((rows, KH * 64), dtype=torch.bfloat16, device=w.device) if need_lo else None
+    _call('tpgsr_kwstack_pack_weights', ptr(w), ptr(hi), ptr(lo), Co, Ci, KH, KW, int(narrow_out), int(transposed), int(flip_kh),
+          int(flip_kw), rows, stream())
+    return hi, lo
+
+
+def kwstack_split(x: torch.Tensor, KW: int, pw: int, P: int, sign: int, need_lo: bool = True) -> FlatPlanes:
+    """fp32 NHWC [B,H,W,C] (C*KW <= 64) -> stacked padded-flat planes [B][H+P][W+P][64], channel kw*C+i = x[.., c + sign*(kw-pw), i]."""
+    B, H, W, C = x.shape
+    rows = B * (H + P) * (W + P)
+    hi = torch.empty((rows, 64), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((rows, 64), dtype=torch.bfloat16, device=x.device) if need_lo else None
+    _call('tpgsr_kwstack_split', ptr(x), C, ptr(hi), ptr(lo), B, H, W, C, KW, pw, P, sign, stream())
+    return FlatPlanes(hi, lo, B, H, W, 64, P)
+
+
+def kwsum(p: torch.Tensor, bias, C: int, KW: int, pw: int, act=ACT_NONE, act_param=None, out_nchw=False,
+          out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """y[.., c, o] = act(bias[o] + sum_kw p[.., c + kw - pw, kw*C + o]);  p NHWC [B,H,W,>=KW*C] -> NHWC [B,H,W,C] or NCHW."""
+    B, H, W, ldp = p.shape
+    if out is None:
+        out = torch.empty((B, C, H, W) if out_nchw else (B, H, W, C), dtype=torch.float32, device=p.device)
+        accumulate = False
+    _call('tpgsr_kwsum', ptr(p), ldp, ptr(bias), ptr(out), B, H, W, C, KW, pw, C if out_nchw else out.shape[-1], act, ptr(act_param),
+          OUT_NCHW if out_nchw else OUT_NHWC, int(accumulate), stream())
+    return out
+
+
+def kwstack_wgrad_scatter(dwp: torch.Tensor, dw: torch.Tensor, layout: int, accumulate: bool) -> None:
+    Co, Ci, KH, KW = dw.shape
+    _call('tpgsr_kwstack_wgrad_scatter', ptr(dwp), ptr(dw), Co, Ci, KH, KW, layout, int(accumulate), stream())
+
+
 def colsum(x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> None:
     """out[C] (+)= sum over rows of x [M,C] (bias gradients)."""
     M, C = x2d.shape
