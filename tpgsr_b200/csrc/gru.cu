@@ -44,17 +44,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// gate non-linearities on the SFU (ex2.approx + rcp.approx: ~2 ulp): sigma(x) = 1 / (1 + e^-x),  tanh(x) = 1 - 2 / (1 + e^2x)
+// (absolute error ~1e-7; the exact expf / IEEE divide / tanhf sequences were ~100 of the ~265 instructions of a step)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+constexpr int PFB = 6;         // backward ring depth (6 operands x 2 sequences per step: 48 KB static shared memory limit)
+// NS (template parameter below): sequences advanced together by one warp = independent dependency chains (instruction-level
+// parallelism).  2 when there are enough sequences to fill the chip with half as many warps, 1 otherwise (the T=64 row GRU).
+
 // gx: [M, 192] = [dir][gate r,z,n][32] pre-activations from the input side (bias_ih included)
 // y:  [M, ldy] GRU output (dir0 -> cols 0..31, dir1 -> cols 32..63); ysum = y + residual (optional)
 // stash: [M][2][4][32] = r, z, n, (W_hn h + b_hn)   (training only; may be NULL)
+template <int NS>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, const float* __restrict__ bhh,
                float* __restrict__ y, int ldy, const float* __restrict__ residual, int ldr, float* __restrict__ ysum,
                int ldys, float* __restrict__ stash, SeqGeom g) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    __shared__ __align__(16) float hbuf[WARPS][H];
-
     // row `lane` of W_hr / W_hz / W_hn as 16 (even, odd) pairs: one FFMA2 covers two recurrent inputs
     float2 wr[H / 2], wz[H / 2], wn[H / 2];
     const float* W = whh + (size_t)dir * 3 * H * H;
@@ -67,64 +75,92 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, cons
     const float bhr = __ldg(bhh + dir * 3 * H + lane), bhz = __ldg(bhh + dir * 3 * H + H + lane),
                 bhn = __ldg(bhh + dir * 3 * H + 2 * H + lane);
     const bool has_res = ysum != nullptr;
-    __shared__ float ring[WARPS][PF][4][H];       // [step slot][gx_r, gx_z, gx_n, residual][lane]
+    __shared__ float ring[WARPS][PF][NS][4][H];       // [step slot][sequence][gx_r, gx_z, gx_n, residual][lane]
+    __shared__ __align__(16) float hb[WARPS][NS][H];
 
-    for (int s = blockIdx.x * WARPS + warp; s < g.S; s += gridDim.x * WARPS) {
-        const long m0 = seq_base(g, s) + (dir ? (long)(g.T - 1) * g.t_stride : 0);
+    for (int s0 = (blockIdx.x * WARPS + warp) * NS; s0 < g.S; s0 += gridDim.x * WARPS * NS) {
+        long m0[NS];
+        bool live[NS];
+#pragma unroll
+        for (int v = 0; v < NS; ++v) {
+            live[v] = s0 + v < g.S;
+            m0[v] = seq_base(g, live[v] ? s0 + v : s0) + (dir ? (long)(g.T - 1) * g.t_stride : 0);
+        }
         const long step = dir ? -g.t_stride : g.t_stride;
         // one commit group per step (empty beyond the end) keeps the wait_group arithmetic uniform
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
             if (u < g.T) {
-                const long m = m0 + u * step;
-                const float* gp = gx + (size_t)m * 6 * H + dir * 3 * H + lane;
-                cp_async4(&ring[warp][u][0][lane], gp);
-                cp_async4(&ring[warp][u][1][lane], gp + H);
-                cp_async4(&ring[warp][u][2][lane], gp + 2 * H);
-                if (has_res) cp_async4(&ring[warp][u][3][lane], residual + (size_t)m * ldr + dir * H + lane);
+#pragma unroll
+                for (int v = 0; v < NS; ++v) {
+                    const long m = m0[v] + u * step;
+                    const float* gp = gx + (size_t)m * 6 * H + dir * 3 * H + lane;
+                    cp_async4(&ring[warp][u][v][0][lane], gp);
+                    cp_async4(&ring[warp][u][v][1][lane], gp + H);
+                    cp_async4(&ring[warp][u][v][2][lane], gp + 2 * H);
+                    if (has_res) cp_async4(&ring[warp][u][v][3][lane], residual + (size_t)m * ldr + dir * H + lane);
+                }
             }
             cp_async_commit();
         }
-        float h = 0.f;
+        float h[NS];
         __syncwarp();
-        hbuf[warp][lane] = 0.f;
+#pragma unroll
+        for (int v = 0; v < NS; ++v) { h[v] = 0.f; hb[warp][v][lane] = 0.f; }
         __syncwarp();
         for (int t = 0; t < g.T; ++t) {
-            const long m = m0 + t * step;
             const int slot = t % PF;
             cp_async_wait<PF - 1>();               // this lane's copies for step t have landed (each lane reads only its own)
-            const float gxr = ring[warp][slot][0][lane], gxz = ring[warp][slot][1][lane], gxn = ring[warp][slot][2][lane];
-            const float res = has_res ? ring[warp][slot][3][lane] : 0.f;
+            float gxr[NS], gxz[NS], gxn[NS], res[NS];
+#pragma unroll
+            for (int v = 0; v < NS; ++v) {
+                gxr[v] = ring[warp][slot][v][0][lane]; gxz[v] = ring[warp][slot][v][1][lane]; gxn[v] = ring[warp][slot][v][2][lane];
+                res[v] = has_res ? ring[warp][slot][v][3][lane] : 0.f;
+            }
             if (t + PF < g.T) {                    // refill the slot just consumed with the operands of step t + PF
-                const long mn = m + PF * step;
-                const float* np = gx + (size_t)mn * 6 * H + dir * 3 * H + lane;
-                cp_async4(&ring[warp][slot][0][lane], np);
-                cp_async4(&ring[warp][slot][1][lane], np + H);
-                cp_async4(&ring[warp][slot][2][lane], np + 2 * H);
-                if (has_res) cp_async4(&ring[warp][slot][3][lane], residual + (size_t)mn * ldr + dir * H + lane);
+#pragma unroll
+                for (int v = 0; v < NS; ++v) {
+                    const long mn = m0[v] + (long)(t + PF) * step;
+                    const float* np = gx + (size_t)mn * 6 * H + dir * 3 * H + lane;
+                    cp_async4(&ring[warp][slot][v][0][lane], np);
+                    cp_async4(&ring[warp][slot][v][1][lane], np + H);
+                    cp_async4(&ring[warp][slot][v][2][lane], np + 2 * H);
+                    if (has_res) cp_async4(&ring[warp][slot][v][3][lane], residual + (size_t)mn * ldr + dir * H + lane);
+                }
             }
             cp_async_commit();
-            float2 ar = make_float2(bhr, 0.f), az = make_float2(bhz, 0.f), an = make_float2(bhn, 0.f);
+            float2 ar[NS], az[NS], an[NS];
+#pragma unroll
+            for (int v = 0; v < NS; ++v) { ar[v] = make_float2(bhr, 0.f); az[v] = make_float2(bhz, 0.f); an[v] = make_float2(bhn, 0.f); }
 #pragma unroll
             for (int q = 0; q < H / 4; ++q) {
-                const float4 hv = *reinterpret_cast<const float4*>(&hbuf[warp][q * 4]);
-                const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
-                ar = ffma2(wr[2 * q], h01, ar); az = ffma2(wz[2 * q], h01, az); an = ffma2(wn[2 * q], h01, an);
-                ar = ffma2(wr[2 * q + 1], h23, ar); az = ffma2(wz[2 * q + 1], h23, az); an = ffma2(wn[2 * q + 1], h23, an);
+#pragma unroll
+                for (int v = 0; v < NS; ++v) {
+                    const float4 hv = *reinterpret_cast<const float4*>(&hb[warp][v][q * 4]);
+                    const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+                    ar[v] = ffma2(wr[2 * q], h01, ar[v]); az[v] = ffma2(wz[2 * q], h01, az[v]); an[v] = ffma2(wn[2 * q], h01, an[v]);
+                    ar[v] = ffma2(wr[2 * q + 1], h23, ar[v]); az[v] = ffma2(wz[2 * q + 1], h23, az[v]); an[v] = ffma2(wn[2 * q + 1], h23, an[v]);
+                }
             }
-            const float hn = an.x + an.y;
-            const float r = sigmoid_f(gxr + (ar.x + ar.y));
-            const float z = sigmoid_f(gxz + (az.x + az.y));
-            const float n = tanhf(gxn + r * hn);
-            h = (1.f - z) * n + z * h;
-            y[(size_t)m * ldy + dir * H + lane] = h;
-            if (has_res) ysum[(size_t)m * ldys + dir * H + lane] = h + res;
-            if (stash) {
-                float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
-                sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = hn;
+            __syncwarp();                          // every lane has read the old h before it is overwritten
+#pragma unroll
+            for (int v = 0; v < NS; ++v) {
+                const float hn = an[v].x + an[v].y;
+                const float r = fast_sigmoid(gxr[v] + (ar[v].x + ar[v].y));
+                const float z = fast_sigmoid(gxz[v] + (az[v].x + az[v].y));
+                const float n = fast_tanh(gxn[v] + r * hn);
+                h[v] = (1.f - z) * n + z * h[v];
+                hb[warp][v][lane] = h[v];
+                if (live[v]) {
+                    const long m = m0[v] + (long)t * step;
+                    y[(size_t)m * ldy + dir * H + lane] = h[v];
+                    if (has_res) ysum[(size_t)m * ldys + dir * H + lane] = h[v] + res[v];
+                    if (stash) {
+                        float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
+                        sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = hn;
+                    }
+                }
             }
-            __syncwarp();
-            hbuf[warp][lane] = h;
             __syncwarp();
         }
         cp_async_wait<0>();
@@ -139,13 +175,14 @@ constexpr int PART = 3 * H * H + 6 * H;
 
 // BPTT, serial part.  dy: grad wrt GRU output [M, lddy]; y: forward output (h values); stash from forward.
 // Writes dgx [M,192] = (dr_pre, dz_pre, dn_pre) and per-block bias-gradient partials.
+template <int NS>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 gru_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
                const float* __restrict__ stash, const float* __restrict__ whh, float* __restrict__ dgx,
                float* __restrict__ part, SeqGeom g) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    __shared__ __align__(16) float dg[WARPS][3][H];          // broadcast of (dr_pre, dz_pre, d_hn)
+    __shared__ __align__(16) float dg[WARPS][NS][3][H];      // broadcast of (dr_pre, dz_pre, d_hn) per sequence
     __shared__ float red[WARPS][6][H];
 
     // column `lane` of W_hr / W_hz / W_hn as (j, j+1) pairs:  dh_prev[lane] += sum_j W[g*32+j][lane] * dgate_g[j]
@@ -158,70 +195,98 @@ gru_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__
         wn[j] = make_float2(__ldg(W + (2 * H + 2 * j) * H + lane), __ldg(W + (2 * H + 2 * j + 1) * H + lane));
     }
     float dbh[3] = {0.f, 0.f, 0.f}, dbi[3] = {0.f, 0.f, 0.f};
-    __shared__ float ring[WARPS][PF][6][H];       // [step slot][r, z, n, hn, dy, h_prev][lane]
+    __shared__ float ring[WARPS][PFB][NS][6][H];       // [step slot][sequence][r, z, n, hn, dy, h_prev][lane]
 
-    for (int s = blockIdx.x * WARPS + warp; s < g.S; s += gridDim.x * WARPS) {
+    for (int s0 = (blockIdx.x * WARPS + warp) * NS; s0 < g.S; s0 += gridDim.x * WARPS * NS) {
         // BPTT walks the processing order backwards: dir0 processed t=0..T-1 -> walk T-1..0; dir1 processed T-1..0 -> walk 0..T-1
-        const long m0 = seq_base(g, s) + (dir ? 0 : (long)(g.T - 1) * g.t_stride);
+        long m0[NS];
+        bool live[NS];
+#pragma unroll
+        for (int v = 0; v < NS; ++v) {
+            live[v] = s0 + v < g.S;
+            m0[v] = seq_base(g, live[v] ? s0 + v : s0) + (dir ? 0 : (long)(g.T - 1) * g.t_stride);
+        }
         const long step = dir ? g.t_stride : -g.t_stride;      // towards the previously processed element
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
+        for (int u = 0; u < PFB; ++u) {
             if (u < g.T) {
-                const long m = m0 + u * step;
-                const float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
-                cp_async4(&ring[warp][u][0][lane], sp);
-                cp_async4(&ring[warp][u][1][lane], sp + H);
-                cp_async4(&ring[warp][u][2][lane], sp + 2 * H);
-                cp_async4(&ring[warp][u][3][lane], sp + 3 * H);
-                cp_async4(&ring[warp][u][4][lane], dy + (size_t)m * lddy + dir * H + lane);
-                if (u + 1 < g.T) cp_async4(&ring[warp][u][5][lane], y + (size_t)(m + step) * ldy + dir * H + lane);
+#pragma unroll
+                for (int v = 0; v < NS; ++v) {
+                    const long m = m0[v] + u * step;
+                    const float* sp = stash + ((size_t)m * 2 + dir) * 4 * H + lane;
+                    cp_async4(&ring[warp][u][v][0][lane], sp);
+                    cp_async4(&ring[warp][u][v][1][lane], sp + H);
+                    cp_async4(&ring[warp][u][v][2][lane], sp + 2 * H);
+                    cp_async4(&ring[warp][u][v][3][lane], sp + 3 * H);
+                    cp_async4(&ring[warp][u][v][4][lane], dy + (size_t)m * lddy + dir * H + lane);
+                    if (u + 1 < g.T) cp_async4(&ring[warp][u][v][5][lane], y + (size_t)(m + step) * ldy + dir * H + lane);
+                }
             }
             cp_async_commit();
         }
-        float dh = 0.f;
+        float dh[NS];
+#pragma unroll
+        for (int v = 0; v < NS; ++v) dh[v] = 0.f;
         for (int t = 0; t < g.T; ++t) {
-            const long m = m0 + t * step;
-            const int slot = t % PF;
-            cp_async_wait<PF - 1>();
-            const float r = ring[warp][slot][0][lane], z = ring[warp][slot][1][lane], n = ring[warp][slot][2][lane],
-                        hn = ring[warp][slot][3][lane];
-            dh += ring[warp][slot][4][lane];
-            const float hprev = (t + 1 < g.T) ? ring[warp][slot][5][lane] : 0.f;
-            if (t + PF < g.T) {
-                const long mn = m + PF * step;
-                const float* sp = stash + ((size_t)mn * 2 + dir) * 4 * H + lane;
-                cp_async4(&ring[warp][slot][0][lane], sp);
-                cp_async4(&ring[warp][slot][1][lane], sp + H);
-                cp_async4(&ring[warp][slot][2][lane], sp + 2 * H);
-                cp_async4(&ring[warp][slot][3][lane], sp + 3 * H);
-                cp_async4(&ring[warp][slot][4][lane], dy + (size_t)mn * lddy + dir * H + lane);
-                if (t + PF + 1 < g.T) cp_async4(&ring[warp][slot][5][lane], y + (size_t)(mn + step) * ldy + dir * H + lane);
+            const int slot = t % PFB;
+            cp_async_wait<PFB - 1>();
+            float r[NS], z[NS], n[NS], hn[NS], hprev[NS];
+#pragma unroll
+            for (int v = 0; v < NS; ++v) {
+                r[v] = ring[warp][slot][v][0][lane]; z[v] = ring[warp][slot][v][1][lane]; n[v] = ring[warp][slot][v][2][lane];
+                hn[v] = ring[warp][slot][v][3][lane];
+                dh[v] += ring[warp][slot][v][4][lane];
+                hprev[v] = (t + 1 < g.T) ? ring[warp][slot][v][5][lane] : 0.f;
+            }
+            if (t + PFB < g.T) {
+#pragma unroll
+                for (int v = 0; v < NS; ++v) {
+                    const long mn = m0[v] + (long)(t + PFB) * step;
+                    const float* sp = stash + ((size_t)mn * 2 + dir) * 4 * H + lane;
+                    cp_async4(&ring[warp][slot][v][0][lane], sp);
+                    cp_async4(&ring[warp][slot][v][1][lane], sp + H);
+                    cp_async4(&ring[warp][slot][v][2][lane], sp + 2 * H);
+                    cp_async4(&ring[warp][slot][v][3][lane], sp + 3 * H);
+                    cp_async4(&ring[warp][slot][v][4][lane], dy + (size_t)mn * lddy + dir * H + lane);
+                    if (t + PFB + 1 < g.T) cp_async4(&ring[warp][slot][v][5][lane], y + (size_t)(mn + step) * ldy + dir * H + lane);
+                }
             }
             cp_async_commit();
-            const float dn = dh * (1.f - z);
-            const float dz = dh * (hprev - n);
-            const float dn_pre = dn * (1.f - n * n);
-            const float dr_pre = dn_pre * hn * r * (1.f - r);
-            const float dz_pre = dz * z * (1.f - z);
-            const float dhn = dn_pre * r;
-            float* gp = dgx + (size_t)m * 6 * H + dir * 3 * H + lane;
-            gp[0] = dr_pre; gp[H] = dz_pre; gp[2 * H] = dn_pre;
-            dbi[0] += dr_pre; dbi[1] += dz_pre; dbi[2] += dn_pre;
-            dbh[0] += dr_pre; dbh[1] += dz_pre; dbh[2] += dhn;
+            float dhz[NS];
             __syncwarp();
-            dg[warp][0][lane] = dr_pre; dg[warp][1][lane] = dz_pre; dg[warp][2][lane] = dhn;
-            __syncwarp();
-            float2 c0 = make_float2(dh * z, 0.f), c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < H / 4; ++q) {
-                const float4 vr = *reinterpret_cast<const float4*>(&dg[warp][0][q * 4]);
-                const float4 vz = *reinterpret_cast<const float4*>(&dg[warp][1][q * 4]);
-                const float4 vn = *reinterpret_cast<const float4*>(&dg[warp][2][q * 4]);
-                c0 = ffma2(wr[2 * q], make_float2(vr.x, vr.y), c0); c0 = ffma2(wr[2 * q + 1], make_float2(vr.z, vr.w), c0);
-                c1 = ffma2(wz[2 * q], make_float2(vz.x, vz.y), c1); c1 = ffma2(wz[2 * q + 1], make_float2(vz.z, vz.w), c1);
-                c2 = ffma2(wn[2 * q], make_float2(vn.x, vn.y), c2); c2 = ffma2(wn[2 * q + 1], make_float2(vn.z, vn.w), c2);
+            for (int v = 0; v < NS; ++v) {
+                const float dn = dh[v] * (1.f - z[v]);
+                const float dz = dh[v] * (hprev[v] - n[v]);
+                const float dn_pre = dn * (1.f - n[v] * n[v]);
+                const float dr_pre = dn_pre * hn[v] * r[v] * (1.f - r[v]);
+                const float dz_pre = dz * z[v] * (1.f - z[v]);
+                const float dhn = dn_pre * r[v];
+                dhz[v] = dh[v] * z[v];
+                if (live[v]) {
+                    const long m = m0[v] + (long)t * step;
+                    float* gp = dgx + (size_t)m * 6 * H + dir * 3 * H + lane;
+                    gp[0] = dr_pre; gp[H] = dz_pre; gp[2 * H] = dn_pre;
+                    dbi[0] += dr_pre; dbi[1] += dz_pre; dbi[2] += dn_pre;
+                    dbh[0] += dr_pre; dbh[1] += dz_pre; dbh[2] += dhn;
+                }
+                dg[warp][v][0][lane] = dr_pre; dg[warp][v][1][lane] = dz_pre; dg[warp][v][2][lane] = dhn;
             }
-            dh = (c0.x + c0.y) + (c1.x + c1.y) + (c2.x + c2.y);
+            __syncwarp();
+#pragma unroll
+            for (int v = 0; v < NS; ++v) {
+                float2 c0 = make_float2(dhz[v], 0.f), c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < H / 4; ++q) {
+                    const float4 vr = *reinterpret_cast<const float4*>(&dg[warp][v][0][q * 4]);
+                    const float4 vz = *reinterpret_cast<const float4*>(&dg[warp][v][1][q * 4]);
+                    const float4 vn = *reinterpret_cast<const float4*>(&dg[warp][v][2][q * 4]);
+                    c0 = ffma2(wr[2 * q], make_float2(vr.x, vr.y), c0); c0 = ffma2(wr[2 * q + 1], make_float2(vr.z, vr.w), c0);
+                    c1 = ffma2(wz[2 * q], make_float2(vz.x, vz.y), c1); c1 = ffma2(wz[2 * q + 1], make_float2(vz.z, vz.w), c1);
+                    c2 = ffma2(wn[2 * q], make_float2(vn.x, vn.y), c2); c2 = ffma2(wn[2 * q + 1], make_float2(vn.z, vn.w), c2);
+                }
+                dh[v] = (c0.x + c0.y) + (c1.x + c1.y) + (c2.x + c2.y);
+            }
         }
         cp_async_wait<0>();
     }
@@ -253,50 +318,61 @@ gru_dwhh_kernel(const float* __restrict__ dgx, const float* __restrict__ stash, 
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-    const long total = (long)g.S * g.T;
-    const long chunks = (total + DW_ROWS - 1) / DW_ROWS;
-    // Software pipeline: the 12 + 4 global loads of chunk i+1 are issued into registers (all independent, all in flight) before the
-    // outer products of chunk i run from shared memory.  (The first version loaded inside the staging loop: one DRAM latency per
-    // element, 123 us per launch.)
-    float gv[12], hv4[4];
-    auto load_chunk = [&](long ch) {
+    const int total = g.S * g.T;                      // (sequence, step) rows; < 2^31
+    const int chunks = (total + DW_ROWS - 1) / DW_ROWS;
+    // Software pipeline: the 12 (+12 r factors) + 4 global loads of chunk i+1 are issued into registers (independent, all in flight)
+    // before the outer products of chunk i run from shared memory; the row -> pixel-row maps (the only divisions) are computed once per
+    // row by 32 threads, one chunk ahead.  (v1 loaded inside the staging loop: one DRAM latency per element, 123 us; v2 did two 64-bit
+    // divisions per element: 137 us.)
+    __shared__ int rowM[2][DW_ROWS], rowP[2][DW_ROWS];
+    float gv[12], rv[12], hv4[4];
+    auto map_rows = [&](int ch, int buf) {
+        if (tid < DW_ROWS) {
+            const int rho = ch * DW_ROWS + tid;
+            int m = -1, mp = -1;
+            if (rho < total) {
+                const int sq = rho / g.T, t = rho - sq * g.T;
+                const int base = (int)seq_base(g, sq);
+                m = base + t * (int)g.t_stride;
+                const int tp = dir ? t + 1 : t - 1;           // previously processed position
+                if (tp >= 0 && tp < g.T) mp = base + tp * (int)g.t_stride;
+            }
+            rowM[buf][tid] = m; rowP[buf][tid] = mp;
+        }
+    };
+    auto load_chunk = [&](int buf) {
 #pragma unroll
         for (int u = 0; u < 12; ++u) {
             const int e = tid + u * 256;
             const int row = e / (3 * H), c = e - row * (3 * H);
-            const long rho = ch * DW_ROWS + row;
-            float v = 0.f;
-            if (rho < total) {
-                const int sq = (int)(rho / g.T), t = (int)(rho - (long)sq * g.T);
-                const long m = seq_base(g, sq) + (long)t * g.t_stride;
-                v = __ldg(dgx + (size_t)m * 6 * H + dir * 3 * H + c);
-                if (c >= 2 * H) v *= __ldg(stash + ((size_t)m * 2 + dir) * 4 * H + (c - 2 * H));      // dn_pre * r
-            }
-            gv[u] = v;
+            const int m = rowM[buf][row];
+            const bool ok = m >= 0;
+            const size_t mm = ok ? (size_t)m : 0;
+            gv[u] = ok ? __ldg(dgx + mm * 6 * H + dir * 3 * H + c) : 0.f;
+            rv[u] = (ok && c >= 2 * H) ? __ldg(stash + (mm * 2 + dir) * 4 * H + (c - 2 * H)) : 1.f;      // third gate: dn_pre * r
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = tid + u * 256;
             const int row = e / H, c = e - row * H;
-            const long rho = ch * DW_ROWS + row;
-            float v = 0.f;
-            if (rho < total) {
-                const int sq = (int)(rho / g.T), t = (int)(rho - (long)sq * g.T);
-                const int tp = dir ? t + 1 : t - 1;           // previously processed position
-                if (tp >= 0 && tp < g.T) v = __ldg(y + (size_t)(seq_base(g, sq) + (long)tp * g.t_stride) * ldy + dir * H + c);
-            }
-            hv4[u] = v;
+            const int mp = rowP[buf][row];
+            hv4[u] = mp >= 0 ? __ldg(y + (size_t)mp * ldy + dir * H + c) : 0.f;
         }
     };
-    long ch = blockIdx.x;
-    if (ch < chunks) load_chunk(ch);
-    for (; ch < chunks; ch += gridDim.x) {
+    int ch = blockIdx.x, it = 0;
+    if (ch < chunks) map_rows(ch, 0);
+    __syncthreads();
+    if (ch < chunks) load_chunk(0);
+    for (; ch < chunks; ch += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const bool more = ch + (int)gridDim.x < chunks;
 #pragma unroll
-        for (int u = 0; u < 12; ++u) { const int e = tid + u * 256; Gs[e / (3 * H)][e % (3 * H)] = gv[u]; }
+        for (int u = 0; u < 12; ++u) { const int e = tid + u * 256; Gs[e / (3 * H)][e % (3 * H)] = gv[u] * rv[u]; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) { const int e = tid + u * 256; Hs[e / H][e % H] = hv4[u]; }
+        if (more) map_rows(ch + gridDim.x, cur ^ 1);
         __syncthreads();
-        if (ch + gridDim.x < chunks) load_chunk(ch + gridDim.x);
+        if (more) load_chunk(cur ^ 1);
 #pragma unroll 4
         for (int row = 0; row < DW_ROWS; ++row) {
             const float hv = Hs[row][i];
@@ -347,8 +423,10 @@ __global__ void gru_bwd_reduce_kernel(const float* __restrict__ part, int nb_w, 
 }
 
 // one resident wave: 3 CTAs of 4 warps per SM, two directions
+int gru_ns(int S) { return 2 * S >= 2 * 148 * 3 * WARPS * 2 ? 2 : 1; }      // two directions; 2 per warp only if that still fills 3 CTAs per SM
 int gru_blocks(int S) {
-    int b = (S + WARPS - 1) / WARPS;
+    const int NS = gru_ns(S);
+    int b = (S + WARPS * NS - 1) / (WARPS * NS);
     int cap = 148 * 3 / 2;
     return b < cap ? b : cap;
 }
@@ -375,7 +453,8 @@ int tpgsr_gru_fwd(const float* gx, const float* whh, const float* bhh, float* y,
     if (ysum && !residual) return TPGSR_ERR_BAD_ARG;
     SeqGeom g{S, T, inner, outer_stride, inner_stride, t_stride};
     dim3 grid(gru_blocks(S), 2);
-    gru_fwd_kernel<<<grid, WARPS * 32, 0, stream>>>(gx, whh, bhh, y, ldy, residual, ldr, ysum, ldys, stash, g);
+    if (gru_ns(S) == 2) gru_fwd_kernel<2><<<grid, WARPS * 32, 0, stream>>>(gx, whh, bhh, y, ldy, residual, ldr, ysum, ldys, stash, g);
+    else gru_fwd_kernel<1><<<grid, WARPS * 32, 0, stream>>>(gx, whh, bhh, y, ldy, residual, ldr, ysum, ldys, stash, g);
     return tpgsr_launch_status();
 }
 
@@ -389,7 +468,8 @@ int tpgsr_gru_bwd(const float* dy, int lddy, const float* y, int ldy, const floa
     SeqGeom g{S, T, inner, outer_stride, inner_stride, t_stride};
     float* part = static_cast<float*>(workspace);
     const int nb = gru_blocks(S), nbw = dw_blocks(S, T);
-    gru_bwd_kernel<<<dim3(nb, 2), WARPS * 32, 0, stream>>>(dy, lddy, y, ldy, stash, whh, dgx, part, g);
+    if (gru_ns(S) == 2) gru_bwd_kernel<2><<<dim3(nb, 2), WARPS * 32, 0, stream>>>(dy, lddy, y, ldy, stash, whh, dgx, part, g);
+    else gru_bwd_kernel<1><<<dim3(nb, 2), WARPS * 32, 0, stream>>>(dy, lddy, y, ldy, stash, whh, dgx, part, g);
     int rc = tpgsr_launch_status();
     if (rc) return rc;
     gru_dwhh_kernel<<<dim3(nbw, 2), 256, 0, stream>>>(dgx, stash, y, ldy, part, g);
