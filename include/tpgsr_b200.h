@@ -169,6 +169,17 @@ int tpgsr_softmax_prior_fwd(const float* logits, float* probs, float* prior, int
 int tpgsr_softmax_prior_bwd(const float* probs, const float* dprobs, const float* dprior, float* dlogits, int T, int B, int C,
                             int drop_first, cudaStream_t stream);
 
+/* ---- general 2-D resampling for the SRResNet_TL text-prior branch (model/srresnet.py:139-195,223-234; BASELINE config 5) -------------
+ * ConvTranspose2d on H > 1 maps as zero-upsample + stride-1 conv, F.interpolate(bilinear, align_corners=True) 2-D, nn.PixelShuffle(2). */
+int tpgsr_zero_upsample2d(const float* x, float* y, int B, int H, int W, int C, int sh, int sw, cudaStream_t stream);
+int tpgsr_zero_upsample2d_bwd(const float* dy, float* dx, int B, int H, int W, int C, int sh, int sw, cudaStream_t stream);
+int tpgsr_tconv_weight2d_fwd(const float* wt, float* wc, int Ci, int Co, int KH, int KW, cudaStream_t stream);
+int tpgsr_tconv_weight2d_bwd(const float* dwc, float* dwt, int Ci, int Co, int KH, int KW, int accumulate, cudaStream_t stream);
+int tpgsr_bilinear2d_fwd(const float* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo, int ldo, cudaStream_t stream);
+int tpgsr_bilinear2d_bwd(const float* dout, float* din, int B, int Hi, int Wi, int C, int Ho, int Wo, int ldo, cudaStream_t stream);
+int tpgsr_pixelshuffle_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
+int tpgsr_pixelshuffle_bwd(const float* dy, float* dx, int B, int H, int W, int C, cudaStream_t stream);
+
 /* ---- bidirectional LSTM recurrence -----------------------------------------------------------------------------------------------
  * nn.LSTM(nIn, 256, bidirectional=True) in BidirectionalLSTM: model/crnn/crnn.py:5-26 (cuDNN RNN). */
 int tpgsr_lstm_transpose_whh(const float* whh, float* whhT, cudaStream_t stream);
@@ -208,6 +219,12 @@ int tpgsr_semantic_loss_fwd(const float* pred, const float* gt, long n, float ou
                             void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int tpgsr_semantic_loss_bwd(const float* pred, const float* gt, long n, const float* upstream, float scale, float* dpred,
                             int accumulate, cudaStream_t stream);
+
+/* ---- evaluation metrics -----------------------------------------------------------------------------------------------
+ * calculate_psnr / SSIM on RGB: utils/ssim_psnr.py:9-15,18-78 (F.conv2d gaussian windows + ATen elementwise). */
+size_t tpgsr_psnr_ssim_workspace_bytes(int B, int C);
+int tpgsr_psnr_ssim(const float* a, const float* b, int B, int C, int H, int W, long sab, long sac, long sah, long saw, long sbb, long sbc,
+                    long sbh, long sbw, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- optimiser step --------------------------------------------------------------------------------------------------
  * clip_grad_norm_(SR params, 0.25) + optim.Adam(lr, (beta1, 0.999)): interfaces/super_resolution.py:419-424,

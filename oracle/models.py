@@ -107,6 +107,28 @@ def tsrn(x: Tensor, p: P, training: bool, stn: bool = True, srb_nums: int = 5,
     return (out, aux) if return_aux else out
 
 
+def srresnet_tl(x: Tensor, p: P, training: bool, text_emb: Optional[Tensor] = None, return_aux: bool = False):
+    """SRResNet_TL.forward, STN off (model/srresnet.py:139-163; ResidualBlock_TL :198-220; UpsampleBLock :223-234; InfoGen variant
+    :166-195 — tconv1/2 without padding, so the prior map is [B,32,25,213] before the bilinear(align_corners=True) resize)."""
+    if text_emb is None:
+        text_emb = x.new_zeros(x.shape[0], p['infoGen.tconv1.weight'].shape[0], 1, 26)
+    t = info_gen(text_emb, p, 'infoGen.', training, variant='srresnet')
+    text = ops.resize_separable(t, ops.bilinear_ac_matrix(t.shape[2], x.shape[2]), ops.bilinear_ac_matrix(t.shape[3], x.shape[3]))
+    b1 = ops.prelu(F.conv2d(x, p['block1.0.weight'], p['block1.0.bias'], padding=4), p['block1.1.weight'])
+    b = b1
+    for i in range(2, 7):
+        q = f'block{i}.'
+        r = F.conv2d(b, p[q + 'conv1.weight'], p[q + 'conv1.bias'], padding=1)
+        r = ops.prelu(_bn(r, p, q + 'bn1.', training), p[q + 'prelu.weight'])
+        r = F.conv2d(torch.cat([r, text], 1), p[q + 'conv2.weight'], p[q + 'conv2.bias'], padding=1)
+        b = b + _bn(r, p, q + 'bn2.', training)
+    b7 = _bn(F.conv2d(b, p['block7.0.weight'], p['block7.0.bias'], padding=1), p, 'block7.1.', training)
+    u = F.conv2d(b1 + b7, p['block8.0.conv.weight'], p['block8.0.conv.bias'], padding=1)
+    u = ops.prelu(ops.pixel_shuffle(u, 2), p['block8.0.prelu.weight'])
+    out = torch.tanh(F.conv2d(u, p['block8.1.weight'], p['block8.1.bias'], padding=4))
+    return (out, {'text': text, 't': t}) if return_aux else out
+
+
 def crnn(x: Tensor, p: P, training: bool) -> Tensor:
     """CRNN.forward (model/crnn/crnn.py:29-90) → logits [26,B,37]."""
     def conv(i, x, pad):

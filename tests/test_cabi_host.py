@@ -98,3 +98,18 @@ def test_layout_rules_product_never_imports_oracle():
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
     assert 'TEST INFRASTRUCTURE' in open(os.path.join(ROOT, 'oracle', '__init__.py')).read()
+
+
+def test_srcnn_and_srresnet_state_dict_surfaces(shapes):
+    """configs 1 and 5: constructor kwargs and state_dict keys / shapes of the drop-in modules equal the reference's."""
+    from tpgsr_b200.model.srcnn import SRCNN
+    from tpgsr_b200.model.srresnet import SRResNet_TL
+    for net, key in ((SRCNN(scale_factor=2, width=128, height=32, STN=False), 'srcnn'),
+                     (SRResNet_TL(scale_factor=2, width=128, height=32, STN=False, mask=True), 'srresnet_tl')):
+        sd = net.state_dict()
+        assert set(sd) == set(shapes[key]), set(sd) ^ set(shapes[key])
+        assert all(list(sd[k].shape) == shapes[key][k] for k in sd)
+        with pytest.raises(RuntimeError):
+            net(torch.zeros(1, net.in_planes, 16, 64))          # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        SRResNet_TL(STN=True)

@@ -229,3 +229,39 @@ def test_srcnn_config1_vs_golden_and_oracle(shapes):
         net.eval()
         sr2 = net(lr[:, :3])
     assert rel_err(sr2, g['sr']) < 1e-4
+
+
+def test_srresnet_tl_config5_vs_golden_and_oracle(shapes):
+    """BASELINE config 5 module (SRResNet_TL + text prior, MSE*100): forward, loss, every parameter gradient and the prior gradient
+    vs the fixture recorded from the reference module; eval mode with and without a prior."""
+    from oracle.weights import synth_state_dict
+    from tpgsr_b200.model.srresnet import SRResNet_TL
+    g = load_golden('srresnet_tl')
+    sd = synth_state_dict(shapes['srresnet_tl'], 9)
+    for k, v in g.items():
+        if k.startswith('slope/'):
+            sd[k[len('slope/'):]] = torch.from_numpy(v)
+    net = SRResNet_TL(scale_factor=2, width=128, height=32, STN=False, mask=True)
+    net.load_state_dict(sd)
+    net = net.to(_dev()).train()
+    lr, hr = torch.from_numpy(g['lr']).to(_dev()), torch.from_numpy(g['hr']).to(_dev())
+    prior = torch.from_numpy(g['prior']).to(_dev()).requires_grad_(True)
+    sr = net(lr, prior)
+    loss = torch.nn.MSELoss()(sr, hr) * 100
+    loss.backward()
+    assert rel_err(sr, g['sr']) < 2e-4, rel_err(sr, g['sr'])
+    assert abs(float(loss) - float(g['loss'])) < 1e-3 * float(g['loss'])
+    assert rel_err(prior.grad, g['grad_prior']) < 5e-3, rel_err(prior.grad, g['grad_prior'])
+    for k, p in net.named_parameters():
+        want = g['g/' + k]
+        if p.numel() == 1:       # PReLU slopes: sums of ~10^6 signed terms
+            assert abs(float(p.grad) - float(want[1])) < 1e-2 * abs(float(want[1])) + 1e-4, k
+        else:
+            assert_fp_close(fingerprint(p.grad), want, k, rtol=5e-3)
+    for k, b in net.named_buffers():
+        if 'running_' in k:
+            assert_fp_close(fingerprint(b), g['buf/' + k], k, rtol=2e-3)
+    with torch.no_grad():
+        net.eval()
+        assert rel_err(net(lr, prior.detach()), g['sr_eval']) < 2e-4
+        assert rel_err(net(lr), g['sr_eval_noprior']) < 2e-4

@@ -310,3 +310,19 @@ def test_conv_tensor_core_path(B, Ci, Co, H, W, k, mode):
             assert rel_err(base - 1, nhwc(x.grad)) < 10 * tol
     finally:
         ops.CONV_MODE = old
+
+
+def test_psnr_ssim_against_golden_and_oracle():
+    """utils/ssim_psnr.py parity metrics: the fixture recorded from the reference and the oracle on a second, sliced pair."""
+    from oracle import ops as o
+    from tpgsr_b200.utils.ssim_psnr import SSIM, calculate_psnr
+    g = load_golden('psnr_ssim')
+    d = _dev()
+    a, b = torch.from_numpy(g['a']).to(d), torch.from_numpy(g['b']).to(d)
+    assert abs(float(calculate_psnr(a, b)) - float(g['psnr'])) < 1e-3
+    assert abs(float(SSIM()(a, b)) - float(g['ssim'])) < 1e-5
+    x = rnd(5, 4, 32, 128, seed=71).abs().clamp(0, 1)
+    y = (x + 0.05 * rnd(5, 4, 32, 128, seed=72)).clamp(0, 1)
+    assert abs(float(calculate_psnr(x.to(d), y.to(d))) - float(o.calculate_psnr(x, y))) < 1e-3
+    assert abs(float(SSIM()(x.to(d), y.to(d))) - float(o.ssim(x, y))) < 1e-5
+    assert float(calculate_psnr(a, a)) == float('inf')

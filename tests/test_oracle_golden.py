@@ -235,3 +235,37 @@ def test_tpgsr_cascade_steps(shapes):
                 elif k.startswith('g0/stu'):
                     j = int(k[6])
                     assert_fp_close(fingerprint(out['stu_grads'][j][k[8:]]), v, k, rtol=5e-2, atol=1e-3, check_head=False)
+
+
+def _srresnet_sd(shapes, g):
+    sd = _sd(shapes, 'srresnet_tl', 9)
+    for k, v in g.items():
+        if k.startswith('slope/'):
+            sd[k[len('slope/'):]] = T(v)
+    return sd
+
+
+def test_srresnet_tl(shapes):
+    """BASELINE config 5 module (model/srresnet.py:139-163): the oracle vs the fixture recorded from the reference."""
+    g = load_golden('srresnet_tl')
+    p = _srresnet_sd(shapes, g)
+    leaves = {k: v.requires_grad_(True) for k, v in p.items() if step.is_param(k)}
+    prior = T(g['prior']).requires_grad_(True)
+    sr = models.srresnet_tl(T(g['lr']), p, True, prior)
+    loss = ((sr - T(g['hr'])) ** 2).mean() * 100
+    loss.backward()
+    assert rel_err(sr, g['sr']) < 2e-5 and abs(float(loss) - float(g['loss'])) < 1e-4 * float(g['loss'])
+    assert rel_err(prior.grad, g['grad_prior']) < 2e-3
+    # the one-element PReLU slope gradients are sums of ~10^6 signed terms: fp32 summation order alone moves them by a few 1e-3
+    slopes = {k for k in g if k.startswith('g/') and k.endswith(('prelu.weight', 'block1.1.weight'))}
+    _check_grads({k: v for k, v in g.items() if k not in slopes}, {k: v.grad for k, v in leaves.items()}, rtol=5e-3)
+    for k in slopes:
+        assert abs(float(leaves[k[2:]].grad) - float(g[k][1])) < 1e-2 * abs(float(g[k][1])) + 1e-4, k
+    with torch.no_grad():
+        p2 = _srresnet_sd(shapes, g)
+        # the fixture's eval passes ran after the train pass had updated the running statistics once
+        for k in p2:
+            if 'running_' in k or 'num_batches' in k:
+                p2[k] = p[k].detach().clone()
+        assert rel_err(models.srresnet_tl(T(g['lr']), p2, False, T(g['prior'])), g['sr_eval']) < 2e-5
+        assert rel_err(models.srresnet_tl(T(g['lr']), p2, False, None), g['sr_eval_noprior']) < 2e-5

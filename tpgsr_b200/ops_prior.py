@@ -116,3 +116,60 @@ def lstm_shift_h(y: torch.Tensor, T: int, B: int, batch_first: bool = False) -> 
     hprev = new((T * B, 2, 256), y)
     _call('tpgsr_lstm_shift_h', ptr(y), ptr(hprev), T, B, 256, int(batch_first), stream())
     return hprev
+
+
+# ------------------------------------------------------------------------------------------------ general 2-D resampling (SRResNet_TL)
+def zero_upsample2d(x: torch.Tensor, sh: int, sw: int) -> torch.Tensor:
+    B, H, W, C = x.shape
+    y = new((B, (H - 1) * sh + 1, (W - 1) * sw + 1, C), x)
+    _call('tpgsr_zero_upsample2d', ptr(x), ptr(y), B, H, W, C, sh, sw, stream())
+    return y
+
+
+def zero_upsample2d_bwd(dy: torch.Tensor, H: int, W: int, sh: int, sw: int) -> torch.Tensor:
+    B, _, _, C = dy.shape
+    dx = new((B, H, W, C), dy)
+    _call('tpgsr_zero_upsample2d_bwd', ptr(dy), ptr(dx), B, H, W, C, sh, sw, stream())
+    return dx
+
+
+def tconv_weight2d_fwd(wt: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d weight [Ci,Co,KH,KW] -> equivalent stride-1 conv weight OIHW [Co,Ci,KH,KW] (flipped)."""
+    Ci, Co, KH, KW = wt.shape
+    wc = new((Co, Ci, KH, KW), wt)
+    _call('tpgsr_tconv_weight2d_fwd', ptr(wt), ptr(wc), Ci, Co, KH, KW, stream())
+    return wc
+
+
+def tconv_weight2d_bwd(dwc: torch.Tensor, dwt: torch.Tensor, accumulate: bool) -> None:
+    Ci, Co, KH, KW = dwt.shape
+    _call('tpgsr_tconv_weight2d_bwd', ptr(dwc), ptr(dwt), Ci, Co, KH, KW, int(accumulate), stream())
+
+
+def bilinear2d_fwd(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
+    """NHWC [B,Hi,Wi,C] -> [B,Ho,Wo,C], F.interpolate(mode='bilinear', align_corners=True)."""
+    B, Hi, Wi, C = x.shape
+    out = new((B, Ho, Wo, C), x)
+    _call('tpgsr_bilinear2d_fwd', ptr(x), ptr(out), B, Hi, Wi, C, Ho, Wo, C, stream())
+    return out
+
+
+def bilinear2d_bwd(dout: torch.Tensor, Hi: int, Wi: int) -> torch.Tensor:
+    B, Ho, Wo, C = dout.shape
+    din = new((B, Hi, Wi, C), dout)
+    _call('tpgsr_bilinear2d_bwd', ptr(dout), ptr(din), B, Hi, Wi, C, Ho, Wo, C, stream())
+    return din
+
+
+def pixelshuffle_fwd(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, C4 = x.shape
+    y = new((B, 2 * H, 2 * W, C4 // 4), x)
+    _call('tpgsr_pixelshuffle_fwd', ptr(x), ptr(y), B, H, W, C4 // 4, stream())
+    return y
+
+
+def pixelshuffle_bwd(dy: torch.Tensor) -> torch.Tensor:
+    B, H2, W2, C = dy.shape
+    dx = new((B, H2 // 2, W2 // 2, 4 * C), dy)
+    _call('tpgsr_pixelshuffle_bwd', ptr(dy), ptr(dx), B, H2 // 2, W2 // 2, C, stream())
+    return dx
