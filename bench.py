@@ -38,6 +38,11 @@ PER_GPU_BATCH = 48
 GFLOP_PER_IMG_STEP = 5.53
 
 
+# DRAM traffic per launch of the dominant kernel (3x3, 64->64, B=48) from the committed ncu --set full captures (profiles/r01/ncu_*.csv):
+# 13.8 MB read + 0 written inside the kernel's window (12.6 MB of operand planes; the 12.6 MB fp32 output stays in the 126 MB L2)
+NCU_TRAFFIC_BYTES = {('conv_flat_kernel', 3): 13.77e6, ('conv_tc_kernel', 3): 12.81e6}
+
+
 def _peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -209,7 +214,8 @@ def time_dominant_kernel(device, batch: int, peaks):
     kname = 'conv_flat_kernel' if flat else 'conv_tc_kernel'
     return {'bound': 'tensor', 'kernel': '%s<%d> (tcgen05+TMA implicit GEMM, 3x3, 64->64, M=%d, N=64, K=576, mode %s)' % (kname, nprod, batch * 1024, ops.CONV_MODE),
             'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops_burst'],
-            'traffic': None, 'launch_us': dur * 1e6, 'launch_us_min': min(durs) * 1e6, 'algorithmic_flops_per_launch': flops,
+            'traffic': NCU_TRAFFIC_BYTES.get((kname, nprod)), 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01',
+            'launch_us': dur * 1e6, 'launch_us_min': min(durs) * 1e6, 'algorithmic_flops_per_launch': flops,
             'mma_flops_per_launch': flops * nprod, 'tensor_pipe_tflops': ach * nprod,
             'peak_source': peaks['source'] + ', bf16 burst (kernel timed alone)'}
 
@@ -291,10 +297,15 @@ def run_ours(args):
         'metric': 'SR images/sec (16x64->32x128), TSRN train step', 'value': value, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32 I/O; conv contractions ' + ops.CONV_MODE + ' on tcgen05 (fp32 accumulate in TMEM); recurrences/BN/losses/Adam fp32', 'data': 'synthetic',
+        'dtype': 'f32' if ops.CONV_MODE != 'bf16' else 'bf16', 'data': 'synthetic',
         'config': {'workload': 'BASELINE configs[1]: TSRN single-stage TRAIN step, STN on, mask, ImageLoss(gradient,[1,1e-4])*100, '
                                'clip_grad_norm 0.25, Adam(1e-3,(0.5,0.999))', 'per_gpu_batch': B, 'global_batch': B * world,
                    'lr_hw': [16, 64], 'hr_hw': [32, 128], 'parallelism': f'dp{world}', 'cuda_graph': not args.no_graph,
+                   'precision': {'bf16x3': 'fp32 tensors everywhere; conv / 1x1 / linear contractions as split-bf16 (hi*hi + hi*lo + lo*hi) on tcgen05 with '
+                                           'fp32 TMEM accumulation = fp32-class accuracy (the parity mode, SR output within 1e-3 of the fp32 reference); '
+                                           'GRU / BN / TPS / losses / Adam in fp32',
+                                 'bf16': 'single bf16 product per contraction (throughput mode; misses the 1e-3 parity budget, labelled)',
+                                 'fp32': 'CUDA-core fp32 contractions'}[ops.CONV_MODE],
                    'l2': 'no explicit flush: the step touches >1 GB of activations/stashes per replay (>> 126 MB L2); inputs rotate over 8 distinct batches',
                    'last_loss': last_loss},
         'e2e': {'value': e2e_val, 'unit': 'images/s', 'h2d_bytes_per_step': B * (4 * 16 * 64 + 4 * 32 * 128) * 4, 'd2h_bytes_per_step': 4,

@@ -35,7 +35,7 @@ psnr_ssim_partial_kernel(const float* __restrict__ a, const float* __restrict__ 
     const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
         const int h = i / W, w = i - h * W;
-        const float d = pa[i] * 255.f - pb[i] * 255.f;
+        const float d = __fmul_rn(pa[i], 255.f) - __fmul_rn(pb[i], 255.f);      // no FMA contraction: identical images must give exactly 0
         se += (double)(d * d);
         float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
         for (int dy = -HALF; dy <= HALF; ++dy) {
