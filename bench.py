@@ -230,6 +230,8 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
+        if not os.environ.get('TPGSR_KEEP_NCCL_DEBUG'):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # NCCL_DEBUG=VERSION/INFO prints to stdout; rank 0 must print exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
     from tpgsr_b200 import ops
     from tpgsr_b200.model.tsrn import TSRN
