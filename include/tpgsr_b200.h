@@ -199,6 +199,13 @@ int tpgsr_gru_bwd(const float* dy, int lddy, const float* y, int ldy, const floa
                   float* dwhh, float* dbhh, float* dbih, int accumulate, int S, int T, int inner, long outer_stride,
                   long inner_stride, long t_stride, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+int tpgsr_gru_bwd_recurrence(const float* dy, int lddy, const float* y, int ldy, const float* stash, const float* whh, float* dgx, int S,
+                             int T, int inner, long outer_stride, long inner_stride, long t_stride, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream);
+int tpgsr_gru_bwd_weights(const float* dgx, const float* y, int ldy, const float* stash, float* dwhh, float* dbhh, float* dbih, int accumulate,
+                          int S, int T, int inner, long outer_stride, long inner_stride, long t_stride, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- TPS rectification + bilinear sampler ---------------------------------------------------------------------------
  * TPSSpatialTransformer.forward + F.grid_sample: model/tps_spatial_transformer.py:10-18,97-112 (2 bmm + ATen gather). */
 int tpgsr_tps_sample_fwd(const float* img, const float* ctrl, const float* inv_kernel, const float* reprT, float* out,

@@ -479,4 +479,35 @@ int tpgsr_gru_bwd(const float* dy, int lddy, const float* y, int ldy, const floa
     return tpgsr_launch_status();
 }
 
+// The same backward in two calls, so that a caller can queue the weight-gradient half on another stream:
+//   tpgsr_gru_bwd_recurrence  — serial BPTT: dgx and the per-block bias partials (into `workspace`)
+//   tpgsr_gru_bwd_weights     — dW_hh partials (into the same `workspace`) + the reduction into dwhh / dbhh / dbih
+int tpgsr_gru_bwd_recurrence(const float* dy, int lddy, const float* y, int ldy, const float* stash, const float* whh, float* dgx, int S,
+                             int T, int inner, long outer_stride, long inner_stride, long t_stride, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream) {
+    if (!dy || !y || !stash || !whh || !dgx || !workspace || S <= 0 || T <= 0 || inner <= 0) return TPGSR_ERR_BAD_ARG;
+    if (workspace_bytes < tpgsr_gru_bwd_workspace_bytes(S)) return TPGSR_ERR_WORKSPACE;
+    SeqGeom g{S, T, inner, outer_stride, inner_stride, t_stride};
+    float* part = static_cast<float*>(workspace);
+    const int nb = gru_blocks(S);
+    if (gru_ns(S) == 2) gru_bwd_kernel<2><<<dim3(nb, 2), WARPS * 32, 0, stream>>>(dy, lddy, y, ldy, stash, whh, dgx, part, g);
+    else gru_bwd_kernel<1><<<dim3(nb, 2), WARPS * 32, 0, stream>>>(dy, lddy, y, ldy, stash, whh, dgx, part, g);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_gru_bwd_weights(const float* dgx, const float* y, int ldy, const float* stash, float* dwhh, float* dbhh, float* dbih, int accumulate,
+                          int S, int T, int inner, long outer_stride, long inner_stride, long t_stride, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
+    if (!dgx || !y || !stash || !dwhh || !dbhh || !dbih || !workspace || S <= 0 || T <= 0 || inner <= 0) return TPGSR_ERR_BAD_ARG;
+    if (workspace_bytes < tpgsr_gru_bwd_workspace_bytes(S)) return TPGSR_ERR_WORKSPACE;
+    SeqGeom g{S, T, inner, outer_stride, inner_stride, t_stride};
+    float* part = static_cast<float*>(workspace);
+    const int nb = gru_blocks(S), nbw = dw_blocks(S, T);
+    gru_dwhh_kernel<<<dim3(nbw, 2), 256, 0, stream>>>(dgx, stash, y, ldy, part, g);
+    int rc = tpgsr_launch_status();
+    if (rc) return rc;
+    gru_bwd_reduce_kernel<<<ceil_div(2 * PART, 32), dim3(32, 8), 0, stream>>>(part, nbw, nb, dwhh, dbhh, dbih, accumulate);
+    return tpgsr_launch_status();
+}
+
 }  // extern "C"

@@ -8,6 +8,7 @@ Layout: activations are NHWC fp32 tensors [B,H,W,C]; ``x.view(-1, C)`` is the [M
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, Optional
 
 import torch
@@ -33,9 +34,31 @@ class Ctx:
         self._packed_bf16: Dict[str, tuple] = share._packed_bf16 if share is not None else {}
         self._planes: Dict[int, tuple] = {}
         self._written = share._written if share is not None else set()
+        # gradient side work (weight gradients, bias sums, GRU dW_hh) is queued on a second stream and runs concurrently with the
+        # data-gradient chain; tensors it still reads are kept alive here until join() (the caching allocator reuses freed blocks)
+        any_p = next(iter(params.values()))
+        self.device = any_p.device
+        self.side = ops.side_stream(self.device) if (grads is not None and any_p.is_cuda) else None
+        self._keep = []
 
     def P(self, name: str) -> Tensor:
         return self.params[name]
+
+    @contextlib.contextmanager
+    def on_side(self, *keep):
+        """Run the enclosed launches on the side stream, after everything queued so far on the current stream."""
+        if self.side is None:
+            yield
+            return
+        self._keep.extend(t for t in keep if t is not None)
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            yield
+
+    def join(self) -> None:
+        """The current stream waits for the side stream; side-stream operands may be released afterwards."""
+        ops.join_side(self.device)
+        self._keep.clear()
 
     def G(self, name: str):
         """(grad tensor, accumulate?) — first write in a backward overwrites, later writes accumulate."""
@@ -175,17 +198,18 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     P = max(ph, pw)
     kind = _kwstack_kind(x, Ci, Co, kh, kw, ph, pw, ldx, as4d) if dy.is_contiguous() else None
     if kind is not None:
-        dwp = torch.empty(((kw * Co) if kind == 'N' else 64, 64, kh, 1), dtype=torch.float32, device=x.device)
+        # operands shared by the weight gradient (side stream) and the data gradient (this stream) are produced here, before the fork
         if kind == 'N':     # final conv: dY is the narrow side -> stack it (sign -1), shared by the weight and the data gradient
-            dys = ctx.stacked(dy, kw, pw, ph, -1)
-            ops.conv_wgrad_flat(ctx.flat(x, ph), dys, dwp, kw * Co, kh, 1, ph, 0, False)
-            ops.kwstack_wgrad_scatter(dwp, gw, 0, acc)
+            xp, dyp = ctx.flat(x, ph), ctx.stacked(dy, kw, pw, ph, -1)
         else:               # block1: the stacked input planes of the forward pass against the plain dY planes
-            ops.conv_wgrad_flat(ctx.stacked(x, kw, pw, ph, 1), ctx.flat(dy, ph), dwp, 64, kh, 1, ph, 0, False)
-            ops.kwstack_wgrad_scatter(dwp, gw, 1, acc)
-        if bname:
-            gb, accb = ctx.G(bname)
-            ops.colsum(dy.view(-1, Co), gb, accb)
+            xp, dyp = ctx.stacked(x, kw, pw, ph, 1), ctx.flat(dy, ph)
+        gb, accb = ctx.G(bname) if bname else (None, False)
+        with ctx.on_side(dy):
+            dwp = torch.empty(((kw * Co) if kind == 'N' else 64, 64, kh, 1), dtype=torch.float32, device=x.device)
+            ops.conv_wgrad_flat(xp, dyp, dwp, (kw * Co) if kind == 'N' else 64, kh, 1, ph, 0, False)
+            ops.kwstack_wgrad_scatter(dwp, gw, 0 if kind == 'N' else 1, acc)
+            if bname:
+                ops.colsum(dy.view(-1, Co), gb, accb)
         if not need_dx:
             return None
         if kind == 'N':     # dX[q][ci] = sum_t sum_j DYS[q + (t-ph)*Wp][j] * W[co(j)][ci][KH-1-t][kw(j)]
@@ -195,16 +219,25 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
         part = ops.conv_flat(ctx.flat(dy, ph), wpk, None, kw * Ci, kh, 1, ph, 0)
         return ops.kwsum(part, None, Ci, kw, pw, out=dx_out, accumulate=dx_accumulate)
     same = (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 2 * ph == kh - 1 and 2 * pw == kw - 1)
+    gb, accb = ctx.G(bname) if bname else (None, False)
     if same and ops.wgrad_flat_supported(B, H, W, P, Ci, Co, kh, kw):
-        ops.conv_wgrad_flat(ctx.flat(x, P), ctx.flat(dy, P, (Co + 63) // 64 * 64), gw, Co, kh, kw, ph, pw, acc)
+        xp, dyp = ctx.flat(x, P), ctx.flat(dy, P, (Co + 63) // 64 * 64)          # shared with the data gradient: before the fork
+        with ctx.on_side(dy):
+            ops.conv_wgrad_flat(xp, dyp, gw, Co, kh, kw, ph, pw, acc)
+            if bname:
+                ops.colsum(dy.view(-1, Co), gb, accb)
     elif (same and ops.wgrad_tc_supported(B, H, W, Ci, Co, kh, kw)):
+        xp = ctx.planes(x)
         dyp = ctx.planes(dy) if Co % 64 == 0 else ctx.planes_padded(dy, (Co + 63) // 64 * 64)
-        ops.conv_wgrad_tc(ctx.planes(x), dyp, gw, B, H, W, Ci, Co, kh, kw, ph, pw, acc)
+        with ctx.on_side(dy):
+            ops.conv_wgrad_tc(xp, dyp, gw, B, H, W, Ci, Co, kh, kw, ph, pw, acc)
+            if bname:
+                ops.colsum(dy.view(-1, Co), gb, accb)
     else:
-        ops.conv_wgrad(x, dy, gw, kh, kw, ph, pw, acc, ldx=ldx, Ci=Ci)
-    if bname:
-        gb, accb = ctx.G(bname)
-        ops.colsum(dy.view(-1, Co), gb, accb)
+        with ctx.on_side(x, dy):
+            ops.conv_wgrad(x, dy, gw, kh, kw, ph, pw, acc, ldx=ldx, Ci=Ci)
+            if bname:
+                ops.colsum(dy.view(-1, Co), gb, accb)
     if not need_dx:
         return None
     dense_out = dx_out is None or dx_out.shape[-1] == Ci
@@ -270,7 +303,10 @@ def gru_block_bwd(ctx: Ctx, saved, dout: Tensor, need_dx: bool = True, dx_out: O
     gwhh, acc = ctx.G(pre + 'gru.weight_hh')
     gbhh, _ = ctx.G(pre + 'gru.bias_hh')
     gbih, _ = ctx.G(pre + 'gru.bias_ih')
-    dgx = ops.gru_bwd(dout.view(-1, 64), y, stash, whh, gwhh, gbhh, gbih, acc, B, H, W, vertical).view(B, H, W, 192)
+    dgx, part = ops.gru_bwd_recurrence(dout.view(-1, 64), y, stash, whh, B, H, W, vertical)
+    with ctx.on_side(dgx, y, stash, part):      # dW_hh outer products + bias reductions: off the data-gradient chain
+        ops.gru_bwd_weights(dgx, y, stash, part, gwhh, gbhh, gbih, acc, B, H, W, vertical)
+    dgx = dgx.view(B, H, W, 192)
     # input projection (bias grad already produced by the recurrence kernel)
     x_ih, wname, _, kh, kw, ph, pw, as4d, ldx = s_ih
     dy1 = conv_bwd(ctx, (x_ih, wname, None, kh, kw, ph, pw, as4d, ldx), dgx)

@@ -82,6 +82,7 @@ class CRNN(nn.Module):
         st = self._flat
         ectx._written = set(st.live_grads())
         dgray = crnn_engine.crnn_bwd(ectx, saved, dlogits.contiguous())
+        ectx.join()
         members = {f: names for f, names, _ in st.fused}
         params = dict(self.named_parameters())
         for name in ectx._written:

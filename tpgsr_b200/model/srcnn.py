@@ -88,6 +88,7 @@ class SRCNN(nn.Module):
         if not dsr.is_contiguous():
             dsr = dsr.contiguous()
         srcnn_bwd(ectx, saved, dsr)
+        ectx.join()
         params = dict(self.named_parameters())
         for name in ectx._written:
             p = params.get(name)

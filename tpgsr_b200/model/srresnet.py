@@ -226,6 +226,7 @@ class SRResNet_TL(nn.Module):
         dtext = torch.zeros_like(s_text['text'])
         srresnet_bwd(ectx, saved, dsr, dtext)
         dprior = info_gen2d_bwd(ectx, s_text, dtext, text_requires_grad)
+        ectx.join()
         params = dict(self.named_parameters())
         for name in ectx._written:
             p = params.get(name)

@@ -184,6 +184,7 @@ class _TSRNBase(nn.Module):
         dprior = None
         if self._tl:
             dprior = self._expand_prior_bwd(ectx, s_text, dtext_map, text_requires_grad)
+        ectx.join()
         self._publish(ectx)
         return dprior
 

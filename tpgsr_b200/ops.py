@@ -20,7 +20,8 @@ LAUNCHES = 0
 _KERNELS_PER_CALL = {
     'tpgsr_conv2d_wgrad': 2, 'tpgsr_bn_stats': 2, 'tpgsr_bn_bwd': 3, 'tpgsr_colsum': 2, 'tpgsr_gru_bwd': 3,
     'tpgsr_image_loss_fwd': 2, 'tpgsr_semantic_loss_fwd': 2, 'tpgsr_optim_prepare': 2, 'tpgsr_lstm_bwd': 2,
-    'tpgsr_conv2d_tc': 1, 'tpgsr_conv2d_wgrad_tc': 2, 'tpgsr_conv2d_flat': 1, 'tpgsr_conv2d_wgrad_flat': 2,
+    'tpgsr_conv2d_tc': 1, 'tpgsr_conv2d_wgrad_tc': 2, 'tpgsr_conv2d_flat': 1, 'tpgsr_conv2d_wgrad_flat': 2, 'tpgsr_gru_bwd_weights': 2,
+    'tpgsr_psnr_ssim': 2,
 }
 
 
@@ -42,10 +43,45 @@ _WS = {}
 _WS_RETIRED = []     # outgrown buffers are kept alive: captured CUDA graphs may still reference their addresses
 
 
+# ---- side stream: gradient side work (weight gradients, bias column sums, GRU dW_hh) runs concurrently with the data-gradient chain ------
+# TPGSR_SIDE_STREAM=0 keeps everything on one stream.
+SIDE_STREAM = os.environ.get('TPGSR_SIDE_STREAM', '1') != '0'
+_SIDE = {}
+
+
+def _dev_index(device) -> int:
+    d = torch.device(device)
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def side_stream(device):
+    """The per-device side stream (None when disabled)."""
+    if not SIDE_STREAM:
+        return None
+    key = _dev_index(device)
+    st = _SIDE.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=torch.device('cuda', key))
+        _SIDE[key] = st
+    return st
+
+
+def join_side(device) -> None:
+    """Make the current stream wait for everything queued on the device's side stream (no-op if nothing was ever forked)."""
+    st = _SIDE.get(_dev_index(device))
+    if st is not None:
+        cur = torch.cuda.current_stream(torch.device('cuda', _dev_index(device)))
+        if cur.cuda_stream != st.cuda_stream:
+            cur.wait_stream(st)
+
+
 def workspace(nbytes: int, device) -> Tuple[int, int]:
-    """A per-device scratch buffer (grown on demand; stable pointer once large enough — safe under graph capture
-    because every kernel that uses it runs on the same stream)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """A scratch buffer per (device, main / side stream), grown on demand; stable pointer once large enough — safe under graph
+    capture because every kernel that uses one buffer runs on the same stream."""
+    idx = _dev_index(device)
+    side = _SIDE.get(idx)
+    on_side = side is not None and torch.cuda.current_stream(torch.device('cuda', idx)).cuda_stream == side.cuda_stream
+    key = (idx, on_side)
     buf = _WS.get(key)
     need = max(int(nbytes), 1)
     if buf is None or buf.numel() < need:
@@ -54,6 +90,16 @@ def workspace(nbytes: int, device) -> Tuple[int, int]:
         buf = torch.empty(max(need, 64 << 20), dtype=torch.uint8, device=device)
         _WS[key] = buf
     return buf.data_ptr(), buf.numel()
+
+
+def prime_workspaces(nbytes: int, device) -> None:
+    """Allocate the main and side scratch buffers up front (outside any graph capture)."""
+    workspace(nbytes, device)
+    st = side_stream(device)
+    if st is not None:
+        with torch.cuda.stream(st):
+            workspace(nbytes, device)
+        torch.cuda.current_stream(torch.device('cuda', _dev_index(device))).wait_stream(st)
 
 
 def new(shape, like: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
@@ -463,6 +509,7 @@ def gru_fwd(gx: torch.Tensor, whh: torch.Tensor, bhh: torch.Tensor, B: int, H: i
 
 def gru_bwd(dy: torch.Tensor, y: torch.Tensor, stash: torch.Tensor, whh: torch.Tensor, dwhh, dbhh, dbih, accumulate: bool,
             B: int, H: int, W: int, vertical: bool) -> torch.Tensor:
+    """BPTT + dW_hh + bias gradients in one call (three kernels on the current stream)."""
     M = y.shape[0]
     dgx = new((M, 192), y)
     S, T, inner, so, si, st = _seq_geom(B, H, W, vertical)
@@ -470,6 +517,26 @@ def gru_bwd(dy: torch.Tensor, y: torch.Tensor, stash: torch.Tensor, whh: torch.T
     _call('tpgsr_gru_bwd', ptr(dy), 64, ptr(y), 64, ptr(stash), ptr(whh), ptr(dgx), ptr(dwhh), ptr(dbhh), ptr(dbih),
           int(accumulate), S, T, inner, so, si, st, wp, wn, stream())
     return dgx
+
+
+def gru_bwd_recurrence(dy: torch.Tensor, y: torch.Tensor, stash: torch.Tensor, whh: torch.Tensor, B: int, H: int, W: int,
+                       vertical: bool):
+    """The serial BPTT only: returns (dgx [M,192], part) — ``part`` holds the per-block bias partials and is completed and reduced
+    by :func:`gru_bwd_weights` (which may run on the side stream)."""
+    M = y.shape[0]
+    dgx = new((M, 192), y)
+    S, T, inner, so, si, st = _seq_geom(B, H, W, vertical)
+    part = torch.empty(query('tpgsr_gru_bwd_workspace_bytes', S), dtype=torch.uint8, device=y.device)
+    _call('tpgsr_gru_bwd_recurrence', ptr(dy), 64, ptr(y), 64, ptr(stash), ptr(whh), ptr(dgx), S, T, inner, so, si, st, ptr(part),
+          part.numel(), stream())
+    return dgx, part
+
+
+def gru_bwd_weights(dgx: torch.Tensor, y: torch.Tensor, stash: torch.Tensor, part: torch.Tensor, dwhh, dbhh, dbih, accumulate: bool,
+                    B: int, H: int, W: int, vertical: bool) -> None:
+    S, T, inner, so, si, st = _seq_geom(B, H, W, vertical)
+    _call('tpgsr_gru_bwd_weights', ptr(dgx), ptr(y), 64, ptr(stash), ptr(dwhh), ptr(dbhh), ptr(dbih), int(accumulate), S, T, inner, so, si,
+          st, ptr(part), part.numel(), stream())
 
 
 # ------------------------------------------------------------------------------------------------ TPS

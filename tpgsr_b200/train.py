@@ -40,7 +40,7 @@ class TSRNTrainStep:
         self.use_graph = use_graph
         self._g_fb = None
         self._g_opt = None
-        ops.workspace(256 << 20, dev)
+        ops.prime_workspaces(256 << 20, dev)
 
     # ---- step pieces ------------------------------------------------------------------------------------------------
     def _fwd_bwd(self):
@@ -52,6 +52,7 @@ class TSRNTrainStep:
         ops.image_loss_fwd(sr, self.hr_buf, self.gradient, self.w0, self.w1, 100.0, loss=self.loss, accumulate=False)
         dsr = ops.image_loss_bwd(sr, self.hr_buf, self.gradient, self.w0, self.w1, 100.0)
         engine.tsrn_bwd(ctx, saved, dsr)
+        ctx.join()                      # side-stream weight gradients are complete before the graph / the all-reduce continues
         self.sr = sr
 
     def _optim(self):
@@ -154,7 +155,7 @@ class TPGSRTrainStep:
         self.use_graph = use_graph
         self._g_fb = None
         self._g_opt = None
-        ops.workspace(256 << 20, self.dev)
+        ops.prime_workspaces(256 << 20, self.dev)
 
     def _fwd_bwd(self):
         from . import crnn_engine, infogen, ops_prior
@@ -213,6 +214,7 @@ class TPGSRTrainStep:
             if i > 0:
                 dnext = torch.zeros_like(stages[i - 1][6])
                 ops_prior.bicubic_gray_bwd(dgray, dnext, False)
+        ops.join_side(self.dev)          # side-stream weight gradients are complete before the graph / the all-reduce continues
         self.sr = stages[-1][6]
 
     def _optim(self):
