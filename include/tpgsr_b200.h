@@ -135,6 +135,9 @@ int tpgsr_add(const float* a, const float* b, float* y, long n, cudaStream_t str
 int tpgsr_copy_cols(const float* src, int lds, float* dst, int ldd, long M, int C, float alpha, int accumulate,
                     cudaStream_t stream);
 int tpgsr_add_i64(long long* x, long n, long long v, cudaStream_t stream);
+/* W_ih * (W_1x1 x + b_1x1) + b_ih as one linear map (GruBlock, model/tsrn.py:499-504): wout = w2 w1, bout = w2 b1 + b2 */
+int tpgsr_fuse_linear(const float* w2, const float* b2, const float* w1, const float* b1, float* wout, float* bout, int N2, int N1, int K1,
+                      cudaStream_t stream);
 int tpgsr_maxpool_fwd(const float* x, float* y, int* argmax, int B, int Hi, int Wi, int C, int kh, int kw, int sh,
                       int sw, int ph, int pw, cudaStream_t stream);
 int tpgsr_maxpool_bwd(const float* dy, const int* argmax, float* dx, int B, int Hi, int Wi, int C, int kh, int kw,

@@ -430,6 +430,24 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* 
     }
 }
 
+// wout[n][k] = sum_j w2[n][j] * w1[j][k];  bout[n] = b2[n] + sum_j w2[n][j] * b1[j]     (two chained linear maps without a non-linearity
+// in between — GruBlock's 1x1 conv followed by the GRU input projection, model/tsrn.py:499-504 — collapse into one)
+__global__ void fuse_linear_kernel(const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w1,
+                                   const float* __restrict__ b1, float* __restrict__ wout, float* __restrict__ bout, int N2, int N1, int K1) {
+    const int total = N2 * (K1 + 1);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int n = idx / (K1 + 1), k = idx - n * (K1 + 1);
+        float s = 0.f;
+        if (k < K1) {
+            for (int j = 0; j < N1; ++j) s = fmaf(w2[(size_t)n * N1 + j], w1[(size_t)j * K1 + k], s);
+            wout[(size_t)n * K1 + k] = s;
+        } else {
+            if (b1) for (int j = 0; j < N1; ++j) s = fmaf(w2[(size_t)n * N1 + j], b1[j], s);
+            bout[n] = s + (b2 ? b2[n] : 0.f);
+        }
+    }
+}
+
 __global__ void add_i64_kernel(long long* __restrict__ x, long n, long long v) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] += v;
 }
@@ -549,6 +567,13 @@ int tpgsr_copy_cols(const float* src, int lds, float* dst, int ldd, long M, int 
                     cudaStream_t stream) {
     if (!src || !dst || M <= 0 || C <= 0) return TPGSR_ERR_BAD_ARG;
     copy_cols_kernel<<<ew_grid(M * C), 256, 0, stream>>>(src, lds, dst, ldd, M, C, alpha, accumulate);
+    return tpgsr_launch_status();
+}
+
+int tpgsr_fuse_linear(const float* w2, const float* b2, const float* w1, const float* b1, float* wout, float* bout, int N2, int N1, int K1,
+                      cudaStream_t stream) {
+    if (!w2 || !w1 || !wout || !bout || N2 < 1 || N1 < 1 || K1 < 1) return TPGSR_ERR_BAD_ARG;
+    fuse_linear_kernel<<<ew_grid((long)N2 * (K1 + 1)), 256, 0, stream>>>(w2, b2, w1, b1, wout, bout, N2, N1, K1);
     return tpgsr_launch_status();
 }
 

@@ -283,21 +283,48 @@ def bn_bwd(ctx: Ctx, saved, dy: Tensor, lddy: int = 0) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------------ GruBlock
+def _gru_proj_fused(ctx: Ctx, pre: str):
+    """Packed bf16 operands of W_c = W_ih W_1x1 (and b_c = W_ih b_1x1 + b_ih), cached per step: ((fwd planes), (dgrad planes), b_c)."""
+    key = pre + 'gru.fused'
+    hit = ctx._packed_bf16.get(key)
+    if hit is None:
+        wc, bc = ops.fuse_linear(ctx.P(pre + 'gru.weight_ih'), ctx.P(pre + 'gru.bias_ih'), ctx.P(pre + 'conv1.weight'), ctx.P(pre + 'conv1.bias'))
+        f, d = ops.pack_conv_weights_bf16(wc.view(wc.shape[0], wc.shape[1], 1, 1), ctx.grads is not None, ops.CONV_MODE == 'bf16x3')
+        hit = (f, d, bc)
+        ctx._packed_bf16[key] = hit
+    return hit
+
+
 def gru_block_fwd(ctx: Ctx, x: Tensor, pre: str, vertical: bool, residual: Optional[Tensor] = None, ldx: int = 0):
     """GruBlock (model/tsrn.py:491-508): 1x1 conv -> BiGRU along W (or along H when ``vertical``: the reference's
-    transpose trick).  Returns (y or y+residual) as [B,H,W,64]."""
-    B, H, W, _ = x.shape
+    transpose trick).  Returns (y or y+residual) as [B,H,W,64].
+
+    The 1x1 conv and the GRU input projection are two linear maps with nothing in between (model/tsrn.py:499-504): when the input is a
+    dense 64-channel map they run as ONE tensor-core GEMM with W_c = W_ih W_1x1; the backward pass recomputes the 1x1
+    output it needs for dW_ih on the side stream."""
+    B, H, W, Cx = x.shape
+    whh, bhh = ctx.P(pre + 'gru.weight_hh'), ctx.P(pre + 'gru.bias_hh')
+    res = residual.view(-1, 64) if residual is not None else None
+    fused = (ops.FUSE_GRU_PROJ and ldx in (0, Cx) and x.is_contiguous() and ops.flat_supported(B, H, W, 0, Cx, 192, 1, 1, 0, 0)
+             and ops.flat_supported(B, H, W, 0, 192, Cx, 1, 1, 0, 0) and ops.wgrad_flat_supported(B, H, W, 0, 64, 192, 1, 1)
+             and ops.wgrad_flat_supported(B, H, W, 0, Cx, 64, 1, 1))
+    if fused:
+        wf, _, bc = _gru_proj_fused(ctx, pre)
+        gx = ops.conv_flat(ctx.flat(x, 0), wf, bc, 192, 1, 1, 0, 0)
+        y, ysum, stash = ops.gru_fwd(gx.view(-1, 192), whh, bhh, B, H, W, vertical, res, need_stash=ctx.grads is not None)
+        out = (ysum if residual is not None else y).view(B, H, W, 64)
+        return out, ('fused', x, y, stash, pre, vertical, (B, H, W))
     y1, s_conv = conv_fwd(ctx, x, pre + 'conv1.weight', pre + 'conv1.bias', 1, 0, ldx=ldx)
     gx, s_ih = conv_fwd(ctx, y1, pre + 'gru.weight_ih', pre + 'gru.bias_ih', 1, 0)
-    whh, bhh = ctx.P(pre + 'gru.weight_hh'), ctx.P(pre + 'gru.bias_hh')
-    y, ysum, stash = ops.gru_fwd(gx.view(-1, 192), whh, bhh, B, H, W, vertical,
-                                 residual.view(-1, 64) if residual is not None else None, need_stash=ctx.grads is not None)
+    y, ysum, stash = ops.gru_fwd(gx.view(-1, 192), whh, bhh, B, H, W, vertical, res, need_stash=ctx.grads is not None)
     out = (ysum if residual is not None else y).view(B, H, W, 64)
     return out, (s_conv, s_ih, y, stash, pre, vertical, (B, H, W))
 
 
 def gru_block_bwd(ctx: Ctx, saved, dout: Tensor, need_dx: bool = True, dx_out: Optional[Tensor] = None,
                   dx_accumulate: bool = False):
+    if saved[0] == 'fused':
+        return _gru_block_bwd_fused(ctx, saved, dout, need_dx, dx_out, dx_accumulate)
     s_conv, s_ih, y, stash, pre, vertical, (B, H, W) = saved
     whh = ctx.P(pre + 'gru.weight_hh')
     gwhh, acc = ctx.G(pre + 'gru.weight_hh')
@@ -311,6 +338,35 @@ def gru_block_bwd(ctx: Ctx, saved, dout: Tensor, need_dx: bool = True, dx_out: O
     x_ih, wname, _, kh, kw, ph, pw, as4d, ldx = s_ih
     dy1 = conv_bwd(ctx, (x_ih, wname, None, kh, kw, ph, pw, as4d, ldx), dgx)
     return conv_bwd(ctx, s_conv, dy1, need_dx, dx_out, dx_accumulate)
+
+
+def _gru_block_bwd_fused(ctx: Ctx, saved, dout: Tensor, need_dx: bool, dx_out: Optional[Tensor], dx_accumulate: bool):
+    _, x, y, stash, pre, vertical, (B, H, W) = saved
+    Cx = x.shape[-1]
+    whh = ctx.P(pre + 'gru.weight_hh')
+    gwhh, acc = ctx.G(pre + 'gru.weight_hh')
+    gbhh, _ = ctx.G(pre + 'gru.bias_hh')
+    gbih, _ = ctx.G(pre + 'gru.bias_ih')
+    gwih, acc_ih = ctx.G(pre + 'gru.weight_ih')
+    gw1, acc_w1 = ctx.G(pre + 'conv1.weight')
+    gb1, acc_b1 = ctx.G(pre + 'conv1.bias')
+    dgx, part = ops.gru_bwd_recurrence(dout.view(-1, 64), y, stash, whh, B, H, W, vertical)
+    dgx4 = dgx.view(B, H, W, 192)
+    xp, dgxp = ctx.flat(x, 0), ctx.flat(dgx4, 0)       # shared by both streams: produced before the fork
+    with ctx.on_side(dgx, dgx4, y, stash, part, x):
+        # everything that only feeds parameter gradients: dW_hh / biases, the recomputed 1x1 output, dW_ih, d(1x1 output), dW_1x1, db_1x1
+        ops.gru_bwd_weights(dgx, y, stash, part, gwhh, gbhh, gbih, acc, B, H, W, vertical)
+        w1f, _ = ctx.packed_bf16(pre + 'conv1.weight')
+        y1 = ops.conv_flat(xp, w1f, ctx.P(pre + 'conv1.bias'), 64, 1, 1, 0, 0)
+        ops.conv_wgrad_flat(ops.split_bf16_flat(y1, 0, ops.CONV_MODE == 'bf16x3'), dgxp, gwih, 192, 1, 1, 0, 0, acc_ih)
+        _, wihd = ctx.packed_bf16(pre + 'gru.weight_ih')
+        dy1 = ops.conv_flat(dgxp, wihd, None, 64, 1, 1, 0, 0)
+        ops.conv_wgrad_flat(xp, ops.split_bf16_flat(dy1, 0, ops.CONV_MODE == 'bf16x3'), gw1, 64, 1, 1, 0, 0, acc_w1)
+        ops.colsum(dy1.view(-1, 64), gb1, acc_b1)
+    if not need_dx:
+        return None
+    _, wd, _ = _gru_proj_fused(ctx, pre)
+    return ops.conv_flat(dgxp, wd, None, Cx, 1, 1, 0, 0, out=dx_out, accumulate=dx_accumulate)
 
 
 # ------------------------------------------------------------------------------------------------------------ SRB

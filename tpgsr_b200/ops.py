@@ -258,6 +258,7 @@ def conv_wgrad_tc(x_planes, dy_planes, dw: torch.Tensor, B, H, W, Ci, Co, KH, KW
 # ---- padded-flat tensor-core path (conv_flat.cu): operand planes [B][H+P][W+P][C] with zero pad rows / columns ------------------
 # TPGSR_FLAT=0 falls back to the per-tap TMA kernels above (kept for the shapes the flat kernels do not take).
 FLAT = os.environ.get('TPGSR_FLAT', '1') != '0'
+FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', '1') != '0'      # GruBlock 1x1 conv + GRU input projection as one GEMM
 
 
 class FlatPlanes:
@@ -450,6 +451,15 @@ def copy_cols(src: torch.Tensor, lds: int, dst: torch.Tensor, ldd: int, M: int, 
     """dst[:, dst_off:dst_off+C] (+)= alpha * src[:, src_off:src_off+C] on pitched [M, ld] matrices."""
     _call('tpgsr_copy_cols', src.data_ptr() + 4 * src_off, lds, dst.data_ptr() + 4 * dst_off, ldd, M, C, alpha,
           int(accumulate), stream())
+
+
+def fuse_linear(w2: torch.Tensor, b2, w1: torch.Tensor, b1):
+    """(w2 @ w1, w2 @ b1 + b2) for [N2,N1] x [N1,K1] weight matrices (conv 1x1 weights may be passed as [N,K,1,1])."""
+    N2, N1 = w2.shape[0], w2.shape[1]
+    K1 = w1.numel() // N1
+    wout, bout = new((N2, K1), w2), new((N2,), w2)
+    _call('tpgsr_fuse_linear', ptr(w2), ptr(b2), ptr(w1), ptr(b1), ptr(wout), ptr(bout), N2, N1, K1, stream())
+    return wout, bout
 
 
 def add_i64(x: torch.Tensor, v: int = 1) -> None:
