@@ -32,13 +32,14 @@ if [[ $what == *refarm* ]]; then
 fi
 if [[ $what == *launches* ]]; then
   # eager (non-graphed) step so every launch is listed
-  TPGSR_BENCH_NO_CPU=1 TPGSR_BENCH_NO_ROOFLINE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
+  # only the last ~1.1 eager steps are instrumented (-s skips the accounting pass and the warm-ups): listing all ~2800 launches costs 8 min
+  TPGSR_BENCH_NO_CPU=1 TPGSR_BENCH_NO_ROOFLINE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${LAUNCH_SKIP:-2100} -c 700 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-e2e > gpurun_out/launches.log 2>&1
   echo "launches rc=$?"; wc -l gpurun_out/launches.csv
 fi
 if [[ $what == *full* ]]; then
   TPGSR_BENCH_NO_CPU=1 TPGSR_BENCH_NO_ROOFLINE=1 timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:'conv_flat_kernel|conv_wgrad_flat_kernel|gru_fwd_kernel|gru_bwd_kernel|gru_dwhh_kernel' -s 60 -c 14 -o gpurun_out/prof_top -f \
+      -k regex:'conv_flat_kernel|conv_wgrad_flat_kernel|gru_fwd_kernel|gru_bwd_kernel|gru_dwhh_kernel' -s ${FULL_SKIP:-70} -c ${FULL_COUNT:-10} -o gpurun_out/prof_top -f \
       python bench.py --steps 1 --warmup 3 --no-graph --no-e2e > gpurun_out/full.log 2>&1
   echo "full rc=$?"; ls -la gpurun_out/
 fi

@@ -305,7 +305,8 @@ def gru_block_fwd(ctx: Ctx, x: Tensor, pre: str, vertical: bool, residual: Optio
     B, H, W, Cx = x.shape
     whh, bhh = ctx.P(pre + 'gru.weight_hh'), ctx.P(pre + 'gru.bias_hh')
     res = residual.view(-1, 64) if residual is not None else None
-    fused = (ops.FUSE_GRU_PROJ and ldx in (0, Cx) and x.is_contiguous() and ops.flat_supported(B, H, W, 0, Cx, 192, 1, 1, 0, 0)
+    want = ops.FUSE_GRU_PROJ == '1' or (ops.FUSE_GRU_PROJ == 'infer' and ctx.grads is None)
+    fused = (want and ldx in (0, Cx) and x.is_contiguous() and ops.flat_supported(B, H, W, 0, Cx, 192, 1, 1, 0, 0)
              and ops.flat_supported(B, H, W, 0, 192, Cx, 1, 1, 0, 0) and ops.wgrad_flat_supported(B, H, W, 0, 64, 192, 1, 1)
              and ops.wgrad_flat_supported(B, H, W, 0, Cx, 64, 1, 1))
     if fused:

@@ -258,7 +258,10 @@ def conv_wgrad_tc(x_planes, dy_planes, dw: torch.Tensor, B, H, W, Ci, Co, KH, KW
 # ---- padded-flat tensor-core path (conv_flat.cu): operand planes [B][H+P][W+P][C] with zero pad rows / columns ------------------
 # TPGSR_FLAT=0 falls back to the per-tap TMA kernels above (kept for the shapes the flat kernels do not take).
 FLAT = os.environ.get('TPGSR_FLAT', '1') != '0'
-FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', '1') != '0'      # GruBlock 1x1 conv + GRU input projection as one GEMM
+# GruBlock 1x1 conv + GRU input projection as one GEMM (W_c = W_ih W_1x1): 'infer' (default) = forward-only passes, '1' = training too,
+# '0' = never.  Measured on B200 (round 1): in training the fused path is neutral (5.77 vs 5.70 ms/step) — the backward pass has to
+# recompute the 1x1 output for dW_ih, which costs what the forward pass saves — so it is kept for inference only.
+FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', 'infer')
 
 
 class FlatPlanes:
