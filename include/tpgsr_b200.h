@@ -92,6 +92,9 @@ size_t tpgsr_conv2d_wgrad_flat_plan(int B, int H, int W, int P, int Ci, int Co, 
 int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, int B,
                       int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
                       const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream);
+int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, void* yp_hi,
+                             void* yp_lo, int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
+                             const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream);
 int tpgsr_conv2d_wgrad_flat_supported(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod);
 size_t tpgsr_conv2d_wgrad_flat_workspace_bytes(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod);
 int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw_oihw, int B,

@@ -114,6 +114,8 @@ struct FlatConvParams {
     const float* bias;
     const float* act_param;
     float* y;
+    __nv_bfloat16* yp_hi;      // optional: the (activated) output also as dense bf16 hi/lo planes [M][Co] = the P = 0 operand planes of a following
+    __nv_bfloat16* yp_lo;      // 1x1 conv / weight gradient (saves a tpgsr_split_bf16_flat pass); requires Co % 32 == 0, NHWC output
     int dbg_skip;              // developer experiments: bit0 = skip the global stores, bit1 = skip TMEM load + staging
     long long* dbg;            // optional [grid][16] clock64 timestamps (developer instrumentation, scripts/flat_timeline.py)
 };
@@ -368,6 +370,18 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                     val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
                                 }
                                 *dst = val;
+                                if (p.yp_hi) {
+                                    const float f[4] = {val.x, val.y, val.z, val.w};
+                                    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        h[u] = __float2bfloat16_rn(f[u]);
+                                        l[u] = __float2bfloat16_rn(f[u] - __bfloat162float(h[u]));
+                                    }
+                                    const size_t po = (size_t)px * p.Co + n0 + c0 + c4 * 4;
+                                    *reinterpret_cast<uint2*>(p.yp_hi + po) = *reinterpret_cast<uint2*>(h);
+                                    if (p.yp_lo) *reinterpret_cast<uint2*>(p.yp_lo + po) = *reinterpret_cast<uint2*>(l);
+                                }
                             }
                         }
                     } else if (ncols > 0) {
@@ -475,12 +489,17 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             if (MT * pl.tm_stride > 512) continue;
             const int G = pointwise ? 1 : (pass == 0 ? KH : 1);
             const int n_groups = pointwise ? Ci / 64 : KH / G;
-            const int a_stages = n_groups > 1 ? 2 : 1;
             const int rows = TILE_M * MT + (G - 1) * Wp + (KW - 1);
             int n_box = (rows + 255) / 256;
             int box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8;
             if (box_rows > 256) { ++n_box; box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8; }
-            const size_t a_bytes = (size_t)a_stages * planes * n_box * box_rows * ROW_BYTES;
+            // streamed A groups (one kernel row / channel block per stage): up to 4 stages in flight — with 2 the 9x1 stacked convs waited
+            // one L2 round trip per kernel row (profiles/r01: 154 us for the final conv)
+            int a_stages = n_groups > 1 ? (n_groups < 4 ? n_groups : 4) : 1;
+            const size_t a_stage_b = (size_t)planes * n_box * box_rows * ROW_BYTES;
+            const size_t b_min = (size_t)2 * planes * pl.n_tile * ROW_BYTES * ((n_groups > 1 && KW > 1) ? KW : 1);
+            while (a_stages > 2 && a_stages * a_stage_b + b_min + 4096 > budget) --a_stages;
+            const size_t a_bytes = (size_t)a_stages * a_stage_b;
             // B ring: one tap per stage, 4..2 deep (deepest that fits) — or one kernel row of taps per stage, 2 deep, when the
             // tap tile is small and the kernel rows are streamed.  tile_outer (whole halo resident): the epilogue of one tile runs while
             // the next tile's MMAs read the rings, so its staging area is separate; otherwise it aliases the (drained) rings.
@@ -761,10 +780,23 @@ size_t tpgsr_conv2d_wgrad_flat_plan(int B, int H, int W, int P, int Ci, int Co, 
 // y = act(conv(x) + bias) for a 'same' convolution with 64 input channels.  x_hi/x_lo: padded-flat bf16 planes of the input
 // ([B][H+P][W+P][64], tpgsr_split_bf16_flat); w_hi/w_lo: K-major packed weights [Co][KH*KW*64] (tpgsr_pack_conv_weights_bf16);
 // y: fp32 dense NHWC (pixel pitch ldy) or NCHW.  Data gradient: pass dY planes, the dgrad packing, Co := conv Ci.
+int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, void* yp_hi,
+                             void* yp_lo, int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
+                             const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream);
+
 int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, int B,
                       int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
                       const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream) {
+    return tpgsr_conv2d_flat_planes(x_hi, x_lo, w_hi, w_lo, bias, y, nullptr, nullptr, B, H, W, P, Ci, Co, KH, KW, ph, pw, ldy, act, act_param,
+                                    out_mode, accumulate, nprod, stream);
+}
+
+// as tpgsr_conv2d_flat; additionally writes the output as dense bf16 hi/lo planes [B*H*W][Co] (yp_lo may be NULL in 1-product mode)
+int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, void* yp_hi,
+                             void* yp_lo, int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
+                             const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream) {
     if (!x_hi || !w_hi || !y || (nprod != 1 && nprod != 3) || (nprod == 3 && (!x_lo || !w_lo))) return TPGSR_ERR_BAD_ARG;
+    if (yp_hi && (Co % 32 != 0 || out_mode != TPGSR_OUT_NHWC || ((ldy > 0 ? ldy : Co) & 3))) return TPGSR_ERR_UNSUPPORTED;
     FlatPlan pl;
     int rc = plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl);
     if (rc) return rc;
@@ -777,6 +809,7 @@ int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, cons
     p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
     p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg; p.dbg_skip = g_flat_dbg_skip;
+    p.yp_hi = static_cast<__nv_bfloat16*>(yp_hi); p.yp_lo = static_cast<__nv_bfloat16*>(yp_lo);
 
     const uint64_t K = (uint64_t)KH * KW * Ci;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;

@@ -156,7 +156,9 @@ def _kwstack_kind(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: in
 
 
 def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=ACT_NONE, act_param: Optional[Tensor] = None,
-             out_nchw: bool = False, need_dgrad: bool = True, as4d=None, ldx: int = 0, out: Optional[Tensor] = None):
+             out_nchw: bool = False, need_dgrad: bool = True, as4d=None, ldx: int = 0, out: Optional[Tensor] = None,
+             emit_planes: bool = False):
+    """``emit_planes``: the caller knows the output feeds a 1x1 conv next; the flat epilogue then also writes its P = 0 bf16 planes."""
     w = ctx.P(wname)
     Co = w.shape[0]
     kh, kw = k if isinstance(k, tuple) else (k, k)
@@ -175,6 +177,10 @@ def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=
         return y, saved
     if out is None and _flat_ok(x, Ci, Co, kh, kw, ph, pw, ldx):
         wf, _ = ctx.packed_bf16(wname, as4d)
+        if emit_planes and not out_nchw and Co % 32 == 0:
+            y, yp = ops.conv_flat(ctx.flat(x, max(ph, pw)), wf, bias, Co, kh, kw, ph, pw, act, act_param, emit_planes=True)
+            ctx._planes[(id(y), 'flat', 0, Co)] = (y, yp)
+            return y, saved
         y = ops.conv_flat(ctx.flat(x, max(ph, pw)), wf, bias, Co, kh, kw, ph, pw, act, act_param, out_nchw)
         return y, saved
     if out is None and _tc_ok(x, Ci, Co, kh, kw, ph, pw, ldx):
@@ -187,8 +193,9 @@ def conv_fwd(ctx: Ctx, x: Tensor, wname: str, bname: Optional[str], k, pad, act=
     return y, saved
 
 
-def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional[Tensor] = None, dx_accumulate: bool = False):
-    """dy: NHWC gradient w.r.t. the conv's pre-activation output."""
+def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional[Tensor] = None, dx_accumulate: bool = False,
+             emit_dx_planes: bool = False):
+    """dy: NHWC gradient w.r.t. the conv's pre-activation output.  ``emit_dx_planes``: dx feeds the backward of a 1x1 conv next."""
     x, wname, bname, kh, kw, ph, pw, as4d, ldx = saved
     w = ctx.P(wname)
     Co = w.shape[0]
@@ -243,6 +250,10 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     dense_out = dx_out is None or dx_out.shape[-1] == Ci
     if dense_out and _flat_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)
+        if emit_dx_planes and dx_out is None and Ci % 32 == 0:
+            dx, dxp = ops.conv_flat(ctx.flat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, emit_planes=True)
+            ctx._planes[(id(dx), 'flat', 0, Ci)] = (dx, dxp)
+            return dx
         return ops.conv_flat(ctx.flat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out, accumulate=dx_accumulate)
     if dense_out and _tc_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)
@@ -315,7 +326,7 @@ def gru_block_fwd(ctx: Ctx, x: Tensor, pre: str, vertical: bool, residual: Optio
         y, ysum, stash = ops.gru_fwd(gx.view(-1, 192), whh, bhh, B, H, W, vertical, res, need_stash=ctx.grads is not None)
         out = (ysum if residual is not None else y).view(B, H, W, 64)
         return out, ('fused', x, y, stash, pre, vertical, (B, H, W))
-    y1, s_conv = conv_fwd(ctx, x, pre + 'conv1.weight', pre + 'conv1.bias', 1, 0, ldx=ldx)
+    y1, s_conv = conv_fwd(ctx, x, pre + 'conv1.weight', pre + 'conv1.bias', 1, 0, ldx=ldx, emit_planes=True)   # feeds the 1x1 projection
     gx, s_ih = conv_fwd(ctx, y1, pre + 'gru.weight_ih', pre + 'gru.bias_ih', 1, 0)
     y, ysum, stash = ops.gru_fwd(gx.view(-1, 192), whh, bhh, B, H, W, vertical, res, need_stash=ctx.grads is not None)
     out = (ysum if residual is not None else y).view(B, H, W, 64)
@@ -337,7 +348,7 @@ def gru_block_bwd(ctx: Ctx, saved, dout: Tensor, need_dx: bool = True, dx_out: O
     dgx = dgx.view(B, H, W, 192)
     # input projection (bias grad already produced by the recurrence kernel)
     x_ih, wname, _, kh, kw, ph, pw, as4d, ldx = s_ih
-    dy1 = conv_bwd(ctx, (x_ih, wname, None, kh, kw, ph, pw, as4d, ldx), dgx)
+    dy1 = conv_bwd(ctx, (x_ih, wname, None, kh, kw, ph, pw, as4d, ldx), dgx, emit_dx_planes=True)    # feeds the backward of the 1x1 conv
     return conv_bwd(ctx, s_conv, dy1, need_dx, dx_out, dx_accumulate)
 
 

@@ -293,13 +293,21 @@ def flat_supported(B, H, W, P, Ci, Co, KH, KW, ph, pw) -> bool:
 
 
 def conv_flat(xp: FlatPlanes, w_planes, bias, Co, KH, KW, ph, pw, act=ACT_NONE, act_param=None, out_nchw=False,
-              out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """'same' conv on padded-flat planes -> dense fp32 NHWC [B,H,W,Co] (or NCHW)."""
+              out: Optional[torch.Tensor] = None, accumulate: bool = False, emit_planes: bool = False):
+    """'same' conv on padded-flat planes -> dense fp32 NHWC [B,H,W,Co] (or NCHW).  ``emit_planes``: also return the output's dense
+    bf16 hi/lo planes (= its P = 0 operand planes) written by the same epilogue -> (out, FlatPlanes)."""
     B, H, W = xp.B, xp.H, xp.W
     if out is None:
         out = torch.empty((B, Co, H, W) if out_nchw else (B, H, W, Co), dtype=torch.float32, device=xp.hi.device)
         accumulate = False
     n = 3 if (nprod() == 3 and xp.lo is not None and w_planes[1] is not None) else 1
+    if emit_planes:
+        assert not out_nchw and Co % 32 == 0 and out.shape[-1] == Co
+        hi = torch.empty((B * H * W, Co), dtype=torch.bfloat16, device=out.device)
+        lo = torch.empty((B * H * W, Co), dtype=torch.bfloat16, device=out.device) if nprod() == 3 else None
+        _call('tpgsr_conv2d_flat_planes', ptr(xp.hi), ptr(xp.lo), ptr(w_planes[0]), ptr(w_planes[1]), ptr(bias), ptr(out), ptr(hi), ptr(lo),
+              B, H, W, xp.P, xp.C, Co, KH, KW, ph, pw, Co, act, ptr(act_param), OUT_NHWC, int(accumulate), n, stream())
+        return out, FlatPlanes(hi, lo, B, H, W, Co, 0)
     _call('tpgsr_conv2d_flat', ptr(xp.hi), ptr(xp.lo), ptr(w_planes[0]), ptr(w_planes[1]), ptr(bias), ptr(out), B, H, W, xp.P,
           xp.C, Co, KH, KW, ph, pw, out.shape[-1] if not out_nchw else Co, act, ptr(act_param),
           OUT_NCHW if out_nchw else OUT_NHWC, int(accumulate), n, stream())
