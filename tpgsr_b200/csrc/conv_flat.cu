@@ -105,6 +105,7 @@ struct FlatConvParams {
     int a_stages;              // A ring depth (1 when n_groups == 1)
     int box_rows, n_box;       // one A stage = n_box TMA boxes of box_rows rows (box_rows % 8 == 0)
     int tb, b_stages;          // taps per B stage; B ring depth
+    int nstack;                // 1 (bf16x3, n_tile <= 64): [B_hi; B_lo] is used as ONE N = 2*n_tile operand, 2 MMAs per K step instead of 3
     int tile_outer;            // 1: whole halo resident (n_groups == 1) -> finish tile after tile (weights re-streamed per tile from L2) so
                                //    that the epilogue of tile t overlaps the MMAs of tile t+1;  0: streamed A groups, taps outermost
     int ring_bytes;            // bytes of the A+B rings
@@ -129,6 +130,21 @@ __device__ __forceinline__ void mma_tap(uint32_t d, uint32_t ah, uint32_t al, ui
     for (int k = 1; k < 4; ++k) {          // 16 bf16 = 32 bytes = 2 descriptor units inside the 128-byte swizzle row
         umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
         if (NPROD == 3) { umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc); umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc); }
+    }
+}
+
+// split-bf16 with the weight planes stacked along N: the stage holds B_hi (n_tile rows) immediately followed by B_lo, i.e. one K-major
+// operand of 2*n_tile rows.  D[:, 0:n] += A_hi B_hi^T and D[:, n:2n] += A_hi B_lo^T in ONE MMA (idesc2, N = 2n), then D[:, 0:n] += A_lo B_hi^T
+// (idesc1).  The epilogue adds the two column halves.  Per K step the A_hi tile is read from shared memory once instead of twice: the MMA
+// phase of an N = 64 conv is shared-memory-bandwidth bound (6 KB per 32-cycle MMA), so this is 112 instead of 144 smem cycles per K step.
+template <int FIRST>
+__device__ __forceinline__ void mma_tap_stacked(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t idesc1, uint32_t idesc2) {
+    if (FIRST) umma_lo<0>(d, ah, bh, idesc2); else umma_lo<1>(d, ah, bh, idesc2);
+    umma_lo<1>(d, al, bh, idesc1);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc2);
+        umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc1);
     }
 }
 
@@ -229,6 +245,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);      // same value, provably warp-uniform
         const bool leader = elect_one();
         const uint32_t idesc = tc::idesc_bf16(TILE_M, p.n_tile, 0, 0);
+        const uint32_t idesc2 = tc::idesc_bf16(TILE_M, 2 * p.n_tile, 0, 0);
+        const bool stacked = NPROD == 3 && p.nstack;
         const uint32_t tile_lo = (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
         uint32_t b_it = 0;
         if (p.tile_outer) {
@@ -249,7 +267,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const uint32_t bh = desc_lo(tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes), 16);
                     const uint32_t bl = bh + (b_plane_bytes >> 4);
                     if (leader) {
-                        if (j == 0) mma_tap<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
+                        if (stacked) {
+                            if (j == 0) mma_tap_stacked<1>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
+                            else mma_tap_stacked<0>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
+                        } else if (j == 0) mma_tap<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
                         else mma_tap<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
                         tc::tc_commit(&b_empty[bs]);
                     }
@@ -279,7 +300,13 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         const uint32_t bh = b_hi0 + tt * (b_tap_bytes >> 4), bl = b_lo0 + tt * (b_tap_bytes >> 4);
                         if (!leader) continue;
                         uint32_t ah = a_hi0 + row_off, al = a_lo0 + row_off, d = tmem_u;
-                        if (g == 0 && tl == 0) {
+                        if (stacked) {
+                            if (g == 0 && tl == 0) {
+                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<1>(d, ah, al, bh, idesc, idesc2);
+                            } else {
+                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<0>(d, ah, al, bh, idesc, idesc2);
+                            }
+                        } else if (g == 0 && tl == 0) {
                             for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 1>(d, ah, al, bh, bl, idesc);
                         } else {
                             for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 0>(d, ah, al, bh, bl, idesc);
@@ -328,6 +355,13 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (p.dbg_skip & 2) continue;
                 if (cw == 32) tc::tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
                 tc::tmem_ld_wait();
+                if (NPROD == 3 && p.nstack) {          // stacked weights: columns [n_tile, 2 n_tile) hold the A_hi B_lo^T partial sums
+                    float v2[32];
+                    if (cw == 32) tc::tmem_ld_32x32(taddr + (uint32_t)p.n_tile, v2); else tmem_ld_32x16(taddr + (uint32_t)p.n_tile, v2);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += v2[j];
+                }
                 if (dbg && e == 0 && lane == 0 && item == 0) dbg[8] = clock64();
                 float* drow = stg + (size_t)lane * STG_PITCH;
                 const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
@@ -456,13 +490,14 @@ split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __re
 }
 
 struct FlatPlan {
-    int MT, n_tile, n_tiles, tm_stride, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, tile_outer, ring_bytes, stg_off, bar_off;
+    int MT, n_tile, n_tiles, tm_stride, nstack, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, tile_outer, ring_bytes, stg_off, bar_off;
     size_t smem;
     int grid_x;
 };
 
 long long* g_flat_dbg = nullptr;
 int g_flat_dbg_skip = 0;
+int g_flat_no_nstack = 0;
 
 int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
     if (Co < 1 || B < 1 || H < 1 || W < 1 || Ci < 64 || Ci % 64 != 0) return TPGSR_ERR_UNSUPPORTED;
@@ -474,7 +509,10 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
     const int co16 = (Co + 15) / 16 * 16;
     pl.n_tiles = (co16 + 127) / 128;
     pl.n_tile = ((co16 + pl.n_tiles - 1) / pl.n_tiles + 15) / 16 * 16;
-    pl.tm_stride = (pl.n_tile + 31) / 32 * 32;
+    // stacked weight planes (see mma_tap_stacked): bf16x3, N = 2*n_tile <= 128; forces one tap per B stage (hi and lo tiles adjacent)
+    pl.nstack = (nprod == 3 && pl.n_tile <= 64) ? 1 : 0;
+    if (g_flat_no_nstack) pl.nstack = 0;
+    pl.tm_stride = ((pl.nstack ? 2 : 1) * pl.n_tile + 31) / 32 * 32;
     pl.pointwise = pointwise;
     const long long Qtot = (long long)B * (H + P) * Wp;
     if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
@@ -511,7 +549,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             const size_t tap_bytes = (size_t)planes * pl.n_tile * ROW_BYTES;
             int tb = 1, b_stages = 0, ring_bytes = 0, stg_off = 0, bar_off = 0;
             size_t smem = 0;
-            const bool row_stage = !tile_outer && KW > 1 && tap_bytes * KW <= 40 * 1024;
+            const bool row_stage = !tile_outer && n_groups > 1 && KW > 1 && tap_bytes * KW <= 40 * 1024 && !pl.nstack;
             for (int want = row_stage ? 2 : 4; want >= 2; --want) {
                 tb = row_stage ? KW : 1;
                 int bs = want;
@@ -750,7 +788,7 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
 
 // developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][16]
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
-int tpgsr_conv2d_flat_set_debug_skip(int bits) { g_flat_dbg_skip = bits; return TPGSR_OK; }
+int tpgsr_conv2d_flat_set_debug_skip(int bits) { g_flat_dbg_skip = bits & 3; g_flat_no_nstack = (bits >> 2) & 1; return TPGSR_OK; }
 
 // tiling decided for a geometry (host-only; lets tests / docs inspect the plan without a GPU):
 // out[13] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer}; returns smem bytes (0 = unsupported)
@@ -806,7 +844,7 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     p.MT = pl.MT; p.n_tile = pl.n_tile; p.tm_stride = pl.tm_stride; p.pointwise = pl.pointwise; p.G = pl.G; p.n_groups = pl.n_groups;
     p.a_stages = pl.a_stages;
     p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
-    p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off;
+    p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off; p.nstack = pl.nstack;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
     p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg; p.dbg_skip = g_flat_dbg_skip;
     p.yp_hi = static_cast<__nv_bfloat16*>(yp_hi); p.yp_lo = static_cast<__nv_bfloat16*>(yp_lo);
