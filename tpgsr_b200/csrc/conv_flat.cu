@@ -381,26 +381,39 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (dbg && e == 0 && lane == 0 && item == 0) dbg[9] = clock64();
                 if (p.dbg_skip & 1) continue;
                 if (p.out_mode == TPGSR_OUT_NHWC) {
-                    if (ncols == cw && (p.ldy & 3) == 0 && ((n0 + c0) & 3) == 0) {
-                        // a lane owns one 16-byte column chunk; 4 (cw = 32) or 8 (cw = 16) rows per iteration
+                    if (ncols == cw && (p.ldy & 3) == 0 && ((n0 + c0) & 3) == 0 && (p.act == TPGSR_ACT_NONE || p.act == TPGSR_ACT_RELU)) {
+                        // a lane owns one 16-byte column chunk; 4 (cw = 32) or 8 (cw = 16) rows per step.  All shuffles, then all shared-memory
+                        // loads, then the (predicated) stores: three batches of independent instructions instead of a branchy dependent loop
+                        // (the loop form cost ~200 cycles per row group, profiles/r01/flat_timeline_v4.log)
                         const int sh = cw == 32 ? 3 : 2;
                         const int lr = lane >> sh, c4 = lane & ((1 << sh) - 1);
-                        const int R = 32 >> sh;
+                        const int R = 32 >> sh, nsteps = 32 / R;               // 8 or 4 steps
                         const float* src = stg + (size_t)lr * STG_PITCH + c4 * 4;
                         float* dcol = p.y + n0 + c0 + c4 * 4;
                         const size_t ldy = (size_t)p.ldy;
-#pragma unroll 4
-                        for (int row = lr; row < 32; row += R, src += (size_t)R * STG_PITCH) {
-                            const int px = __shfl_sync(0xffffffffu, pix, row);
-                            if (px >= 0) {
-                                float4 val = *reinterpret_cast<const float4*>(src);
-                                if (p.act != TPGSR_ACT_NONE) {
-                                    val.x = apply_act(val.x, p.act, slope); val.y = apply_act(val.y, p.act, slope);
-                                    val.z = apply_act(val.z, p.act, slope); val.w = apply_act(val.w, p.act, slope);
+                        int pxs[8];
+                        float4 vals[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) pxs[it] = it < nsteps ? __shfl_sync(0xffffffffu, pix, (lr + it * R) & 31) : -1;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it)
+                            if (it < nsteps) vals[it] = *reinterpret_cast<const float4*>(src + (size_t)it * R * STG_PITCH);
+                        if (p.act == TPGSR_ACT_RELU) {          // (other activations take the generic path below)
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                if (it < nsteps) {
+                                    vals[it].x = fmaxf(vals[it].x, 0.f); vals[it].y = fmaxf(vals[it].y, 0.f);
+                                    vals[it].z = fmaxf(vals[it].z, 0.f); vals[it].w = fmaxf(vals[it].w, 0.f);
                                 }
-                                float4* dst = reinterpret_cast<float4*>(dcol + (size_t)px * ldy);
+                            }
+                        }
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            if (it < nsteps && pxs[it] >= 0) {
+                                float4 val = vals[it];
+                                float4* dst = reinterpret_cast<float4*>(dcol + (size_t)pxs[it] * ldy);
                                 if (p.accumulate) {
-                                    float4 o = *dst;
+                                    const float4 o = *dst;
                                     val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
                                 }
                                 *dst = val;
@@ -412,7 +425,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                         h[u] = __float2bfloat16_rn(f[u]);
                                         l[u] = __float2bfloat16_rn(f[u] - __bfloat162float(h[u]));
                                     }
-                                    const size_t po = (size_t)px * p.Co + n0 + c0 + c4 * 4;
+                                    const size_t po = (size_t)pxs[it] * p.Co + n0 + c0 + c4 * 4;
                                     *reinterpret_cast<uint2*>(p.yp_hi + po) = *reinterpret_cast<uint2*>(h);
                                     if (p.yp_lo) *reinterpret_cast<uint2*>(p.yp_lo + po) = *reinterpret_cast<uint2*>(l);
                                 }
@@ -834,7 +847,8 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
                              void* yp_lo, int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
                              const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream) {
     if (!x_hi || !w_hi || !y || (nprod != 1 && nprod != 3) || (nprod == 3 && (!x_lo || !w_lo))) return TPGSR_ERR_BAD_ARG;
-    if (yp_hi && (Co % 32 != 0 || out_mode != TPGSR_OUT_NHWC || ((ldy > 0 ? ldy : Co) & 3))) return TPGSR_ERR_UNSUPPORTED;
+    if (yp_hi && (Co % 32 != 0 || out_mode != TPGSR_OUT_NHWC || ((ldy > 0 ? ldy : Co) & 3) || (act != TPGSR_ACT_NONE && act != TPGSR_ACT_RELU)))
+        return TPGSR_ERR_UNSUPPORTED;
     FlatPlan pl;
     int rc = plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl);
     if (rc) return rc;
