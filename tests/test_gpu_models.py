@@ -257,7 +257,12 @@ def test_srresnet_tl_config5_vs_golden_and_oracle(shapes):
         if p.numel() == 1:       # PReLU slopes: sums of ~10^6 signed terms
             assert abs(float(p.grad) - float(want[1])) < 1e-2 * abs(float(want[1])) + 1e-4, k
         else:
-            assert_fp_close(fingerprint(p.grad), want, k, rtol=5e-3)
+            # norm / sum at 5e-3; the first 8 elements relative to the tensor's norm (train-mode BN on a 4-image batch amplifies fp32
+            # summation-order differences: single small elements move by a few 1e-4 of the norm between correct implementations)
+            got = fingerprint(p.grad)
+            assert_fp_close(got, want, k, rtol=5e-3, check_head=False)
+            if abs(want[0]) >= 2e-3:
+                assert np.all(np.abs(got[2:] - want[2:]) <= 3e-3 * abs(want[0]) + 2e-5), (k, got[2:], want[2:])
     for k, b in net.named_buffers():
         if 'running_' in k:
             assert_fp_close(fingerprint(b), g['buf/' + k], k, rtol=2e-3)
