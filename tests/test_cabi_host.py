@@ -113,3 +113,40 @@ def test_srcnn_and_srresnet_state_dict_surfaces(shapes):
             net(torch.zeros(1, net.in_planes, 16, 64))          # CPU tensors: no fallback
     with pytest.raises(NotImplementedError):
         SRResNet_TL(STN=True)
+
+
+@pytest.mark.parametrize('nprod', [1, 3])
+def test_flat_conv_plans_fit_the_sm(nprod):
+    """Host-side tiling plans of the padded-flat tcgen05 kernels (no GPU needed): shared memory <= 227 KB, TMEM <= 512 columns, every
+    output row covered, for every geometry the TSRN / CRNN / SRResNet paths send through them."""
+    import ctypes
+    from tpgsr_b200._lib import LIB
+    geoms = [  # B, H, W, P, Ci, Co, KH, KW
+        (48, 16, 64, 1, 64, 64, 3, 3), (2, 16, 64, 1, 64, 64, 3, 3), (48, 16, 64, 0, 64, 64, 1, 1), (48, 16, 64, 0, 64, 192, 1, 1),
+        (48, 16, 64, 0, 192, 64, 1, 1), (48, 16, 64, 1, 64, 256, 3, 3), (48, 16, 64, 1, 64, 96, 3, 3), (48, 32, 128, 4, 64, 36, 9, 1),
+        (48, 32, 128, 4, 64, 64, 9, 1), (48, 16, 64, 4, 64, 64, 9, 1), (48, 16, 64, 4, 64, 36, 9, 1), (48, 4, 16, 1, 64, 128, 3, 3),
+        (48, 16, 50, 1, 64, 128, 3, 3), (1248, 1, 1, 0, 512, 2048, 1, 1), (48, 1, 1, 0, 512, 40, 1, 1), (384, 16, 64, 1, 64, 64, 3, 3),
+        (1, 5, 17, 1, 64, 64, 3, 3),
+    ]
+    for (B, H, W, P, Ci, Co, KH, KW) in geoms:
+        out = (ctypes.c_int * 13)()
+        smem = LIB.tpgsr_conv2d_flat_plan(B, H, W, P, Ci, Co, KH, KW, KH // 2, KW // 2, nprod, out)
+        assert 0 < smem <= 227 * 1024, ((B, H, W, P, Ci, Co, KH, KW), smem)
+        MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer = list(out)
+        assert 1 <= MT <= 3 and MT * tm_stride <= 512 and n_tile % 16 == 0 and n_tile <= 128
+        assert n_tile * n_tiles >= Co and box_rows % 8 == 0 and box_rows <= 256
+        assert n_box * box_rows >= 128 * MT + (G - 1) * (W + P) + (KW - 1)          # the staged window covers every tap of every tile
+        assert grid_x * MT * 128 >= B * (H + P) * (W + P)                           # every flat output row belongs to a tile
+        assert b_stages >= 1 and a_stages >= 1 and (n_groups == 1 or a_stages >= 2)
+        assert bool(LIB.tpgsr_conv2d_flat_supported(B, H, W, P, Ci, Co, KH, KW, KH // 2, KW // 2, nprod))
+    # not supported: channel counts that are no multiple of 64, non-'same' padding
+    assert not LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 1, 96, 64, 3, 3, 1, 1, nprod)
+    assert not LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 1, 64, 64, 3, 3, 0, 0, nprod)
+    for (B, H, W, P, Co, K) in [(48, 16, 64, 1, 64, 3), (48, 16, 64, 0, 192, 1), (48, 16, 64, 1, 256, 3), (48, 32, 128, 4, 36, 9)]:
+        out = (ctypes.c_int * 9)()
+        cpad = (Co + 63) // 64 * 64
+        kw = 1 if K == 9 else K
+        stage = LIB.tpgsr_conv2d_wgrad_flat_plan(B, H, W, P, 64, Co, cpad, K, kw, nprod, out)
+        n_tile, n_tiles, kw_groups, taps, x_rows, stages, total_kb, kb_per_split, splits = list(out)
+        assert stage > 0 and stages >= 2 and stages * stage + 2048 <= 227 * 1024
+        assert taps * n_tile <= 512 and n_tile * n_tiles == cpad and splits * kb_per_split >= total_kb
