@@ -101,6 +101,15 @@ int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_h
                             int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int ph, int pw, int accumulate,
                             int nprod, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* ---- all weight re-packs of a train step in one launch (pack_batched.cu) ---------------------------------------------------------------
+ * The reference re-reads its OIHW weights in every cuDNN call (nn.Conv2d, model/tsrn.py:26-43,376-381,467,495); here the packed operand copies
+ * of tpgsr_pack_conv_weights(_bf16) / tpgsr_kwstack_pack_weights persist across steps and are refreshed after optim.Adam.step()
+ * (interfaces/super_resolution.py:424).  jobs = device table of n_jobs records of tpgsr_pack_job_bytes() bytes each:
+ * { const float* w; void* o0, *o1, *o2, *o3; int kind, Co, Ci, KH, KW, C, narrow_out, transposed, flips, rows; }
+ * kind 0: o0..o3 = fwd hi/lo, dgrad hi/lo (bf16);  kind 1: o0/o1 = wk_fwd / wk_dgrad (fp32);  kind 2: o0/o1 = kw-stacked hi/lo. */
+int tpgsr_pack_job_bytes(void);
+int tpgsr_pack_weights_batched(const void* jobs, int n_jobs, int max_elems, cudaStream_t stream);
+
 /* ---- kw-stacking: 9x9 convs with a 4-channel side (model/tsrn.py:26,43) as 9x1 tensor-core convs on 64-channel operands --------------
  * (kwstack.cu) weight packing for tpgsr_conv2d_flat, the stacked operand split, the shift-and-add epilogue, the wgrad scatter. */
 int tpgsr_kwstack_pack_weights(const float* w_oihw, void* hi, void* lo, int Co, int Ci, int KH, int KW, int narrow_out, int transposed,

@@ -150,3 +150,32 @@ def test_flat_conv_plans_fit_the_sm(nprod):
         n_tile, n_tiles, kw_groups, taps, x_rows, stages, total_kb, kb_per_split, splits = list(out)
         assert stage > 0 and stages >= 2 and stages * stage + 2048 <= 227 * 1024
         assert taps * n_tile <= 512 and n_tile * n_tiles == cpad and splits * kb_per_split >= total_kb
+
+
+def test_pack_store_job_table_layout():
+    """ops.PackStore builds the device table tpgsr_pack_weights_batched reads: record size, field order and grid bound (host logic only)."""
+    import struct
+    import torch
+    from tpgsr_b200 import ops
+    from tpgsr_b200._lib import LIB
+    assert LIB.tpgsr_pack_job_bytes() == struct.calcsize('5Q10i') == 80
+    st = ops.PackStore()
+    w0 = torch.zeros(64, 64, 3, 3)
+    outs0 = tuple(torch.zeros(64, 576, dtype=torch.bfloat16) for _ in range(3)) + (None,)
+    st.add('bf16', 'a', 0, w0, outs0)
+    w1 = torch.zeros(4, 64, 9, 9)
+    outs1 = (torch.zeros(48, 576, dtype=torch.bfloat16), torch.zeros(48, 576, dtype=torch.bfloat16))
+    st.add('bf16', ('a', 'kwstack'), 2, w1, outs1, (4, 1, 0, 2, 48))
+    w2 = torch.zeros(32, 3, 3, 3)
+    st.add('fp32', 'a', 1, w2, (torch.zeros(27, 32), None))          # same name in the other dict: a separate job
+    st._build()
+    assert st._n == 3 and st._max == 64 * 64 * 9
+    raw = bytes(st._table.numpy().tobytes())
+    recs = [struct.unpack_from('5Q10i', raw, 80 * i) for i in range(3)]
+    assert recs[0][0] == w0.data_ptr() and recs[0][1:5] == (outs0[0].data_ptr(), outs0[1].data_ptr(), outs0[2].data_ptr(), 0)
+    assert recs[0][5:10] == (0, 64, 64, 3, 3)
+    assert recs[1][5:15] == (2, 4, 64, 9, 9, 4, 1, 0, 2, 48) and recs[1][3:5] == (0, 0)
+    assert recs[2][5:10] == (1, 32, 3, 3, 3) and recs[2][2] == 0
+    # re-registering a key replaces its job and invalidates the table
+    st.add('fp32', 'a', 1, w2, (torch.zeros(27, 32), torch.zeros(288, 3)))
+    assert st._table is None and len(st.jobs) == 3

@@ -23,15 +23,18 @@ class Ctx:
     """Parameter / gradient resolver for one forward(+backward) pass of one module."""
 
     def __init__(self, params: Dict[str, Tensor], grads: Optional[Dict[str, Tensor]], training: bool,
-                 need_input_grad: bool = False, share: Optional['Ctx'] = None):
+                 need_input_grad: bool = False, share: Optional['Ctx'] = None, store: Optional['ops.PackStore'] = None):
         self.params = params          # name -> tensor (parameters and buffers, reference state_dict names + fused views)
         self.grads = grads            # name -> tensor (same names as params) or None when no backward is wanted
         self.training = training
         self.need_input_grad = need_input_grad
         # a second pass over the same module inside one step (shared SR model in the cascade) reuses the packed weights
         # and the first-write/accumulate bookkeeping of the first pass
-        self._packed: Dict[str, tuple] = share._packed if share is not None else {}
-        self._packed_bf16: Dict[str, tuple] = share._packed_bf16 if share is not None else {}
+        # (with a PackStore the packed weights outlive the step: the train step refreshes them after the optimiser, see ops.PackStore)
+        self.store = share.store if share is not None else store
+        self._packed: Dict[str, tuple] = share._packed if share is not None else (store.fp32 if store is not None else {})
+        self._packed_bf16: Dict[str, tuple] = share._packed_bf16 if share is not None else (store.bf16 if store is not None else {})
+        self._derived: Dict[str, tuple] = share._derived if share is not None else {}     # per-step operands computed FROM weights
         self._planes: Dict[int, tuple] = {}
         self._written = share._written if share is not None else set()
         # gradient side work (weight gradients, bias sums, GRU dW_hh) is queued on a second stream and runs concurrently with the
@@ -97,8 +100,13 @@ class Ctx:
         key = (name, 'kwstack', narrow_out, transposed, flip_kh, flip_kw)
         hit = self._packed_bf16.get(key)
         if hit is None:
-            hit = ops.kwstack_pack(self.params[name], narrow_out, transposed, flip_kh, flip_kw, ops.CONV_MODE == 'bf16x3')
+            w = self.params[name]
+            hit = ops.kwstack_pack(w, narrow_out, transposed, flip_kh, flip_kw, ops.CONV_MODE == 'bf16x3')
             self._packed_bf16[key] = hit
+            if self.store is not None:
+                Co, Ci, _, _ = w.shape
+                narrow = (Ci if transposed else Co) if narrow_out else (Co if transposed else Ci)
+                self.store.add('bf16', key, 2, w, hit, (narrow, narrow_out, transposed, int(flip_kh) | int(flip_kw) << 1, hit[0].shape[0]))
         return hit
 
     def planes_padded(self, x: Tensor, c_out: int):
@@ -119,6 +127,8 @@ class Ctx:
                 w = w.view(w.shape[0], w.shape[1], 1, 1)
             hit = ops.pack_conv_weights_bf16(w, self.grads is not None, ops.CONV_MODE == 'bf16x3')
             self._packed_bf16[name] = hit
+            if self.store is not None:
+                self.store.add('bf16', name, 0, w, hit[0] + hit[1])
         return hit
 
     def packed(self, name: str, need_dgrad: bool = True, as4d=None):
@@ -132,6 +142,8 @@ class Ctx:
                 w = w.view(w.shape[0], w.shape[1], 1, 1)
             hit = ops.pack_conv_weights(w, need_dgrad)
             self._packed[key] = hit
+            if self.store is not None:
+                self.store.add('fp32', key, 1, w, hit)
         return hit
 
 
@@ -297,12 +309,12 @@ def bn_bwd(ctx: Ctx, saved, dy: Tensor, lddy: int = 0) -> Tensor:
 def _gru_proj_fused(ctx: Ctx, pre: str):
     """Packed bf16 operands of W_c = W_ih W_1x1 (and b_c = W_ih b_1x1 + b_ih), cached per step: ((fwd planes), (dgrad planes), b_c)."""
     key = pre + 'gru.fused'
-    hit = ctx._packed_bf16.get(key)
+    hit = ctx._derived.get(key)
     if hit is None:
         wc, bc = ops.fuse_linear(ctx.P(pre + 'gru.weight_ih'), ctx.P(pre + 'gru.bias_ih'), ctx.P(pre + 'conv1.weight'), ctx.P(pre + 'conv1.bias'))
         f, d = ops.pack_conv_weights_bf16(wc.view(wc.shape[0], wc.shape[1], 1, 1), ctx.grads is not None, ops.CONV_MODE == 'bf16x3')
         hit = (f, d, bc)
-        ctx._packed_bf16[key] = hit
+        ctx._derived[key] = hit
     return hit
 
 

@@ -362,6 +362,61 @@ def kwstack_pack(w: torch.Tensor, narrow_out: bool, transposed: bool, flip_kh: b
     return hi, lo
 
 
+# ---- persistent packed weights (train steps): filled by the per-weight kernels above during the first step, then refreshed after every
+# optimiser step by ONE launch of tpgsr_pack_weights_batched (pack_batched.cu) ----
+PREPACK = os.environ.get('TPGSR_PREPACK', '0') != '0'
+
+
+class PackStore:
+    """Packed operand copies of a module's weights that outlive one ``engine.Ctx``.
+
+    ``bf16`` / ``fp32`` are the dicts a Ctx caches its packs in; with a store they are shared by every Ctx of the train step, so only the
+    first step launches the per-weight pack kernels.  Each miss also registers a job (source view, outputs, geometry); ``refresh()`` re-packs
+    all registered weights in one launch — the train step calls it after Adam (the packed copies follow the weights) and whenever the
+    parameters are changed from outside."""
+
+    def __init__(self):
+        self.bf16 = {}
+        self.fp32 = {}
+        self.jobs = {}          # (dict id, key) -> (kind, w, outs, geometry)
+        self._table = None
+        self._n = 0
+        self._max = 0
+
+    def add(self, which: str, key, kind: int, w: torch.Tensor, outs, extra=(0, 0, 0, 0, 0)) -> None:
+        self.jobs[(which, key)] = (kind, w, tuple(outs), tuple(int(e) for e in extra))
+        self._table = None
+
+    def _build(self) -> None:
+        import struct
+        size = LIB.tpgsr_pack_job_bytes()
+        fmt = '5Q10i'
+        if struct.calcsize(fmt) != size:
+            raise RuntimeError(f'PackJob layout mismatch: library says {size} bytes, host packs {struct.calcsize(fmt)}')
+        blob = bytearray()
+        dev, mx = None, 1
+        for kind, w, outs, extra in self.jobs.values():
+            Co, Ci, KH, KW = w.shape
+            if not w.is_contiguous():
+                raise RuntimeError('PackStore: weight views must be contiguous')
+            o = [ptr(t) or 0 for t in outs] + [0] * (4 - len(outs))
+            blob += struct.pack(fmt, w.data_ptr(), *o, kind, Co, Ci, KH, KW, *extra)
+            mx = max(mx, (extra[4] * KH * 64) if kind == 2 else Co * Ci * KH * KW)
+            dev = w.device
+        self._n, self._max = len(self.jobs), mx
+        self._table = torch.frombuffer(blob, dtype=torch.uint8).clone().to(dev) if self._n else None
+
+    def refresh(self) -> None:
+        """Re-pack every registered weight from its current values (one launch on the current stream; graph-capturable)."""
+        if not self.jobs:
+            return
+        if self._table is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('PackStore: the job table must be built before graph capture (run one eager step first)')
+            self._build()
+        _call('tpgsr_pack_weights_batched', ptr(self._table), self._n, self._max, stream())
+
+
 def kwstack_split(x: torch.Tensor, KW: int, pw: int, P: int, sign: int, need_lo: bool = True) -> FlatPlanes:
     """fp32 NHWC [B,H,W,C] (C*KW <= 64) -> stacked padded-flat planes [B][H+P][W+P][64], channel kw*C+i = x[.., c + sign*(kw-pw), i]."""
     B, H, W, C = x.shape

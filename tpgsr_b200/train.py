@@ -40,12 +40,19 @@ class TSRNTrainStep:
         self.use_graph = use_graph
         self._g_fb = None
         self._g_opt = None
+        # packed weight operands persist across steps and are refreshed by one launch after Adam (ops.PackStore)
+        self.packs = ops.PackStore() if ops.PREPACK else None
         ops.prime_workspaces(256 << 20, dev)
 
     # ---- step pieces ------------------------------------------------------------------------------------------------
+    def refresh_packs(self) -> None:
+        """Call after changing the model's parameters from outside the step (load_state_dict, manual edits)."""
+        if self.packs is not None:
+            self.packs.refresh()
+
     def _fwd_bwd(self):
         m, st = self.model, self.st
-        ctx = engine.Ctx(st.views, st.gviews, True)
+        ctx = engine.Ctx(st.views, st.gviews, True, store=self.packs)
         if st.nbt is not None:
             ops.add_i64(st.nbt, 1)
         sr, saved = engine.tsrn_fwd(ctx, self.lr_buf, m.stn, m.srb_nums, None)
@@ -57,6 +64,7 @@ class TSRNTrainStep:
 
     def _optim(self):
         self.opt.step(1.0 / self.world)
+        self.refresh_packs()
 
     def _capture(self):
         s = torch.cuda.Stream(device=self.dev)
@@ -75,6 +83,7 @@ class TSRNTrainStep:
                 self.st.views[k].copy_(v)
             if snap[5] is not None:
                 self.st.nbt.copy_(snap[5])
+            self.refresh_packs()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self._g_fb = torch.cuda.CUDAGraph()
@@ -155,6 +164,12 @@ class TPGSRTrainStep:
         self.use_graph = use_graph
         self._g_fb = None
         self._g_opt = None
+        # packed weight operands persist across steps (ops.PackStore): SR model and students are refreshed by one launch each after Adam,
+        # the frozen teacher's are computed once
+        self.packs = {}
+        if ops.PREPACK:
+            self.packs = {'teacher': ops.PackStore(), 'sr': ops.PackStore()}
+            self.packs.update({('stu', i): ops.PackStore() for i in range(len(self.students))})
         ops.prime_workspaces(256 << 20, self.dev)
 
     def _fwd_bwd(self):
@@ -164,7 +179,7 @@ class TPGSRTrainStep:
         drop = B // 4
         st_sr = m._flat
         # ---- teacher prior (eval mode, no grad)
-        tctx = engine.Ctx(self.teacher._flat.views, None, False)
+        tctx = engine.Ctx(self.teacher._flat.views, None, False, store=self.packs.get('teacher'))
         gray_hr = ops_prior.bicubic_gray_fwd(self.hr_buf)
         logits_hr, _ = crnn_engine.crnn_fwd(tctx, gray_hr)
         label_hr, _ = ops_prior.softmax_prior_fwd(logits_hr, 0, need_prior=False)
@@ -177,7 +192,7 @@ class TPGSRTrainStep:
         for i in range(self.stu_iter):
             si = 0 if self.tpg_share else i
             stu = self.students[si]
-            sctx = engine.Ctx(stu._flat.views, stu._flat.gviews, True, share=stu_ctx.get(si))
+            sctx = engine.Ctx(stu._flat.views, stu._flat.gviews, True, share=stu_ctx.get(si), store=self.packs.get(('stu', si)))
             stu_ctx.setdefault(si, sctx)
             if stu._flat.nbt is not None:
                 ops.add_i64(stu._flat.nbt, 1)
@@ -187,7 +202,7 @@ class TPGSRTrainStep:
             if self.use_distill:
                 ops.semantic_loss_fwd(probs, label_hr, 100.0, loss=self.loss_distill, accumulate=not first_dis)
                 first_dis = False
-            ctx = engine.Ctx(st_sr.views, st_sr.gviews, True, share=sr_ctx0)
+            ctx = engine.Ctx(st_sr.views, st_sr.gviews, True, share=sr_ctx0, store=self.packs.get('sr'))
             sr_ctx0 = sr_ctx0 or ctx
             if st_sr.nbt is not None:
                 ops.add_i64(st_sr.nbt, 1)
@@ -217,10 +232,17 @@ class TPGSRTrainStep:
         ops.join_side(self.dev)          # side-stream weight gradients are complete before the graph / the all-reduce continues
         self.sr = stages[-1][6]
 
+    def refresh_packs(self, teacher: bool = True) -> None:
+        """Call after changing any module's parameters from outside the step (load_state_dict, manual edits)."""
+        for k, st in self.packs.items():
+            if teacher or k != 'teacher':
+                st.refresh()
+
     def _optim(self):
         self.opt_sr.step(1.0 / self.world)
         for o in self.opt_stu:
             o.step(1.0 / self.world)
+        self.refresh_packs(teacher=False)        # the teacher is frozen: its packed weights are computed once
 
     def _all_reduce(self):
         if self.world > 1:
@@ -245,6 +267,7 @@ class TPGSRTrainStep:
                     m._flat.views[k].copy_(v)
                 if sn[5] is not None:
                     m._flat.nbt.copy_(sn[5])
+            self.refresh_packs(teacher=False)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self._g_fb = torch.cuda.CUDAGraph()
