@@ -230,8 +230,14 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
+        # rank 0 must print exactly one JSON line on stdout, and NCCL logs there (its version banner at any NCCL_DEBUG level, WARN included):
+        # send NCCL's log to stderr, drop the debug level, and park stdout on stderr until the JSON line is ready
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         if not os.environ.get('TPGSR_KEEP_NCCL_DEBUG'):
-            os.environ['NCCL_DEBUG'] = 'WARN'      # NCCL_DEBUG=VERSION/INFO prints to stdout; rank 0 must print exactly one JSON line
+            os.environ.pop('NCCL_DEBUG', None)
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
     from tpgsr_b200 import ops
     from tpgsr_b200.model.tsrn import TSRN
@@ -325,8 +331,13 @@ def run_ours(args):
         ips, sec_cpu = cpu_port_images_per_s(12, 2, 1, threads)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cpu_port_images_per_s.threads_used, 'host_cpus': threads, 'kind': 'port',
                                 'sample': '2 timed steps of 12 images (1/4 batch) of the same train step, oracle port, torch CPU fp32'}
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)                     # anything NCCL says while shutting down goes to stderr as well
         torch.distributed.destroy_process_group()
 
 
