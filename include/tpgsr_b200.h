@@ -259,6 +259,11 @@ int tpgsr_adam_step(float* params, const float* grads, float* exp_avg, float* ex
                     cudaStream_t stream);
 int tpgsr_scale_inplace(float* x, long n, const float* coef, float s, cudaStream_t stream);
 
+/* ---- eval tail: CTC greedy decode (ctc.cu) — utils/metrics.py:71-88 get_string_crnn (argmax over classes -> collapse repeats -> drop blank 0),
+ * called on every recogniser output in TextSR.eval (interfaces/super_resolution.py:855,920,995,1022-1023).  logits [T][B][C] fp32;
+ * ids [B][T] int32 (decoded class indices, -1 padded), lens [B] int32.  Ties -> lowest class index. */
+int tpgsr_ctc_greedy_decode(const float* logits, int T, int B, int C, int* ids, int* lens, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,3 +269,19 @@ def test_srresnet_tl(shapes):
                 p2[k] = p[k].detach().clone()
         assert rel_err(models.srresnet_tl(T(g['lr']), p2, False, T(g['prior'])), g['sr_eval']) < 2e-5
         assert rel_err(models.srresnet_tl(T(g['lr']), p2, False, None), g['sr_eval_noprior']) < 2e-5
+
+
+def test_ctc_greedy_decode_and_str_filt():
+    """oracle/ctc.py against the strings the reference's own get_string_crnn / str_filt produced (utils/metrics.py:71-88, utils/util.py:12-24)."""
+    from oracle import ctc
+    g = load_golden('ctc_decode')
+    for case in ('crnn', 'noise', 'long', 't1', 'edge'):
+        x = g['x/' + case]
+        want = [str(s) for s in g['s/' + case]]
+        assert ctc.get_string_crnn(x) == want, case
+        ids, lens = ctc.greedy_ids(x)
+        assert ids.shape == (x.shape[1], x.shape[0]) and (ids[np.arange(ids.shape[1])[None, :] >= lens[:, None]] == -1).all()
+    assert [str(s) for s in g['s/edge']] == ['', '4', 'aaaa', 'z0', '', '21']
+    labels = [str(s) for s in g['labels']]
+    for voc in ('digit', 'lower', 'upper', 'all'):
+        assert [ctc.str_filt(s, voc) for s in labels] == [str(s) for s in g['filt/' + voc]], voc
