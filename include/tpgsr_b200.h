@@ -264,6 +264,14 @@ int tpgsr_scale_inplace(float* x, long n, const float* coef, float s, cudaStream
  * ids [B][T] int32 (decoded class indices, -1 padded), lens [B] int32.  Ties -> lowest class index. */
 int tpgsr_ctc_greedy_decode(const float* logits, int T, int B, int C, int* ids, int* lens, cudaStream_t stream);
 
+/* ---- input pipeline: resizeNormalize.__call__ (dataset/dataset.py:615-632) for a batch of ragged RGB crops (resize_input.cu) -----------------
+ * img.resize((W,H), Image.BICUBIC) -> ToTensor -> optional mask channel (convert('L'), 0 if x > mean else 255), bit-identical to Pillow's 8-bit
+ * resampler.  src = the crops' bytes back to back ([h][w][3] uint8 each), offsets[b] = byte offset of crop b relative to src, hs/ws = crop sizes
+ * (device memory); max_h/max_w = host-known upper bounds of hs/ws; out = [B][3+mask][H][W] fp32; workspace = B*max_h*W*3 bytes. */
+size_t tpgsr_resize_normalize_workspace_bytes(int B, int max_h, int W);
+int tpgsr_resize_normalize(const unsigned char* src, const long long* offsets, const int* hs, const int* ws, int B, int max_h, int max_w, int H,
+                           int W, int mask, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,69 @@
+"""GPU parity of the input transform: resizeNormalize for ragged batches through the C ABI, bit-exact against the fixture
+recorded from the reference's own class (Pillow bicubic + ToTensor + mean-threshold mask) and against the oracle (oracle/resize.py).
+(File name sorts last on purpose: the newest rows run after the hot-path suites.)"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+@pytest.mark.parametrize('tag,size', [('hr', (128, 32)), ('lr', (64, 16))])
+@pytest.mark.parametrize('mask', [False, True])
+def test_resize_normalize_matches_reference_fixture_bitwise(tag, size, mask):
+    from tpgsr_b200.dataset import resizeNormalize
+    g = load_golden('resize_normalize')
+    crops = [g[f'x/{i}'] for i in range(int(g['n']))]
+    want = g[f'y/{tag}/{int(mask)}'].astype(np.float32) / np.float32(255)
+    tf = resizeNormalize(size, mask)
+    got = tf.batch(crops).cpu().numpy()
+    assert got.shape == want.shape and got.dtype == np.float32
+    bad = [i for i in range(len(crops)) if not np.array_equal(got[i], want[i])]
+    assert not bad, (bad, [crops[i].shape for i in bad])
+    one = tf(crops[5]).cpu().numpy()                       # the reference's per-image call
+    assert np.array_equal(one, want[5])
+
+
+def test_resize_normalize_ragged_batch_vs_oracle_and_properties():
+    from oracle import resize
+    from tpgsr_b200.dataset import resizeNormalize
+    r = np.random.RandomState(9)
+    crops = [(r.rand(r.randint(1, 80), r.randint(1, 260), 3) * 255).astype(np.uint8) for _ in range(46)]
+    crops.append((r.rand(8, 3000, 3) * 255).astype(np.uint8))          # 23x horizontal reduction: weight tables beyond 48 KB of shared memory
+    crops.append((r.rand(32, 128, 3) * 255).astype(np.uint8))          # already at the target size: both passes skipped
+    tf = resizeNormalize((128, 32), True)
+    got = tf.batch(crops).cpu().numpy()
+    for i, c in enumerate(crops):
+        assert np.array_equal(got[i], resize.resize_normalize(c, (128, 32), True)), (i, c.shape)
+    assert np.array_equal(got[-1, :3], crops[-1].transpose(2, 0, 1).astype(np.float32) / np.float32(255))
+    assert set(np.unique(got[:, 3])) <= {0.0, 1.0} and got[:, :3].min() >= 0.0 and got[:, :3].max() <= 1.0
+    # batch composition does not matter (tables are sized by the largest crop of the batch, results must not depend on it)
+    again = tf.batch(crops[:7]).cpu().numpy()
+    assert np.array_equal(again, got[:7])
+
+
+def test_resize_normalize_host_surface():
+    from tpgsr_b200 import ops
+    from tpgsr_b200._lib import TpgsrError
+    from tpgsr_b200.dataset import resizeNormalize
+    tf = resizeNormalize((64, 16), False)
+    assert tuple(tf.batch([]).shape) == (0, 3, 16, 64)
+    with pytest.raises(ValueError):
+        tf.batch([np.zeros((4, 4), dtype=np.uint8)])
+    with pytest.raises(ValueError):
+        tf.batch([np.zeros((4, 4, 3), dtype=np.float32)])
+    with pytest.raises(NotImplementedError):
+        resizeNormalize((64, 16), False, interpolation=2)
+    # C ABI: a scratch buffer that is too small is refused, not overrun
+    src = torch.zeros(64, dtype=torch.uint8, device=_dev())
+    meta = torch.zeros(4, dtype=torch.int64, device=_dev())
+    out = torch.empty(3 * 16 * 64, device=_dev())
+    with pytest.raises(TpgsrError):
+        ops._call('tpgsr_resize_normalize', src.data_ptr(), meta.data_ptr(), meta.data_ptr(), meta.data_ptr(), 1, 4, 4, 16, 64, 0, out.data_ptr(),
+                  None, 0, ops.stream())

@@ -285,3 +285,26 @@ def test_ctc_greedy_decode_and_str_filt():
     labels = [str(s) for s in g['labels']]
     for voc in ('digit', 'lower', 'upper', 'all'):
         assert [ctc.str_filt(s, voc) for s in labels] == [str(s) for s in g['filt/' + voc]], voc
+
+
+def test_resize_normalize_bit_exact():
+    """oracle/resize.py against what the reference's own resizeNormalize (dataset/dataset.py:615-632, Pillow + ToTensor) produced — bit-exact —
+    and, when Pillow is importable, against Pillow directly on further seeded sizes (the restated algorithm lives in that dependency)."""
+    from oracle import resize
+    g = load_golden('resize_normalize')
+    n = int(g['n'])
+    for tag, size in (('hr', (128, 32)), ('lr', (64, 16))):
+        for mask in (0, 1):
+            want = g[f'y/{tag}/{mask}'].astype(np.float32) / np.float32(255)
+            for i in range(n):
+                got = resize.resize_normalize(g[f'x/{i}'], size, bool(mask))
+                assert got.dtype == np.float32 and np.array_equal(got, want[i]), (tag, mask, i)
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    r = np.random.RandomState(5)
+    for _ in range(40):
+        a = (r.rand(r.randint(1, 70), r.randint(1, 220), 3) * 255).astype(np.uint8)
+        for size in ((128, 32), (64, 16), (100, 32)):
+            assert np.array_equal(resize.resize_bicubic_u8(a, size), np.array(Image.fromarray(a, 'RGB').resize(size, Image.BICUBIC)))
