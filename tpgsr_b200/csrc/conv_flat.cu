@@ -511,8 +511,11 @@ struct FlatPlan {
 long long* g_flat_dbg = nullptr;
 int g_flat_dbg_skip = 0;
 int g_flat_no_nstack = 0;
+int g_flat_occ2 = 0;      // experimental: plan for two co-resident CTAs per SM (see plan_flat)
 
-int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
+// budget: dynamic shared memory a CTA may use; tmem_max: TMEM columns it may allocate; slots: CTAs resident on the GPU at once
+int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, size_t budget, int tmem_max, int slots,
+                  FlatPlan& pl) {
     if (Co < 1 || B < 1 || H < 1 || W < 1 || Ci < 64 || Ci % 64 != 0) return TPGSR_ERR_UNSUPPORTED;
     const int pointwise = (KH == 1 && KW == 1) ? 1 : 0;
     if (!pointwise && Ci != 64) return TPGSR_ERR_UNSUPPORTED;
@@ -529,7 +532,6 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
     pl.pointwise = pointwise;
     const long long Qtot = (long long)B * (H + P) * Wp;
     if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
-    const size_t budget = 226 * 1024;          // of the 227 KB a CTA may use
     // candidate configurations, best first: whole kernel resident (G = KH) with MT = 3, 2, 1; then one kernel row per stage
     // among the feasible MT the one with the fewest (waves x tiles per CTA) wins; near-ties go to the larger MT (less weight traffic)
     const long long tiles = (Qtot + TILE_M - 1) / TILE_M;
@@ -537,7 +539,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
         if (pass == 1 && (KH == 1 || pointwise)) break;
         long long best_cost = -1;
         for (int MT = 3; MT >= 1; --MT) {
-            if (MT * pl.tm_stride > 512) continue;
+            if (MT * pl.tm_stride > tmem_max) continue;
             const int G = pointwise ? 1 : (pass == 0 ? KH : 1);
             const int n_groups = pointwise ? Ci / 64 : KH / G;
             const int rows = TILE_M * MT + (G - 1) * Wp + (KW - 1);
@@ -577,7 +579,7 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
             }
             if (b_stages == 0) continue;
             const long long ctas = (tiles + MT - 1) / MT * pl.n_tiles;
-            const long long cost = ((ctas + 147) / 148) * MT;
+            const long long cost = ((ctas + slots - 1) / slots) * MT;
             if (best_cost >= 0 && cost * 23 >= best_cost * 20) continue;       // a smaller MT must win by > 15%
             best_cost = cost;
             pl.MT = MT; pl.G = G; pl.n_groups = n_groups; pl.a_stages = a_stages; pl.box_rows = box_rows; pl.n_box = n_box;
@@ -588,6 +590,16 @@ int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph
         if (best_cost >= 0) return TPGSR_OK;
     }
     return TPGSR_ERR_UNSUPPORTED;
+}
+
+// One CTA per SM with up to 226 KB of the 227 KB a CTA may use and all 512 TMEM columns — or, experimentally (debug bit 3 /
+// TPGSR_FLAT_OCC2=1), two co-resident CTAs per SM with 112 KB and 256 columns each: smaller tiles per CTA (more halo and weight traffic from
+// L2), but one CTA's loads and epilogue overlap the other's MMAs — the phases that run back to back in the one-CTA plan.
+// The kernel needs 84 registers x 320 threads, so two CTAs fit the register file as it is.  Falls back to the one-CTA plan when a geometry
+// does not fit the halved budget.
+int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
+    if (g_flat_occ2 && plan_flat_for(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 112 * 1024, 256, 2 * 148, pl) == TPGSR_OK) return TPGSR_OK;
+    return plan_flat_for(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 226 * 1024, 512, 148, pl);
 }
 
 // ============================================================================================================ weight gradient
@@ -801,7 +813,13 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
 
 // developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][16]
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
-int tpgsr_conv2d_flat_set_debug_skip(int bits) { g_flat_dbg_skip = bits & 3; g_flat_no_nstack = (bits >> 2) & 1; return TPGSR_OK; }
+// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes; bit 3: plan for two CTAs per SM (experimental)
+int tpgsr_conv2d_flat_set_debug_skip(int bits) {
+    g_flat_dbg_skip = bits & 3;
+    g_flat_no_nstack = (bits >> 2) & 1;
+    g_flat_occ2 = (bits >> 3) & 1;
+    return TPGSR_OK;
+}
 
 // tiling decided for a geometry (host-only; lets tests / docs inspect the plan without a GPU):
 // out[13] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer}; returns smem bytes (0 = unsupported)

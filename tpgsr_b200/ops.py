@@ -262,6 +262,11 @@ FLAT = os.environ.get('TPGSR_FLAT', '1') != '0'
 # '0' = never.  Measured on B200 (round 1): in training the fused path is neutral (5.77 vs 5.70 ms/step) — the backward pass has to
 # recompute the 1x1 output for dW_ih, which costs what the forward pass saves — so it is kept for inference only.
 FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', 'infer')
+# EXPERIMENTAL, not measured yet (written after round 1's GPU minutes were spent): tile the flat convs for two co-resident CTAs per SM
+# (112 KB of shared memory, 256 TMEM columns each) so that one CTA's loads / epilogue overlap the other's MMAs.  Off by default.
+FLAT_OCC2 = os.environ.get('TPGSR_FLAT_OCC2', '0') != '0'
+if FLAT_OCC2:
+    LIB.tpgsr_conv2d_flat_set_debug_skip(8)
 
 
 class FlatPlanes:
