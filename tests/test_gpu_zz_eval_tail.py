@@ -76,3 +76,20 @@ def test_ctc_decode_host_surface():
     with pytest.raises(ValueError):
         get_string_crnn(x, alphabet='-aab' + 'c' * 33)
     assert str_filt('Hello, World!', 'lower') == 'helloworld'
+
+
+def test_psnr_ssim_cache_is_not_fooled_by_recycled_addresses():
+    """cal_psnr(sr, hr); cal_ssim(sr, hr) share one launch, but the next batch — new tensors that the caching allocator puts on the same
+    addresses — must be recomputed."""
+    from tpgsr_b200.utils.ssim_psnr import SSIM, calculate_psnr
+    g = torch.Generator(device='cpu').manual_seed(1)
+    seen = []
+    for it in range(3):
+        a = torch.rand(4, 4, 32, 128, generator=g).to(_dev())
+        b = (a * (0.9 - 0.2 * it) + 0.03).clamp(0, 1)
+        p, s = float(calculate_psnr(a, b)), float(SSIM()(a, b))
+        mse = float((((a[:, :3] * 255) - (b[:, :3] * 255)) ** 2).mean())
+        assert abs(p - 20 * np.log10(255.0 / np.sqrt(mse))) < 1e-2, (it, p)
+        seen.append((p, s))
+        del a, b
+    assert len({round(p, 3) for p, _ in seen}) == 3 and len({round(s, 5) for _, s in seen}) == 3

@@ -5,6 +5,8 @@ Same call surface as the reference (``interfaces/base.py:230-231`` binds ``cal_p
 device tensor.  One launch computes both metrics; the second call on the same pair is served from a one-entry cache."""
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch import nn
 
@@ -19,16 +21,18 @@ def _both(img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
         raise RuntimeError('tpgsr_b200 metrics run on CUDA only — there is no CPU fallback')
     if img1.shape != img2.shape or img1.dim() != 4 or img1.shape[1] < 3:
         raise ValueError(f'expected two NCHW batches with >= 3 channels, got {tuple(img1.shape)} and {tuple(img2.shape)}')
-    key = (img1.data_ptr(), img2.data_ptr(), img1._version, img2._version, tuple(img1.shape))
-    hit = _last.get('key')
-    if hit == key:
-        return _last['out']
+    # one-entry cache for the reference's call pattern cal_psnr(sr, hr); cal_ssim(sr, hr) on the SAME tensor objects
+    # (interfaces/super_resolution.py:1011-1012).  Identity + version, not addresses: the next batch's tensors usually land on the same
+    # addresses with the same version counter, and must not be served the previous batch's result.
+    hit = _last.get('hit')
+    if hit is not None and hit[0]() is img1 and hit[1]() is img2 and hit[2] == (img1._version, img2._version):
+        return hit[3]
     a, b = img1.detach().float(), img2.detach().float()
     B, _, H, W = a.shape
     out = torch.empty(2, dtype=torch.float32, device=a.device)
     wp, wn = workspace(query('tpgsr_psnr_ssim_workspace_bytes', B, 3), a.device)
     _call('tpgsr_psnr_ssim', ptr(a), ptr(b), B, 3, H, W, *a.stride(), *b.stride(), ptr(out), wp, wn, stream())
-    _last['key'], _last['out'] = key, out
+    _last['hit'] = (weakref.ref(img1), weakref.ref(img2), (img1._version, img2._version), out)
     return out
 
 
