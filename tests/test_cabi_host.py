@@ -115,7 +115,7 @@ def test_srcnn_and_srresnet_state_dict_surfaces(shapes):
         SRResNet_TL(STN=True)
 
 
-@pytest.mark.parametrize('nprod', [1, 3])
+@pytest.mark.parametrize('nprod', [1, 2, 3])
 def test_flat_conv_plans_fit_the_sm(nprod):
     """Host-side tiling plans of the padded-flat tcgen05 kernels (no GPU needed): shared memory <= 227 KB, TMEM <= 512 columns, every
     output row covered, for every geometry the TSRN / CRNN / SRResNet paths send through them."""

@@ -17,7 +17,8 @@
 // The weight gradient uses the same planes: dW_tap[ci][co] = sum_q X[q + shift(tap)][ci] * dY[q][co] is a plain GEMM over ALL rows
 // (pads contribute zeros), both operands MN-major straight from the planes, the X window shared by the KW taps of one kernel row.
 //
-// Precision modes as in conv_tc.cu: NPROD = 3 (hi*hi + hi*lo + lo*hi, fp32-class) or 1 (bf16).
+// Precision modes as in conv_tc.cu: NPROD = 3 (hi*hi + hi*lo + lo*hi, fp32-class) or 1 (bf16); NPROD = 2 (A one plane, B hi + lo:
+// A_hi*B_hi + A_hi*B_lo) is the experimental data-gradient mode (dY rounded to bf16 once, exact weights).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
@@ -125,11 +126,13 @@ struct FlatConvParams {
 template <int NPROD, int FIRST>
 __device__ __forceinline__ void mma_tap(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc) {
     if (FIRST) umma_lo<0>(d, ah, bh, idesc); else umma_lo<1>(d, ah, bh, idesc);
-    if (NPROD == 3) { umma_lo<1>(d, ah, bl, idesc); umma_lo<1>(d, al, bh, idesc); }
+    if (NPROD >= 2) umma_lo<1>(d, ah, bl, idesc);
+    if (NPROD == 3) umma_lo<1>(d, al, bh, idesc);
 #pragma unroll
     for (int k = 1; k < 4; ++k) {          // 16 bf16 = 32 bytes = 2 descriptor units inside the 128-byte swizzle row
         umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
-        if (NPROD == 3) { umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc); umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc); }
+        if (NPROD >= 2) umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc);
+        if (NPROD == 3) umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc);
     }
 }
 
@@ -137,29 +140,31 @@ __device__ __forceinline__ void mma_tap(uint32_t d, uint32_t ah, uint32_t al, ui
 // operand of 2*n_tile rows.  D[:, 0:n] += A_hi B_hi^T and D[:, n:2n] += A_hi B_lo^T in ONE MMA (idesc2, N = 2n), then D[:, 0:n] += A_lo B_hi^T
 // (idesc1).  The epilogue adds the two column halves.  Per K step the A_hi tile is read from shared memory once instead of twice: the MMA
 // phase of an N = 64 conv is shared-memory-bandwidth bound (6 KB per 32-cycle MMA), so this is 112 instead of 144 smem cycles per K step.
-template <int FIRST>
+// NPROD = 2 (A has no lo plane): only the stacked MMA — ONE 128 x 2n x 16 MMA per K step.
+template <int NPROD, int FIRST>
 __device__ __forceinline__ void mma_tap_stacked(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t idesc1, uint32_t idesc2) {
     if (FIRST) umma_lo<0>(d, ah, bh, idesc2); else umma_lo<1>(d, ah, bh, idesc2);
-    umma_lo<1>(d, al, bh, idesc1);
+    if (NPROD == 3) umma_lo<1>(d, al, bh, idesc1);
 #pragma unroll
     for (int k = 1; k < 4; ++k) {
         umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc2);
-        umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc1);
+        if (NPROD == 3) umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc1);
     }
 }
 
-template <int NPROD>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+// OCC = CTAs the register allocation must leave room for per SM (2 only for the experimental two-CTA plan: 320 x 2 threads -> <= 102 registers)
+template <int NPROD, int OCC = 1>
+__global__ void __launch_bounds__(FWD_THREADS, OCC)
 conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, FlatConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int planes = NPROD == 3 ? 2 : 1;
+    constexpr int a_planes = NPROD == 3 ? 2 : 1, b_planes = NPROD >= 2 ? 2 : 1;
     const int a_plane_bytes = p.n_box * p.box_rows * ROW_BYTES;
-    const int a_stage_bytes = planes * a_plane_bytes;
+    const int a_stage_bytes = a_planes * a_plane_bytes;
     const int b_tap_bytes = p.n_tile * ROW_BYTES;                 // one tap, one plane: [n_tile co][64 ci] K-major
     const int b_plane_bytes = p.tb * b_tap_bytes;
-    const int b_stage_bytes = planes * b_plane_bytes;
+    const int b_stage_bytes = b_planes * b_plane_bytes;
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared-space provenance (LDS/STS, not generic LD/ST)
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)p.a_stages * a_stage_bytes;
@@ -183,7 +188,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmA_hi);
         tc::prefetch_tmap(&tmB_hi);
-        if (NPROD == 3) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
+        if (NPROD == 3) tc::prefetch_tmap(&tmA_lo);
+        if (NPROD >= 2) tc::prefetch_tmap(&tmB_lo);
         for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
         for (int t = 0; t < 4; ++t) tc::mbar_init(&tmem_full[t], 1);
@@ -231,7 +237,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         for (int tt = 0; tt < p.tb; ++tt) {
                             const int tap = g * taps_per_group + j * p.tb + tt;
                             tc::tma_load_2d(bst + (size_t)tt * b_tap_bytes, &tmB_hi, &b_full[bs], tap * 64, n0);
-                            if (NPROD == 3)
+                            if (NPROD >= 2)
                                 tc::tma_load_2d(bst + b_plane_bytes + (size_t)tt * b_tap_bytes, &tmB_lo, &b_full[bs], tap * 64, n0);
                         }
                     }
@@ -246,7 +252,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const bool leader = elect_one();
         const uint32_t idesc = tc::idesc_bf16(TILE_M, p.n_tile, 0, 0);
         const uint32_t idesc2 = tc::idesc_bf16(TILE_M, 2 * p.n_tile, 0, 0);
-        const bool stacked = NPROD == 3 && p.nstack;
+        const bool stacked = NPROD >= 2 && p.nstack;
         const uint32_t tile_lo = (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
         uint32_t b_it = 0;
         if (p.tile_outer) {
@@ -268,8 +274,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const uint32_t bl = bh + (b_plane_bytes >> 4);
                     if (leader) {
                         if (stacked) {
-                            if (j == 0) mma_tap_stacked<1>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
-                            else mma_tap_stacked<0>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
+                            if (j == 0) mma_tap_stacked<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
+                            else mma_tap_stacked<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
                         } else if (j == 0) mma_tap<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
                         else mma_tap<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
                         tc::tc_commit(&b_empty[bs]);
@@ -302,9 +308,9 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         uint32_t ah = a_hi0 + row_off, al = a_lo0 + row_off, d = tmem_u;
                         if (stacked) {
                             if (g == 0 && tl == 0) {
-                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<1>(d, ah, al, bh, idesc, idesc2);
+                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<NPROD, 1>(d, ah, al, bh, idesc, idesc2);
                             } else {
-                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<0>(d, ah, al, bh, idesc, idesc2);
+                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<NPROD, 0>(d, ah, al, bh, idesc, idesc2);
                             }
                         } else if (g == 0 && tl == 0) {
                             for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 1>(d, ah, al, bh, bl, idesc);
@@ -355,7 +361,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (p.dbg_skip & 2) continue;
                 if (cw == 32) tc::tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
                 tc::tmem_ld_wait();
-                if (NPROD == 3 && p.nstack) {          // stacked weights: columns [n_tile, 2 n_tile) hold the A_hi B_lo^T partial sums
+                if (NPROD >= 2 && p.nstack) {          // stacked weights: columns [n_tile, 2 n_tile) hold the A_hi B_lo^T partial sums
                     float v2[32];
                     if (cw == 32) tc::tmem_ld_32x32(taddr + (uint32_t)p.n_tile, v2); else tmem_ld_32x16(taddr + (uint32_t)p.n_tile, v2);
                     tc::tmem_ld_wait();
@@ -520,13 +526,13 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
     const int pointwise = (KH == 1 && KW == 1) ? 1 : 0;
     if (!pointwise && Ci != 64) return TPGSR_ERR_UNSUPPORTED;
     if (2 * ph != KH - 1 || 2 * pw != KW - 1 || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
-    const int planes = nprod == 3 ? 2 : 1;
+    const int a_planes = nprod == 3 ? 2 : 1, b_planes = nprod >= 2 ? 2 : 1;
     const int Wp = W + P;
     const int co16 = (Co + 15) / 16 * 16;
     pl.n_tiles = (co16 + 127) / 128;
     pl.n_tile = ((co16 + pl.n_tiles - 1) / pl.n_tiles + 15) / 16 * 16;
     // stacked weight planes (see mma_tap_stacked): bf16x3, N = 2*n_tile <= 128; forces one tap per B stage (hi and lo tiles adjacent)
-    pl.nstack = (nprod == 3 && pl.n_tile <= 64) ? 1 : 0;
+    pl.nstack = (nprod >= 2 && pl.n_tile <= 64) ? 1 : 0;
     if (g_flat_no_nstack) pl.nstack = 0;
     pl.tm_stride = ((pl.nstack ? 2 : 1) * pl.n_tile + 31) / 32 * 32;
     pl.pointwise = pointwise;
@@ -549,8 +555,8 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
             // streamed A groups (one kernel row / channel block per stage): up to 4 stages in flight — with 2 the 9x1 stacked convs waited
             // one L2 round trip per kernel row (profiles/r01: 154 us for the final conv)
             int a_stages = n_groups > 1 ? (n_groups < 4 ? n_groups : 4) : 1;
-            const size_t a_stage_b = (size_t)planes * n_box * box_rows * ROW_BYTES;
-            const size_t b_min = (size_t)2 * planes * pl.n_tile * ROW_BYTES * ((n_groups > 1 && KW > 1) ? KW : 1);
+            const size_t a_stage_b = (size_t)a_planes * n_box * box_rows * ROW_BYTES;
+            const size_t b_min = (size_t)2 * b_planes * pl.n_tile * ROW_BYTES * ((n_groups > 1 && KW > 1) ? KW : 1);
             while (a_stages > 2 && a_stages * a_stage_b + b_min + 4096 > budget) --a_stages;
             const size_t a_bytes = (size_t)a_stages * a_stage_b;
             // B ring: one tap per stage, 4..2 deep (deepest that fits) — or one kernel row of taps per stage, 2 deep, when the
@@ -561,7 +567,7 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
             // only 12 MMAs and the 3-deep ring cannot cover the L2 round trip (90 cycles/MMA vs 63 with the taps outermost, where a
             // stage feeds MT x 12 MMAs); the epilogue it would hide is ~2 us.  Kept in the kernel for geometries with many tiles per CTA.
             const int tile_outer = 0;
-            const size_t tap_bytes = (size_t)planes * pl.n_tile * ROW_BYTES;
+            const size_t tap_bytes = (size_t)b_planes * pl.n_tile * ROW_BYTES;
             int tb = 1, b_stages = 0, ring_bytes = 0, stg_off = 0, bar_off = 0;
             size_t smem = 0;
             const bool row_stage = !tile_outer && n_groups > 1 && KW > 1 && tap_bytes * KW <= 40 * 1024 && !pl.nstack;
@@ -595,8 +601,8 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
 // One CTA per SM with up to 226 KB of the 227 KB a CTA may use and all 512 TMEM columns — or, experimentally (debug bit 3 /
 // TPGSR_FLAT_OCC2=1), two co-resident CTAs per SM with 112 KB and 256 columns each: smaller tiles per CTA (more halo and weight traffic from
 // L2), but one CTA's loads and epilogue overlap the other's MMAs — the phases that run back to back in the one-CTA plan.
-// The kernel needs 84 registers x 320 threads, so two CTAs fit the register file as it is.  Falls back to the one-CTA plan when a geometry
-// does not fit the halved budget.
+// The default build of the kernel takes 128 registers x 320 threads (one CTA per SM); the two-CTA plan launches a second instantiation
+// compiled with __launch_bounds__(320, 2) (<= 102 registers).  Falls back to the one-CTA plan when a geometry does not fit the halved budget.
 int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
     if (g_flat_occ2 && plan_flat_for(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 112 * 1024, 256, 2 * 148, pl) == TPGSR_OK) return TPGSR_OK;
     return plan_flat_for(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 226 * 1024, 512, 148, pl);
@@ -621,7 +627,8 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
                        const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo, FlatWgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int planes = NPROD == 3 ? 2 : 1;
+    // NPROD = 2 (experimental): dY as ONE bf16 plane against X hi + lo — X_hi dY + X_lo dY
+    constexpr int dy_planes = NPROD == 3 ? 2 : 1, x_planes = NPROD >= 2 ? 2 : 1;
     const int kh = blockIdx.y / p.kw_groups, kwg = blockIdx.y % p.kw_groups;
     const int kw0 = kwg * p.taps_per_group;
     const int ntaps = (p.KW - kw0) < p.taps_per_group ? (p.KW - kw0) : p.taps_per_group;
@@ -630,7 +637,7 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
     const int dy_tile_bytes = WG_KB * ROW_BYTES;                  // one 64-channel group of dY rows
     const int dy_plane_bytes = ngroups * dy_tile_bytes;
     const int x_plane_bytes = p.x_rows * ROW_BYTES;
-    const int stage_bytes = planes * (dy_plane_bytes + x_plane_bytes);
+    const int stage_bytes = dy_planes * dy_plane_bytes + x_planes * x_plane_bytes;
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared-space provenance (LDS/STS, not generic LD/ST)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty = full + p.stages;
@@ -647,7 +654,8 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmX_hi);
         tc::prefetch_tmap(&tmD_hi);
-        if (NPROD == 3) { tc::prefetch_tmap(&tmX_lo); tc::prefetch_tmap(&tmD_lo); }
+        if (NPROD >= 2) tc::prefetch_tmap(&tmX_lo);
+        if (NPROD == 3) tc::prefetch_tmap(&tmD_lo);
         for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
@@ -674,10 +682,10 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
                     tc::tma_load_2d(st + gI * dy_tile_bytes, &tmD_hi, &full[s], n0 + gI * 64, qk);
                     if (NPROD == 3) tc::tma_load_2d(st + dy_plane_bytes + gI * dy_tile_bytes, &tmD_lo, &full[s], n0 + gI * 64, qk);
                 }
-                uint8_t* xs = st + planes * dy_plane_bytes;
+                uint8_t* xs = st + dy_planes * dy_plane_bytes;
                 const int xr = qk + (kh - p.ph) * p.Wp + (kw0 - p.pw);
                 tc::tma_load_2d(xs, &tmX_hi, &full[s], 0, xr);
-                if (NPROD == 3) tc::tma_load_2d(xs + x_plane_bytes, &tmX_lo, &full[s], 0, xr);
+                if (NPROD >= 2) tc::tma_load_2d(xs + x_plane_bytes, &tmX_lo, &full[s], 0, xr);
             }
         }
     } else if (warp == 1) {
@@ -692,24 +700,27 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
                 const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
                 // MN-major SWIZZLE_128B: LBO = bytes between 64-element M/N chunks (one chunk for A; dY groups for B), SBO = 1024
                 const uint32_t dy_hi = desc_lo(st, dy_tile_bytes), dy_lo = dy_hi + (dy_plane_bytes >> 4);
-                const uint32_t x_hi = desc_lo(st + planes * dy_plane_bytes, 1024), x_lo = x_hi + (x_plane_bytes >> 4);
+                const uint32_t x_hi = desc_lo(st + dy_planes * dy_plane_bytes, 1024), x_lo = x_hi + (x_plane_bytes >> 4);
                 for (int t = 0; t < ntaps; ++t) {
                     if (!leader) continue;
                     const uint32_t d = tmem_u + (uint32_t)(t * p.n_tile);
                     const uint32_t xh = x_hi + (uint32_t)t * (ROW_BYTES >> 4), xl = x_lo + (uint32_t)t * (ROW_BYTES >> 4);   // tap t = window shifted by t rows
                     if (i == 0) {
                         umma_lo<0>(d, xh, dy_hi, idesc);
-                        if (NPROD == 3) { umma_lo<1>(d, xh, dy_lo, idesc); umma_lo<1>(d, xl, dy_hi, idesc); }
+                        if (NPROD == 3) umma_lo<1>(d, xh, dy_lo, idesc);
+                        if (NPROD >= 2) umma_lo<1>(d, xl, dy_hi, idesc);
 #pragma unroll
                         for (int k = 1; k < WG_KB / 16; ++k) {      // 16 K rows = 2048 bytes = 128 descriptor units
                             umma_lo<1>(d, xh + 128 * k, dy_hi + 128 * k, idesc);
-                            if (NPROD == 3) { umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc); umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc); }
+                            if (NPROD == 3) umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc);
+                            if (NPROD >= 2) umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc);
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < WG_KB / 16; ++k) {
                             umma_lo<1>(d, xh + 128 * k, dy_hi + 128 * k, idesc);
-                            if (NPROD == 3) { umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc); umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc); }
+                            if (NPROD == 3) umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc);
+                            if (NPROD >= 2) umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc);
                         }
                     }
                 }
@@ -753,7 +764,7 @@ struct FlatWgradPlan {
 
 int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, FlatWgradPlan& pl) {
     if (Ci != 64 || Cpad % 64 != 0 || Cpad < Co || 2 * P < KH - 1 || 2 * P < KW - 1) return TPGSR_ERR_UNSUPPORTED;
-    const int planes = nprod == 3 ? 2 : 1;
+    const int dy_planes = nprod == 3 ? 2 : 1, x_planes = nprod >= 2 ? 2 : 1;
     // co tile: the candidate (multiple of 64 dividing Cpad, <= 256) with the fewest CTAs per pixel split whose ring is >= 2 deep
     int best = -1, best_cost = 1 << 30;
     for (int nt = 64; nt <= 256 && nt <= Cpad; nt += 64) {
@@ -762,7 +773,7 @@ int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH
         int kwg = (KW + max_taps - 1) / max_taps;
         int tpg = (KW + kwg - 1) / kwg;
         int xr = (WG_KB + tpg - 1 + 7) / 8 * 8;
-        int sb = planes * ((nt / 64) * WG_KB + xr) * ROW_BYTES;
+        int sb = (dy_planes * (nt / 64) * WG_KB + x_planes * xr) * ROW_BYTES;
         if ((212 * 1024) / sb < 2) continue;
         int cost = kwg * (Cpad / nt);
         if (cost < best_cost || (cost == best_cost && nt < best)) { best = nt; best_cost = cost; }
@@ -774,7 +785,7 @@ int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH
     pl.kw_groups = (KW + max_taps - 1) / max_taps;
     pl.taps_per_group = (KW + pl.kw_groups - 1) / pl.kw_groups;
     pl.x_rows = (WG_KB + pl.taps_per_group - 1 + 7) / 8 * 8;
-    pl.stage_bytes = planes * ((pl.n_tile / 64) * WG_KB + pl.x_rows) * ROW_BYTES;
+    pl.stage_bytes = (dy_planes * (pl.n_tile / 64) * WG_KB + x_planes * pl.x_rows) * ROW_BYTES;
     pl.stages = (212 * 1024) / pl.stage_bytes;
     if (pl.stages > 4) pl.stages = 4;
     const long long Qtot = (long long)B * (H + P) * (W + P);
@@ -864,7 +875,7 @@ int tpgsr_conv2d_flat(const void* x_hi, const void* x_lo, const void* w_hi, cons
 int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, void* yp_hi,
                              void* yp_lo, int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int ldy, int act,
                              const float* act_param, int out_mode, int accumulate, int nprod, cudaStream_t stream) {
-    if (!x_hi || !w_hi || !y || (nprod != 1 && nprod != 3) || (nprod == 3 && (!x_lo || !w_lo))) return TPGSR_ERR_BAD_ARG;
+    if (!x_hi || !w_hi || !y || nprod < 1 || nprod > 3 || (nprod == 3 && !x_lo) || (nprod >= 2 && !w_lo)) return TPGSR_ERR_BAD_ARG;
     if (yp_hi && (Co % 32 != 0 || out_mode != TPGSR_OUT_NHWC || ((ldy > 0 ? ldy : Co) & 3) || (act != TPGSR_ACT_NONE && act != TPGSR_ACT_RELU)))
         return TPGSR_ERR_UNSUPPORTED;
     FlatPlan pl;
@@ -891,18 +902,23 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     uint32_t bbox[2] = {64, (uint32_t)pl.n_tile};
     if (tpgsr_make_tmap_bf16(&tmA_hi, x_hi, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
     if (tpgsr_make_tmap_bf16(&tmB_hi, w_hi, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
-    if (nprod == 3) {
-        if (tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
-        if (tpgsr_make_tmap_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
-    } else {
-        tmA_lo = tmA_hi;
-        tmB_lo = tmB_hi;
-    }
+    tmA_lo = tmA_hi;
+    tmB_lo = tmB_hi;
+    if (nprod == 3 && tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
+    if (nprod >= 2 && tpgsr_make_tmap_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
     dim3 grid(pl.grid_x, pl.n_tiles);
-    if (nprod == 3) {
+    if (g_flat_occ2 && pl.smem <= 112 * 1024 && nprod >= 2) {      // two-CTA plan: the register-capped build, or the CTAs would not co-reside
+        auto kern = nprod == 3 ? conv_flat_kernel<3, 2> : conv_flat_kernel<2, 2>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return TPGSR_ERR_LAUNCH;
+        kern<<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    } else if (nprod == 3) {
         if (cudaFuncSetAttribute(conv_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
         conv_flat_kernel<3><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    } else if (nprod == 2) {
+        if (cudaFuncSetAttribute(conv_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        conv_flat_kernel<2><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else {
         if (cudaFuncSetAttribute(conv_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
@@ -927,7 +943,7 @@ size_t tpgsr_conv2d_wgrad_flat_workspace_bytes(int B, int H, int W, int P, int C
 int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw_oihw, int B, int H,
                             int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int ph, int pw, int accumulate, int nprod,
                             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    if (!x_hi || !dy_hi || !dw_oihw || !workspace || (nprod != 1 && nprod != 3) || (nprod == 3 && (!x_lo || !dy_lo)))
+    if (!x_hi || !dy_hi || !dw_oihw || !workspace || nprod < 1 || nprod > 3 || (nprod >= 2 && !x_lo) || (nprod == 3 && !dy_lo))
         return TPGSR_ERR_BAD_ARG;
     if (2 * ph != KH - 1 || 2 * pw != KW - 1 || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
     FlatWgradPlan pl;
@@ -950,19 +966,20 @@ int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_h
     uint32_t dbox[2] = {64, (uint32_t)WG_KB};
     if (tpgsr_make_tmap_bf16(&tmX_hi, x_hi, 2, xd, xs, xbox)) return TPGSR_ERR_DRIVER;
     if (tpgsr_make_tmap_bf16(&tmD_hi, dy_hi, 2, dd, ds, dbox)) return TPGSR_ERR_DRIVER;
-    if (nprod == 3) {
-        if (tpgsr_make_tmap_bf16(&tmX_lo, x_lo, 2, xd, xs, xbox)) return TPGSR_ERR_DRIVER;
-        if (tpgsr_make_tmap_bf16(&tmD_lo, dy_lo, 2, dd, ds, dbox)) return TPGSR_ERR_DRIVER;
-    } else {
-        tmX_lo = tmX_hi;
-        tmD_lo = tmD_hi;
-    }
+    tmX_lo = tmX_hi;
+    tmD_lo = tmD_hi;
+    if (nprod >= 2 && tpgsr_make_tmap_bf16(&tmX_lo, x_lo, 2, xd, xs, xbox)) return TPGSR_ERR_DRIVER;
+    if (nprod == 3 && tpgsr_make_tmap_bf16(&tmD_lo, dy_lo, 2, dd, ds, dbox)) return TPGSR_ERR_DRIVER;
     const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + 256;
     dim3 grid(pl.splits, KH * pl.kw_groups, pl.n_tiles);
     if (nprod == 3) {
         if (cudaFuncSetAttribute(conv_wgrad_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
         conv_wgrad_flat_kernel<3><<<grid, 192, smem, stream>>>(tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
+    } else if (nprod == 2) {
+        if (cudaFuncSetAttribute(conv_wgrad_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        conv_wgrad_flat_kernel<2><<<grid, 192, smem, stream>>>(tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
     } else {
         if (cudaFuncSetAttribute(conv_wgrad_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;

@@ -96,6 +96,28 @@ class Ctx:
             self._planes[key] = hit
         return hit[1]
 
+    def dflat(self, dy: Tensor, P: int, c_out: int = 0):
+        """Operand planes of a GRADIENT tensor: flat(), or ONE bf16 plane when the gradient GEMMs run with two products (ops.BWD2)."""
+        if not ops.BWD2:
+            return self.flat(dy, P, c_out)
+        key = (id(dy), 'dflat', P, c_out or dy.shape[-1])
+        hit = self._planes.get(key)
+        if hit is None:
+            hit = (dy, ops.split_bf16_flat(dy, P, False, c_out))
+            self._planes[key] = hit
+        return hit[1]
+
+    def dstacked(self, dy: Tensor, KW: int, pw: int, P: int, sign: int):
+        """kw-stacked planes of a gradient tensor (see dflat)."""
+        if not ops.BWD2:
+            return self.stacked(dy, KW, pw, P, sign)
+        key = (id(dy), 'dkwstack', KW, pw, P, sign)
+        hit = self._planes.get(key)
+        if hit is None:
+            hit = (dy, ops.kwstack_split(dy, KW, pw, P, sign, False))
+            self._planes[key] = hit
+        return hit[1]
+
     def packed_kwstack(self, name: str, narrow_out: bool, transposed: bool, flip_kh: bool, flip_kw: bool):
         key = (name, 'kwstack', narrow_out, transposed, flip_kh, flip_kw)
         hit = self._packed_bf16.get(key)
@@ -219,9 +241,9 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     if kind is not None:
         # operands shared by the weight gradient (side stream) and the data gradient (this stream) are produced here, before the fork
         if kind == 'N':     # final conv: dY is the narrow side -> stack it (sign -1), shared by the weight and the data gradient
-            xp, dyp = ctx.flat(x, ph), ctx.stacked(dy, kw, pw, ph, -1)
+            xp, dyp = ctx.flat(x, ph), ctx.dstacked(dy, kw, pw, ph, -1)
         else:               # block1: the stacked input planes of the forward pass against the plain dY planes
-            xp, dyp = ctx.stacked(x, kw, pw, ph, 1), ctx.flat(dy, ph)
+            xp, dyp = ctx.stacked(x, kw, pw, ph, 1), ctx.dflat(dy, ph)
         gb, accb = ctx.G(bname) if bname else (None, False)
         with ctx.on_side(dy):
             dwp = torch.empty(((kw * Co) if kind == 'N' else 64, 64, kh, 1), dtype=torch.float32, device=x.device)
@@ -233,14 +255,14 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
             return None
         if kind == 'N':     # dX[q][ci] = sum_t sum_j DYS[q + (t-ph)*Wp][j] * W[co(j)][ci][KH-1-t][kw(j)]
             wpk = ctx.packed_kwstack(wname, False, True, True, False)
-            return ops.conv_flat(ctx.stacked(dy, kw, pw, ph, -1), wpk, None, Ci, kh, 1, ph, 0, out=dx_out, accumulate=dx_accumulate)
+            return ops.conv_flat(ctx.dstacked(dy, kw, pw, ph, -1), wpk, None, Ci, kh, 1, ph, 0, out=dx_out, accumulate=dx_accumulate)
         wpk = ctx.packed_kwstack(wname, True, True, True, True)      # narrow output: dX = shift-and-add of the stacked partial sums
-        part = ops.conv_flat(ctx.flat(dy, ph), wpk, None, kw * Ci, kh, 1, ph, 0)
+        part = ops.conv_flat(ctx.dflat(dy, ph), wpk, None, kw * Ci, kh, 1, ph, 0)
         return ops.kwsum(part, None, Ci, kw, pw, out=dx_out, accumulate=dx_accumulate)
     same = (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 2 * ph == kh - 1 and 2 * pw == kw - 1)
     gb, accb = ctx.G(bname) if bname else (None, False)
     if same and ops.wgrad_flat_supported(B, H, W, P, Ci, Co, kh, kw):
-        xp, dyp = ctx.flat(x, P), ctx.flat(dy, P, (Co + 63) // 64 * 64)          # shared with the data gradient: before the fork
+        xp, dyp = ctx.flat(x, P), ctx.dflat(dy, P, (Co + 63) // 64 * 64)         # shared with the data gradient: before the fork
         with ctx.on_side(dy):
             ops.conv_wgrad_flat(xp, dyp, gw, Co, kh, kw, ph, pw, acc)
             if bname:
@@ -263,10 +285,10 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     if dense_out and _flat_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)
         if emit_dx_planes and dx_out is None and Ci % 32 == 0:
-            dx, dxp = ops.conv_flat(ctx.flat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, emit_planes=True)
-            ctx._planes[(id(dx), 'flat', 0, Ci)] = (dx, dxp)
+            dx, dxp = ops.conv_flat(ctx.dflat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, emit_planes=True, emit_lo=not ops.BWD2)
+            ctx._planes[(id(dx), 'dflat' if ops.BWD2 else 'flat', 0, Ci)] = (dx, dxp)       # dx is the next backward conv's dY
             return dx
-        return ops.conv_flat(ctx.flat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out, accumulate=dx_accumulate)
+        return ops.conv_flat(ctx.dflat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out, accumulate=dx_accumulate)
     if dense_out and _tc_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)
         return ops.conv_tc(ctx.planes(dy), wd, None, B, H, W, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out,

@@ -281,6 +281,20 @@ def nprod() -> int:
     return 3 if CONV_MODE == 'bf16x3' else 1
 
 
+# EXPERIMENTAL, not measured yet: gradient GEMMs with TWO products — dY enters as ONE bf16 plane (no lo plane is split, staged or multiplied)
+# against the exact (hi + lo) weights / activations: dX = dY_hi (W_hi + W_lo), dW = (X_hi + X_lo) dY_hi.  The forward pass keeps three products,
+# so the SR output is untouched; on the oracle graph the non-STN gradients move from 1.7e-4 to 2.9e-4 relative L2 against fp32
+# (scripts/study_operand_precision.py, mode 'bwd2').  Off by default.
+BWD2 = os.environ.get('TPGSR_BWD_PRODUCTS', '3') == '2' and CONV_MODE == 'bf16x3'
+
+
+def _nprod_for(a_lo, b_lo) -> int:
+    """Products the flat kernels run for the planes at hand: 3 = both operands split, 2 = only the B / X side split, 1 = bf16."""
+    if nprod() != 3 or b_lo is None:
+        return 1
+    return 3 if a_lo is not None else 2
+
+
 def split_bf16_flat(x: torch.Tensor, P: int, need_lo: bool = True, c_out: int = 0) -> FlatPlanes:
     """fp32 NHWC [B,H,W,C] (dense) -> padded-flat bf16 planes with c_out >= C channels (extra channels zero)."""
     B, H, W, C = x.shape
@@ -298,18 +312,18 @@ def flat_supported(B, H, W, P, Ci, Co, KH, KW, ph, pw) -> bool:
 
 
 def conv_flat(xp: FlatPlanes, w_planes, bias, Co, KH, KW, ph, pw, act=ACT_NONE, act_param=None, out_nchw=False,
-              out: Optional[torch.Tensor] = None, accumulate: bool = False, emit_planes: bool = False):
+              out: Optional[torch.Tensor] = None, accumulate: bool = False, emit_planes: bool = False, emit_lo: bool = True):
     """'same' conv on padded-flat planes -> dense fp32 NHWC [B,H,W,Co] (or NCHW).  ``emit_planes``: also return the output's dense
     bf16 hi/lo planes (= its P = 0 operand planes) written by the same epilogue -> (out, FlatPlanes)."""
     B, H, W = xp.B, xp.H, xp.W
     if out is None:
         out = torch.empty((B, Co, H, W) if out_nchw else (B, H, W, Co), dtype=torch.float32, device=xp.hi.device)
         accumulate = False
-    n = 3 if (nprod() == 3 and xp.lo is not None and w_planes[1] is not None) else 1
+    n = _nprod_for(xp.lo, w_planes[1])
     if emit_planes:
         assert not out_nchw and Co % 32 == 0 and out.shape[-1] == Co
         hi = torch.empty((B * H * W, Co), dtype=torch.bfloat16, device=out.device)
-        lo = torch.empty((B * H * W, Co), dtype=torch.bfloat16, device=out.device) if nprod() == 3 else None
+        lo = torch.empty((B * H * W, Co), dtype=torch.bfloat16, device=out.device) if (nprod() == 3 and emit_lo) else None
         _call('tpgsr_conv2d_flat_planes', ptr(xp.hi), ptr(xp.lo), ptr(w_planes[0]), ptr(w_planes[1]), ptr(bias), ptr(out), ptr(hi), ptr(lo),
               B, H, W, xp.P, xp.C, Co, KH, KW, ph, pw, Co, act, ptr(act_param), OUT_NHWC, int(accumulate), n, stream())
         return out, FlatPlanes(hi, lo, B, H, W, Co, 0)
@@ -327,7 +341,7 @@ def wgrad_flat_supported(B, H, W, P, Ci, Co, KH, KW) -> bool:
 
 def conv_wgrad_flat(xp: FlatPlanes, dyp: FlatPlanes, dw: torch.Tensor, Co, KH, KW, ph, pw, accumulate: bool) -> None:
     assert (xp.B, xp.H, xp.W, xp.P) == (dyp.B, dyp.H, dyp.W, dyp.P)
-    n = 3 if (nprod() == 3 and xp.lo is not None and dyp.lo is not None) else 1
+    n = _nprod_for(dyp.lo, xp.lo)            # 2: dY one plane against X hi + lo
     nbytes = query('tpgsr_conv2d_wgrad_flat_workspace_bytes', xp.B, xp.H, xp.W, xp.P, xp.C, Co, dyp.C, KH, KW, n)
     wp, wn = workspace(nbytes, dw.device)
     _call('tpgsr_conv2d_wgrad_flat', ptr(xp.hi), ptr(xp.lo), ptr(dyp.hi), ptr(dyp.lo), ptr(dw), xp.B, xp.H, xp.W, xp.P, xp.C, Co,
