@@ -637,7 +637,7 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
     const int dy_tile_bytes = WG_KB * ROW_BYTES;                  // one 64-channel group of dY rows
     const int dy_plane_bytes = ngroups * dy_tile_bytes;
     const int x_plane_bytes = p.x_rows * ROW_BYTES;
-    const int stage_bytes = dy_planes * dy_plane_bytes + x_planes * x_plane_bytes;
+    const int stage_bytes = dy_planes == x_planes ? dy_planes * (dy_plane_bytes + x_plane_bytes) : dy_planes * dy_plane_bytes + x_planes * x_plane_bytes;
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared-space provenance (LDS/STS, not generic LD/ST)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty = full + p.stages;
