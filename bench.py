@@ -34,6 +34,10 @@ import torch  # noqa: E402
 
 KW = dict(scale_factor=2, width=128, height=32, STN=True, mask=True, srb_nums=5, hidden_units=32)
 PER_GPU_BATCH = 48
+METRIC = 'SR images/sec (16x64->32x128), TSRN train step'
+# one description of the workload for both arms (the driver compares the two lines' metric / config)
+WORKLOAD = ('BASELINE configs[1]: TSRN single-stage TRAIN step, STN on, mask, ImageLoss(gradient,[1,1e-4])*100, '
+            'clip_grad_norm 0.25, Adam(1e-3,(0.5,0.999))')
 # SURVEY §8d / BASELINE.md §3: TSRN train-mode forward = 1.8445 GFLOP/img, train step = 3x forward
 GFLOP_PER_IMG_STEP = 5.53
 
@@ -161,11 +165,11 @@ def run_reference_arm(args):
     sample = 12
     ips, sec = cpu_port_images_per_s(sample, args.steps, args.warmup, threads)
     line = {
-        'impl': 'reference', 'metric': 'SR images/sec (16x64->32x128), TSRN train step', 'value': ips, 'unit': 'images/s',
+        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'TSRN single-stage train step (STN on, mask, ImageLoss gradient, clip 0.25, Adam), CPU oracle port',
-                   'batch_per_step': sample, 'full_batch': PER_GPU_BATCH},
+        'config': {'workload': WORKLOAD, 'per_gpu_batch': PER_GPU_BATCH, 'lr_hw': [16, 64], 'hr_hw': [32, 128],
+                   'implementation': 'CPU oracle port of the same step (oracle/step.py), torch CPU fp32', 'sample_batch_per_step': sample},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cpu_port_images_per_s.threads_used, 'host_cpus': threads, 'kind': 'port',
                          'sample': f'{args.steps} timed steps of {sample} images (1/4 of the 48-image batch), torch {torch.__version__} CPU fp32'},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -302,12 +306,11 @@ def run_ours(args):
         return
     peaks = _peaks()
     line = {
-        'metric': 'SR images/sec (16x64->32x128), TSRN train step', 'value': value, 'unit': 'images/s', 'n_gpus': world,
+        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32' if ops.CONV_MODE != 'bf16' else 'bf16', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[1]: TSRN single-stage TRAIN step, STN on, mask, ImageLoss(gradient,[1,1e-4])*100, '
-                               'clip_grad_norm 0.25, Adam(1e-3,(0.5,0.999))', 'per_gpu_batch': B, 'global_batch': B * world,
+        'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': B * world,
                    'lr_hw': [16, 64], 'hr_hw': [32, 128], 'parallelism': f'dp{world}', 'cuda_graph': not args.no_graph,
                    'precision': {'bf16x3': 'fp32 tensors everywhere; conv / 1x1 / linear contractions as split-bf16 (hi*hi + hi*lo + lo*hi) on tcgen05 with '
                                            'fp32 TMEM accumulation = fp32-class accuracy (the parity mode, SR output within 1e-3 of the fp32 reference); '
