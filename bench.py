@@ -318,7 +318,10 @@ def run_ours(args):
                                  'bf16': 'single bf16 product per contraction (throughput mode; misses the 1e-3 parity budget, labelled)',
                                  'fp32': 'CUDA-core fp32 contractions'}[ops.CONV_MODE],
                    'l2': 'no explicit flush: the step touches >1 GB of activations/stashes per replay (>> 126 MB L2); inputs rotate over 8 distinct batches',
-                   'last_loss': last_loss},
+                   'last_loss': last_loss,
+                   # non-default (experimental) switches in force, so that A/B lines describe themselves
+                   'switches': {k: True for k, on in (('TPGSR_PREPACK', ops.PREPACK), ('TPGSR_FLAT_OCC2', ops.FLAT_OCC2),
+                                                      ('TPGSR_BWD_PRODUCTS=2', ops.BWD2)) if on}},
         'e2e': {'value': e2e_val, 'unit': 'images/s', 'h2d_bytes_per_step': B * (4 * 16 * 64 + 4 * 32 * 128) * 4, 'd2h_bytes_per_step': 4,
                 'ms_per_step': sec_e2e / args.steps * 1e3, 'api': 'tpgsr_b200.train.TSRNTrainStep(images_lr_pinned, images_hr_pinned) -> loss.cpu()'},
         'gpu_launches': launches_per_step * args.steps,
