@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call for the switches that were written but not measured in round 1 (each default-off):
 #   TPGSR_FLAT_OCC2=1      flat convs tiled for two co-resident CTAs per SM        TPGSR_PREPACK=1  persistent packed weights
-#   TPGSR_BWD_PRODUCTS=2   gradient GEMMs with dY as one bf16 plane (two products)
+#   TPGSR_BWD_PRODUCTS=2   gradient GEMMs with dY as one bf16 plane (two products)     TPGSR_WGRAD_PRODUCTS=1  one-product weight gradient
 # First the kernels' own tests (tests/test_gpu_zz_experimental.py), then the flat-conv / model suites with a switch on, then bench.py
 # (no CPU leg) beside the default.
 set -u
@@ -28,4 +28,7 @@ run_bench occ2 TPGSR_FLAT_OCC2=1
 run_bench occ2_bf16 TPGSR_FLAT_OCC2=1 TPGSR_CONV_MODE=bf16
 run_bench default_bf16 TPGSR_CONV_MODE=bf16
 run_bench bwd2 TPGSR_BWD_PRODUCTS=2
-run_bench bwd2_occ2 TPGSR_BWD_PRODUCTS=2 TPGSR_FLAT_OCC2=1
+run_bench bwd2_w1 TPGSR_BWD_PRODUCTS=2 TPGSR_WGRAD_PRODUCTS=1
+run_bench bwd2_w1_occ2 TPGSR_BWD_PRODUCTS=2 TPGSR_WGRAD_PRODUCTS=1 TPGSR_FLAT_OCC2=1
+TPGSR_BWD_PRODUCTS=2 TPGSR_WGRAD_PRODUCTS=1 timeout 400 python -m pytest tests/test_gpu_models.py tests/test_gpu_cascade.py -m gpu -q > gpurun_out/pytest_bwd2_w1.log 2>&1; echo "pytest bwd2+w1 rc=$? (the default suite's gradient tolerances applied to the reduced-product backward)"
+tail -5 gpurun_out/pytest_bwd2_w1.log

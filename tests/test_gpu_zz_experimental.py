@@ -85,8 +85,8 @@ def test_two_cta_plan_same_results():
 
 
 def test_two_product_backward_train_step_stays_close(shapes, monkeypatch):
-    """TSRN train step with TPGSR_BWD_PRODUCTS=2 semantics: identical loss (forward untouched), gradients within 1e-3 of the default step's
-    outside the (chaotic) STN head."""
+    """TSRN train step with TPGSR_BWD_PRODUCTS=2 (and additionally TPGSR_WGRAD_PRODUCTS=1) semantics: identical loss (forward untouched),
+    gradients within 1e-3 of the default step's outside the (chaotic) STN head."""
     import copy
     from oracle.weights import synth_images, synth_state_dict
     from tpgsr_b200 import ops
@@ -97,8 +97,9 @@ def test_two_product_backward_train_step_stays_close(shapes, monkeypatch):
     sd = synth_state_dict(shapes['tsrn_train'], 1)
     lr, hr = synth_images(4, seed=70)
     runs = []
-    for bwd2 in (False, True):
-        monkeypatch.setattr(ops, 'BWD2', bwd2)
+    for bwd2 in (False, True, 'w1'):
+        monkeypatch.setattr(ops, 'BWD2', bool(bwd2))
+        monkeypatch.setattr(ops, 'WGRAD1', bwd2 == 'w1')
         net = TSRN(**KW)
         net.load_state_dict(copy.deepcopy(sd), strict=False)
         net = net.to(d).train()
@@ -107,8 +108,9 @@ def test_two_product_backward_train_step_stays_close(shapes, monkeypatch):
         ts._fwd_bwd()
         torch.cuda.synchronize()
         runs.append((float(ts.loss), {k: v.clone() for k, v in ts.st.gviews.items()}))
-    (l0, g0), (l1, g1) = runs
-    assert l0 == l1
-    num = sum(float((g1[k] - g0[k]).norm() ** 2) for k in g0 if 'stn_head' not in k)
-    den = sum(float(g0[k].norm() ** 2) for k in g0 if 'stn_head' not in k)
-    assert 0 < (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+    (l0, g0) = runs[0]
+    for (l1, g1) in runs[1:]:
+        assert l0 == l1
+        num = sum(float((g1[k] - g0[k]).norm() ** 2) for k in g0 if 'stn_head' not in k)
+        den = sum(float(g0[k].norm() ** 2) for k in g0 if 'stn_head' not in k)
+        assert 0 < (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5

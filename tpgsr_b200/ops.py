@@ -286,6 +286,10 @@ def nprod() -> int:
 # so the SR output is untouched; on the oracle graph the non-STN gradients move from 1.7e-4 to 2.9e-4 relative L2 against fp32
 # (scripts/study_operand_precision.py, mode 'bwd2').  Off by default.
 BWD2 = os.environ.get('TPGSR_BWD_PRODUCTS', '3') == '2' and CONV_MODE == 'bf16x3'
+# EXPERIMENTAL, not measured yet: the flat weight gradient with ONE product (X_hi dY_hi, the kernel's bf16 instantiation).  A weight gradient
+# sums over every pixel of the batch (49 152 at B = 48), so the operands' independent rounding errors average out: on the oracle graph the
+# non-STN gradients are at 3.1e-4 relative L2 with it (2.9e-4 with two products, 1.7e-4 with three; study script, mode 'bwd2w1').  Off by default.
+WGRAD1 = os.environ.get('TPGSR_WGRAD_PRODUCTS', '3') == '1' and CONV_MODE == 'bf16x3'
 
 
 def _nprod_for(a_lo, b_lo) -> int:
@@ -341,7 +345,7 @@ def wgrad_flat_supported(B, H, W, P, Ci, Co, KH, KW) -> bool:
 
 def conv_wgrad_flat(xp: FlatPlanes, dyp: FlatPlanes, dw: torch.Tensor, Co, KH, KW, ph, pw, accumulate: bool) -> None:
     assert (xp.B, xp.H, xp.W, xp.P) == (dyp.B, dyp.H, dyp.W, dyp.P)
-    n = _nprod_for(dyp.lo, xp.lo)            # 2: dY one plane against X hi + lo
+    n = 1 if WGRAD1 else _nprod_for(dyp.lo, xp.lo)            # 2: dY one plane against X hi + lo
     nbytes = query('tpgsr_conv2d_wgrad_flat_workspace_bytes', xp.B, xp.H, xp.W, xp.P, xp.C, Co, dyp.C, KH, KW, n)
     wp, wn = workspace(nbytes, dw.device)
     _call('tpgsr_conv2d_wgrad_flat', ptr(xp.hi), ptr(xp.lo), ptr(dyp.hi), ptr(dyp.lo), ptr(dw), xp.B, xp.H, xp.W, xp.P, xp.C, Co,
