@@ -14,6 +14,7 @@ Formats:  fp32    reference
           bf16a   activations ONE bf16 plane, weights bf16 hi+lo
           bwd2    forward as bf16x3; backward with dY as ONE bf16 plane against split weights / activations (2 products per gradient GEMM)
           bwd2w1  as bwd2, and the weight gradient with ONE product (X_hi dY_hi)
+          bwd1    forward as bf16x3; the whole backward pass in plain bf16 (one product per gradient GEMM)
 """
 import json
 import os
@@ -36,7 +37,7 @@ def _split(t, dt=torch.bfloat16):
 class QConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, padding, mode):
-        if mode in ('bf16x3', 'bwd2', 'bwd2w1'):
+        if mode in ('bf16x3', 'bwd2', 'bwd2w1', 'bwd1'):
             xh, xl = _split(x); wh, wl = _split(w)
             y = _conv(xh, wh, None, padding=padding) + _conv(xh, wl, None, padding=padding) + _conv(xl, wh, None, padding=padding)
             xs = xh + xl
@@ -58,9 +59,10 @@ class QConv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         xs, w = ctx.saved_tensors
-        dyq = dy.bfloat16().float() if ctx.mode in ('bwd2', 'bwd2w1') else dy   # dY as ONE bf16 plane in both gradient GEMMs (2 products)
-        dx = torch.nn.grad.conv2d_input(xs.shape, w, dyq, padding=ctx.padding)
-        xw = xs.bfloat16().float() if ctx.mode == 'bwd2w1' else xs                # 'bwd2w1': the weight gradient with ONE product (X_hi dY_hi)
+        dyq = dy.bfloat16().float() if ctx.mode in ('bwd2', 'bwd2w1', 'bwd1') else dy   # dY as ONE bf16 plane in both gradient GEMMs
+        wq = w.bfloat16().float() if ctx.mode == 'bwd1' else w                    # 'bwd1': the data gradient with ONE product as well
+        dx = torch.nn.grad.conv2d_input(xs.shape, wq, dyq, padding=ctx.padding)
+        xw = xs.bfloat16().float() if ctx.mode in ('bwd2w1', 'bwd1') else xs      # the weight gradient with ONE product (X_hi dY_hi)
         dw = torch.nn.grad.conv2d_weight(xw, w.shape, dyq, padding=ctx.padding)
         return dx, dw, (dy.sum((0, 2, 3)) if ctx.has_b else None), None, None
 
@@ -82,7 +84,7 @@ def main():
     shapes = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'shapes.json')))['tsrn_train']
     lr, hr = synth_images(8, seed=50)
     res = {}
-    for mode in ('fp32', 'bf16x3', 'bwd2', 'bwd2w1', 'f16a', 'bf16a', 'bf16'):
+    for mode in ('fp32', 'bf16x3', 'bwd2', 'bwd2w1', 'bwd1', 'f16a', 'bf16a', 'bf16'):
         p = synth_state_dict(shapes, 1)
         p.update({'tps.' + k: v for k, v in tps_buffers(16, 64).items()})
         models.F.conv2d = make_conv(mode)
