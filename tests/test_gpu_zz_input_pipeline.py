@@ -67,3 +67,24 @@ def test_resize_normalize_host_surface():
     with pytest.raises(TpgsrError):
         ops._call('tpgsr_resize_normalize', src.data_ptr(), meta.data_ptr(), meta.data_ptr(), meta.data_ptr(), 1, 4, 4, 16, 64, 0, out.data_ptr(),
                   None, 0, ops.stream())
+
+
+def test_batch_prefetcher_matches_direct_transform_and_feeds_a_train_step():
+    """BatchPrefetcher (worker-thread packing, copy-stream H2D + resize, event hand-off) yields exactly what resizeNormalize.batch computes,
+    in order, and its tensors can be consumed by kernels on the compute stream right away."""
+    from tpgsr_b200.dataset import BatchPrefetcher, resizeNormalize
+    r = np.random.RandomState(21)
+    hr = [(r.rand(r.randint(8, 70), r.randint(16, 220), 3) * 255).astype(np.uint8) for _ in range(22)]
+    lr = [(r.rand(r.randint(4, 40), r.randint(8, 120), 3) * 255).astype(np.uint8) for _ in range(22)]
+    samples = [(hr[i], lr[i], f'word{i}') for i in range(22)]
+    tf_hr, tf_lr = resizeNormalize((128, 32), True), resizeNormalize((64, 16), True)
+    seen = 0
+    sums = []
+    for k, (bh, bl, labels) in enumerate(BatchPrefetcher(samples, 8, size_hr=(128, 32), down_sample_scale=2, mask=True, drop_last=False)):
+        sl = slice(8 * k, 8 * k + len(labels))
+        assert labels == [f'word{i}' for i in range(sl.start, sl.start + len(labels))]
+        assert tuple(bh.shape) == (len(labels), 4, 32, 128) and tuple(bl.shape) == (len(labels), 4, 16, 64)
+        sums.append(bh.sum() + bl.sum())                      # consumed on the compute stream immediately (no explicit sync)
+        assert torch.equal(bh, tf_hr.batch(hr[sl])) and torch.equal(bl, tf_lr.batch(lr[sl]))
+        seen += len(labels)
+    assert seen == 22 and all(torch.isfinite(s) for s in sums)

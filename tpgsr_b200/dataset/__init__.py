@@ -1,1 +1,2 @@
-from .dataset import resizeNormalize  # noqa: F401
+from .dataset import resizeNormalize, stage  # noqa: F401
+from .loader import BatchPrefetcher, batches  # noqa: F401
