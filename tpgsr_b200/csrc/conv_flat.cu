@@ -907,8 +907,8 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     if (nprod == 3 && tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
     if (nprod >= 2 && tpgsr_make_tmap_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
     dim3 grid(pl.grid_x, pl.n_tiles);
-    if (g_flat_occ2 && pl.smem <= 112 * 1024 && nprod >= 2) {      // two-CTA plan: the register-capped build, or the CTAs would not co-reside
-        auto kern = nprod == 3 ? conv_flat_kernel<3, 2> : conv_flat_kernel<2, 2>;
+    if (g_flat_occ2 && pl.smem <= 112 * 1024) {      // two-CTA plan: the register-capped build, or the CTAs would not co-reside
+        auto kern = nprod == 3 ? conv_flat_kernel<3, 2> : (nprod == 2 ? conv_flat_kernel<2, 2> : conv_flat_kernel<1, 2>);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return TPGSR_ERR_LAUNCH;
         kern<<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else if (nprod == 3) {
