@@ -337,6 +337,28 @@ def run_ours(args):
         ips, sec_cpu = cpu_port_images_per_s(12, 2, 1, threads)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cpu_port_images_per_s.threads_used, 'host_cpus': threads, 'kind': 'port',
                                 'sample': '2 timed steps of 12 images (1/4 batch) of the same train step, oracle port, torch CPU fp32'}
+    if world == 1 and os.environ.get('TPGSR_BENCH_INFER') == '1':
+        # optional extra (SURVEY §8d also asks for inference images/s): eval-mode forward through the public nn.Module API (no STN, running BN
+        # statistics), device-resident inputs, eager launches.  Off by default: the contract line is the train step.
+        try:
+            net.eval()
+            x = dev_batches[0][0]
+            with torch.no_grad():
+                for _ in range(args.warmup):
+                    net(x)
+                torch.cuda.synchronize(dev)
+                i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                i0.record()
+                for i in range(args.steps):
+                    net(dev_batches[i % len(dev_batches)][0])
+                i1.record()
+                torch.cuda.synchronize(dev)
+            line['inference'] = {'value': B * args.steps / (i0.elapsed_time(i1) * 1e-3), 'unit': 'images/s', 'batch': B,
+                                 'api': 'TSRN.eval()(images_lr) under torch.no_grad(), eager'}
+        except Exception as e:      # never let the optional leg cost the contract line
+            line['inference'] = {'error': repr(e)}
+        finally:
+            net.train()
     if world > 1:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
