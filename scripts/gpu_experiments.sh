@@ -23,7 +23,7 @@ TPGSR_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_experim
 tail -5 gpurun_out/pytest_experimental.log
 TPGSR_FLAT_OCC2=1 timeout 400 python -m pytest tests/test_gpu_flat.py tests/test_gpu_models.py -m gpu -x -q > gpurun_out/pytest_occ2.log 2>&1; echo "pytest occ2 rc=$?"
 tail -3 gpurun_out/pytest_occ2.log
-run_bench default TPGSR_FLAT_OCC2=0
+run_bench default TPGSR_FLAT_OCC2=0 TPGSR_BENCH_INFER=1
 run_bench occ2 TPGSR_FLAT_OCC2=1
 run_bench occ2_bf16 TPGSR_FLAT_OCC2=1 TPGSR_CONV_MODE=bf16
 run_bench default_bf16 TPGSR_CONV_MODE=bf16
