@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — SR images/sec of the TPGSR hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py --gpus 1 --steps 20 --warmup 5            # our CUDA path (default arm)
+    python bench.py --gpus 1 --steps 20 --warmup 5            # our CUDA path (default arm), config 3
+    python bench.py --config 2                                # TSRN single-stage (BASELINE configs[1])
     python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (oracle port) on host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W                # one rank per GPU, weak scaling (48 images / GPU)
 
-Workload at N=1 (BASELINE.json configs[1]): TSRN single-stage, STN on, mask on, batch 48, 16x64 -> 32x128, one TRAIN
-step = forward + ImageLoss(gradient)*100 + backward + clip_grad_norm_(0.25) + Adam(1e-3, (0.5, 0.999)); synthetic
-U[0,1) crops, random-init weights of the reference architecture.
+Workloads (``--config``, numbered as SURVEY §8d; BASELINE.json ``configs`` is the same list 0-based):
+  2  TSRN single-stage TRAIN step, STN on, mask, batch 48 per GPU
+  3  TPGSR-TSRN (tsrn_tl_cascade) stu_iter=1 + CRNN student/teacher prior + distillation, batch 48 per GPU    [default, every N]
+  4  TPGSR-TSRN stu_iter=3, three students, shared SR model, batch 48 per GPU (384 at 8 GPUs)              [--config 4 / TPGSR_BENCH_CONFIG=4]
+  5  TPGSR-SRResNet_TL + CRNN prior, MSE, batch 32 per GPU (256 at 8 GPUs)
+One step = forward + losses*100 + backward + clip_grad_norm_(SR, 0.25) + Adam(1e-3, (0.5, 0.999)) over SR + student parameters;
+synthetic U[0,1) crops 16x64 -> 32x128, random-init weights of the reference architectures.
 
-  value    images/s with the step's inputs already resident in HBM (CUDA-graphed step, CUDA-event timing, max over ranks)
-  e2e      images/s through the public API with HOST (pinned) input buffers: H2D of LR+HR and D2H of the loss inside the
-           timed region, every step
-  roofline dominant kernel (3x3 64->64 conv, the shape that is 11 of the 18 conv launches per forward), timed live with
-           CUDA events on the launch stream; achieved = algorithmic FLOPs / launch time vs MEASURED_PEAKS.json
-  cpu_baseline  the oracle port of the same step on the box's host cores (bounded sample), rank 0, N=1 only
+  value     images/s with the step's inputs already resident in HBM (CUDA-graphed step, CUDA-event timing, max over ranks)
+  e2e       images/s through the public API with HOST (pinned) input buffers: H2D of LR+HR and D2H of the loss inside the timed
+            region, every step
+  roofline  the dominant TSRN conv (3x3 64->64, 11 of 18 conv launches per SR forward) timed live with CUDA events on the launch
+            stream, cold L2; achieved = algorithmic FLOPs / launch time vs MEASURED_PEAKS.json.  roofline_crnn: the dominant CRNN
+            conv (conv5 3x3 512->512 on 4x26 maps) the same way.
+  cpu_baseline   the oracle port of the same step on the box's host cores (bounded sample), rank 0, N=1 only
+  gpu_eager_baseline  developer leg: the same step in stock PyTorch (cuDNN / cuBLAS / ATen, TF32 off, eager autograd) on the same GPU
+  inference / parity  eval-mode images/s (CUDA-graphed) and SR output vs the CPU oracle on a sample (rel. L2, PSNR / SSIM)
 """
 from __future__ import annotations
 
@@ -33,17 +41,25 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 KW = dict(scale_factor=2, width=128, height=32, STN=True, mask=True, srb_nums=5, hidden_units=32)
-PER_GPU_BATCH = 48
-METRIC = 'SR images/sec (16x64->32x128), TSRN train step'
-# one description of the workload for both arms (the driver compares the two lines' metric / config)
-WORKLOAD = ('BASELINE configs[1]: TSRN single-stage TRAIN step, STN on, mask, ImageLoss(gradient,[1,1e-4])*100, '
-            'clip_grad_norm 0.25, Adam(1e-3,(0.5,0.999))')
-# SURVEY §8d / BASELINE.md §3: TSRN train-mode forward = 1.8445 GFLOP/img, train step = 3x forward
-GFLOP_PER_IMG_STEP = 5.53
+METRIC = 'SR images/sec (16x64->32x128), train step'
+STEP_TAIL = 'clip_grad_norm_(SR, 0.25), Adam(1e-3,(0.5,0.999))'
+# per config: description, per-GPU batch, stu_iter, #students, GFLOP per image per train step (3x forward for every module with
+# grad, 1x for the teacher), the fraction of the batch the bounded CPU sample runs
+CONFIGS = {
+    2: dict(workload='BASELINE configs[1]: TSRN single-stage TRAIN step, STN on, mask, ImageLoss(gradient,[1,1e-4])*100, ' + STEP_TAIL,
+            batch=48, stu_iter=0, students=0, gflop=5.53, golden='tsrn_train'),
+    3: dict(workload='BASELINE configs[2]: TPGSR-TSRN (tsrn_tl_cascade) TRAIN step, stu_iter=1, CRNN student + frozen teacher prior, '
+                     'distillation (SemanticLoss*100) + ImageLoss(gradient)*100, STN on, mask, ' + STEP_TAIL + ' over SR + student',
+            batch=48, stu_iter=1, students=1, gflop=11.51, golden='tsrn_tl_train'),
+    4: dict(workload='BASELINE configs[3]: TPGSR-TSRN TRAIN step, stu_iter=3 multi-stage (shared SR model, three students), mask, gradient loss, '
+                     'distillation, ' + STEP_TAIL + ' over SR + students; 48 images per GPU (384 at 8 GPUs)',
+            batch=48, stu_iter=3, students=3, gflop=31.71, golden='tsrn_tl_train'),
+    5: dict(workload='BASELINE configs[4]: TPGSR-SRResNet_TL TRAIN step with CRNN prior (the ASTER evaluation recogniser is outside the train step), '
+                     'MSE*100, mask, ' + STEP_TAIL + ' over SR + student; 32 images per GPU (256 at 8 GPUs)',
+            batch=32, stu_iter=1, students=1, gflop=11.47, golden='srresnet_tl'),
+}
 
-
-# DRAM traffic per launch of the dominant kernel (3x3, 64->64, B=48) from the committed ncu --set full captures (profiles/r01/ncu_*.csv):
-# 13.8 MB read + 0 written inside the kernel's window (12.6 MB of operand planes; the 12.6 MB fp32 output stays in the 126 MB L2)
+# DRAM traffic per launch of the roofline kernels from the committed ncu --set full captures (profiles/r0*/): bytes read + written
 NCU_TRAFFIC_BYTES = {('conv_flat_kernel', 3): 13.77e6, ('conv_tc_kernel', 3): 12.81e6}
 
 
@@ -118,26 +134,47 @@ def synth_batches(n_batches: int, batch: int, seed: int, device, pin: bool):
     return out
 
 
-# ----------------------------------------------------------------------------------------------------------------------
-def cpu_port_images_per_s(sample_batch: int, steps: int, warmup: int, threads: int):
-    """The reference's step on host cores: oracle port of TSRN(STN)+ImageLoss+clip+Adam (oracle/step.py)."""
-    from oracle import step as ostep
-    from oracle.weights import synth_images, synth_state_dict
+# ---------------------------------------------------------------------------------------------------------------------- CPU arm
+def _oracle_state(cfg_id: int):
+    """Reference-keyed parameter dicts (synthetic, seeded) for the oracle step of a config: (sr, [students], teacher)."""
     from oracle.ops import tps_buffers
-    shapes = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'shapes.json')))['tsrn_train']
-    p = synth_state_dict(shapes, 0)
-    for k, v in tps_buffers(16, 64).items():
-        p['tps.' + k] = v
+    from oracle.weights import synth_state_dict
+    shapes = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'shapes.json')))
+    cfg = CONFIGS[cfg_id]
+    sr = synth_state_dict(shapes[cfg['golden']], 0)
+    if cfg_id != 5:
+        for k, v in tps_buffers(16, 64).items():
+            sr['tps.' + k] = v
+    students = [synth_state_dict(shapes['crnn'], 7 + 10 * j) for j in range(cfg['students'])]
+    teacher = synth_state_dict(shapes['crnn'], 7) if cfg['students'] else None
+    return sr, students, teacher
+
+
+def _oracle_step_fn(cfg_id: int):
+    from oracle import step as ostep
+    cfg = CONFIGS[cfg_id]
+    sr, students, teacher = _oracle_state(cfg_id)
     opt = ostep.AdamState()
-    # pick the intra-op thread count that is fastest for this op mix (many small GEMMs: all 128 hyper-threads of the
-    # GPU box are ~100x slower than 16); candidates are timed on a 2-image step
+    if cfg_id == 2:
+        return lambda lr, hr, o=True: ostep.tsrn_train_step(sr, lr, hr, opt if o else None)
+    if cfg_id == 5:
+        return lambda lr, hr, o=True: ostep.srresnet_train_step(sr, students, teacher, lr, hr, opt if o else None)
+    return lambda lr, hr, o=True: ostep.tpgsr_train_step(sr, students, teacher, lr, hr, opt if o else None, stu_iter=cfg['stu_iter'])
+
+
+def cpu_port_images_per_s(cfg_id: int, sample_batch: int, steps: int, warmup: int, threads: int):
+    """The reference's step on host cores: oracle port of the config's train step (oracle/step.py)."""
+    from oracle.weights import synth_images
+    fn = _oracle_step_fn(cfg_id)
+    # pick the intra-op thread count that is fastest for this op mix (many small GEMMs: all hyper-threads of the GPU box are far slower than
+    # 8-32); candidates are timed on a 4-image step
     best = None
     for th in sorted({t for t in (8, 16, 32, 64, threads) if t <= threads}):
         torch.set_num_threads(th)
-        lr, hr = synth_images(2, seed=99)
-        ostep.tsrn_train_step(p, lr, hr, None)
+        lr, hr = synth_images(4, seed=99)
+        fn(lr, hr, False)
         t0 = time.perf_counter()
-        ostep.tsrn_train_step(p, lr, hr, None)
+        fn(lr, hr, False)
         dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
             best = (dt, th)
@@ -149,7 +186,7 @@ def cpu_port_images_per_s(sample_batch: int, steps: int, warmup: int, threads: i
     for i in range(warmup + steps):
         lr, hr = synth_images(sample_batch, seed=1234 + i)
         t0 = time.perf_counter()
-        ostep.tsrn_train_step(p, lr, hr, opt)
+        fn(lr, hr)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -161,49 +198,33 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    cfg_id = args.config
+    cfg = CONFIGS[cfg_id]
     threads = os.cpu_count() or 1
-    sample = 12
-    ips, sec = cpu_port_images_per_s(sample, args.steps, args.warmup, threads)
+    sample = 12 if cfg['batch'] % 12 == 0 else 8
+    ips, sec = cpu_port_images_per_s(cfg_id, sample, args.steps, args.warmup, threads)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'per_gpu_batch': PER_GPU_BATCH, 'lr_hw': [16, 64], 'hr_hw': [32, 128],
+        'config': {'workload': cfg['workload'], 'config_id': cfg_id, 'per_gpu_batch': cfg['batch'], 'lr_hw': [16, 64], 'hr_hw': [32, 128],
                    'implementation': 'CPU oracle port of the same step (oracle/step.py), torch CPU fp32', 'sample_batch_per_step': sample},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cpu_port_images_per_s.threads_used, 'host_cpus': threads, 'kind': 'port',
-                         'sample': f'{args.steps} timed steps of {sample} images (1/4 of the 48-image batch), torch {torch.__version__} CPU fp32'},
+                         'sample': f'{args.steps} timed steps of {sample} images (1/{cfg["batch"] // sample} of the {cfg["batch"]}-image batch), '
+                                   f'torch {torch.__version__} CPU fp32'},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# ----------------------------------------------------------------------------------------------------------------------
-def time_dominant_kernel(device, batch: int, peaks):
-    """3x3 64->64 conv forward on [batch,16,64,64] NHWC through the tcgen05 kernel (tpgsr_conv2d_tc) in the active
-    CONV_MODE: CUDA-event timing on the launch stream (torch's current stream = the stream the C ABI is handed), L2
-    flushed between launches.  achieved = ALGORITHMIC flops (2*M*N*K, one product — the 3 MMAs of split-bf16 are not
-    counted three times) / launch time."""
-    from tpgsr_b200 import ops
-    x = torch.randn(batch, 16, 64, 64, device=device)
-    w = torch.randn(64, 64, 3, 3, device=device) * 0.05
-    b = torch.zeros(64, device=device)
-    need_lo = ops.CONV_MODE == 'bf16x3'
-    (wf, _) = ops.pack_conv_weights_bf16(w, False, need_lo)
-    y = torch.empty(batch, 16, 64, 64, device=device)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    flat = ops.flat_supported(batch, 16, 64, 1, 64, 64, 3, 3, 1, 1)
-    if flat:
-        fp = ops.split_bf16_flat(x, 1, need_lo)
-        run = lambda: ops.conv_flat(fp, wf, b, 64, 3, 3, 1, 1, out=y)
-    else:
-        xp = ops.split_bf16(x, need_lo)
-        run = lambda: ops.conv_tc(xp, wf, b, batch, 16, 64, 64, 64, 3, 3, 1, 1, out=y)
+# ---------------------------------------------------------------------------------------------------------------------- roofline kernels
+def _time_launch(run, flush, n=20):
     for _ in range(3):
         run()
-    torch.cuda.synchronize(device)
+    torch.cuda.synchronize()
     durs = []
-    for _ in range(20):
+    for _ in range(n):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -211,17 +232,205 @@ def time_dominant_kernel(device, batch: int, peaks):
         e1.record()
         e1.synchronize()
         durs.append(e0.elapsed_time(e1) * 1e-3)
-    dur = sum(durs) / len(durs)
-    flops = 2.0 * batch * 16 * 64 * 64 * 576
+    return sum(durs) / len(durs), min(durs)
+
+
+def time_conv_kernel(device, batch: int, H: int, W: int, Ci: int, Co: int, peaks, flush):
+    """One 3x3 'same' conv forward on [batch,H,W,Ci] NHWC through the tensor-core path the engine picks for that geometry, in the active
+    CONV_MODE: CUDA-event timing on the launch stream (torch's current stream = the stream the C ABI is handed), L2 flushed between
+    launches.  achieved = ALGORITHMIC flops (2*M*N*K, one product — the 3 MMAs of split-bf16 are not counted three times) / launch time."""
+    from tpgsr_b200 import ops
+    x = torch.randn(batch, H, W, Ci, device=device)
+    w = torch.randn(Co, Ci, 3, 3, device=device) * 0.05
+    b = torch.zeros(Co, device=device)
+    need_lo = ops.CONV_MODE == 'bf16x3'
+    (wf, _) = ops.pack_conv_weights_bf16(w, False, need_lo)
+    y = torch.empty(batch, H, W, Co, device=device)
+    flat = ops.flat_supported(batch, H, W, 1, Ci, Co, 3, 3, 1, 1)
+    if flat:
+        fp = ops.split_bf16_flat(x, 1, need_lo)
+        run = lambda: ops.conv_flat(fp, wf, b, Co, 3, 3, 1, 1, out=y)
+    else:
+        xp = ops.split_bf16(x, need_lo)
+        run = lambda: ops.conv_tc(xp, wf, b, batch, H, W, Ci, Co, 3, 3, 1, 1, out=y)
+    dur, dmin = _time_launch(run, flush)
+    flops = 2.0 * batch * H * W * Co * Ci * 9
     ach = flops / dur / 1e12
     nprod = 3 if need_lo else 1
     kname = 'conv_flat_kernel' if flat else 'conv_tc_kernel'
-    return {'bound': 'tensor', 'kernel': '%s<%d> (tcgen05+TMA implicit GEMM, 3x3, 64->64, M=%d, N=64, K=576, mode %s)' % (kname, nprod, batch * 1024, ops.CONV_MODE),
+    return {'bound': 'tensor', 'kernel': '%s<%d> (tcgen05+TMA implicit GEMM, 3x3, %d->%d, M=%d, N=%d, K=%d, mode %s)' % (
+                kname, nprod, Ci, Co, batch * H * W, Co, 9 * Ci, ops.CONV_MODE),
             'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops_burst'],
-            'traffic': NCU_TRAFFIC_BYTES.get((kname, nprod)), 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01',
-            'launch_us': dur * 1e6, 'launch_us_min': min(durs) * 1e6, 'algorithmic_flops_per_launch': flops,
+            'traffic': NCU_TRAFFIC_BYTES.get((kname, nprod)) if (Ci, Co) == (64, 64) else None,
+            'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/',
+            'launch_us': dur * 1e6, 'launch_us_min': dmin * 1e6, 'algorithmic_flops_per_launch': flops,
             'mma_flops_per_launch': flops * nprod, 'tensor_pipe_tflops': ach * nprod,
             'peak_source': peaks['source'] + ', bf16 burst (kernel timed alone)'}
+
+
+# ---------------------------------------------------------------------------------------------------------------------- our arm
+def build_workload(cfg_id: int, dev, B: int, use_graph: bool):
+    """(step object, sr module, students, teacher) for a config, weights from torch.manual_seed(0) default initialisers."""
+    from tpgsr_b200.train import TPGSRTrainStep, TSRNTrainStep
+    cfg = CONFIGS[cfg_id]
+    torch.manual_seed(0)
+    if cfg_id == 2:
+        from tpgsr_b200.model.tsrn import TSRN
+        net = TSRN(**KW).to(dev).train()
+        return TSRNTrainStep(net, batch=B, use_graph=use_graph), net, [], None
+    from tpgsr_b200.model.crnn import CRNN
+    if cfg_id == 5:
+        from tpgsr_b200.model.srresnet import SRResNet_TL
+        net = SRResNet_TL(scale_factor=2, width=128, height=32, STN=False, mask=True).to(dev).train()
+    else:
+        from tpgsr_b200.model.tsrn import TSRN_TL
+        net = TSRN_TL(**KW).to(dev).train()
+    students = [CRNN(32, 1, 37, 256).to(dev).train() for _ in range(cfg['students'])]
+    teacher = CRNN(32, 1, 37, 256).to(dev)
+    teacher.load_state_dict(students[0].state_dict())       # no crnn.pth offline: teacher = copy of student 0 at step 0 (SURVEY §8d)
+    teacher.eval()
+    ts = TPGSRTrainStep(net, students, teacher, batch=B, stu_iter=cfg['stu_iter'], use_distill=True, use_graph=use_graph)
+    return ts, net, students, teacher
+
+
+def eager_baseline(cfg_id: int, dev, net, students, teacher, batches, steps: int, warmup: int):
+    """Developer leg: the same step in stock PyTorch on this GPU (oracle/torch_eager.py), weights copied from our modules."""
+    from oracle import torch_eager as te
+    cfg = CONFIGS[cfg_id]
+    if cfg_id == 5:
+        return {'skipped': 'no stock-torch statement of SRResNet_TL'}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sr = te.EagerTSRN(tl=cfg_id != 2)
+        sr.load_state_dict(net.state_dict(), strict=True)
+        sr = sr.to(dev).train()
+        studs = []
+        for s in students:
+            m = te.EagerCRNN()
+            m.load_state_dict(s.state_dict(), strict=True)
+            studs.append(m.to(dev).train())
+        tea = None
+        if teacher is not None:
+            tea = te.EagerCRNN()
+            tea.load_state_dict(teacher.state_dict(), strict=True)
+            tea = tea.to(dev).eval()
+        step = te.EagerStep(sr, studs, tea, cfg['stu_iter'])
+        for i in range(warmup):
+            step(*batches[i % len(batches)])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = step(*batches[i % len(batches)])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sec = e0.elapsed_time(e1) * 1e-3
+        B = batches[0][0].shape[0]
+        out = {'value': B * steps / sec, 'unit': 'images/s', 'ms_per_step': sec / steps * 1e3, 'last_loss': float(loss),
+               'implementation': 'stock PyTorch %s eager: nn.Conv2d/BatchNorm2d/GRU/LSTM (cuDNN %s), F.grid_sample/interpolate, autograd, '
+                                 'clip_grad_norm_, torch.optim.Adam; TF32 off; device-resident inputs; same batches' % (
+                                     torch.__version__, torch.backends.cudnn.version())}
+        # eval-mode forward of the same modules
+        sr.eval()
+        for s in studs:
+            s.eval()
+        x = batches[0][0]
+        fwd = (lambda: te.infer(sr, studs, x, cfg['stu_iter'])) if studs else (lambda: sr(x))
+        with torch.no_grad():
+            for _ in range(warmup):
+                fwd()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(steps):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize(dev)
+        out['inference_images_per_s'] = B * steps / (e0.elapsed_time(e1) * 1e-3)
+        return out
+    except Exception as e:          # a developer leg never costs the contract line
+        return {'error': repr(e)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def inference_and_parity(cfg_id: int, dev, net, students, batches, steps: int, warmup: int):
+    """Eval-mode throughput (CUDA-graphed forward through tpgsr_b200.train.tpgsr_infer / the module) and SR parity vs the CPU oracle."""
+    from tpgsr_b200.train import tpgsr_infer
+    cfg = CONFIGS[cfg_id]
+    out = {}
+    try:
+        net.eval()
+        for s in students:
+            s.eval()
+        B = batches[0][0].shape[0]
+        xbuf = torch.empty_like(batches[0][0])
+        if cfg_id == 2:
+            fwd = lambda: net(xbuf)
+        elif cfg_id == 5:
+            from tpgsr_b200.train import srresnet_infer
+            fwd = lambda: srresnet_infer(net, students, xbuf)
+        else:
+            fwd = lambda: tpgsr_infer(net, students, xbuf, cfg['stu_iter'])
+        with torch.no_grad():
+            xbuf.copy_(batches[0][0])
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                fwd()
+            torch.cuda.current_stream(dev).wait_stream(s)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                y = fwd()
+            for i in range(warmup):
+                xbuf.copy_(batches[i % len(batches)][0])
+                g.replay()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                xbuf.copy_(batches[i % len(batches)][0])
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            out['inference'] = {'value': B * steps / (e0.elapsed_time(e1) * 1e-3), 'unit': 'images/s', 'batch': B,
+                                'api': 'eval-mode forward (no STN, running BN statistics, no prior dropout), CUDA-graphed, device-resident inputs'}
+            # parity: the first 8 images of batch 0 through our eval path vs the CPU oracle with the same (trained-for-K-steps) weights
+            n = 8
+            xs = batches[0][0][:n].contiguous()
+            hr = batches[0][1][:n].cpu()
+            if cfg_id == 2:
+                ours = net(xs)
+            elif cfg_id == 5:
+                ours = srresnet_infer(net, students, xs)
+            else:
+                ours = tpgsr_infer(net, students, xs, cfg['stu_iter'])
+            ours = ours.cpu()
+        from oracle import models as omodels, ops as oops, step as ostep
+        sr_p = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+        stu_p = [{k: v.detach().cpu().clone() for k, v in s.state_dict().items()} for s in students]
+        with torch.no_grad():
+            if cfg_id == 2:
+                ref = omodels.tsrn(xs.cpu(), sr_p, training=False, stn=True)
+            elif cfg_id == 5:
+                ref = ostep.srresnet_infer(sr_p, stu_p, xs.cpu())
+            else:
+                ref = ostep.tpgsr_infer(sr_p, stu_p, xs.cpu(), cfg['stu_iter'])
+        out['parity'] = {'sr_rel_l2_vs_oracle': float((ours - ref).norm() / ref.norm()), 'sr_max_abs_vs_oracle': float((ours - ref).abs().max()),
+                         'psnr': [round(float(oops.calculate_psnr(ours, hr)), 3), round(float(oops.calculate_psnr(ref, hr)), 3)],
+                         'ssim': [round(float(oops.ssim(ours, hr)), 3), round(float(oops.ssim(ref, hr)), 3)],
+                         'what': 'eval-mode SR of %d images after the timed steps: [ours, CPU oracle]; metrics vs the synthetic HR target' % n,
+                         'tolerance': 'north_star: 1e-3 relative, PSNR/SSIM equal to 3 dp'}
+    except Exception as e:
+        out.setdefault('inference', {'error': repr(e)})
+        out.setdefault('parity', {'error': repr(e)})
+    finally:
+        net.train()
+        for s in students:
+            s.train()
+    return out
 
 
 def run_ours(args):
@@ -234,22 +443,17 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
-        # rank 0 must print exactly one JSON line on stdout, and NCCL logs there (its version banner at any NCCL_DEBUG level, WARN included):
-        # send NCCL's log to stderr, drop the debug level, and park stdout on stderr until the JSON line is ready
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        if not os.environ.get('TPGSR_KEEP_NCCL_DEBUG'):
-            os.environ.pop('NCCL_DEBUG', None)
+        # rank 0 must print exactly one JSON line on stdout, and NCCL logs there (its version banner at any NCCL_DEBUG level): park stdout on
+        # stderr until the JSON line is ready.  NCCL_DEBUG is left as the launcher set it, so the driver can read the rank count from the log.
         sys.stdout.flush()
         real_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
     from tpgsr_b200 import ops
-    from tpgsr_b200.model.tsrn import TSRN
-    from tpgsr_b200.train import TSRNTrainStep
-    torch.manual_seed(0)
-    net = TSRN(**KW).to(dev).train()
-    B = args.batch
-    ts = TSRNTrainStep(net, batch=B, use_graph=not args.no_graph)
+    cfg_id = args.config
+    cfg = CONFIGS[cfg_id]
+    B = args.batch or cfg['batch']
+    ts, net, students, teacher = build_workload(cfg_id, dev, B, not args.no_graph)
     dev_batches = synth_batches(8, B, 1234 + 100 * rank, dev, pin=False)
     host_batches = synth_batches(8, B, 1234 + 100 * rank, dev, pin=True)
 
@@ -273,6 +477,9 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        prof = bool(os.environ.get('TPGSR_BENCH_PROFILE')) and not e2e      # ncu --profile-from-start off: only the timed steps are listed
+        if prof:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(args.steps):
             loss = ts(*batches[i % len(batches)])
@@ -280,10 +487,10 @@ def run_ours(args):
                 losses.append(loss.to('cpu', non_blocking=False))      # D2H of the step's result, every step
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
-        if e2e:
-            ms = max(ms, 0.0)
         t = torch.tensor([ms], device=dev)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -305,16 +512,17 @@ def run_ours(args):
             torch.distributed.destroy_process_group()
         return
     peaks = _peaks()
+    api = 'tpgsr_b200.train.%s(images_lr_pinned, images_hr_pinned) -> loss.cpu()' % type(ts).__name__
     line = {
         'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32' if ops.CONV_MODE != 'bf16' else 'bf16', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': B * world,
+        'config': {'workload': cfg['workload'], 'config_id': cfg_id, 'per_gpu_batch': B, 'global_batch': B * world,
                    'lr_hw': [16, 64], 'hr_hw': [32, 128], 'parallelism': f'dp{world}', 'cuda_graph': not args.no_graph,
                    'precision': {'bf16x3': 'fp32 tensors everywhere; conv / 1x1 / linear contractions as split-bf16 (hi*hi + hi*lo + lo*hi) on tcgen05 with '
                                            'fp32 TMEM accumulation = fp32-class accuracy (the parity mode, SR output within 1e-3 of the fp32 reference); '
-                                           'GRU / BN / TPS / losses / Adam in fp32',
+                                           'GRU / LSTM / BN / TPS / losses / Adam in fp32',
                                  'bf16': 'single bf16 product per contraction (throughput mode; misses the 1e-3 parity budget, labelled)',
                                  'fp32': 'CUDA-core fp32 contractions'}[ops.CONV_MODE],
                    'l2': 'no explicit flush: the step touches >1 GB of activations/stashes per replay (>> 126 MB L2); inputs rotate over 8 distinct batches',
@@ -323,42 +531,29 @@ def run_ours(args):
                    'switches': {k: True for k, on in (('TPGSR_PREPACK', ops.PREPACK), ('TPGSR_FLAT_OCC2', ops.FLAT_OCC2),
                                                       ('TPGSR_BWD_PRODUCTS=2', ops.BWD2), ('TPGSR_WGRAD_PRODUCTS=1', ops.WGRAD1)) if on}},
         'e2e': {'value': e2e_val, 'unit': 'images/s', 'h2d_bytes_per_step': B * (4 * 16 * 64 + 4 * 32 * 128) * 4, 'd2h_bytes_per_step': 4,
-                'ms_per_step': sec_e2e / args.steps * 1e3, 'api': 'tpgsr_b200.train.TSRNTrainStep(images_lr_pinned, images_hr_pinned) -> loss.cpu()'},
+                'ms_per_step': sec_e2e / args.steps * 1e3, 'api': api},
         'gpu_launches': launches_per_step * args.steps,
         'launches_per_step': launches_per_step,
         'clocks': clocks.summary(),
-        'step_tflops': value * GFLOP_PER_IMG_STEP / 1e3,
-        'step_frac_of_sustained_bf16_peak': value * GFLOP_PER_IMG_STEP / 1e3 / peaks['tflops_sustained'],
+        'step_tflops': value * cfg['gflop'] / 1e3,
+        'step_frac_of_sustained_bf16_peak': value * cfg['gflop'] / 1e3 / peaks['tflops_sustained'],
     }
     if world == 1 and not os.environ.get('TPGSR_BENCH_NO_ROOFLINE'):
-        line['roofline'] = time_dominant_kernel(dev, B, peaks)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        line['roofline'] = time_conv_kernel(dev, B, 16, 64, 64, 64, peaks, flush)
+        if cfg['students']:
+            line['roofline_crnn'] = time_conv_kernel(dev, B, 4, 26, 512, 512, peaks, flush)
+        del flush
+    if world == 1 and not os.environ.get('TPGSR_BENCH_NO_INFER'):
+        line.update(inference_and_parity(cfg_id, dev, net, students, dev_batches, args.steps, args.warmup))
+    if world == 1 and not os.environ.get('TPGSR_BENCH_NO_EAGER'):
+        line['gpu_eager_baseline'] = eager_baseline(cfg_id, dev, net, students, teacher, dev_batches, max(args.steps // 2, 3), 3)
     if world == 1 and not os.environ.get('TPGSR_BENCH_NO_CPU'):     # (developer switch: skip the ~60 s CPU leg)
         threads = os.cpu_count() or 1
-        ips, sec_cpu = cpu_port_images_per_s(12, 2, 1, threads)
+        sample = 12 if B % 12 == 0 else 8
+        ips, sec_cpu = cpu_port_images_per_s(cfg_id, sample, 2, 1, threads)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cpu_port_images_per_s.threads_used, 'host_cpus': threads, 'kind': 'port',
-                                'sample': '2 timed steps of 12 images (1/4 batch) of the same train step, oracle port, torch CPU fp32'}
-    if world == 1 and os.environ.get('TPGSR_BENCH_INFER') == '1':
-        # optional extra (SURVEY §8d also asks for inference images/s): eval-mode forward through the public nn.Module API (no STN, running BN
-        # statistics), device-resident inputs, eager launches.  Off by default: the contract line is the train step.
-        try:
-            net.eval()
-            x = dev_batches[0][0]
-            with torch.no_grad():
-                for _ in range(args.warmup):
-                    net(x)
-                torch.cuda.synchronize(dev)
-                i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                i0.record()
-                for i in range(args.steps):
-                    net(dev_batches[i % len(dev_batches)][0])
-                i1.record()
-                torch.cuda.synchronize(dev)
-            line['inference'] = {'value': B * args.steps / (i0.elapsed_time(i1) * 1e-3), 'unit': 'images/s', 'batch': B,
-                                 'api': 'TSRN.eval()(images_lr) under torch.no_grad(), eager'}
-        except Exception as e:      # never let the optional leg cost the contract line
-            line['inference'] = {'error': repr(e)}
-        finally:
-            net.train()
+                                'sample': f'2 timed steps of {sample} images of the same train step (config {cfg_id}), oracle port, torch CPU fp32'}
     if world > 1:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -375,13 +570,18 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)
+    ap.add_argument('--config', type=int, default=0, choices=[0] + sorted(CONFIGS),
+                    help='workload (SURVEY §8d numbering); default 3 (or $TPGSR_BENCH_CONFIG)')
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the config\'s)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='developer switch: skip the host-buffer leg (profiler runs)')
     args = ap.parse_args()
     if os.environ.get('TPGSR_BENCH_TRACE'):
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ['TPGSR_BENCH_TRACE']), exit=True)
+    if args.config == 0:
+        # the same per-GPU workload at every N (weak scaling): a default that changed with N would make the 1 -> 8 curve compare two workloads
+        args.config = int(os.environ.get('TPGSR_BENCH_CONFIG', '0')) or 3
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference_arm(args)

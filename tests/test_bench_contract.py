@@ -21,7 +21,8 @@ def test_reference_arm_prints_one_contract_line():
     sys.path.insert(0, ROOT)
     import bench
     assert d['impl'] == 'reference' and d['metric'] == bench.METRIC and d['unit'] == 'images/s' and d['higher_is_better'] is True
-    assert d['config']['workload'] == bench.WORKLOAD and d['config']['per_gpu_batch'] == bench.PER_GPU_BATCH
+    cfg = bench.CONFIGS[3]                      # the default workload at every N
+    assert d['config']['workload'] == cfg['workload'] and d['config']['per_gpu_batch'] == cfg['batch'] and d['config']['config_id'] == 3
     assert d['n_gpus'] == 1 and d['steps'] == 1 and d['warmup'] == 0 and d['value'] > 0 and d['ms_per_step'] > 0
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'images' in cb['sample']

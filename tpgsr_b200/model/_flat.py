@@ -25,6 +25,7 @@ class FlatState:
         self.gviews: Dict[str, torch.Tensor] = {}
         self.offsets: Dict[str, Tuple[int, int]] = {}
         self.nbt = None
+        self.frozen = False           # set by the train steps once CUDA graphs hold this buffer's addresses
 
     # -- layout -----------------------------------------------------------------------------------------------------
     def _order(self, params: Dict[str, nn.Parameter]) -> List[str]:
@@ -39,12 +40,25 @@ class FlatState:
     def is_current(self) -> bool:
         if self.flat is None:
             return False
+        # EVERY parameter is checked (a few hundred pointer compares): ``module._apply`` (.to / .cuda / .float) re-runs
+        # ``RNNBase.flatten_parameters`` on torch 2.11, which moves the GRU / LSTM weights into a fresh cuDNN buffer while the conv weights
+        # keep their flat-buffer storage — looking at the first parameter only would miss that and keep training the stale flat copy
+        base, dev = self.flat.data_ptr(), self.flat.device
+        n = 0
         for name, p in self.module.named_parameters():
-            off, _ = self.offsets[name]
-            if p.device != self.flat.device or p.data_ptr() != self.flat.data_ptr() + 4 * off:
+            ent = self.offsets.get(name)
+            if ent is None or p.device != dev or p.data_ptr() != base + 4 * ent[0]:
                 return False
-            break
-        return True
+            n += 1
+        return n == len(self.offsets)
+
+    def assert_attached(self) -> None:
+        """Per-step guard of the train steps (two pointer compares): the first parameter in flat order is an RNN weight whenever the module
+        has one (fused groups are laid out first) — the tensors ``flatten_parameters`` moves — and the last one is a conv / BN parameter."""
+        for name, p in self._sentinels:
+            if p.data_ptr() != self.flat.data_ptr() + 4 * self.offsets[name][0]:
+                raise RuntimeError('parameter %s of %s no longer lives in the flat buffer the captured CUDA graphs use (a .to()/.cuda()/.float() '
+                                   'after the train step was built?) — rebuild the train step' % (name, type(self.module).__name__))
 
     def rebuild(self) -> None:
         params = dict(self.module.named_parameters())
@@ -77,6 +91,7 @@ class FlatState:
             self.views[fname] = flat[o0:o0 + k].view(*shape)
             self.gviews[fname] = gflat[o0:o0 + k].view(*shape)
         self.flat, self.gflat, self.n = flat, gflat, total
+        self._sentinels = [(order[0], params[order[0]]), (order[-1], params[order[-1]])] if order else []
         # BatchNorm counters -> one flat int64 buffer
         owners = [(m, 'num_batches_tracked') for m in self.module.modules()
                   if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
@@ -93,6 +108,10 @@ class FlatState:
 
     def ensure(self) -> None:
         if not self.is_current():
+            if self.flat is not None and self.frozen:
+                raise RuntimeError('the flat parameter buffer of %s was detached (a .to()/.cuda()/.float() after the train step was built moved '
+                                   'parameters out of it) — captured CUDA graphs still point at the old buffer; rebuild the train step'
+                                   % type(self.module).__name__)
             self.rebuild()
         else:
             for name, b in self.module.named_buffers():

@@ -53,7 +53,12 @@ class TPSSpatialTransformer(nn.Module):
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
-        self.reprT = self.target_coordinate_repr.t().contiguous()
+        # in place: captured CUDA graphs (train steps) hold this buffer's address
+        rt = self.target_coordinate_repr.t()
+        if self.reprT.shape == rt.shape and self.reprT.device == rt.device:
+            self.reprT.copy_(rt)
+        else:
+            self.reprT = rt.contiguous()
 
     def forward(self, input, source_control_points):
         raise RuntimeError('TPSSpatialTransformer is executed inside TSRN/TSRN_TL.forward by the tpgsr_b200 CUDA path')

@@ -150,6 +150,9 @@ class _TSRNBase(nn.Module):
             raise ValueError(f'expected float32 NCHW input with {self.in_planes} channels, got {tuple(x.shape)} {x.dtype}')
         if self.in_planes != 4:
             raise NotImplementedError('mask=False (3 input planes) is not wired to the sm_100a kernels yet')
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError('TSRN input-image gradients are not produced (the reference feeds data tensors; the cascade without '
+                                      '--sr_share is out of scope) — detach the image or use tpgsr_b200.train.TPGSRTrainStep')
 
     def _run_forward(self, x, text_emb, want_backward: bool):
         self._check_input(x)
@@ -171,7 +174,8 @@ class _TSRNBase(nn.Module):
 
     def _run_backward(self, saved_all, dsr, text_requires_grad: bool):
         if saved_all is None:
-            raise RuntimeError('backward through a TSRN forward that ran without grad enabled')
+            raise RuntimeError('no saved state for this backward: either the forward ran without grad enabled, or this is a second backward '
+                               'through the same forward (retain_graph / double backward are not supported: the stash is released after use)')
         ectx, saved, s_text = saved_all
         st = self._flat
         ectx._written = set(st.live_grads())

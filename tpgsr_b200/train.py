@@ -92,6 +92,7 @@ class TSRNTrainStep:
         self._g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
             self._optim()
+        self.st.frozen = True            # the graphs hold the flat buffers' addresses: a later rebuild must raise, not silently detach
 
     # ---- public -----------------------------------------------------------------------------------------------------
     def load_batch(self, images_lr: torch.Tensor, images_hr: torch.Tensor) -> None:
@@ -104,6 +105,7 @@ class TSRNTrainStep:
         if self.use_graph:
             if self._g_fb is None:
                 self._capture()
+            self.st.assert_attached()
             self._g_fb.replay()
             if self.world > 1:
                 torch.distributed.all_reduce(self.st.gflat, group=self.pg)
@@ -276,6 +278,8 @@ class TPGSRTrainStep:
         self._g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
             self._optim()
+        for m in mods + [self.teacher]:
+            m._flat.frozen = True        # the graphs hold the flat buffers' addresses: a later rebuild must raise, not silently detach
 
     def load_batch(self, images_lr, images_hr):
         self.lr_buf.copy_(images_lr, non_blocking=True)
@@ -285,6 +289,8 @@ class TPGSRTrainStep:
         if self.use_graph:
             if self._g_fb is None:
                 self._capture()
+            for m in [self.model] + self.students:
+                m._flat.assert_attached()
             self._g_fb.replay()
             self._all_reduce()
             self._g_opt.replay()
