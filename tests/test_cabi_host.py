@@ -208,3 +208,41 @@ def test_pack_store_job_table_layout():
     # re-registering a key replaces its job and invalidates the table
     st.add('fp32', 'a', 1, w2, (torch.zeros(27, 32), torch.zeros(288, 3)))
     assert st._table is None and len(st.jobs) == 3
+
+
+def test_flat_arena_one_bucket_for_sr_and_students():
+    """Host logic of the multi-GPU bucket: SR model + students live in ONE parameter / gradient arena (one all-reduce, one
+    clip+Adam launch pair), the clip range is the SR model, state_dict values survive the move, a detached parameter is detected."""
+    from tpgsr_b200.model._flat import FlatArena
+    from tpgsr_b200.model.crnn import CRNN
+    from tpgsr_b200.model.tsrn import TSRN_TL
+    torch.manual_seed(3)
+    sr = TSRN_TL(scale_factor=2, width=128, height=32, STN=True, mask=True, srb_nums=5, hidden_units=32)
+    studs = [CRNN(32, 1, 37, 256) for _ in range(2)]
+    before = [{k: v.clone() for k, v in m.state_dict().items()} for m in [sr] + studs]
+    arena = FlatArena([sr] + studs)
+    n_sr = sum(p.numel() for p in sr.parameters())
+    assert arena.n_clipped == n_sr and arena.flat.numel() == sum(n for _, n in arena.ranges) == arena.gflat.numel()
+    base = arena.flat.data_ptr()
+    for (off, n), m in zip(arena.ranges, [sr] + studs):
+        assert m._flat.is_current() and m._flat.arena is arena
+        for p in m.parameters():
+            assert base + 4 * off <= p.data_ptr() < base + 4 * (off + n)
+    for m, sd in zip([sr] + studs, before):
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+    # gradients written through a module's views land in the arena's gradient buffer
+    studs[1]._flat.gviews['cnn.conv0.weight'].fill_(2.0)
+    off, n = arena.ranges[2]
+    assert float(arena.gflat[off:off + n].sum()) == 2.0 * studs[1].cnn.conv0.weight.numel()
+    # a parameter moved out of the arena (what RNNBase.flatten_parameters does on .to()) is detected: every parameter is checked
+    w = studs[0].rnn[0].rnn.weight_hh_l0
+    w.data = w.data.clone()
+    assert not studs[0]._flat.is_current()
+    with pytest.raises(RuntimeError):
+        studs[0]._flat.ensure()
+    # the per-step guard looks at two sentinels only; flatten_parameters moves every RNN weight, the first in flat order included
+    for q in studs[1].rnn[0].rnn.parameters():
+        q.data = q.data.clone()
+    with pytest.raises(RuntimeError):
+        studs[1]._flat.assert_attached()

@@ -1,0 +1,232 @@
+"""GPU parity at the BENCHED shapes and over trajectories:
+
+* the B=48 TSRN train step bench.py times (config 2) vs the CPU oracle: SR output, loss, every gradient tensor element-wise, grad norm;
+* a 3-step trajectory on smooth (well-conditioned) crops with ELEMENT-WISE comparison of every updated weight against the oracle's
+  trajectory — the quantity compared is the update p_k - p_0 per element, in units of the learning rate;
+* the cascade step with stu_iter=3 (config 4's depth) and B=48 eval-mode PSNR / SSIM to 3 dp.
+
+Tolerances (north_star: 1e-3 relative fp32 on outputs; PSNR/SSIM equal to 3 dp): written next to each assert.  Parameters whose gradient
+is mathematically zero (a conv bias feeding a train-mode BatchNorm) receive +-lr noise steps from Adam in the reference as well: they are
+checked for boundedness only.  STN-head parameters: d(loss)/d(control points) is ill-conditioned on any input with a binarised mask
+channel, so trajectories use a smooth 4th channel, where the head is pinned like every other tensor.
+"""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+KW = dict(scale_factor=2, width=128, height=32, STN=True, mask=True, srb_nums=5, hidden_units=32)
+LR_RATE = 1e-3
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def _note(name, obj):
+    """Statistics the tolerances were set from: dropped next to the other GPU-run artefacts (scratch, not asserted on)."""
+    try:
+        os.makedirs(OUT, exist_ok=True)
+        with open(os.path.join(OUT, 'parity_stats.jsonl'), 'a') as f:
+            f.write(json.dumps({'test': name, **obj}) + '\n')
+    except OSError:
+        pass
+
+
+def _smooth_batch(n, seed):
+    from oracle.weights import synth_images
+    lr, hr = synth_images(n, seed=seed, smooth=True)
+    lr[:, 3] = lr[:, :3].mean(1)
+    hr[:, 3] = hr[:, :3].mean(1)
+    return lr, hr
+
+
+def _tsrn_sd(shapes, seed=1):
+    from oracle.weights import synth_state_dict
+    sd = synth_state_dict(shapes['tsrn_train'], seed)
+    for k, v in load_golden('tsrn_train').items():
+        if k.startswith('tps.'):
+            sd[k] = torch.from_numpy(v)
+    return sd
+
+
+def _is_zero_grad_param(k, g_ref):
+    return float(g_ref.norm()) < 2e-3
+
+
+def _compare_updates(name, p0, ours, ref, grads_ref, steps, frac_tol, elem_tol_lr, skip=()):
+    """Element-wise: |(ours - p0) - (ref - p0)| <= elem_tol_lr * lr * steps for all but `frac_tol` of each tensor's elements."""
+    stats = []
+    for k, r in ref.items():
+        if any(s in k for s in skip) or k not in ours:
+            continue
+        du, dr = (ours[k].cpu() - p0[k]).double(), (r - p0[k]).double()
+        bound = 2.05 * LR_RATE * steps                   # Adam's |step| <= lr / (1 - beta1) ~ 2 lr early on
+        assert float(du.abs().max()) <= bound, (k, float(du.abs().max()))
+        if _is_zero_grad_param(k, grads_ref[k]):
+            continue
+        bad = float(((du - dr).abs() > elem_tol_lr * LR_RATE * steps).double().mean())
+        stats.append((bad, rel_err(du, dr), k))
+    stats.sort(reverse=True)
+    _note(name, {'worst_bad_fraction': stats[:6], 'worst_rel': sorted(((r, k) for _, r, k in stats), reverse=True)[:6]})
+    assert stats[0][0] <= frac_tol, stats[:8]
+    return stats
+
+
+def test_tsrn_b48_train_step_vs_oracle(shapes):
+    """The exact shape bench.py --config 2 times: B=48, STN on, one CUDA-graphed step."""
+    from oracle import step as ostep
+    from tpgsr_b200.model.tsrn import TSRN
+    from tpgsr_b200.train import TSRNTrainStep
+    sd = _tsrn_sd(shapes)
+    lr, hr = _smooth_batch(48, 31)
+    p = {k: v.clone() for k, v in sd.items()}
+    out = ostep.tsrn_train_step(p, lr, hr, ostep.AdamState())
+    net = TSRN(**KW)
+    net.load_state_dict(sd, strict=False)
+    net = net.to(_dev()).train()
+    ts = TSRNTrainStep(net, batch=48, use_graph=True)
+    loss = float(ts(lr.to(_dev()), hr.to(_dev())))
+    assert abs(loss - float(out['loss'])) < 1e-4 * abs(float(out['loss'])), (loss, float(out['loss']))      # 1e-4 relative
+    assert rel_err(ts.sr, out['sr']) < 3e-4, rel_err(ts.sr, out['sr'])                                          # budget 1e-3
+    assert float((ts.sr.cpu() - out['sr']).abs().max()) < 1e-3
+    assert abs(ts.opt.grad_norm - float(out['grad_norm'])) < 5e-3 * float(out['grad_norm']), (ts.opt.grad_norm, float(out['grad_norm']))
+    worst = []
+    for k, g_ref in out['grads'].items():
+        got = net._flat.gviews[k].cpu()
+        if _is_zero_grad_param(k, g_ref):
+            assert float(got.norm()) < 5e-2, (k, float(got.norm()))
+            continue
+        worst.append((rel_err(got, g_ref), k))
+    worst.sort(reverse=True)
+    _note('tsrn_b48_step', {'loss': [loss, float(out['loss'])], 'sr_rel': rel_err(ts.sr, out['sr']), 'worst_grads': worst[:8]})
+    assert worst[0][0] < 5e-3, worst[:8]                   # every gradient tensor, STN head included (smooth 4th channel), rel. L2
+    ours = {k: v.detach() for k, v in net.state_dict().items()}
+    ref = {k: v for k, v in p.items() if ostep.is_param(k)}
+    _compare_updates('tsrn_b48_step_updates', sd, ours, ref, out['grads'], 1, frac_tol=0.01, elem_tol_lr=0.05)
+
+
+def test_tsrn_three_step_trajectory_elementwise(shapes):
+    """3 graphed steps on smooth crops (B=8), every weight compared element-wise with the oracle's trajectory after each step."""
+    from oracle import step as ostep
+    from tpgsr_b200.model.tsrn import TSRN
+    from tpgsr_b200.train import TSRNTrainStep
+    sd = _tsrn_sd(shapes)
+    p = {k: v.clone() for k, v in sd.items()}
+    opt = ostep.AdamState()
+    net = TSRN(**KW)
+    net.load_state_dict(sd, strict=False)
+    net = net.to(_dev()).train()
+    ts = TSRNTrainStep(net, batch=8, use_graph=True)
+    for it in range(3):
+        lr, hr = _smooth_batch(8, 40 + it)
+        out = ostep.tsrn_train_step(p, lr, hr, opt)
+        loss = float(ts(lr.to(_dev()), hr.to(_dev())))
+        assert abs(loss - float(out['loss'])) < (1e-4 if it == 0 else 2e-3) * abs(float(out['loss'])), (it, loss, float(out['loss']))
+        assert abs(ts.opt.grad_norm - float(out['grad_norm'])) < (5e-3 if it == 0 else 3e-2) * float(out['grad_norm']), (it, ts.opt.grad_norm)
+        ours = {k: v.detach() for k, v in net.state_dict().items()}
+        ref = {k: v for k, v in p.items() if ostep.is_param(k)}
+        # after step 1 an element's update is -lr*sign(g): equal unless the gradient element is at the noise level; later steps are smooth
+        # functions of the gradient history: allow 10% of lr per step on all but a few % of a tensor's elements.  The STN head is compared
+        # after the first step only: from the second step on its trajectory is chaotic even between two fp32 CPU implementations of the
+        # same math (oracle vs stock torch modules, 1e-6 apart: 35% of its elements differ by > 0.1 lr per step after 3 steps, while
+        # every other tensor stays below 1% — measured with oracle/torch_eager.py)
+        _compare_updates(f'tsrn_traj_step{it}', sd, ours, ref, out['grads'], it + 1, frac_tol=0.02 if it == 0 else 0.05 * it,
+                         elem_tol_lr=0.10, skip=() if it == 0 else ('stn_head.',))
+        for k, v in net.state_dict().items():
+            if 'running_' in k:
+                assert rel_err(v, p[k]) < 2e-4, (it, k)
+
+
+def _cascade_models(shapes, n_students):
+    from oracle.weights import synth_state_dict
+    from tpgsr_b200.model.crnn import CRNN
+    from tpgsr_b200.model.tsrn import TSRN_TL
+    sd = synth_state_dict(shapes['tsrn_tl_train'], 2)
+    for k, v in load_golden('tsrn_tl_train').items():
+        if k.startswith('tps.'):
+            sd[k] = torch.from_numpy(v)
+    sr = TSRN_TL(**KW)
+    sr.load_state_dict(sd, strict=False)
+    stu_sd = [synth_state_dict(shapes['crnn'], 7 + 10 * j) for j in range(n_students)]
+    students = []
+    for s in stu_sd:
+        m = CRNN(32, 1, 37, 256)
+        m.load_state_dict(s)
+        students.append(m.to(_dev()).train())
+    tea_sd = synth_state_dict(shapes['crnn'], 7)
+    teacher = CRNN(32, 1, 37, 256)
+    teacher.load_state_dict(tea_sd)
+    return sr.to(_dev()).train(), students, teacher.to(_dev()).eval(), sd, stu_sd, tea_sd
+
+
+def test_cascade_stu_iter3_step_vs_oracle(shapes):
+    """Config 4's depth: three stages, three students, shared SR model, one arena / one Adam launch; B=8 smooth crops."""
+    from oracle import step as ostep
+    from tpgsr_b200.train import TPGSRTrainStep
+    sr, students, teacher, sd, stu_sd, tea_sd = _cascade_models(shapes, 3)
+    lr, hr = _smooth_batch(8, 61)
+    p_sr = {k: v.clone() for k, v in sd.items()}
+    p_stu = [{k: v.clone() for k, v in s.items()} for s in stu_sd]
+    out = ostep.tpgsr_train_step(p_sr, p_stu, {k: v.clone() for k, v in tea_sd.items()}, lr, hr, ostep.AdamState(), stu_iter=3)
+    ts = TPGSRTrainStep(sr, students, teacher, batch=8, stu_iter=3, use_distill=True, use_graph=True)
+    loss = float(ts(lr.to(_dev()), hr.to(_dev())))
+    assert abs(loss - float(out['loss'])) < 2e-4 * abs(float(out['loss'])), (loss, float(out['loss']))
+    assert abs(float(ts.loss_img) - float(out['loss_img'])) < 2e-4 * abs(float(out['loss_img']))
+    assert abs(float(ts.loss_distill) - float(out['loss_distill'])) < 1e-3 * abs(float(out['loss_distill']))
+    assert rel_err(ts.sr, out['sr']) < 5e-4, rel_err(ts.sr, out['sr'])
+    assert abs(ts.opt.grad_norm - float(out['grad_norm'])) < 1e-2 * float(out['grad_norm']), (ts.opt.grad_norm, float(out['grad_norm']))
+    worst = []
+    for k, g_ref in out['sr_grads'].items():
+        if _is_zero_grad_param(k, g_ref):
+            continue
+        worst.append((rel_err(sr._flat.gviews[k], g_ref), 'sr.' + k))
+    for j, gd in enumerate(out['stu_grads']):
+        for k, g_ref in gd.items():
+            if _is_zero_grad_param(k, g_ref):
+                continue
+            worst.append((rel_err(students[j]._flat.gviews[k], g_ref), f'stu{j}.' + k))
+    worst.sort(reverse=True)
+    _note('cascade_stu3', {'worst_grads': worst[:10], 'loss': [loss, float(out['loss'])]})
+    assert worst[0][0] < 2e-2, worst[:10]           # three chained CRNN+SR stages: 2e-2 per tensor (non-STN tensors sit near 2e-3)
+    ours = {k: v.detach() for k, v in sr.state_dict().items()}
+    _compare_updates('cascade_stu3_sr_updates', sd, ours, {k: v for k, v in p_sr.items() if ostep.is_param(k)}, out['sr_grads'], 1, 0.02, 0.05)
+    for j in range(3):
+        ours = {k: v.detach() for k, v in students[j].state_dict().items()}
+        _compare_updates(f'cascade_stu3_stu{j}_updates', stu_sd[j], ours, {k: v for k, v in p_stu[j].items() if ostep.is_param(k)},
+                         out['stu_grads'][j], 1, 0.02, 0.05)
+    assert int(sr.block2.bn1.num_batches_tracked) == 3 and int(students[2].cnn.batchnorm2.num_batches_tracked) == 1
+
+
+def test_eval_b48_psnr_ssim_3dp(shapes):
+    """B=48 eval-mode SR of TSRN and of the cascade (stu_iter=1) vs the oracle: 1e-3 relative, PSNR / SSIM equal to 3 dp."""
+    from oracle import models, ops as o, step as ostep
+    from oracle.weights import synth_images
+    from tpgsr_b200.model.tsrn import TSRN
+    from tpgsr_b200.train import tpgsr_infer
+    lr, hr = synth_images(48, seed=90)
+    sd = _tsrn_sd(shapes)
+    net = TSRN(**KW)
+    net.load_state_dict(sd, strict=False)
+    net = net.to(_dev()).eval()
+    with torch.no_grad():
+        ours = net(lr.to(_dev())).cpu()
+        ref = models.tsrn(lr, {k: v.clone() for k, v in sd.items()}, training=False, stn=True)
+    assert rel_err(ours, ref) < 2e-4
+    assert abs(float(o.calculate_psnr(ours, hr)) - float(o.calculate_psnr(ref, hr))) < 5e-4
+    assert abs(float(o.ssim(ours, hr)) - float(o.ssim(ref, hr))) < 5e-4
+    sr, students, _, sd_tl, stu_sd, _ = _cascade_models(shapes, 1)
+    sr.eval()
+    students[0].eval()
+    ours = tpgsr_infer(sr, students, lr.to(_dev()), stu_iter=1).cpu()
+    ref = ostep.tpgsr_infer({k: v.clone() for k, v in sd_tl.items()}, [dict(stu_sd[0])], lr, stu_iter=1)
+    assert rel_err(ours, ref) < 3e-4
+    assert abs(float(o.calculate_psnr(ours, hr)) - float(o.calculate_psnr(ref, hr))) < 5e-4
+    assert abs(float(o.ssim(ours, hr)) - float(o.ssim(ref, hr))) < 5e-4

@@ -308,3 +308,30 @@ def test_resize_normalize_bit_exact():
         a = (r.rand(r.randint(1, 70), r.randint(1, 220), 3) * 255).astype(np.uint8)
         for size in ((128, 32), (64, 16), (100, 32)):
             assert np.array_equal(resize.resize_bicubic_u8(a, size), np.array(Image.fromarray(a, 'RGB').resize(size, Image.BICUBIC)))
+
+
+def test_torch_eager_matches_oracle(shapes):
+    """oracle/torch_eager.py (the stock-PyTorch statement bench.py times as `gpu_eager_baseline`) computes the same cascade step as the
+    oracle: identical loss, and identical updates wherever Adam's first step is not a coin flip on a noise-level gradient."""
+    from oracle import step as ostep, torch_eager as te
+    from oracle.ops import tps_buffers
+    from oracle.weights import synth_images, synth_state_dict
+    sd = synth_state_dict(shapes['tsrn_tl_train'], 2)
+    sd.update({'tps.' + k: v for k, v in tps_buffers(16, 64).items()})
+    sr = te.EagerTSRN(tl=True)
+    sr.load_state_dict(sd, strict=True)
+    stu, tea = te.EagerCRNN(), te.EagerCRNN()
+    stu.load_state_dict(synth_state_dict(shapes['crnn'], 7), strict=True)
+    tea.load_state_dict(synth_state_dict(shapes['crnn'], 7), strict=True)
+    lr, hr = synth_images(4, seed=60, smooth=True)
+    loss = te.EagerStep(sr.train(), [stu.train()], tea.eval(), 1)(lr, hr)
+    p_sr = {k: v.clone() for k, v in sd.items()}
+    out = ostep.tpgsr_train_step(p_sr, [synth_state_dict(shapes['crnn'], 7)], synth_state_dict(shapes['crnn'], 7), lr, hr,
+                                 ostep.AdamState(), 1)
+    assert abs(float(loss) - float(out['loss'])) < 1e-5 * abs(float(out['loss']))
+    new = sr.state_dict()
+    for k, g in out['sr_grads'].items():
+        if 'stn_head' in k or float(g.norm()) < 2e-3:
+            continue
+        du, dr = new[k] - sd[k], p_sr[k] - sd[k]
+        assert float(((du - dr).abs() > 1e-4).float().mean()) < 0.01, k

@@ -63,3 +63,20 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// Deterministic block-wide sum of one double per thread (blockDim.x = 256): fixed shuffle tree inside the warps, then the eight warp
+// totals are added in order by thread 0, which alone receives the result.  Used by the scalar "finalize" tails of the two-stage
+// reductions (loss values, PReLU slope gradient, gradient norm) — a single thread looping over the partials cost 30-60 us per scalar.
+__device__ __forceinline__ double block_sum_d256(double v) {
+    __shared__ double sh_block_sum[8];
+    v = warp_sum_d(v);
+    if ((threadIdx.x & 31) == 0) sh_block_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sh_block_sum[i];
+    }
+    __syncthreads();
+    return s;
+}

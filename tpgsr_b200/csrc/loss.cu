@@ -55,11 +55,13 @@ image_loss_fwd_kernel(const float* __restrict__ o, const float* __restrict__ tg,
     }
 }
 
-__global__ void image_loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double n_mse, double n_gp,
+__global__ void __launch_bounds__(256) image_loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double n_mse, double n_gp,
                                            float w0, float w1, float* __restrict__ loss, int accumulate, float out_scale) {
-    if (threadIdx.x || blockIdx.x) return;
     double a = 0.0, b = 0.0;
-    for (int i = 0; i < nblocks; ++i) { a += partial[i * 2]; b += partial[i * 2 + 1]; }
+    for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[i * 2]; b += partial[i * 2 + 1]; }
+    a = block_sum_d256(a);
+    b = block_sum_d256(b);
+    if (threadIdx.x) return;
     float v = (float)((double)w0 * (a / n_mse) + (n_gp > 0 ? (double)w1 * (b / n_gp) : 0.0)) * out_scale;
     loss[0] = accumulate ? loss[0] + v : v;
 }
@@ -129,11 +131,13 @@ semantic_loss_fwd_kernel(const float* __restrict__ p, const float* __restrict__ 
     }
 }
 
-__global__ void semantic_loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double n, float* __restrict__ loss,
+__global__ void __launch_bounds__(256) semantic_loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double n, float* __restrict__ loss,
                                               int accumulate, float out_scale) {
-    if (threadIdx.x || blockIdx.x) return;
     double a = 0.0, b = 0.0;
-    for (int i = 0; i < nblocks; ++i) { a += partial[i * 2]; b += partial[i * 2 + 1]; }
+    for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[i * 2]; b += partial[i * 2 + 1]; }
+    a = block_sum_d256(a);
+    b = block_sum_d256(b);
+    if (threadIdx.x) return;
     float v = (float)(a / n + b / n) * out_scale;
     loss[0] = accumulate ? loss[0] + v : v;
 }
@@ -174,7 +178,7 @@ int tpgsr_image_loss_fwd(const float* out, const float* target, int B, int C, in
     int rc = tpgsr_launch_status();
     if (rc) return rc;
     int cg = C < 3 ? C : 3;
-    image_loss_finalize_kernel<<<1, 32, 0, stream>>>(partial, grid, (double)n, gradient ? (double)B * cg * H * W : 0.0, w0, w1,
+    image_loss_finalize_kernel<<<1, 256, 0, stream>>>(partial, grid, (double)n, gradient ? (double)B * cg * H * W : 0.0, w0, w1,
                                                      loss, accumulate, out_scale);
     return tpgsr_launch_status();
 }
@@ -199,7 +203,7 @@ int tpgsr_semantic_loss_fwd(const float* pred, const float* gt, long n, float ou
     semantic_loss_fwd_kernel<<<grid, 256, 0, stream>>>(pred, gt, n, partial);
     int rc = tpgsr_launch_status();
     if (rc) return rc;
-    semantic_loss_finalize_kernel<<<1, 32, 0, stream>>>(partial, grid, (double)n, loss, accumulate, out_scale);
+    semantic_loss_finalize_kernel<<<1, 256, 0, stream>>>(partial, grid, (double)n, loss, accumulate, out_scale);
     return tpgsr_launch_status();
 }
 

@@ -254,12 +254,11 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     }
 }
 
-__global__ void scalar_finalize_kernel(const float* __restrict__ partial, int n, float* __restrict__ out, int accumulate) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) s += partial[i];
-        out[0] = accumulate ? out[0] + (float)s : (float)s;
-    }
+__global__ void __launch_bounds__(256) scalar_finalize_kernel(const float* __restrict__ partial, int n, float* __restrict__ out, int accumulate) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    s = block_sum_d256(s);
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + (float)s : (float)s;
 }
 
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long n) {
@@ -552,7 +551,7 @@ int tpgsr_act_bwd(const float* dy, const float* ref, float* dx, long n, int act,
     act_bwd_kernel<<<grid, 256, 0, stream>>>(dy, ref, dx, n, act, slope, partial);
     int rc = tpgsr_launch_status();
     if (rc || !partial) return rc;
-    scalar_finalize_kernel<<<1, 32, 0, stream>>>(partial, grid, dslope, accumulate);
+    scalar_finalize_kernel<<<1, 256, 0, stream>>>(partial, grid, dslope, accumulate);
     return tpgsr_launch_status();
 }
 

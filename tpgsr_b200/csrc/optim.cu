@@ -23,11 +23,12 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 // state[0] = step (as float), [1] = 1-beta1^t, [2] = 1-beta2^t, [3] = last grad norm, [4] = clip coefficient
-__global__ void optim_prepare_kernel(const float* __restrict__ partial, int nblocks, float max_norm, float beta1, float beta2,
-                                     float* __restrict__ state, int advance, float grad_scale) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void __launch_bounds__(256) optim_prepare_kernel(const float* __restrict__ partial, int nblocks, float max_norm, float beta1,
+                                                            float beta2, float* __restrict__ state, int advance, float grad_scale) {
     double s = 0.0;
-    for (int i = 0; i < nblocks; ++i) s += partial[i];
+    for (int i = threadIdx.x; i < nblocks; i += 256) s += partial[i];
+    s = block_sum_d256(s);
+    if (threadIdx.x) return;
     float norm = (float)sqrt(s) * grad_scale;
     float coef = max_norm / (norm + 1e-6f);
     state[3] = norm;
@@ -84,7 +85,7 @@ int tpgsr_optim_prepare(const float* grads, long n_clipped, float max_norm, floa
     sumsq_kernel<<<grid, 256, 0, stream>>>(grads, n_clipped, static_cast<float*>(workspace));
     int rc = tpgsr_launch_status();
     if (rc) return rc;
-    optim_prepare_kernel<<<1, 32, 0, stream>>>(static_cast<float*>(workspace), grid, max_norm, beta1, beta2, state, advance, grad_scale);
+    optim_prepare_kernel<<<1, 256, 0, stream>>>(static_cast<float*>(workspace), grid, max_norm, beta1, beta2, state, advance, grad_scale);
     return tpgsr_launch_status();
 }
 

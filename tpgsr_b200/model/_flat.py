@@ -8,7 +8,7 @@ directions' input projections are a single GEMM.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 from torch import nn
@@ -25,6 +25,7 @@ class FlatState:
         self.gviews: Dict[str, torch.Tensor] = {}
         self.offsets: Dict[str, Tuple[int, int]] = {}
         self.nbt = None
+        self.arena = None             # the FlatArena this state lives in, if any
         self.frozen = False           # set by the train steps once CUDA graphs hold this buffer's addresses
 
     # -- layout -----------------------------------------------------------------------------------------------------
@@ -60,15 +61,26 @@ class FlatState:
                 raise RuntimeError('parameter %s of %s no longer lives in the flat buffer the captured CUDA graphs use (a .to()/.cuda()/.float() '
                                    'after the train step was built?) — rebuild the train step' % (name, type(self.module).__name__))
 
-    def rebuild(self) -> None:
+    def padded_numel(self) -> int:
+        return (sum(p.numel() for p in self.module.parameters()) + 3) // 4 * 4
+
+    def rebuild(self, into: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> None:
+        """``into``: (parameter slice, gradient slice) of a :class:`FlatArena` to live in instead of private buffers."""
         params = dict(self.module.named_parameters())
         first = next(iter(params.values()))
         dev = first.device
         order = self._order(params)
         total = sum(params[n].numel() for n in order)
         total_pad = (total + 3) // 4 * 4
-        flat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
-        gflat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
+        if into is None and self.arena is not None:
+            raise RuntimeError('%s lives in a shared FlatArena (one all-reduce bucket for a train step) and one of its parameters was moved '
+                               'out of it — rebuild the train step' % type(self.module).__name__)
+        if into is not None:
+            flat, gflat = into
+            assert flat.numel() == total_pad and gflat.numel() == total_pad and flat.device == dev
+        else:
+            flat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
+            gflat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
         off = 0
         self.offsets, self.views, self.gviews = {}, {}, {}
         for n in order:
@@ -143,3 +155,25 @@ class FlatState:
         for name, p in self.module.named_parameters():
             if p.requires_grad:
                 p.grad = self.gviews[name]
+
+
+class FlatArena:
+    """ONE parameter buffer and ONE gradient buffer for several modules (the SR model first, then the students): the whole train step
+    then needs a single ``ncclAllReduce`` and a single clip+Adam launch pair ("one flat gradient buffer"); the clip
+    covers ``[0, n_clipped)`` = the first module."""
+
+    def __init__(self, modules: Sequence[nn.Module]):
+        states = [m._flat for m in modules]
+        sizes = [st.padded_numel() for st in states]
+        dev = next(modules[0].parameters()).device
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.gflat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.ranges = []
+        off = 0
+        for st, n in zip(states, sizes):
+            st.arena = None
+            st.rebuild(into=(self.flat[off:off + n], self.gflat[off:off + n]))
+            st.arena = self
+            self.ranges.append((off, n))
+            off += n
+        self.n_clipped = states[0].n

@@ -11,7 +11,8 @@ from typing import Optional
 
 import torch
 
-from . import engine, ops
+from . import dist as tdist, engine, ops
+from .model._flat import FlatArena
 from .optim import FlatAdam
 
 
@@ -107,13 +108,11 @@ class TSRNTrainStep:
                 self._capture()
             self.st.assert_attached()
             self._g_fb.replay()
-            if self.world > 1:
-                torch.distributed.all_reduce(self.st.gflat, group=self.pg)
+            tdist.all_reduce_flat_(self.st.gflat, self.pg)
             self._g_opt.replay()
         else:
             self._fwd_bwd()
-            if self.world > 1:
-                torch.distributed.all_reduce(self.st.gflat, group=self.pg)
+            tdist.all_reduce_flat_(self.st.gflat, self.pg)
             self._optim()
         return self.loss
 
@@ -147,12 +146,13 @@ class TPGSRTrainStep:
         self.gradient, self.w0, self.w1 = bool(gradient), float(loss_weight[0]), float(loss_weight[1])
         self.tpg_share = len(self.students) == 1 and stu_iter > 1
         assert self.tpg_share or len(self.students) == stu_iter
-        for m in [model] + self.students + [teacher]:
-            m._flat.ensure()
-        self.opt_sr = FlatAdam(model._flat.flat, n_clipped=model._flat.n, lr=lr, betas=(beta1, 0.999), max_norm=max_norm,
-                               grads=model._flat.gflat)
-        self.opt_stu = [FlatAdam(s._flat.flat, n_clipped=0, lr=lr, betas=(beta1, 0.999), max_norm=0.0, grads=s._flat.gflat)
-                        for s in self.students]
+        teacher._flat.ensure()
+        # SR model + students share one parameter / gradient arena: ONE all-reduce and ONE clip+Adam launch pair per step; the clip
+        # covers the SR model's range only (interfaces/super_resolution.py:422-423), Adam everything (interfaces/base.py:449-450)
+        self.arena = FlatArena([model] + self.students)
+        self.opt = FlatAdam(self.arena.flat, n_clipped=self.arena.n_clipped, lr=lr, betas=(beta1, 0.999), max_norm=max_norm,
+                            grads=self.arena.gflat)
+        self.opt_sr = self.opt           # (grad_norm of the clipped range = the SR model's, as clip_grad_norm_ returns it)
         H, W = model.tps_inputsize
         self.lr_buf = torch.zeros(batch, model.in_planes, H, W, device=self.dev)
         self.hr_buf = torch.zeros(batch, model.in_planes, 2 * H, 2 * W, device=self.dev)
@@ -241,34 +241,30 @@ class TPGSRTrainStep:
                 st.refresh()
 
     def _optim(self):
-        self.opt_sr.step(1.0 / self.world)
-        for o in self.opt_stu:
-            o.step(1.0 / self.world)
+        self.opt.step(1.0 / self.world)
         self.refresh_packs(teacher=False)        # the teacher is frozen: its packed weights are computed once
 
     def _all_reduce(self):
-        if self.world > 1:
-            torch.distributed.all_reduce(self.model._flat.gflat, group=self.pg)
-            for s in self.students:
-                torch.distributed.all_reduce(s._flat.gflat, group=self.pg)
+        tdist.all_reduce_flat_(self.arena.gflat, self.pg)      # the one collective of the step
 
     def _capture(self):
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         mods = [self.model] + self.students
-        opts = [self.opt_sr] + self.opt_stu
+        o = self.opt
         with torch.cuda.stream(s):
-            snap = [(m._flat.flat.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.state.clone(),
-                     {k: v.clone() for k, v in m._flat.views.items() if 'running_' in k},
-                     m._flat.nbt.clone() if m._flat.nbt is not None else None) for m, o in zip(mods, opts)]
+            snap_opt = (self.arena.flat.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.state.clone())
+            snap = [({k: v.clone() for k, v in m._flat.views.items() if 'running_' in k},
+                     m._flat.nbt.clone() if m._flat.nbt is not None else None) for m in mods]
             self._fwd_bwd()
             self._optim()
-            for (m, o), sn in zip(zip(mods, opts), snap):
-                m._flat.flat.copy_(sn[0]); o.exp_avg.copy_(sn[1]); o.exp_avg_sq.copy_(sn[2]); o.state.copy_(sn[3])
-                for k, v in sn[4].items():
+            # undo the warm-up step so capture does not change the trajectory
+            self.arena.flat.copy_(snap_opt[0]); o.exp_avg.copy_(snap_opt[1]); o.exp_avg_sq.copy_(snap_opt[2]); o.state.copy_(snap_opt[3])
+            for m, sn in zip(mods, snap):
+                for k, v in sn[0].items():
                     m._flat.views[k].copy_(v)
-                if sn[5] is not None:
-                    m._flat.nbt.copy_(sn[5])
+                if sn[1] is not None:
+                    m._flat.nbt.copy_(sn[1])
             self.refresh_packs(teacher=False)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
