@@ -127,13 +127,16 @@ def test_flat_conv_plans_fit_the_sm(nprod):
         (48, 32, 128, 4, 64, 64, 9, 1), (48, 16, 64, 4, 64, 64, 9, 1), (48, 16, 64, 4, 64, 36, 9, 1), (48, 4, 16, 1, 64, 128, 3, 3),
         (48, 16, 50, 1, 64, 128, 3, 3), (1248, 1, 1, 0, 512, 2048, 1, 1), (48, 1, 1, 0, 512, 40, 1, 1), (384, 16, 64, 1, 64, 64, 3, 3),
         (1, 5, 17, 1, 64, 64, 3, 3),
+        # CRNN conv2..5 and the deep STN-head convs: Ci = 64 * (2, 4, 8) channel blocks
+        (48, 8, 25, 1, 128, 256, 3, 3), (48, 8, 25, 1, 256, 256, 3, 3), (48, 4, 26, 1, 256, 512, 3, 3), (48, 4, 26, 1, 512, 512, 3, 3),
+        (48, 4, 26, 1, 512, 256, 3, 3), (48, 2, 8, 1, 128, 256, 3, 3), (48, 1, 4, 1, 256, 256, 3, 3), (2, 4, 26, 1, 512, 512, 3, 3),
     ]
     for (B, H, W, P, Ci, Co, KH, KW) in geoms:
         out = (ctypes.c_int * 13)()
         smem = LIB.tpgsr_conv2d_flat_plan(B, H, W, P, Ci, Co, KH, KW, KH // 2, KW // 2, nprod, out)
         assert 0 < smem <= 227 * 1024, ((B, H, W, P, Ci, Co, KH, KW), smem)
         MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer = list(out)
-        assert 1 <= MT <= 3 and MT * tm_stride <= 512 and n_tile % 16 == 0 and n_tile <= 128
+        assert 1 <= MT <= 3 and MT * tm_stride <= 512 and n_tile % 16 == 0 and n_tile <= 128 and tm_stride <= 256
         assert n_tile * n_tiles >= Co and box_rows % 8 == 0 and box_rows <= 256
         assert n_box * box_rows >= 128 * MT + (G - 1) * (W + P) + (KW - 1)          # the staged window covers every tap of every tile
         assert grid_x * MT * 128 >= B * (H + P) * (W + P)                           # every flat output row belongs to a tile

@@ -54,6 +54,13 @@ def _flat_fwd(ops, xd, w, b, Co, k, pad, lo, **kw):
     (5, 64, 128, 16, 50, 3),      # CRNN conv1 geometry
     (7, 512, 37, 1, 1, 1),        # linear layer as a pointwise conv (8 channel blocks, ragged N)
     (24, 64, 4, 32, 128, 9),      # final conv at a batch large enough for 2 tiles per CTA
+    (6, 128, 256, 8, 25, 3),      # CRNN conv2: two channel blocks x whole 3x3 halo per A stage
+    (5, 256, 256, 8, 25, 3),      # CRNN conv3
+    (7, 256, 512, 4, 26, 3),      # CRNN conv4: four N tiles of 128 (stacked N = 256 MMAs)
+    (9, 512, 512, 4, 26, 3),      # CRNN conv5: K = 4608, eight channel blocks
+    (48, 512, 512, 4, 26, 3),     # ... at the bench batch (two tiles per CTA)
+    (4, 128, 256, 2, 8, 3),       # STN head conv 128 -> 256 on a 2x8 map
+    (4, 256, 256, 1, 4, 3),       # STN head conv on a 1x4 map (more pad rows than pixels)
 ])
 @pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
 def test_conv_flat_fwd_dgrad(B, Ci, Co, H, W, k, mode):
@@ -82,20 +89,24 @@ def test_conv_flat_fwd_dgrad(B, Ci, Co, H, W, k, mode):
         ops.CONV_MODE = old
 
 
-@pytest.mark.parametrize('B,Co,H,W,k', [
-    (3, 64, 16, 64, 3),       # SRB conv
-    (2, 64, 16, 64, 1),       # GruBlock 1x1 conv
-    (2, 192, 16, 64, 1),      # GRU input projection (three N tiles of 64)
-    (2, 256, 16, 64, 3),      # upsample conv
-    (1, 4, 32, 128, 9),       # final conv: Co = 4 padded to 64, 9 kw taps in two groups
-    (3, 64, 5, 17, 3),        # ragged map
-    (48, 64, 16, 64, 3),      # full batch: 47 pixel splits
-    (16, 4, 32, 128, 9),      # final conv, many K blocks per split
+@pytest.mark.parametrize('B,Co,H,W,k,Ci', [
+    (3, 64, 16, 64, 3, 64),       # SRB conv
+    (2, 64, 16, 64, 1, 64),       # GruBlock 1x1 conv
+    (2, 192, 16, 64, 1, 64),      # GRU input projection (three N tiles of 64)
+    (2, 256, 16, 64, 3, 64),      # upsample conv
+    (1, 4, 32, 128, 9, 64),       # final conv: Co = 4 padded to 64, 9 kw taps in two groups
+    (3, 64, 5, 17, 3, 64),        # ragged map
+    (48, 64, 16, 64, 3, 64),      # full batch: 47 pixel splits
+    (16, 4, 32, 128, 9, 64),      # final conv, many K blocks per split
+    (6, 256, 8, 25, 3, 128),      # CRNN conv2: two input channel blocks
+    (9, 512, 4, 26, 3, 512),      # CRNN conv5: eight channel blocks, four N tiles
+    (48, 512, 4, 26, 3, 256),     # CRNN conv4 at the bench batch
+    (4, 256, 1, 4, 3, 256),       # STN head conv on a 1x4 map
 ])
 @pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
-def test_wgrad_flat(B, Co, H, W, k, mode):
+def test_wgrad_flat(B, Co, H, W, k, Ci, mode):
     from tpgsr_b200 import ops
-    Ci, pad = 64, k // 2
+    pad = k // 2
     x = rnd(B, Ci, H, W, seed=51)
     w = (rnd(Co, Ci, k, k, seed=52) / np.sqrt(Ci * k * k)).requires_grad_(True)
     y = F.conv2d(x, w, None, padding=pad)

@@ -101,8 +101,9 @@ struct FlatConvParams {
     int MT;                    // 128-row output tiles per CTA
     int n_tile;                // output channels per CTA (multiple of 16, <= 128)
     int tm_stride;             // TMEM columns between the accumulators of consecutive tiles (n_tile rounded up to 32)
-    int pointwise;             // 1x1 conv with Ci = 64*n_groups: the A "groups" are channel blocks instead of kernel rows
-    int G, n_groups;           // kernel rows per A stage; KH / G   (pointwise: G = 1, n_groups = Ci / 64)
+    int Ci;                    // input channels (multiple of 64): the planes are [Qtot][Ci], an A stage holds ONE 64-channel block
+    int G, kgroups, n_groups;  // kernel rows per A stage; kgroups = KH / G; n_groups = (Ci / 64) * kgroups A stages per CTA: group g =
+                               // (channel block g / kgroups, kernel rows (g % kgroups) * G ..)   (1x1 conv: G = kgroups = 1, n_groups = Ci / 64)
     int a_stages;              // A ring depth (1 when n_groups == 1)
     int box_rows, n_box;       // one A stage = n_box TMA boxes of box_rows rows (box_rows % 8 == 0)
     int tb, b_stages;          // taps per B stage; B ring depth
@@ -218,9 +219,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 mbar_wait_safe(&a_empty[as], ((g / p.a_stages) & 1) ^ 1);
                 uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
                 tc::mbar_expect_tx(&a_full[as], (uint32_t)a_stage_bytes);
-                // first halo row of this group of kernel rows (pointwise: same rows, next 64-channel block)
-                const long long row0 = p.pointwise ? q0 : q0 + (long long)(g * p.G - p.ph) * p.Wp - p.pw;
-                const int ch0 = p.pointwise ? g * 64 : 0;
+                // first halo row of this group's kernel rows, in this group's 64-channel block
+                const int cb = g / p.kgroups, gk = g - cb * p.kgroups;
+                const long long row0 = q0 + (long long)(gk * p.G - p.ph) * p.Wp - p.pw;
+                const int ch0 = cb * 64;
                 for (int bx = 0; bx < p.n_box; ++bx) {
                     const int r = (int)(row0 + (long long)bx * p.box_rows);
                     tc::tma_load_2d(ast + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_hi, &a_full[as], ch0, r);
@@ -235,10 +237,11 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         uint8_t* bst = b_ring + (size_t)bs * b_stage_bytes;
                         tc::mbar_expect_tx(&b_full[bs], (uint32_t)b_stage_bytes);
                         for (int tt = 0; tt < p.tb; ++tt) {
-                            const int tap = g * taps_per_group + j * p.tb + tt;
-                            tc::tma_load_2d(bst + (size_t)tt * b_tap_bytes, &tmB_hi, &b_full[bs], tap * 64, n0);
+                            const int tap = gk * taps_per_group + j * p.tb + tt;
+                            const int k0 = tap * p.Ci + ch0;                   // K index of the packed weights [Co][KH*KW*Ci]
+                            tc::tma_load_2d(bst + (size_t)tt * b_tap_bytes, &tmB_hi, &b_full[bs], k0, n0);
                             if (NPROD >= 2)
-                                tc::tma_load_2d(bst + b_plane_bytes + (size_t)tt * b_tap_bytes, &tmB_lo, &b_full[bs], tap * 64, n0);
+                                tc::tma_load_2d(bst + b_plane_bytes + (size_t)tt * b_tap_bytes, &tmB_lo, &b_full[bs], k0, n0);
                         }
                     }
                 }
@@ -509,7 +512,7 @@ split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __re
 }
 
 struct FlatPlan {
-    int MT, n_tile, n_tiles, tm_stride, nstack, pointwise, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, tile_outer, ring_bytes, stg_off, bar_off;
+    int MT, n_tile, n_tiles, tm_stride, nstack, pointwise, G, kgroups, n_groups, a_stages, box_rows, n_box, tb, b_stages, tile_outer, ring_bytes, stg_off, bar_off;
     size_t smem;
     int grid_x;
 };
@@ -524,15 +527,15 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
                   FlatPlan& pl) {
     if (Co < 1 || B < 1 || H < 1 || W < 1 || Ci < 64 || Ci % 64 != 0) return TPGSR_ERR_UNSUPPORTED;
     const int pointwise = (KH == 1 && KW == 1) ? 1 : 0;
-    if (!pointwise && Ci != 64) return TPGSR_ERR_UNSUPPORTED;
+    const int cbs = Ci / 64;                                      // 64-channel blocks of the input
     if (2 * ph != KH - 1 || 2 * pw != KW - 1 || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
     const int a_planes = nprod == 3 ? 2 : 1, b_planes = nprod >= 2 ? 2 : 1;
     const int Wp = W + P;
     const int co16 = (Co + 15) / 16 * 16;
     pl.n_tiles = (co16 + 127) / 128;
     pl.n_tile = ((co16 + pl.n_tiles - 1) / pl.n_tiles + 15) / 16 * 16;
-    // stacked weight planes (see mma_tap_stacked): bf16x3, N = 2*n_tile <= 128; forces one tap per B stage (hi and lo tiles adjacent)
-    pl.nstack = (nprod >= 2 && pl.n_tile <= 64) ? 1 : 0;
+    // stacked weight planes (see mma_tap_stacked): bf16x3, one MMA of N = 2*n_tile <= 256; forces one tap per B stage (hi and lo tiles adjacent)
+    pl.nstack = (nprod >= 2 && pl.n_tile <= 128) ? 1 : 0;
     if (g_flat_no_nstack) pl.nstack = 0;
     pl.tm_stride = ((pl.nstack ? 2 : 1) * pl.n_tile + 31) / 32 * 32;
     pl.pointwise = pointwise;
@@ -547,7 +550,8 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
         for (int MT = 3; MT >= 1; --MT) {
             if (MT * pl.tm_stride > tmem_max) continue;
             const int G = pointwise ? 1 : (pass == 0 ? KH : 1);
-            const int n_groups = pointwise ? Ci / 64 : KH / G;
+            const int kgroups = KH / G;
+            const int n_groups = cbs * kgroups;
             const int rows = TILE_M * MT + (G - 1) * Wp + (KW - 1);
             int n_box = (rows + 255) / 256;
             int box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8;
@@ -588,7 +592,7 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
             const long long cost = ((ctas + slots - 1) / slots) * MT;
             if (best_cost >= 0 && cost * 23 >= best_cost * 20) continue;       // a smaller MT must win by > 15%
             best_cost = cost;
-            pl.MT = MT; pl.G = G; pl.n_groups = n_groups; pl.a_stages = a_stages; pl.box_rows = box_rows; pl.n_box = n_box;
+            pl.MT = MT; pl.G = G; pl.kgroups = kgroups; pl.n_groups = n_groups; pl.a_stages = a_stages; pl.box_rows = box_rows; pl.n_box = n_box;
             pl.tb = tb; pl.b_stages = b_stages; pl.smem = smem; pl.ring_bytes = ring_bytes; pl.stg_off = stg_off; pl.bar_off = bar_off;
             pl.tile_outer = tile_outer;
             pl.grid_x = (int)((tiles + MT - 1) / MT);
@@ -613,6 +617,7 @@ constexpr int WG_KB = 128;            // flat rows (pixels) per K block
 
 struct FlatWgradParams {
     int Wp, Co, Ci, KH, KW, ph, pw;
+    int cbs;                         // 64-channel blocks of the input: blockIdx.y = (kh * kw_groups + kwg) * cbs + cb
     int kw_groups, taps_per_group;   // the KW taps of a kernel row are split into groups that fit TMEM
     int n_tile;                      // co per CTA (multiple of 64)
     int x_rows;                      // rows of the X window per K block (WG_KB + taps_per_group - 1, rounded up to 8)
@@ -629,7 +634,8 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // NPROD = 2 (experimental): dY as ONE bf16 plane against X hi + lo — X_hi dY + X_lo dY
     constexpr int dy_planes = NPROD == 3 ? 2 : 1, x_planes = NPROD >= 2 ? 2 : 1;
-    const int kh = blockIdx.y / p.kw_groups, kwg = blockIdx.y % p.kw_groups;
+    const int cb = blockIdx.y % p.cbs, khw = blockIdx.y / p.cbs;
+    const int kh = khw / p.kw_groups, kwg = khw % p.kw_groups;
     const int kw0 = kwg * p.taps_per_group;
     const int ntaps = (p.KW - kw0) < p.taps_per_group ? (p.KW - kw0) : p.taps_per_group;
     const int n0 = blockIdx.z * p.n_tile;
@@ -684,8 +690,8 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
                 }
                 uint8_t* xs = st + dy_planes * dy_plane_bytes;
                 const int xr = qk + (kh - p.ph) * p.Wp + (kw0 - p.pw);
-                tc::tma_load_2d(xs, &tmX_hi, &full[s], 0, xr);
-                if (NPROD >= 2) tc::tma_load_2d(xs + x_plane_bytes, &tmX_lo, &full[s], 0, xr);
+                tc::tma_load_2d(xs, &tmX_hi, &full[s], cb * 64, xr);
+                if (NPROD >= 2) tc::tma_load_2d(xs + x_plane_bytes, &tmX_lo, &full[s], cb * 64, xr);
             }
         }
     } else if (warp == 1) {
@@ -733,7 +739,7 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
         const int q = warp & 3;
         mbar_wait_safe(tmem_full, 0);
         tc::tc_fence_after();
-        const int ci = 16 * q + lane;
+        const int ci = cb * 64 + 16 * q + lane;
         const int K = p.KH * p.KW * p.Ci;
         for (int t = 0; t < ntaps; ++t) {
             const int tap = kh * p.KW + kw0 + t;
@@ -759,11 +765,12 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
 }
 
 struct FlatWgradPlan {
-    int n_tile, n_tiles, kw_groups, taps_per_group, x_rows, stages, stage_bytes, total_kb, kb_per_split, splits;
+    int n_tile, n_tiles, cbs, kw_groups, taps_per_group, x_rows, stages, stage_bytes, total_kb, kb_per_split, splits;
 };
 
 int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, FlatWgradPlan& pl) {
-    if (Ci != 64 || Cpad % 64 != 0 || Cpad < Co || 2 * P < KH - 1 || 2 * P < KW - 1) return TPGSR_ERR_UNSUPPORTED;
+    if (Ci < 64 || Ci % 64 != 0 || Cpad % 64 != 0 || Cpad < Co || 2 * P < KH - 1 || 2 * P < KW - 1) return TPGSR_ERR_UNSUPPORTED;
+    const int cbs = Ci / 64;
     const int dy_planes = nprod == 3 ? 2 : 1, x_planes = nprod >= 2 ? 2 : 1;
     // co tile: the candidate (multiple of 64 dividing Cpad, <= 256) with the fewest CTAs per pixel split whose ring is >= 2 deep
     int best = -1, best_cost = 1 << 30;
@@ -780,6 +787,7 @@ int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH
     }
     if (best < 0) return TPGSR_ERR_UNSUPPORTED;
     pl.n_tile = best;
+    pl.cbs = cbs;
     pl.n_tiles = Cpad / pl.n_tile;
     const int max_taps = 512 / pl.n_tile;
     pl.kw_groups = (KW + max_taps - 1) / max_taps;
@@ -791,10 +799,19 @@ int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH
     const long long Qtot = (long long)B * (H + P) * (W + P);
     if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
     pl.total_kb = (int)((Qtot + WG_KB - 1) / WG_KB);
-    const int ctas_per_split = KH * pl.kw_groups * pl.n_tiles;
-    int want = 148 / ctas_per_split;                      // one wave of CTAs (1 CTA per SM: the ring takes the whole shared memory)
-    if (want < 1) want = 1;
-    if (want > pl.total_kb) want = pl.total_kb;
+    const int ctas_per_split = KH * pl.kw_groups * pl.n_tiles * cbs;
+    // pixel splits: the count with the shortest modelled critical path = rounds of CTAs (1 CTA per SM: the ring takes the whole shared
+    // memory) x (K blocks per CTA + 2 blocks' worth of prologue / epilogue) x MMA time per K block, + the split reduction, which reads
+    // splits x K x Co floats at ~3 TB/s; ties go to fewer splits
+    int want = 1;
+    double best_path = -1.0;
+    const double t_kb = pl.taps_per_group * (WG_KB / 16) * nprod * (pl.n_tile / 2) / 1965.0;           // us: M = 64 MMAs take N / 2 cycles
+    const double t_red = (double)KH * KW * Ci * Co * 4.0 / 3.0e6;                                       // us per split
+    for (int s = 1; s <= 148 && s <= pl.total_kb; ++s) {
+        const long long rounds = ((long long)ctas_per_split * s + 147) / 148;
+        const double path = rounds * ((pl.total_kb + s - 1) / s + 2) * t_kb + s * t_red;
+        if (best_path < 0 || path < best_path - 1e-9) { best_path = path; want = s; }
+    }
     pl.kb_per_split = (pl.total_kb + want - 1) / want;
     pl.splits = (pl.total_kb + pl.kb_per_split - 1) / pl.kb_per_split;
     return TPGSR_OK;
@@ -884,7 +901,7 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     FlatConvParams p;
     p.B = B; p.H = H; p.W = W; p.Hp = H + P; p.Wp = W + P; p.Qtot = (long long)B * p.Hp * p.Wp;
     p.Co = Co; p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw;
-    p.MT = pl.MT; p.n_tile = pl.n_tile; p.tm_stride = pl.tm_stride; p.pointwise = pl.pointwise; p.G = pl.G; p.n_groups = pl.n_groups;
+    p.MT = pl.MT; p.n_tile = pl.n_tile; p.tm_stride = pl.tm_stride; p.Ci = Ci; p.G = pl.G; p.kgroups = pl.kgroups; p.n_groups = pl.n_groups;
     p.a_stages = pl.a_stages;
     p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
     p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off; p.nstack = pl.nstack;
@@ -953,7 +970,7 @@ int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_h
     const long long Qtot = (long long)B * (H + P) * (W + P);
     FlatWgradParams p;
     p.Wp = W + P; p.Co = Co; p.Ci = Ci; p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw;
-    p.kw_groups = pl.kw_groups; p.taps_per_group = pl.taps_per_group; p.n_tile = pl.n_tile; p.x_rows = pl.x_rows;
+    p.cbs = pl.cbs; p.kw_groups = pl.kw_groups; p.taps_per_group = pl.taps_per_group; p.n_tile = pl.n_tile; p.x_rows = pl.x_rows;
     p.total_kb = pl.total_kb; p.kb_per_split = pl.kb_per_split; p.stages = pl.stages;
     p.ws = static_cast<float*>(workspace);
 
@@ -971,7 +988,7 @@ int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_h
     if (nprod >= 2 && tpgsr_make_tmap_bf16(&tmX_lo, x_lo, 2, xd, xs, xbox)) return TPGSR_ERR_DRIVER;
     if (nprod == 3 && tpgsr_make_tmap_bf16(&tmD_lo, dy_lo, 2, dd, ds, dbox)) return TPGSR_ERR_DRIVER;
     const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + 256;
-    dim3 grid(pl.splits, KH * pl.kw_groups, pl.n_tiles);
+    dim3 grid(pl.splits, KH * pl.kw_groups * pl.cbs, pl.n_tiles);
     if (nprod == 3) {
         if (cudaFuncSetAttribute(conv_wgrad_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
