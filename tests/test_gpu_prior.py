@@ -92,10 +92,11 @@ def test_infogen_vs_golden_and_oracle(shapes):
             assert rel_err(st.gviews[k], v.grad) < 2e-3, k
 
 
-def test_bilstm_recurrence_vs_oracle():
+@pytest.mark.parametrize('B', [11, 3, 48])      # 11: one full batch group of 8 plus a ragged one; 3: the 4-item groups; 48: bench batch
+def test_bilstm_recurrence_vs_oracle(B):
     from oracle import ops as o
     from tpgsr_b200 import ops, ops_prior
-    Tn, B, I, H = 26, 11, 256, 256          # B = 11: one full batch chunk of 8 plus a ragged one
+    Tn, I, H = 26, 256, 256
     r = np.random.RandomState(9)
     k = 1 / np.sqrt(H)
     p = {}

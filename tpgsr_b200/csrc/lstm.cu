@@ -4,15 +4,14 @@
 // the reference).  The input projection x W_ih^T + b_ih for both directions is one GEMM (N = 2*4*256) done by the conv/GEMM
 // kernels; this file is the serial part.  Gate order i,f,g,o; h0 = c0 = 0.
 //
-// One CTA per (batch chunk of 8, direction), thread j = hidden unit j.  Per step every thread forms its 4 gate pre-activations
-// for the 8 batch items: 256 x 4 coalesced loads of W_hh^T (1 MiB per direction, L2-resident) against h broadcast from shared
-// memory.  Latency/L2-bound by construction (T = 26 serial steps); reported as steps/us, not against the tensor roofline.
+// Latency-bound by construction (T = 26 serial steps): reported as us per step, not against the tensor roofline.
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int LH = 256;      // hidden units per direction
-constexpr int BC = 8;        // batch items per CTA
 
 // row of (t, b) in the [T*B, ...] matrices: time-first (nn.LSTM's layout) or batch-first (what the NHWC conv stack produces)
 #define LROW(t, b) (bf ? ((size_t)(b) * T + (t)) : ((size_t)(t) * B + (b)))
@@ -29,112 +28,227 @@ __global__ void lstm_transpose_whh_kernel(const float* __restrict__ whh, float* 
     for (int i = threadIdx.y; i < 32; i += 8) dst[(size_t)(c0 + i) * 4 * LH + r0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Cluster recurrence.  The serial part of an LSTM layer is T dependent steps of h W_hh^T ([B,256] x [256,1024] per direction): tiny
+// GEMMs whose weight matrix (1 MiB fp32 per direction) does not fit one SM.  A thread-block CLUSTER of 8 CTAs owns one (batch group,
+// direction): CTA r keeps the 128 gate rows of hidden units [32r, 32r+32) resident in shared memory (128 KB fp32) for all T steps, forms
+// its units' gates for the group's batch items from the full h vector, and pushes its 32 new h values per batch item into the h buffers
+// of all 8 CTAs through distributed shared memory (one cluster barrier per step, h double-buffered).  Nothing but gx / y / stash touches
+// HBM or L2 inside the loop.  The round-1 kernel streamed the whole W_hh from L2 in every CTA at every step (766 us per layer at B = 48,
+// profiles/r02/call1_stdout.log).
+// FMA phase: warp w covers k in [32w, 32w+32), lane u = hidden unit: 4 gates x BG batch accumulators, W as one LDS.128 per k (layout
+// [k][u][gate]), h as broadcast LDS.128; the 8 warps' partial sums meet in shared memory.  Gate phase: thread (b, u).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int LS = 8;             // CTAs per cluster = hidden slices
+constexpr int LU = LH / LS;       // hidden units per CTA (32)
+
+template <int BG>
+struct LstmSmem {
+    static constexpr int W_FLOATS = LH * LU * 4;              // fwd: [k][u][gate]; bwd: [gate][u][j]
+    static constexpr int HS_FLOATS = 2 * LH * BG;             // fwd: h double buffer [2][k][b]; bwd: partial dh [2 halves][j][b]
+    static constexpr int RED_FLOATS = 8 * 4 * BG * LU;        // fwd: [warp][gate*BG + b][u]; bwd: receive slots [2][src][u][b] (+ dgate [128][b])
+    static constexpr int LOC_FLOATS = LU * BG;
+    static constexpr size_t BYTES = (size_t)(W_FLOATS + HS_FLOATS + RED_FLOATS + LOC_FLOATS) * sizeof(float);
+};
+
 // gx: [T,B,2,4H] (input projection incl. bias_ih); bhh: [2][4H]; y: [T,B,2H]; stash: [T,B,2,5,H] = i,f,g,o,c
-__global__ void __launch_bounds__(LH)
-lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whhT, const float* __restrict__ bhh,
-                float* __restrict__ y, float* __restrict__ stash, int T, int B, int bf) {
-    const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * BC;
-    const int nb = (B - b0) < BC ? (B - b0) : BC;
-    __shared__ __align__(16) float hs[LH][BC];
-    const float* WT = whhT + (size_t)dir * 4 * LH * LH;
-    float bias[4];
+template <int BG>
+__global__ void __cluster_dims__(LS, 1, 1) __launch_bounds__(256, 1)
+lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ whhT, const float* __restrict__ bhh,
+                        float* __restrict__ y, float* __restrict__ stash, int T, int B, int bf) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float lsm[];
+    float* Ws = lsm;
+    float* hs = Ws + LstmSmem<BG>::W_FLOATS;
+    float* red = hs + LstmSmem<BG>::HS_FLOATS;
+    float* hloc = red + LstmSmem<BG>::RED_FLOATS;
+    const int r = (int)cluster.block_rank();
+    const int dir = blockIdx.z, b0 = blockIdx.y * BG;
+    const int nb = (B - b0) < BG ? (B - b0) : BG;
+    const int tid = threadIdx.x, w = tid >> 5, u = tid & 31;
+    constexpr int Q = BG / 4;                                 // float4s per h row
+    const float* WT = whhT + (size_t)dir * 4 * LH * LH;       // [k][gate*256 + j]
+    for (int idx = tid; idx < LH * 4 * LU; idx += 256) {
+        const int k = idx >> 7, rem = idx & 127, g = rem >> 5, uu = rem & 31;
+        Ws[(k * LU + uu) * 4 + g] = __ldg(WT + (size_t)k * 4 * LH + g * LH + LU * r + uu);
+    }
+    for (int idx = tid; idx < LH * BG; idx += 256) hs[idx] = 0.f;
+    // gate-phase role: thread (pb, u) owns hidden unit 32r + u of batch item b0 + pb
+    const int pb = w;
+    const bool gate_thread = pb < BG;
+    float bias[4], c = 0.f;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) bias[g] = __ldg(bhh + dir * 4 * LH + g * LH + j);
-    float c[BC], h[BC];
-#pragma unroll
-    for (int b = 0; b < BC; ++b) { c[b] = 0.f; h[b] = 0.f; hs[j][b] = 0.f; }
-    __syncthreads();
+    for (int g = 0; g < 4; ++g) bias[g] = __ldg(bhh + dir * 4 * LH + g * LH + LU * r + u);
+    cluster.sync();                                           // every CTA of the cluster is running and has cleared its h buffer
     for (int s = 0; s < T; ++s) {
         const int t = dir ? T - 1 - s : s;
-        float acc[4][BC];
+        const float* hb = hs + (s & 1) * LH * BG;
+        float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (gate_thread && pb < nb) {
+            const float* gp = gx + (LROW(t, b0 + pb) * 2 + dir) * 4 * LH + LU * r + u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gxv[g] = __ldg(gp + g * LH);
+        }
+        float acc[4][BG];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-            for (int b = 0; b < BC; ++b)
-                acc[g][b] = bias[g] + (b < nb ? __ldg(gx + (LROW(t, b0 + b) * 2 + dir) * 4 * LH + g * LH + j) : 0.f);
+            for (int b = 0; b < BG; ++b) acc[g][b] = 0.f;
 #pragma unroll 4
-        for (int k = 0; k < LH; ++k) {
-            float4 h0 = *reinterpret_cast<const float4*>(&hs[k][0]);
-            float4 h1 = *reinterpret_cast<const float4*>(&hs[k][4]);
-            float hv[BC] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        for (int kk = 0; kk < 32; ++kk) {
+            const int k = 32 * w + kk;
+            const float4 wv = *reinterpret_cast<const float4*>(Ws + (k * LU + u) * 4);
+            float hv[BG];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hb + k * BG + 4 * q);
+                hv[4 * q] = h4.x; hv[4 * q + 1] = h4.y; hv[4 * q + 2] = h4.z; hv[4 * q + 3] = h4.w;
+            }
+#pragma unroll
+            for (int b = 0; b < BG; ++b) {
+                acc[0][b] = fmaf(wv.x, hv[b], acc[0][b]);
+                acc[1][b] = fmaf(wv.y, hv[b], acc[1][b]);
+                acc[2][b] = fmaf(wv.z, hv[b], acc[2][b]);
+                acc[3][b] = fmaf(wv.w, hv[b], acc[3][b]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int b = 0; b < BG; ++b) red[(w * 4 * BG + g * BG + b) * LU + u] = acc[g][b];
+        __syncthreads();
+        if (gate_thread) {
+            float pre[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                float w = __ldg(WT + (size_t)k * 4 * LH + g * LH + j);
+                float sacc = bias[g] + gxv[g];
 #pragma unroll
-                for (int b = 0; b < BC; ++b) acc[g][b] = fmaf(w, hv[b], acc[g][b]);
+                for (int ww = 0; ww < 8; ++ww) sacc += red[(ww * 4 * BG + g * BG + pb) * LU + u];
+                pre[g] = sacc;
             }
-        }
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
-            float ig = sigmoid_f(acc[0][b]), fg = sigmoid_f(acc[1][b]), gg = tanhf(acc[2][b]), og = sigmoid_f(acc[3][b]);
-            c[b] = fg * c[b] + ig * gg;
-            h[b] = og * tanhf(c[b]);
-            if (b < nb) {
-                y[LROW(t, b0 + b) * 2 * LH + dir * LH + j] = h[b];
+            const float ig = sigmoid_f(pre[0]), fg = sigmoid_f(pre[1]), gg = tanhf(pre[2]), og = sigmoid_f(pre[3]);
+            c = fg * c + ig * gg;
+            const float h = og * tanhf(c);
+            if (pb < nb) {
+                y[LROW(t, b0 + pb) * 2 * LH + dir * LH + LU * r + u] = h;
                 if (stash) {
-                    float* sp = stash + ((LROW(t, b0 + b) * 2 + dir) * 5) * LH + j;
-                    sp[0] = ig; sp[LH] = fg; sp[2 * LH] = gg; sp[3 * LH] = og; sp[4 * LH] = c[b];
+                    float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + LU * r + u;
+                    sp[0] = ig; sp[LH] = fg; sp[2 * LH] = gg; sp[3 * LH] = og; sp[4 * LH] = c;
                 }
             }
+            hloc[u * BG + pb] = pb < nb ? h : 0.f;
         }
         __syncthreads();
-#pragma unroll
-        for (int b = 0; b < BC; ++b) hs[j][b] = h[b];
-        __syncthreads();
+        // push this CTA's [32 units][BG] block of h_t into the next-step h buffer of every CTA of the cluster (itself included)
+        const int nxt = (s + 1) & 1;
+        for (int i = tid; i < LS * LU * Q; i += 256) {
+            const int dst = i / (LU * Q), q = i - dst * (LU * Q);
+            const float4 v = *reinterpret_cast<const float4*>(hloc + 4 * q);
+            float* remote = cluster.map_shared_rank(hs, dst);
+            *reinterpret_cast<float4*>(remote + nxt * LH * BG + (LU * r) * BG + 4 * q) = v;
+        }
+        cluster.sync();                                       // h_t complete everywhere (release / acquire at cluster scope)
     }
 }
 
-// BPTT: dy [T,B,2H] -> dgx [T,B,2,4H] (gradient w.r.t. the gate pre-activations).  whh: original [2][4H][H] layout
-// (dh_prev[j] = sum_rows W_hh[row][j] * dgate[row] reads it coalesced over j).
-__global__ void __launch_bounds__(LH)
-lstm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ stash, const float* __restrict__ whh,
-                float* __restrict__ dgx, int T, int B, int bf) {
-    const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * BC;
-    const int nb = (B - b0) < BC ? (B - b0) : BC;
-    __shared__ __align__(16) float dgs[4 * LH][BC];      // 32 KiB
-    const float* W = whh + (size_t)dir * 4 * LH * LH;
-    float dh[BC], dc[BC];
-#pragma unroll
-    for (int b = 0; b < BC; ++b) { dh[b] = 0.f; dc[b] = 0.f; }
-    for (int s = T - 1; s >= 0; --s) {                   // walk the processing order backwards
+// BPTT: dy [T,B,2H] -> dgx [T,B,2,4H] (gradient w.r.t. the gate pre-activations).  whh: original [2][4H][H] layout.  Same cluster
+// decomposition: CTA r owns the gates of units [32r, 32r+32) (its 128 rows of W_hh, all 256 columns, resident); per step it forms its
+// dgates, multiplies them into a partial dh_prev for ALL 256 units, and reduce-scatters the partials through distributed shared memory
+// (slot [source CTA] in the owner's receive buffer, summed in a fixed order: deterministic).
+template <int BG>
+__global__ void __cluster_dims__(LS, 1, 1) __launch_bounds__(256, 1)
+lstm_bwd_cluster_kernel(const float* __restrict__ dy, const float* __restrict__ stash, const float* __restrict__ whh,
+                        float* __restrict__ dgx, int T, int B, int bf) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float lsm[];
+    float* Wb = lsm;                                          // [gate*32 + u][j]
+    float* pbuf = Wb + LstmSmem<BG>::W_FLOATS;                // [2 row halves][j][b]
+    float* recv = pbuf + LstmSmem<BG>::HS_FLOATS;             // [2][src][u][b]  (2 * 8 * 32 * BG floats)
+    float* dgs = recv + 2 * LS * LU * BG;                     // [gate*32 + u][b]  (128 * BG floats; RED_FLOATS = 1024 * BG covers both)
+    const int r = (int)cluster.block_rank();
+    const int dir = blockIdx.z, b0 = blockIdx.y * BG;
+    const int nb = (B - b0) < BG ? (B - b0) : BG;
+    const int tid = threadIdx.x, w = tid >> 5, u = tid & 31;
+    constexpr int Q = BG / 4;
+    const float* W = whh + (size_t)dir * 4 * LH * LH;         // [gate*256 + unit][j]
+    for (int idx = tid; idx < 4 * LU * LH; idx += 256) {
+        const int row = idx >> 8, j = idx & 255, g = row >> 5, uu = row & 31;
+        Wb[row * LH + j] = __ldg(W + (size_t)(g * LH + LU * r + uu) * LH + j);
+    }
+    const int pb = w;
+    const bool gate_thread = pb < BG;
+    const int half = tid >> 7, jp = tid & 127;                // FMA phase: columns 2jp, 2jp+1 over rows [64*half, 64*half + 64)
+    float dc = 0.f;
+    cluster.sync();
+    for (int s = T - 1; s >= 0; --s) {                        // walk the processing order backwards
         const int t = dir ? T - 1 - s : s;
-        const int tprev = dir ? t + 1 : t - 1;           // the step processed just before t (holds c_{prev})
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
+        const int tprev = dir ? t + 1 : t - 1;                // the step processed just before t (holds c_prev)
+        if (gate_thread) {
             float di_p = 0.f, df_p = 0.f, dg_p = 0.f, do_p = 0.f;
-            if (b < nb) {
-                const float* sp = stash + ((LROW(t, b0 + b) * 2 + dir) * 5) * LH + j;
-                float ig = sp[0], fg = sp[LH], gg = sp[2 * LH], og = sp[3 * LH], cc = sp[4 * LH];
-                float cprev = s > 0 ? stash[((LROW(tprev, b0 + b) * 2 + dir) * 5 + 4) * LH + j] : 0.f;
-                float dht = dh[b] + __ldg(dy + LROW(t, b0 + b) * 2 * LH + dir * LH + j);
-                float tc = tanhf(cc);
-                float dct = dc[b] + dht * og * (1.f - tc * tc);
-                do_p = dht * tc * og * (1.f - og);
+            if (pb < nb) {
+                float dh = 0.f;
+                if (s < T - 1) {
+                    const float* rv = recv + ((s + 1) & 1) * LS * LU * BG + u * BG + pb;
+#pragma unroll
+                    for (int src = 0; src < LS; ++src) dh += rv[src * LU * BG];
+                }
+                const size_t col = (size_t)LU * r + u;
+                const float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + col;
+                const float ig = sp[0], fg = sp[LH], gg = sp[2 * LH], og = sp[3 * LH], cc = sp[4 * LH];
+                const float cprev = s > 0 ? stash[((LROW(tprev, b0 + pb) * 2 + dir) * 5 + 4) * LH + col] : 0.f;
+                const float dht = dh + __ldg(dy + LROW(t, b0 + pb) * 2 * LH + dir * LH + col);
+                const float tcc = tanhf(cc);
+                const float dct = dc + dht * og * (1.f - tcc * tcc);
+                do_p = dht * tcc * og * (1.f - og);
                 di_p = dct * gg * ig * (1.f - ig);
                 dg_p = dct * ig * (1.f - gg * gg);
                 df_p = dct * cprev * fg * (1.f - fg);
-                dc[b] = dct * fg;
-                float* gp = dgx + (LROW(t, b0 + b) * 2 + dir) * 4 * LH + j;
+                dc = dct * fg;
+                float* gp = dgx + (LROW(t, b0 + pb) * 2 + dir) * 4 * LH + col;
                 gp[0] = di_p; gp[LH] = df_p; gp[2 * LH] = dg_p; gp[3 * LH] = do_p;
             }
-            dgs[j][b] = di_p; dgs[LH + j][b] = df_p; dgs[2 * LH + j][b] = dg_p; dgs[3 * LH + j][b] = do_p;
+            dgs[(0 * LU + u) * BG + pb] = di_p; dgs[(1 * LU + u) * BG + pb] = df_p;
+            dgs[(2 * LU + u) * BG + pb] = dg_p; dgs[(3 * LU + u) * BG + pb] = do_p;
         }
+        if (s == 0) break;                                    // nothing consumes dh before the first processed step (uniform: no barrier skipped unevenly)
         __syncthreads();
-        float acc[BC];
+        float acc[2][BG];
 #pragma unroll
-        for (int b = 0; b < BC; ++b) acc[b] = 0.f;
+        for (int b = 0; b < BG; ++b) { acc[0][b] = 0.f; acc[1][b] = 0.f; }
 #pragma unroll 4
-        for (int r = 0; r < 4 * LH; ++r) {
-            float w = __ldg(W + (size_t)r * LH + j);
-            float4 g0 = *reinterpret_cast<const float4*>(&dgs[r][0]);
-            float4 g1 = *reinterpret_cast<const float4*>(&dgs[r][4]);
-            acc[0] = fmaf(w, g0.x, acc[0]); acc[1] = fmaf(w, g0.y, acc[1]); acc[2] = fmaf(w, g0.z, acc[2]); acc[3] = fmaf(w, g0.w, acc[3]);
-            acc[4] = fmaf(w, g1.x, acc[4]); acc[5] = fmaf(w, g1.y, acc[5]); acc[6] = fmaf(w, g1.z, acc[6]); acc[7] = fmaf(w, g1.w, acc[7]);
+        for (int rr = 0; rr < 64; ++rr) {
+            const int row = 64 * half + rr;
+            const float2 wv = *reinterpret_cast<const float2*>(Wb + row * LH + 2 * jp);
+            float gv[BG];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 g4 = *reinterpret_cast<const float4*>(dgs + row * BG + 4 * q);
+                gv[4 * q] = g4.x; gv[4 * q + 1] = g4.y; gv[4 * q + 2] = g4.z; gv[4 * q + 3] = g4.w;
+            }
+#pragma unroll
+            for (int b = 0; b < BG; ++b) {
+                acc[0][b] = fmaf(wv.x, gv[b], acc[0][b]);
+                acc[1][b] = fmaf(wv.y, gv[b], acc[1][b]);
+            }
         }
 #pragma unroll
-        for (int b = 0; b < BC; ++b) dh[b] = acc[b];
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                *reinterpret_cast<float4*>(pbuf + (half * LH + 2 * jp + jj) * BG + 4 * q) =
+                    make_float4(acc[jj][4 * q], acc[jj][4 * q + 1], acc[jj][4 * q + 2], acc[jj][4 * q + 3]);
         __syncthreads();
+        // reduce-scatter: the partial dh_prev of units [32 dst, 32 dst + 32) goes to slot r of CTA dst's receive buffer (parity s & 1)
+        for (int i = tid; i < LS * LU * Q; i += 256) {
+            const int dst = i / (LU * Q), q = i - dst * (LU * Q);
+            const float4 a = *reinterpret_cast<const float4*>(pbuf + (LU * dst) * BG + 4 * q);
+            const float4 b4 = *reinterpret_cast<const float4*>(pbuf + (LH + LU * dst) * BG + 4 * q);
+            float* remote = cluster.map_shared_rank(recv, dst);
+            *reinterpret_cast<float4*>(remote + ((s & 1) * LS + r) * LU * BG + 4 * q) = make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
+        }
+        cluster.sync();
     }
+    cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
 }
 
 // hprev[t,b,dir,:] = y[t_prev,b,dir*H:] (the hidden state that entered step t), zero at each direction's first step
@@ -166,7 +280,17 @@ int tpgsr_lstm_fwd(const float* gx, const float* whhT, const float* bhh, float* 
                    int batch_first, cudaStream_t stream) {
     if (!gx || !whhT || !bhh || !y || T <= 0 || B <= 0) return TPGSR_ERR_BAD_ARG;
     if (hidden != LH) return TPGSR_ERR_UNSUPPORTED;
-    lstm_fwd_kernel<<<dim3((B + BC - 1) / BC, 2), LH, 0, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first);
+    if (B <= 4) {
+        constexpr int BG = 4;
+        if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        lstm_fwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first);
+    } else {
+        constexpr int BG = 8;
+        if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        lstm_fwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first);
+    }
     return tpgsr_launch_status();
 }
 
@@ -174,7 +298,17 @@ int tpgsr_lstm_bwd(const float* dy, const float* stash, const float* whh, float*
                    int batch_first, cudaStream_t stream) {
     if (!dy || !stash || !whh || !dgx || T <= 0 || B <= 0) return TPGSR_ERR_BAD_ARG;
     if (hidden != LH) return TPGSR_ERR_UNSUPPORTED;
-    lstm_bwd_kernel<<<dim3((B + BC - 1) / BC, 2), LH, 0, stream>>>(dy, stash, whh, dgx, T, B, batch_first);
+    if (B <= 4) {
+        constexpr int BG = 4;
+        if (cudaFuncSetAttribute(lstm_bwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        lstm_bwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(dy, stash, whh, dgx, T, B, batch_first);
+    } else {
+        constexpr int BG = 8;
+        if (cudaFuncSetAttribute(lstm_bwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        lstm_bwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(dy, stash, whh, dgx, T, B, batch_first);
+    }
     return tpgsr_launch_status();
 }
 
