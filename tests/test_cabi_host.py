@@ -142,9 +142,14 @@ def test_flat_conv_plans_fit_the_sm(nprod):
         assert grid_x * MT * 128 >= B * (H + P) * (W + P)                           # every flat output row belongs to a tile
         assert b_stages >= 1 and a_stages >= 1 and (n_groups == 1 or a_stages >= 2)
         assert bool(LIB.tpgsr_conv2d_flat_supported(B, H, W, P, Ci, Co, KH, KW, KH // 2, KW // 2, nprod))
-    # not supported: channel counts that are no multiple of 64, non-'same' padding
+    # not supported: channel counts that are no multiple of 64, padding the planes' zero rows / columns do not cover
     assert not LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 1, 96, 64, 3, 3, 1, 1, nprod)
-    assert not LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 1, 64, 64, 3, 3, 0, 0, nprod)
+    assert not LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 0, 64, 64, 3, 3, 1, 1, nprod)
+    assert not LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 2, 64, 64, 3, 3, 3, 1, nprod)
+    # 'valid' and 'full' convolutions (CRNN conv6 2x2 and its data gradient) are
+    assert LIB.tpgsr_conv2d_flat_supported(48, 2, 27, 0, 512, 512, 2, 2, 0, 0, nprod)
+    assert LIB.tpgsr_conv2d_flat_supported(48, 1, 26, 1, 512, 512, 2, 2, 1, 1, nprod)
+    assert LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 1, 64, 64, 3, 3, 0, 0, nprod)
     for (B, H, W, P, Co, K) in [(48, 16, 64, 1, 64, 3), (48, 16, 64, 0, 192, 1), (48, 16, 64, 1, 256, 3), (48, 32, 128, 4, 36, 9)]:
         out = (ctypes.c_int * 9)()
         cpad = (Co + 63) // 64 * 64

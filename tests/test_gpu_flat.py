@@ -193,3 +193,42 @@ def test_kwstack_conv_through_engine(B, Ci, Co, H, W, k, nchw_out, mode):
         assert rel_err(grads['w'], 2 * w.grad) < tol
     finally:
         ops.CONV_MODE = old
+
+
+@pytest.mark.parametrize('B,Ci,Co,H,W,k,pad', [
+    (5, 512, 512, 2, 27, 2, 0),       # CRNN conv6: 'valid' 2x2 (its data gradient is a 'full' conv, its dY planes are padded up to x's grid)
+    (48, 512, 512, 2, 27, 2, 0),      # ... at the bench batch
+    (3, 64, 64, 6, 9, 3, 0),          # 'valid' 3x3
+    (3, 128, 64, 1, 51, 3, 1),        # a 1-row map ('same' 1x3 in effect: InfoGen's equivalent convs use (1,3) kernels, see test_gpu_prior)
+])
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
+def test_valid_and_full_convs_through_engine(B, Ci, Co, H, W, k, pad, mode):
+    """Non-'same' stride-1 convs on the flat tcgen05 kernels through engine.conv_fwd / conv_bwd (forward, dX, dW, db) vs fp32 autograd."""
+    from tpgsr_b200 import engine, ops
+    x = rnd(B, Ci, H, W, seed=71).requires_grad_(True)
+    w = (rnd(Co, Ci, k, k, seed=72) / np.sqrt(Ci * k * k)).requires_grad_(True)
+    b = rnd(Co, seed=73, scale=0.1).requires_grad_(True)
+    y = F.conv2d(x, w, b, padding=pad)
+    gy = rnd(*y.shape, seed=74)
+    (y * gy).sum().backward()
+    d = torch.device('cuda:0')
+    old = ops.CONV_MODE
+    ops.CONV_MODE = mode
+    tol = 5e-5 if mode == 'bf16x3' else 1e-2
+    try:
+        params = {'w': w.detach().to(d), 'b': b.detach().to(d)}
+        grads = {'w': torch.full_like(params['w'], 7.0), 'b': torch.zeros_like(params['b'])}
+        ctx = engine.Ctx(params, grads, True)
+        xd = nhwc(x.detach()).to(d)
+        assert engine._flat_ok(xd, Ci, Co, k, k, pad, pad, 0)
+        l0 = ops.LAUNCHES
+        yd, saved = engine.conv_fwd(ctx, xd, 'w', 'b', k, pad)
+        assert yd.shape == (B, y.shape[2], y.shape[3], Co)
+        assert rel_err(nchw(yd), y) < tol, rel_err(nchw(yd), y)
+        dx = engine.conv_bwd(ctx, saved, nhwc(gy).to(d), need_dx=True)
+        ctx.join()
+        assert rel_err(grads['w'], w.grad) < tol, rel_err(grads['w'], w.grad)
+        assert rel_err(grads['b'], b.grad) < 1e-4
+        assert rel_err(nchw(dx), x.grad) < tol, rel_err(nchw(dx), x.grad)
+    finally:
+        ops.CONV_MODE = old

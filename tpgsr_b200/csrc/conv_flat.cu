@@ -96,6 +96,7 @@ constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;
 
 struct FlatConvParams {
     int B, H, W, Hp, Wp;
+    int Ho, Wo;                // output map: H + 2 ph - KH + 1, W + 2 pw - KW + 1 ('same' convs: H, W); output (r, c) sits at plane position (r, c)
     long long Qtot;            // B*Hp*Wp rows in the planes
     int Co, KH, KW, ph, pw;
     int MT;                    // 128-row output tiles per CTA
@@ -353,7 +354,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const unsigned ub = qrow / img, rem = qrow - ub * img;
                     const unsigned ur = rem / (unsigned)p.Wp, uc = rem - ur * (unsigned)p.Wp;
                     bi = (int)ub; r = (int)ur; c = (int)uc;
-                    pix = (qrow < qtot && r < p.H && c < p.W) ? (bi * p.H + r) * p.W + c : -1;
+                    pix = (qrow < qtot && r < p.Ho && c < p.Wo) ? (bi * p.Ho + r) * p.Wo + c : -1;
                 }
                 const int c0 = ch * 32;
                 const int cw = (p.n_tile - c0) >= 32 ? 32 : (p.n_tile - c0);       // 32 or 16 columns in this chunk
@@ -456,7 +457,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     // NCHW: for a fixed channel the 32 lanes hold 32 consecutive flat positions = (mostly) consecutive columns
                     for (int n = 0; n < ncols; ++n) {
                         const float val = apply_act(drow[n], p.act, slope);
-                        float* dst = p.y + (((size_t)bi * p.Co + n0 + c0 + n) * p.H + r) * p.W + c;
+                        float* dst = p.y + (((size_t)bi * p.Co + n0 + c0 + n) * p.Ho + r) * p.Wo + c;
                         *dst = p.accumulate ? *dst + val : val;
                     }
                 }
@@ -528,7 +529,10 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
     if (Co < 1 || B < 1 || H < 1 || W < 1 || Ci < 64 || Ci % 64 != 0) return TPGSR_ERR_UNSUPPORTED;
     const int pointwise = (KH == 1 && KW == 1) ? 1 : 0;
     const int cbs = Ci / 64;                                      // 64-channel blocks of the input
-    if (2 * ph != KH - 1 || 2 * pw != KW - 1 || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
+    // any padding 0 <= ph < KH, 0 <= pw < KW that the planes' shared zero rows / columns cover ('same': 2 ph = KH - 1; 'valid': ph = 0;
+    // 'full' = the data gradient of a valid conv: ph = KH - 1); the output map must fit the plane grid
+    if (ph < 0 || ph >= KH || pw < 0 || pw >= KW || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
+    if (H + 2 * ph - KH + 1 < 1 || W + 2 * pw - KW + 1 < 1 || H + 2 * ph - KH + 1 > H + P || W + 2 * pw - KW + 1 > W + P) return TPGSR_ERR_UNSUPPORTED;
     const int a_planes = nprod == 3 ? 2 : 1, b_planes = nprod >= 2 ? 2 : 1;
     const int Wp = W + P;
     const int co16 = (Co + 15) / 16 * 16;
@@ -769,7 +773,7 @@ struct FlatWgradPlan {
 };
 
 int plan_wgrad_flat(int B, int H, int W, int P, int Ci, int Co, int Cpad, int KH, int KW, int nprod, FlatWgradPlan& pl) {
-    if (Ci < 64 || Ci % 64 != 0 || Cpad % 64 != 0 || Cpad < Co || 2 * P < KH - 1 || 2 * P < KW - 1) return TPGSR_ERR_UNSUPPORTED;
+    if (Ci < 64 || Ci % 64 != 0 || Cpad % 64 != 0 || Cpad < Co) return TPGSR_ERR_UNSUPPORTED;
     const int cbs = Ci / 64;
     const int dy_planes = nprod == 3 ? 2 : 1, x_planes = nprod >= 2 ? 2 : 1;
     // co tile: the candidate (multiple of 64 dividing Cpad, <= 256) with the fewest CTAs per pixel split whose ring is >= 2 deep
@@ -874,7 +878,7 @@ size_t tpgsr_conv2d_wgrad_flat_plan(int B, int H, int W, int P, int Ci, int Co, 
     return (size_t)pl.stage_bytes;
 }
 
-// y = act(conv(x) + bias) for a 'same' convolution with 64 input channels.  x_hi/x_lo: padded-flat bf16 planes of the input
+// y = act(conv(x) + bias) for a stride-1 convolution with 64 k input channels and padding (ph, pw) <= P; y is [B, H + 2 ph - KH + 1, W + 2 pw - KW + 1, Co].  x_hi/x_lo: padded-flat bf16 planes of the input
 // ([B][H+P][W+P][64], tpgsr_split_bf16_flat); w_hi/w_lo: K-major packed weights [Co][KH*KW*64] (tpgsr_pack_conv_weights_bf16);
 // y: fp32 dense NHWC (pixel pitch ldy) or NCHW.  Data gradient: pass dY planes, the dgrad packing, Co := conv Ci.
 int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y, void* yp_hi,
@@ -900,6 +904,7 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     if (rc) return rc;
     FlatConvParams p;
     p.B = B; p.H = H; p.W = W; p.Hp = H + P; p.Wp = W + P; p.Qtot = (long long)B * p.Hp * p.Wp;
+    p.Ho = H + 2 * ph - KH + 1; p.Wo = W + 2 * pw - KW + 1;
     p.Co = Co; p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw;
     p.MT = pl.MT; p.n_tile = pl.n_tile; p.tm_stride = pl.tm_stride; p.Ci = Ci; p.G = pl.G; p.kgroups = pl.kgroups; p.n_groups = pl.n_groups;
     p.a_stages = pl.a_stages;
@@ -962,7 +967,7 @@ int tpgsr_conv2d_wgrad_flat(const void* x_hi, const void* x_lo, const void* dy_h
                             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (!x_hi || !dy_hi || !dw_oihw || !workspace || nprod < 1 || nprod > 3 || (nprod >= 2 && !x_lo) || (nprod == 3 && !dy_lo))
         return TPGSR_ERR_BAD_ARG;
-    if (2 * ph != KH - 1 || 2 * pw != KW - 1 || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
+    if (ph < 0 || ph >= KH || pw < 0 || pw >= KW || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
     FlatWgradPlan pl;
     int rc = plan_wgrad_flat(B, H, W, P, Ci, Co, Cpad, KH, KW, nprod, pl);
     if (rc) return rc;

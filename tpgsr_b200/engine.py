@@ -149,7 +149,7 @@ class Ctx:
                 w = w.view(w.shape[0], w.shape[1], 1, 1)
             hit = ops.pack_conv_weights_bf16(w, self.grads is not None, ops.CONV_MODE == 'bf16x3')
             self._packed_bf16[name] = hit
-            if self.store is not None:
+            if self.store is not None and '#' not in name:          # ('#': weights derived per step, e.g. InfoGen's equivalent convs)
                 self.store.add('bf16', name, 0, w, hit[0] + hit[1])
         return hit
 
@@ -177,8 +177,9 @@ def _tc_ok(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: int, ldx:
 
 
 def _flat_ok(x: Tensor, Ci: int, Co: int, kh: int, kw: int, ph: int, pw: int, ldx: int) -> bool:
+    """Stride-1 convs with 64 k input channels and any padding below the kernel size ('same', 'valid', 'full') run on the flat kernels."""
     B, H, W, Cx = x.shape
-    return (ldx in (0, Cx) and Cx == Ci and 2 * ph == kh - 1 and 2 * pw == kw - 1 and x.is_contiguous()
+    return (ldx in (0, Cx) and Cx == Ci and 0 <= ph < kh and 0 <= pw < kw and x.is_contiguous()
             and ops.flat_supported(B, H, W, max(ph, pw), Ci, Co, kh, kw, ph, pw))
 
 
@@ -261,8 +262,13 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
         return ops.kwsum(part, None, Ci, kw, pw, out=dx_out, accumulate=dx_accumulate)
     same = (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 2 * ph == kh - 1 and 2 * pw == kw - 1)
     gb, accb = ctx.G(bname) if bname else (None, False)
-    if same and ops.wgrad_flat_supported(B, H, W, P, Ci, Co, kh, kw):
-        xp, dyp = ctx.flat(x, P), ctx.dflat(dy, P, (Co + 63) // 64 * 64)         # shared with the data gradient: before the fork
+    # flat weight gradient: x and dY planes on ONE plane grid.  'same' convs: both padded by P; 'valid' convs (CRNN conv6): dY
+    # [B, H-KH+1, W-KW+1] padded up to x's grid
+    Pdy = H + P - dy.shape[1]
+    flat_w = (ldx in (0, Cx) and Cx == Ci and x.is_contiguous() and dy.is_contiguous() and 0 <= ph < kh and 0 <= pw < kw
+              and Pdy == W + P - dy.shape[2] and Pdy >= 0 and ops.wgrad_flat_supported(B, H, W, P, Ci, Co, kh, kw))
+    if flat_w:
+        xp, dyp = ctx.flat(x, P), ctx.dflat(dy, Pdy, (Co + 63) // 64 * 64)         # shared with the data gradient: before the fork
         with ctx.on_side(dy):
             ops.conv_wgrad_flat(xp, dyp, gw, Co, kh, kw, ph, pw, acc)
             if bname:
@@ -282,13 +288,14 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
     if not need_dx:
         return None
     dense_out = dx_out is None or dx_out.shape[-1] == Ci
+    Pd = max(kh - 1 - ph, kw - 1 - pw)                  # padding of the data-gradient conv = plane padding of dY ('same' convs: P)
     if dense_out and _flat_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)
-        if emit_dx_planes and dx_out is None and Ci % 32 == 0:
-            dx, dxp = ops.conv_flat(ctx.dflat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, emit_planes=True, emit_lo=not ops.BWD2)
+        if emit_dx_planes and dx_out is None and Ci % 32 == 0 and same:
+            dx, dxp = ops.conv_flat(ctx.dflat(dy, Pd), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, emit_planes=True, emit_lo=not ops.BWD2)
             ctx._planes[(id(dx), 'dflat' if ops.BWD2 else 'flat', 0, Ci)] = (dx, dxp)       # dx is the next backward conv's dY
             return dx
-        return ops.conv_flat(ctx.dflat(dy, P), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out, accumulate=dx_accumulate)
+        return ops.conv_flat(ctx.dflat(dy, Pd), wd, None, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out, accumulate=dx_accumulate)
     if dense_out and _tc_ok(dy, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, 0):
         _, wd = ctx.packed_bf16(wname, as4d)
         return ops.conv_tc(ctx.planes(dy), wd, None, B, H, W, Co, Ci, kh, kw, kh - 1 - ph, kw - 1 - pw, out=dx_out,

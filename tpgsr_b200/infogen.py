@@ -36,12 +36,22 @@ def info_gen_fwd(ctx: engine.Ctx, x_nchw: torch.Tensor, text_emb: Optional[torch
         wt = ctx.P(wname)
         Ci, Co, KH, KW = wt.shape
         wc = ops_prior.tconv_weight_fwd(wt)                         # OIHW [Co,Ci,1,3]
-        wf, wd = ops.pack_conv_weights(wc, ctx.grads is not None)
+        wd = None
         up = ops_prior.zero_upsample_w(t, stride) if stride > 1 else t
         pad = KW - 1 - pad_t
-        c = ops.conv_fwd(up, wf, None, Co, 1, KW, 0, pad)
+        s_conv = None
+        if Ci % 64 == 0 and 2 * pad == KW - 1 and engine._flat_ok(up, Ci, Co, 1, KW, 0, pad, 0):
+            # tconv2 / tconv3 (512 -> 128 -> 64 channels): the equivalent stride-1 conv runs on the tensor-core path.  Its weight is DERIVED
+            # from the parameter, so it enters the engine under a synthetic name; its gradient is scattered back by tconv_weight_bwd.
+            dname = wname + '#conv'
+            ctx.params[dname] = wc
+            ctx._packed_bf16.pop(dname, None)
+            c, s_conv = engine.conv_fwd(ctx, up, dname, None, (1, KW), (0, pad))
+        else:
+            wf, wd = ops.pack_conv_weights(wc, ctx.grads is not None)
+            c = ops.conv_fwd(up, wf, None, Co, 1, KW, 0, pad)
         a, s_bn = engine.bn_fwd(ctx, c, f'infoGen.bn{i}.', ACT_RELU)
-        saved.append((wname, wd, up, t.shape[2], stride, pad, KW, Ci, Co, s_bn))
+        saved.append((wname, wd, up, t.shape[2], stride, pad, KW, Ci, Co, s_bn, s_conv, wc))
         t = a
     text = ops_prior.bilinear_rows_fwd(t, H, W)
     return text, {'layers': saved, 'text': text, 'w_last': t.shape[2], 'prior_shape': tuple(text_emb.shape)}
@@ -51,14 +61,25 @@ def info_gen_bwd(ctx: engine.Ctx, s_text, dtext: torch.Tensor, need_dprior: bool
     d = ops_prior.bilinear_rows_bwd(dtext, s_text['w_last'])        # [B,1,203,32]
     layers = s_text['layers']
     for idx in range(len(layers) - 1, -1, -1):
-        wname, wd, up, w_in, stride, pad, KW, Ci, Co, s_bn = layers[idx]
+        wname, wd, up, w_in, stride, pad, KW, Ci, Co, s_bn, s_conv, wc = layers[idx]
         dc = engine.bn_bwd(ctx, s_bn, d)
         dwc = ops.new((Co, Ci, 1, KW), dc)
-        ops.conv_wgrad(up, dc, dwc, 1, KW, 0, pad, False)
         gw, acc = ctx.G(wname)
-        ops_prior.tconv_weight_bwd(dwc, gw, acc)
-        if idx == 0 and not need_dprior:
-            return None
-        dup = ops.conv_dgrad(dc, wd, (1, up.shape[2]), Ci, 1, KW, 0, pad)
+        if s_conv is not None:
+            dname = wname + '#conv'
+            ctx.params[dname] = wc                                  # (a shared Ctx of a later cascade stage may have re-derived it)
+            ctx.grads[dname] = dwc
+            ctx._written.discard(dname)                             # dwc is a fresh buffer: overwrite, the accumulation happens below
+            dup = engine.conv_bwd(ctx, s_conv, dc, need_dx=not (idx == 0 and not need_dprior))
+            with ctx.on_side(dwc):                                  # behind the weight gradient on the side stream (same stream: ordered)
+                ops_prior.tconv_weight_bwd(dwc, gw, acc)
+            if dup is None:
+                return None
+        else:
+            ops.conv_wgrad(up, dc, dwc, 1, KW, 0, pad, False)
+            ops_prior.tconv_weight_bwd(dwc, gw, acc)
+            if idx == 0 and not need_dprior:
+                return None
+            dup = ops.conv_dgrad(dc, wd, (1, up.shape[2]), Ci, 1, KW, 0, pad)
         d = ops_prior.zero_upsample_w_bwd(dup, w_in, stride) if stride > 1 else dup
     return d if nhwc_out else ops.nhwc_to_nchw(d)                    # [B,1,26,37] or the reference's [B,37,1,26]

@@ -92,6 +92,28 @@ class CRNN(nn.Module):
                     p.grad = st.gviews[n]
         return dgray
 
+    @property
+    def module(self):
+        """The un-wrapped model (callers written for ``nn.DataParallel`` read ``.module``; one process per GPU has no wrapper)."""
+        return self
+
+    def complexity_info(self, input_res):
+        """Multiply-accumulates of one ``(1, 32, W)`` image (what ``ptflops`` prints for the reference module, interfaces/base.py:638)."""
+        _, H, W = input_res
+        macs, h, w, cin = 0, H, W, 1
+        for i, (co, k, p) in enumerate(zip([64, 128, 256, 256, 512, 512, 512], [3, 3, 3, 3, 3, 3, 2], [1, 1, 1, 1, 1, 1, 0])):
+            h, w = h + 2 * p - k + 1, w + 2 * p - k + 1
+            macs += cin * co * k * k * h * w
+            cin = co
+            if i in (0, 1):
+                h, w = h // 2, w // 2
+            elif i in (3, 5):
+                h, w = h // 2, w + 1
+        T, nh = w, 256
+        macs += T * 2 * 4 * nh * (512 + nh) + T * 2 * nh * nh            # BiLSTM 1 + embedding
+        macs += T * 2 * 4 * nh * (nh + nh) + T * 2 * nh * self.rnn[1].embedding.out_features
+        return macs
+
     def forward(self, input):
         anchor = next(self.parameters())
         return _CRNNFunction.apply(self, input, anchor, torch.is_grad_enabled())

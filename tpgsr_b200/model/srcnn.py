@@ -95,6 +95,17 @@ class SRCNN(nn.Module):
             if p is not None and p.requires_grad:
                 p.grad = st.gviews[name]
 
+    @property
+    def module(self):
+        """The un-wrapped model (``save_checkpoint`` reads ``netG.module``, interfaces/base.py:556; one process per GPU has no wrapper)."""
+        return self
+
+    def complexity_info(self, input_res):
+        """Multiply-accumulates of the forward for one ``(C, H, W)`` image (what ``ptflops`` prints, interfaces/base.py:376)."""
+        c_in, H, W = input_res
+        hw = H * W * self.upscale_factor ** 2
+        return (c_in * 64 * 81 + 64 * 32 + 32 * c_in * 25) * hw
+
     def forward(self, x):
         anchor = next(self.parameters())
         return _SRCNNFunction.apply(self, x, anchor, torch.is_grad_enabled())

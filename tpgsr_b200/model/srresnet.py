@@ -234,6 +234,23 @@ class SRResNet_TL(nn.Module):
                 p.grad = st.gviews[name]
         return dprior
 
+    @property
+    def module(self):
+        """The un-wrapped model (``save_checkpoint`` reads ``netG.module``, interfaces/base.py:556; one process per GPU has no wrapper)."""
+        return self
+
+    def complexity_info(self, input_res):
+        """Multiply-accumulates of the eval-mode forward for one ``(C, H, W)`` image (what ``ptflops`` prints, interfaces/base.py:376)."""
+        c_in, H, W = input_res
+        hw, c, t_ch = H * W, 64, 32
+        macs = c_in * c * 81 * hw + 5 * (c * c * 9 + (c + t_ch) * c * 9) * hw + c * c * 9 * hw + c * 4 * c * 9 * hw + c * c_in * 81 * 4 * hw
+        h, w = 1, 26
+        for i, (s_, p_) in enumerate([((2, 2), (0, 0)), ((2, 2), (0, 0)), ((2, 2), (1, 1)), ((2, 1), (1, 1))], 1):
+            wt = getattr(self.infoGen, f'tconv{i}').weight
+            macs += h * w * wt.shape[0] * wt.shape[1] * 9
+            h, w = (h - 1) * s_[0] - 2 * p_[0] + 3, (w - 1) * s_[1] - 2 * p_[1] + 3
+        return macs
+
     def forward(self, x, text_emb=None):
         anchor = next(self.parameters())
         return _SRResNetFunction.apply(self, x, text_emb, anchor, torch.is_grad_enabled())

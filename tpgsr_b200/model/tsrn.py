@@ -202,6 +202,35 @@ class _TSRNBase(nn.Module):
                 if p is not None and p.requires_grad:
                     p.grad = st.gviews[n]
 
+    # ---------------------------------------------------------------------------------------------------- caller conveniences
+    @property
+    def module(self):
+        """``save_checkpoint`` reads ``netG.module.state_dict()`` when the model was wrapped in ``nn.DataParallel``
+        (interfaces/base.py:556); with one process per GPU there is no wrapper, so the model is its own ``.module``."""
+        return self
+
+    def complexity_info(self, input_res):
+        """Multiply-accumulates of the eval-mode forward for one ``input_res = (C, H, W)`` image — what ``ptflops`` prints for the
+        reference module (interfaces/base.py:376); analytic, because the fused CUDA path never runs the ``nn.Conv2d`` children."""
+        c_in, H, W = input_res
+        hw, c = H * W, 64
+        gru = 2 * 96 * (c + 32)                                # per position: 2 directions x 3 gates x 32 units x (64 inputs + 32 hidden)
+        macs = c_in * c * 81 * hw                              # block1 9x9
+        t_ch = self.infoGen.tconv4.weight.shape[1] if self._tl else 0
+        for _ in range(self.srb_nums):
+            macs += 2 * c * c * 9 * hw                         # conv1, conv2
+            macs += ((c + t_ch) * c + gru) * hw                # gru1: 1x1 conv on [features ; prior] + BiGRU
+            macs += (c * c + gru) * hw                         # gru2
+        macs += c * c * 9 * hw + c * 4 * c * 9 * hw            # block7 conv, upsample conv
+        macs += c * c_in * 81 * 4 * hw                         # final 9x9 on the 2x map
+        if self._tl:
+            w_in = 26
+            for i in range(1, 5):
+                wt = getattr(self.infoGen, f'tconv{i}').weight
+                macs += w_in * wt.shape[0] * wt.shape[1] * 9   # transposed conv: every input position feeds 9 taps
+                w_in = (w_in - 1) * (2 if i < 4 else 1) - (2 if i < 4 else 0) + 3
+        return macs
+
     def _forward(self, x, text_emb=None):
         anchor = next(self.parameters())
         return _TSRNFunction.apply(self, x, text_emb, anchor, torch.is_grad_enabled())

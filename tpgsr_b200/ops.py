@@ -75,6 +75,26 @@ def join_side(device) -> None:
             cur.wait_stream(st)
 
 
+class on_stream_after_current:
+    """``with on_stream_after_current(side, device):`` — run the enclosed launches on ``side`` after everything queued so far on the
+    current stream (no-op when ``side`` is None).  The caller joins with :func:`join_side` before consuming the results."""
+
+    def __init__(self, side, device):
+        self.side, self.device, self._ctx = side, device, None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream(torch.device('cuda', _dev_index(self.device))))
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+
 def workspace(nbytes: int, device) -> Tuple[int, int]:
     """A scratch buffer per (device, main / side stream), grown on demand; stable pointer once large enough — safe under graph
     capture because every kernel that uses one buffer runs on the same stream."""
@@ -320,12 +340,13 @@ def conv_flat(xp: FlatPlanes, w_planes, bias, Co, KH, KW, ph, pw, act=ACT_NONE, 
     """'same' conv on padded-flat planes -> dense fp32 NHWC [B,H,W,Co] (or NCHW).  ``emit_planes``: also return the output's dense
     bf16 hi/lo planes (= its P = 0 operand planes) written by the same epilogue -> (out, FlatPlanes)."""
     B, H, W = xp.B, xp.H, xp.W
+    Ho, Wo = H + 2 * ph - KH + 1, W + 2 * pw - KW + 1           # 'same' convs: (H, W); 'valid': smaller; 'full': larger (fits the plane grid)
     if out is None:
-        out = torch.empty((B, Co, H, W) if out_nchw else (B, H, W, Co), dtype=torch.float32, device=xp.hi.device)
+        out = torch.empty((B, Co, Ho, Wo) if out_nchw else (B, Ho, Wo, Co), dtype=torch.float32, device=xp.hi.device)
         accumulate = False
     n = _nprod_for(xp.lo, w_planes[1])
     if emit_planes:
-        assert not out_nchw and Co % 32 == 0 and out.shape[-1] == Co
+        assert not out_nchw and Co % 32 == 0 and out.shape[-1] == Co and (Ho, Wo) == (H, W)
         hi = torch.empty((B * H * W, Co), dtype=torch.bfloat16, device=out.device)
         lo = torch.empty((B * H * W, Co), dtype=torch.bfloat16, device=out.device) if (nprod() == 3 and emit_lo) else None
         _call('tpgsr_conv2d_flat_planes', ptr(xp.hi), ptr(xp.lo), ptr(w_planes[0]), ptr(w_planes[1]), ptr(bias), ptr(out), ptr(hi), ptr(lo),
@@ -344,7 +365,7 @@ def wgrad_flat_supported(B, H, W, P, Ci, Co, KH, KW) -> bool:
 
 
 def conv_wgrad_flat(xp: FlatPlanes, dyp: FlatPlanes, dw: torch.Tensor, Co, KH, KW, ph, pw, accumulate: bool) -> None:
-    assert (xp.B, xp.H, xp.W, xp.P) == (dyp.B, dyp.H, dyp.W, dyp.P)
+    assert (xp.B, xp.H + xp.P, xp.W + xp.P) == (dyp.B, dyp.H + dyp.P, dyp.W + dyp.P)      # same plane grid (valid convs: dY is padded up to it)
     n = 1 if WGRAD1 else _nprod_for(dyp.lo, xp.lo)            # 2: dY one plane against X hi + lo
     nbytes = query('tpgsr_conv2d_wgrad_flat_workspace_bytes', xp.B, xp.H, xp.W, xp.P, xp.C, Co, dyp.C, KH, KW, n)
     wp, wn = workspace(nbytes, dw.device)

@@ -180,11 +180,15 @@ class TPGSRTrainStep:
         B = self.batch
         drop = B // 4
         st_sr = m._flat
-        # ---- teacher prior (eval mode, no grad)
-        tctx = engine.Ctx(self.teacher._flat.views, None, False, store=self.packs.get('teacher'))
-        gray_hr = ops_prior.bicubic_gray_fwd(self.hr_buf)
-        logits_hr, _ = crnn_engine.crnn_fwd(tctx, gray_hr)
-        label_hr, _ = ops_prior.softmax_prior_fwd(logits_hr, 0, need_prior=False)
+        # ---- teacher prior (eval mode, no grad).  It depends on the HR batch only, so it runs on the side stream (idle during the forward
+        #      pass) concurrently with the first student / SR stage; the main stream joins right before the first distillation loss.
+        side = ops.side_stream(self.dev) if self.use_distill else None
+        with ops.on_stream_after_current(side, self.dev):
+            tctx = engine.Ctx(self.teacher._flat.views, None, False, store=self.packs.get('teacher'))
+            gray_hr = ops_prior.bicubic_gray_fwd(self.hr_buf)
+            logits_hr, _ = crnn_engine.crnn_fwd(tctx, gray_hr)
+            label_hr, _ = ops_prior.softmax_prior_fwd(logits_hr, 0, need_prior=False)
+        teacher_joined = side is None
         # ---- cascade forward
         stages = []
         cascade = self.lr_buf
@@ -202,6 +206,9 @@ class TPGSRTrainStep:
             logits, s_crnn = crnn_engine.crnn_fwd(sctx, gray, need_input_grad=i > 0)
             probs, prior = ops_prior.softmax_prior_fwd(logits, drop)
             if self.use_distill:
+                if not teacher_joined:
+                    ops.join_side(self.dev)
+                    teacher_joined = True
                 ops.semantic_loss_fwd(probs, label_hr, 100.0, loss=self.loss_distill, accumulate=not first_dis)
                 first_dis = False
             ctx = engine.Ctx(st_sr.views, st_sr.gviews, True, share=sr_ctx0, store=self.packs.get('sr'))
