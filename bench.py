@@ -158,7 +158,8 @@ def _oracle_step_fn(cfg_id: int):
     if cfg_id == 2:
         return lambda lr, hr, o=True: ostep.tsrn_train_step(sr, lr, hr, opt if o else None)
     if cfg_id == 5:
-        return lambda lr, hr, o=True: ostep.srresnet_train_step(sr, students, teacher, lr, hr, opt if o else None)
+        return lambda lr, hr, o=True: ostep.tpgsr_train_step(sr, students, teacher, lr, hr, opt if o else None, stu_iter=1, gradient=False,
+                                                             arch='srresnet_tl')
     return lambda lr, hr, o=True: ostep.tpgsr_train_step(sr, students, teacher, lr, hr, opt if o else None, stu_iter=cfg['stu_iter'])
 
 
@@ -289,7 +290,7 @@ def build_workload(cfg_id: int, dev, B: int, use_graph: bool):
     teacher = CRNN(32, 1, 37, 256).to(dev)
     teacher.load_state_dict(students[0].state_dict())       # no crnn.pth offline: teacher = copy of student 0 at step 0
     teacher.eval()
-    ts = TPGSRTrainStep(net, students, teacher, batch=B, stu_iter=cfg['stu_iter'], use_distill=True, use_graph=use_graph)
+    ts = TPGSRTrainStep(net, students, teacher, batch=B, stu_iter=cfg['stu_iter'], use_distill=True, gradient=cfg_id != 5, use_graph=use_graph)
     return ts, net, students, teacher
 
 
@@ -368,9 +369,6 @@ def inference_and_parity(cfg_id: int, dev, net, students, batches, steps: int, w
         xbuf = torch.empty_like(batches[0][0])
         if cfg_id == 2:
             fwd = lambda: net(xbuf)
-        elif cfg_id == 5:
-            from tpgsr_b200.train import srresnet_infer
-            fwd = lambda: srresnet_infer(net, students, xbuf)
         else:
             fwd = lambda: tpgsr_infer(net, students, xbuf, cfg['stu_iter'])
         with torch.no_grad():
@@ -403,8 +401,6 @@ def inference_and_parity(cfg_id: int, dev, net, students, batches, steps: int, w
             hr = batches[0][1][:n].cpu()
             if cfg_id == 2:
                 ours = net(xs)
-            elif cfg_id == 5:
-                ours = srresnet_infer(net, students, xs)
             else:
                 ours = tpgsr_infer(net, students, xs, cfg['stu_iter'])
             ours = ours.cpu()
@@ -414,10 +410,8 @@ def inference_and_parity(cfg_id: int, dev, net, students, batches, steps: int, w
         with torch.no_grad():
             if cfg_id == 2:
                 ref = omodels.tsrn(xs.cpu(), sr_p, training=False, stn=True)
-            elif cfg_id == 5:
-                ref = ostep.srresnet_infer(sr_p, stu_p, xs.cpu())
             else:
-                ref = ostep.tpgsr_infer(sr_p, stu_p, xs.cpu(), cfg['stu_iter'])
+                ref = ostep.tpgsr_infer(sr_p, stu_p, xs.cpu(), cfg['stu_iter'], arch='srresnet_tl' if cfg_id == 5 else 'tsrn_tl')
         out['parity'] = {'sr_rel_l2_vs_oracle': float((ours - ref).norm() / ref.norm()), 'sr_max_abs_vs_oracle': float((ours - ref).abs().max()),
                          'psnr': [round(float(oops.calculate_psnr(ours, hr)), 3), round(float(oops.calculate_psnr(ref, hr)), 3)],
                          'ssim': [round(float(oops.ssim(ours, hr)), 3), round(float(oops.ssim(ref, hr)), 3)],

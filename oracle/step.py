@@ -75,11 +75,18 @@ def tsrn_train_step(p: P, lr_img: Tensor, hr_img: Tensor, opt: Optional[AdamStat
     return out
 
 
+def _sr_model(arch: str, lr_img: Tensor, sr_p: P, training: bool, stn: bool, prior: Tensor) -> Tensor:
+    if arch == 'srresnet_tl':
+        return models.srresnet_tl(lr_img, sr_p, training=training, text_emb=prior)
+    return models.tsrn(lr_img, sr_p, training=training, stn=stn, text_emb=prior, tl=True)
+
+
 def tpgsr_train_step(sr_p: P, students: List[P], teacher: P, lr_img: Tensor, hr_img: Tensor,
                      opt: Optional[AdamState] = None, stu_iter: int = 1, use_distill: bool = True,
-                     stn: bool = True, gradient: bool = True, tpg_share: bool = False):
+                     stn: bool = True, gradient: bool = True, tpg_share: bool = False, arch: str = 'tsrn_tl'):
     """Configs 3/4: interfaces/super_resolution.py:297-424 with ``sr_share`` (one SR model).
-    Students are in train mode, teacher in eval mode; Adam covers SR + student params, the clip only SR."""
+    Students are in train mode, teacher in eval mode; Adam covers SR + student params, the clip only SR.
+    Config 5: ``arch='srresnet_tl'``, ``gradient=False`` (nn.MSELoss, interfaces/base.py:359-362)."""
     sr_leaves = _leaf_params(sr_p)
     stu_leaves = [_leaf_params(s) for s in students]
     with torch.no_grad():
@@ -95,7 +102,7 @@ def tpgsr_train_step(sr_p: P, students: List[P], teacher: P, lr_img: Tensor, hr_
         probs, prior = models.prior_from_logits(logits, True)
         if use_distill:
             loss_dis = loss_dis + ops.semantic_loss(probs, label_hr) * 100
-        cascade = models.tsrn(lr_img, sr_p, training=True, stn=stn, text_emb=prior, tl=True)
+        cascade = _sr_model(arch, lr_img, sr_p, True, stn, prior)
         loss_img = loss_img + ops.image_loss(cascade, hr_img, gradient) * 100
     loss = loss_img + loss_dis
     all_leaves = list(sr_leaves.values()) + [t for sl in stu_leaves for t in sl.values()]
@@ -128,12 +135,12 @@ def tpgsr_train_step(sr_p: P, students: List[P], teacher: P, lr_img: Tensor, hr_
 
 
 @torch.no_grad()
-def tpgsr_infer(sr_p: P, students: List[P], lr_img: Tensor, stu_iter: int = 1, tpg_share: bool = False) -> Tensor:
+def tpgsr_infer(sr_p: P, students: List[P], lr_img: Tensor, stu_iter: int = 1, tpg_share: bool = False, arch: str = 'tsrn_tl') -> Tensor:
     """Evaluation data-flow (interfaces/super_resolution.py:748-768): eval mode, no STN, no prior dropout."""
     cascade = lr_img
     for i in range(stu_iter):
         sp = students[0 if tpg_share else i]
         logits = models.crnn(ops.parse_crnn_data(cascade), sp, training=False)
         _, prior = models.prior_from_logits(logits, False)
-        cascade = models.tsrn(lr_img, sr_p, training=False, stn=True, text_emb=prior, tl=True)
+        cascade = _sr_model(arch, lr_img, sr_p, False, True, prior)
     return cascade

@@ -287,3 +287,44 @@ def test_eval_b48_psnr_ssim_3dp(shapes):
     assert rel_err(ours, ref) < 3e-4
     assert abs(float(o.calculate_psnr(ours, hr)) - float(o.calculate_psnr(ref, hr))) < 5e-4
     assert abs(float(o.ssim(ours, hr)) - float(o.ssim(ref, hr))) < 5e-4
+
+
+def test_config5_srresnet_cascade_step_vs_oracle(shapes):
+    """BASELINE config 5's train step (SRResNet_TL + CRNN student / teacher prior, MSE*100, clip on the SR model, Adam over both) through
+    TPGSRTrainStep vs the CPU oracle: losses, SR output, every gradient tensor, the element-wise Adam update."""
+    from oracle import step as ostep
+    from oracle.weights import synth_state_dict
+    from tpgsr_b200.model.crnn import CRNN
+    from tpgsr_b200.model.srresnet import SRResNet_TL
+    from tpgsr_b200.train import TPGSRTrainStep
+    sd = synth_state_dict(shapes['srresnet_tl'], 9)
+    stu_sd, tea_sd = synth_state_dict(shapes['crnn'], 7), synth_state_dict(shapes['crnn'], 17)
+    sr = SRResNet_TL(scale_factor=2, width=128, height=32, STN=False, mask=True)
+    sr.load_state_dict(sd)
+    stu, tea = CRNN(32, 1, 37, 256), CRNN(32, 1, 37, 256)
+    stu.load_state_dict(stu_sd)
+    tea.load_state_dict(tea_sd)
+    sr, stu, tea = sr.to(_dev()).train(), stu.to(_dev()).train(), tea.to(_dev()).eval()
+    lr, hr = _smooth_batch(8, 83)
+    p_sr, p_stu = {k: v.clone() for k, v in sd.items()}, {k: v.clone() for k, v in stu_sd.items()}
+    out = ostep.tpgsr_train_step(p_sr, [p_stu], dict(tea_sd), lr, hr, ostep.AdamState(), stu_iter=1, gradient=False, arch='srresnet_tl')
+    ts = TPGSRTrainStep(sr, [stu], tea, batch=8, stu_iter=1, use_distill=True, gradient=False, use_graph=True)
+    loss = float(ts(lr.to(_dev()), hr.to(_dev())))
+    assert abs(loss - float(out['loss'])) < 2e-4 * abs(float(out['loss'])), (loss, float(out['loss']))
+    assert abs(float(ts.loss_distill) - float(out['loss_distill'])) < 1e-3 * abs(float(out['loss_distill']))
+    assert rel_err(ts.sr, out['sr']) < 5e-4, rel_err(ts.sr, out['sr'])
+    assert abs(ts.opt.grad_norm - float(out['grad_norm'])) < 1e-2 * float(out['grad_norm']), (ts.opt.grad_norm, float(out['grad_norm']))
+    worst = []
+    for k, g_ref in out['sr_grads'].items():
+        if not _is_zero_grad_param(k, g_ref):
+            worst.append((rel_err(sr._flat.gviews[k], g_ref), 'sr.' + k))
+    for k, g_ref in out['stu_grads'][0].items():
+        if not _is_zero_grad_param(k, g_ref):
+            worst.append((rel_err(stu._flat.gviews[k], g_ref), 'stu.' + k))
+    worst.sort(reverse=True)
+    _note('config5_step', {'worst_grads': worst[:10], 'median': worst[len(worst) // 2], 'loss': [loss, float(out['loss'])]})
+    assert worst[0][0] < 5e-2 and worst[len(worst) // 2][0] < 1e-2, worst[:10]      # no STN here; the CRNN's max-pool / ReLU kinks remain
+    _compare_updates('config5_sr_updates', sd, {k: v.detach() for k, v in sr.state_dict().items()},
+                     {k: v for k, v in p_sr.items() if ostep.is_param(k)}, out['sr_grads'], 1, 0.05, 0.05)
+    _compare_updates('config5_stu_updates', stu_sd, {k: v.detach() for k, v in stu.state_dict().items()},
+                     {k: v for k, v in p_stu.items() if ostep.is_param(k)}, out['stu_grads'][0], 1, 0.05, 0.05)

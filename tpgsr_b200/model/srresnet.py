@@ -55,9 +55,10 @@ class InfoGen(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------------------------- engine pieces
-def info_gen2d_fwd(ctx: engine.Ctx, text_emb: torch.Tensor, out_hw):
-    """[B,37,1,26] NCHW prior -> NHWC prior map [B,H,W,32]: 4 x (ConvTranspose2d + BN + ReLU) then bilinear(align_corners=True)."""
-    t = ops.nchw_to_nhwc(text_emb)                                   # [B,1,26,37]
+def info_gen2d_fwd(ctx: engine.Ctx, text_emb: Optional[torch.Tensor], out_hw, prior_nhwc: Optional[torch.Tensor] = None):
+    """[B,37,1,26] NCHW prior -> NHWC prior map [B,H,W,32]: 4 x (ConvTranspose2d + BN + ReLU) then bilinear(align_corners=True).
+    The fused train step passes the NHWC prior [B,1,26,37] the softmax / prior kernel produced (``prior_nhwc``)."""
+    t = prior_nhwc if prior_nhwc is not None else ops.nchw_to_nhwc(text_emb)      # [B,1,26,37]
     saved = []
     for i, ((sh, sw), (ph, pw)) in enumerate(_TCONV, 1):
         wname = f'infoGen.tconv{i}.weight'
@@ -74,7 +75,7 @@ def info_gen2d_fwd(ctx: engine.Ctx, text_emb: torch.Tensor, out_hw):
     return text, {'layers': saved, 'text': text, 'hw_last': (t.shape[1], t.shape[2])}
 
 
-def info_gen2d_bwd(ctx: engine.Ctx, s_text, dtext: torch.Tensor, need_dprior: bool):
+def info_gen2d_bwd(ctx: engine.Ctx, s_text, dtext: torch.Tensor, need_dprior: bool, nhwc_out: bool = False):
     d = ops_prior.bilinear2d_bwd(dtext, *s_text['hw_last'])
     layers = s_text['layers']
     for idx in range(len(layers) - 1, -1, -1):
@@ -88,7 +89,7 @@ def info_gen2d_bwd(ctx: engine.Ctx, s_text, dtext: torch.Tensor, need_dprior: bo
             return None
         dup = ops.conv_dgrad(dc, wd, (up.shape[1], up.shape[2]), Ci, KH, KW, cph, cpw)
         d = ops_prior.zero_upsample2d_bwd(dup, hin, win, sh, sw)
-    return ops.nhwc_to_nchw(d)                                       # the reference's [B,37,1,26]
+    return d if nhwc_out else ops.nhwc_to_nchw(d)                    # [B,1,26,37] or the reference's [B,37,1,26]
 
 
 def _res_block_fwd(ctx: engine.Ctx, x: torch.Tensor, pre: str, text: torch.Tensor):

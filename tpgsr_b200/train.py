@@ -131,7 +131,9 @@ class TPGSRTrainStep:
         backward through every stage (the stage-i SR output feeds stage i+1's recogniser un-detached),
         clip_grad_norm_(SR params, 0.25), Adam over SR + student parameters.
 
-    Configs 3 (stu_iter=1) and 4 (stu_iter=3) of BASELINE.json.  ``students`` may hold one module (``tpg_share``) or stu_iter."""
+    Configs 3 (stu_iter=1) and 4 (stu_iter=3) of BASELINE.json, and config 5 when ``model`` is an ``SRResNet_TL`` (arch ``srresnet_tl`` shares
+    the loop, ``ABLATION_SET`` at interfaces/super_resolution.py:44; its criterion is ``nn.MSELoss`` = ``gradient=False``,
+    interfaces/base.py:359-362).  ``students`` may hold one module (``tpg_share``) or stu_iter."""
 
     def __init__(self, model, students, teacher, batch: int, stu_iter: int = 1, use_distill: bool = True, gradient: bool = True,
                  loss_weight=(1.0, 1e-4), lr: float = 1e-3, beta1: float = 0.5, max_norm: float = 0.25, use_graph: bool = True,
@@ -143,6 +145,7 @@ class TPGSRTrainStep:
             raise RuntimeError('tpgsr_b200 runs on CUDA only — move the models to a B200 first')
         self.dev = p0.device
         self.stu_iter, self.use_distill = stu_iter, use_distill
+        self._srresnet = type(model).__name__ == 'SRResNet_TL'      # config 5: pass gradient=False (the reference pairs it with nn.MSELoss)
         self.gradient, self.w0, self.w1 = bool(gradient), float(loss_weight[0]), float(loss_weight[1])
         self.tpg_share = len(self.students) == 1 and stu_iter > 1
         assert self.tpg_share or len(self.students) == stu_iter
@@ -173,6 +176,30 @@ class TPGSRTrainStep:
             self.packs = {'teacher': ops.PackStore(), 'sr': ops.PackStore()}
             self.packs.update({('stu', i): ops.PackStore() for i in range(len(self.students))})
         ops.prime_workspaces(256 << 20, self.dev)
+
+    # ---- SR model adapters: TSRN_TL (configs 3 / 4) or SRResNet_TL (config 5; model/srresnet.py:139-163) -------------------------------
+    def _sr_forward(self, ctx, prior_nhwc):
+        m = self.model
+        if self._srresnet:
+            from .model import srresnet as sres
+            H, W = self.lr_buf.shape[2], self.lr_buf.shape[3]
+            text, s_text = sres.info_gen2d_fwd(ctx, None, (H, W), prior_nhwc=prior_nhwc)
+            sr, s_sr = sres.srresnet_fwd(ctx, self.lr_buf, text)
+        else:
+            from . import infogen
+            text, s_text = infogen.info_gen_fwd(ctx, self.lr_buf, None, m.emb_cls, prior_nhwc=prior_nhwc)
+            sr, s_sr = engine.tsrn_fwd(ctx, self.lr_buf, m.stn, m.srb_nums, text)
+        return sr, s_text, s_sr
+
+    def _sr_backward(self, ctx, s_text, s_sr, dsr):
+        dtext = torch.zeros_like(s_text['text'])
+        if self._srresnet:
+            from .model import srresnet as sres
+            sres.srresnet_bwd(ctx, s_sr, dsr, dtext)
+            return sres.info_gen2d_bwd(ctx, s_text, dtext, True, nhwc_out=True)
+        from . import infogen
+        engine.tsrn_bwd(ctx, s_sr, dsr, dtext)
+        return infogen.info_gen_bwd(ctx, s_text, dtext, True, nhwc_out=True)
 
     def _fwd_bwd(self):
         from . import crnn_engine, infogen, ops_prior
@@ -215,8 +242,7 @@ class TPGSRTrainStep:
             sr_ctx0 = sr_ctx0 or ctx
             if st_sr.nbt is not None:
                 ops.add_i64(st_sr.nbt, 1)
-            text, s_text = infogen.info_gen_fwd(ctx, self.lr_buf, None, m.emb_cls, prior_nhwc=prior)
-            sr, s_sr = engine.tsrn_fwd(ctx, self.lr_buf, m.stn, m.srb_nums, text)
+            sr, s_text, s_sr = self._sr_forward(ctx, prior)
             ops.image_loss_fwd(sr, self.hr_buf, self.gradient, self.w0, self.w1, 100.0, loss=self.loss_img, accumulate=not first_img)
             first_img = False
             stages.append((sctx, s_crnn, probs, ctx, s_text, s_sr, sr))
@@ -229,9 +255,7 @@ class TPGSRTrainStep:
         for i in range(self.stu_iter - 1, -1, -1):
             sctx, s_crnn, probs, ctx, s_text, s_sr, sr = stages[i]
             dsr = ops.image_loss_bwd(sr, self.hr_buf, self.gradient, self.w0, self.w1, 100.0, dout=dnext, accumulate=dnext is not None)
-            dtext = torch.zeros_like(s_text['text'])
-            engine.tsrn_bwd(ctx, s_sr, dsr, dtext)
-            dprior = infogen.info_gen_bwd(ctx, s_text, dtext, True, nhwc_out=True)
+            dprior = self._sr_backward(ctx, s_text, s_sr, dsr)
             dprobs = ops.semantic_loss_bwd(probs, label_hr, 100.0) if self.use_distill else None
             dlogits = ops_prior.softmax_prior_bwd(probs, dprobs, dprior, drop)
             dgray = crnn_engine.crnn_bwd(sctx, s_crnn, dlogits)
@@ -322,6 +346,11 @@ def tpgsr_infer(model, students, images_lr: torch.Tensor, stu_iter: int = 1) -> 
         logits, _ = crnn_engine.crnn_fwd(sctx, ops_prior.bicubic_gray_fwd(cascade))
         _, prior = ops_prior.softmax_prior_fwd(logits, 0)
         ctx = engine.Ctx(model._flat.views, None, False)
-        text, _ = infogen.info_gen_fwd(ctx, images_lr, None, model.emb_cls, prior_nhwc=prior)
-        cascade, _ = engine.tsrn_fwd(ctx, images_lr, model.stn, model.srb_nums, text)
+        if type(model).__name__ == 'SRResNet_TL':
+            from .model import srresnet as sres
+            text, _ = sres.info_gen2d_fwd(ctx, None, (images_lr.shape[2], images_lr.shape[3]), prior_nhwc=prior)
+            cascade, _ = sres.srresnet_fwd(ctx, images_lr, text)
+        else:
+            text, _ = infogen.info_gen_fwd(ctx, images_lr, None, model.emb_cls, prior_nhwc=prior)
+            cascade, _ = engine.tsrn_fwd(ctx, images_lr, model.stn, model.srb_nums, text)
     return cascade
