@@ -523,8 +523,7 @@ def run_ours(args):
                    'last_loss': last_loss,
                    # non-default (experimental) switches in force, so that A/B lines describe themselves
                    'switches': {k: True for k, on in (('TPGSR_PREPACK', ops.PREPACK), ('TPGSR_FLAT_OCC2', ops.FLAT_OCC2),
-                                                      ('TPGSR_BWD_PRODUCTS=2', ops.BWD2), ('TPGSR_WGRAD_PRODUCTS=1', ops.WGRAD1),
-                                                      ('TPGSR_FLAT_PIPE=0', not ops.FLAT_PIPE)) if on}},
+                                                      ('TPGSR_BWD_PRODUCTS=2', ops.BWD2), ('TPGSR_WGRAD_PRODUCTS=1', ops.WGRAD1)) if on}},
         'e2e': {'value': e2e_val, 'unit': 'images/s', 'h2d_bytes_per_step': B * (4 * 16 * 64 + 4 * 32 * 128) * 4, 'd2h_bytes_per_step': 4,
                 'ms_per_step': sec_e2e / args.steps * 1e3, 'api': api},
         'gpu_launches': launches_per_step * args.steps,

@@ -109,11 +109,8 @@ struct FlatConvParams {
     int box_rows, n_box;       // one A stage = n_box TMA boxes of box_rows rows (box_rows % 8 == 0)
     int tb, b_stages;          // taps per B stage; B ring depth
     int nstack;                // 1 (bf16x3, n_tile <= 64): [B_hi; B_lo] is used as ONE N = 2*n_tile operand, 2 MMAs per K step instead of 3
-    int tile_outer;            // 1 = PIPELINED plan (whole halo resident, n_groups == 1): tile after tile, weights re-streamed per tile from L2
-                               //    through a >= 3 deep ring, so that the epilogue of tile t overlaps the MMAs of tile t+1 and the halo boxes
-                               //    of later tiles land while tile 0 is multiplied;  0: streamed A groups, taps outermost
-    int epi_warps;             // epilogue warps: 8 (two per TMEM lane quarter) or 4 (pipelined plan: the staging area is not aliased)
-    int need_box[4];           // pipelined plan: halo boxes that must have landed before tile t's first MMA
+    int tile_outer;            // 1: whole halo resident (n_groups == 1) -> finish tile after tile (weights re-streamed per tile from L2) so
+                               //    that the epilogue of tile t overlaps the MMAs of tile t+1;  0: streamed A groups, taps outermost
     int ring_bytes;            // bytes of the A+B rings
     int stg_off;               // byte offset of the epilogue staging area (== 0: aliases the rings, only legal when !tile_outer)
     int bar_off;               // byte offset of the barrier block
@@ -178,8 +175,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint64_t* b_full = a_empty + p.a_stages;
     uint64_t* b_empty = b_full + p.b_stages;
     uint64_t* tmem_full = b_empty + p.b_stages;                   // [MT] one per tile (tile_outer) / only [0] used otherwise
-    uint64_t* abox_full = tmem_full + 4;                          // [n_box <= 8] pipelined plan: one per halo box
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(abox_full + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 4);
     float* bias_s = reinterpret_cast<float*>(smem + p.bar_off + 256);      // [n_tile], 16-byte aligned (barrier block <= 256 bytes)
 
     const long long q0 = (long long)blockIdx.x * p.MT * TILE_M;   // first output row of this CTA
@@ -199,7 +195,6 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
         for (int t = 0; t < 4; ++t) tc::mbar_init(&tmem_full[t], 1);
-        for (int t = 0; t < 8; ++t) tc::mbar_init(&abox_full[t], 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) {
@@ -207,7 +202,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tc::tmem_relinquish();
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < p.n_tile; i += p.epi_warps * 32)
+        for (int i = threadIdx.x - 64; i < p.n_tile; i += EPI_WARPS * 32)
             bias_s[i] = (p.bias && n0 + i < p.Co) ? __ldg(p.bias + n0 + i) : 0.f;
     }
     tc::tc_fence_before();
@@ -220,28 +215,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (lane == 0) {
             // ================= TMA producer =================
             uint32_t b_it = 0;
-            if (p.tile_outer) {
-                // pipelined plan: every halo box with its own barrier, all issued up front; then the taps, once per tile
-                const long long row0 = q0 - (long long)p.ph * p.Wp - p.pw;
-                for (int bx = 0; bx < p.n_box; ++bx) {
-                    const int r = (int)(row0 + (long long)bx * p.box_rows);
-                    tc::mbar_expect_tx(&abox_full[bx], (uint32_t)(a_planes * p.box_rows * ROW_BYTES));
-                    tc::tma_load_2d(a_ring + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_hi, &abox_full[bx], 0, r);
-                    if (NPROD == 3)
-                        tc::tma_load_2d(a_ring + a_plane_bytes + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_lo, &abox_full[bx], 0, r);
-                }
-                for (int rep = 0; rep < p.MT; ++rep) {
-                    for (int j = 0; j < taps_per_group; ++j, ++b_it) {
-                        const int bs = b_it % p.b_stages;
-                        mbar_wait_safe(&b_empty[bs], ((b_it / p.b_stages) & 1) ^ 1);
-                        uint8_t* bst = b_ring + (size_t)bs * b_stage_bytes;
-                        tc::mbar_expect_tx(&b_full[bs], (uint32_t)b_stage_bytes);
-                        tc::tma_load_2d(bst, &tmB_hi, &b_full[bs], j * p.Ci, n0);
-                        if (NPROD >= 2) tc::tma_load_2d(bst + b_plane_bytes, &tmB_lo, &b_full[bs], j * p.Ci, n0);
-                    }
-                }
-            }
-            for (int g = 0; g < (p.tile_outer ? 0 : p.n_groups); ++g) {
+            for (int g = 0; g < p.n_groups; ++g) {
                 const int as = g % p.a_stages;
                 mbar_wait_safe(&a_empty[as], ((g / p.a_stages) & 1) ^ 1);
                 uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
@@ -286,13 +260,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t tile_lo = (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
         uint32_t b_it = 0;
         if (p.tile_outer) {
+            mbar_wait_safe(&a_full[0], 0);
+            tc::tc_fence_after();
+            if (dbg && leader) dbg[2] = clock64();
             const uint32_t a_hi0 = desc_lo(tc::smem_u32(a_ring), 16);
             const uint32_t a_lo0 = a_hi0 + (a_plane_bytes >> 4);
-            int box_ready = 0;
             for (int t = 0; t < p.MT; ++t) {
-                for (; box_ready < p.need_box[t]; ++box_ready) mbar_wait_safe(&abox_full[box_ready], 0);      // tile t's halo has landed
-                tc::tc_fence_after();
-                if (dbg && leader && t == 0) dbg[2] = clock64();
                 const uint32_t d = tmem_u + (uint32_t)(t * p.tm_stride);
                 for (int j = 0; j < taps_per_group; ++j, ++b_it) {            // tb == 1 in this mode
                     const int bs = b_it % p.b_stages;
@@ -370,7 +343,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             bool waited = false;
             int pix = -1, bi = 0, r = 0, c = 0;
             for (int ch = 0; ch < nchunks; ++ch, ++item) {
-                if (p.epi_warps == 8 && (item & 1) != half) continue;
+                if ((item & 1) != half) continue;
                 if (!waited) {
                     mbar_wait_safe(&tmem_full[p.tile_outer ? t : 0], 0);
                     tc::tc_fence_after();
@@ -541,7 +514,6 @@ split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __re
 
 struct FlatPlan {
     int MT, n_tile, n_tiles, tm_stride, nstack, pointwise, G, kgroups, n_groups, a_stages, box_rows, n_box, tb, b_stages, tile_outer, ring_bytes, stg_off, bar_off;
-    int epi_warps, need_box[4];
     size_t smem;
     int grid_x;
 };
@@ -550,7 +522,6 @@ long long* g_flat_dbg = nullptr;
 int g_flat_dbg_skip = 0;
 int g_flat_no_nstack = 0;
 int g_flat_occ2 = 0;      // experimental: plan for two co-resident CTAs per SM (see plan_flat)
-int g_flat_no_pipe = 0;   // developer switch (debug bit 4): disable the pipelined plan (A/B measurements)
 
 // budget: dynamic shared memory a CTA may use; tmem_max: TMEM columns it may allocate; slots: CTAs resident on the GPU at once
 int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, size_t budget, int tmem_max, int slots,
@@ -586,62 +557,39 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
             const int kgroups = KH / G;
             const int n_groups = cbs * kgroups;
             const int rows = TILE_M * MT + (G - 1) * Wp + (KW - 1);
+            int n_box = (rows + 255) / 256;
+            int box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8;
+            if (box_rows > 256) { ++n_box; box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8; }
+            // streamed A groups (one kernel row / channel block per stage): up to 4 stages in flight — with 2 the 9x1 stacked convs waited
+            // one L2 round trip per kernel row (profiles/r01: 154 us for the final conv)
+            int a_stages = n_groups > 1 ? (n_groups < 4 ? n_groups : 4) : 1;
+            const size_t a_stage_b = (size_t)a_planes * n_box * box_rows * ROW_BYTES;
+            const size_t b_min = (size_t)2 * b_planes * pl.n_tile * ROW_BYTES * ((n_groups > 1 && KW > 1) ? KW : 1);
+            while (a_stages > 2 && a_stages * a_stage_b + b_min + 4096 > budget) --a_stages;
+            const size_t a_bytes = (size_t)a_stages * a_stage_b;
+            // B ring: one tap per stage, 4..2 deep (deepest that fits) — or one kernel row of taps per stage, 2 deep, when the
+            // tap tile is small and the kernel rows are streamed.  tile_outer (whole halo resident): the epilogue of one tile runs while
+            // the next tile's MMAs read the rings, so its staging area is separate; otherwise it aliases the (drained) rings.
             const int taps_per_group = G * KW;
+            // tile_outer measured slower on B200 (profiles/r01/flat_timeline_v3.log): with the taps re-streamed per tile a B stage feeds
+            // only 12 MMAs and the 3-deep ring cannot cover the L2 round trip (90 cycles/MMA vs 63 with the taps outermost, where a
+            // stage feeds MT x 12 MMAs); the epilogue it would hide is ~2 us.  Kept in the kernel for geometries with many tiles per CTA.
+            const int tile_outer = 0;
             const size_t tap_bytes = (size_t)b_planes * pl.n_tile * ROW_BYTES;
-            int n_box = 0, box_rows = 0, a_stages = 1, tb = 1, b_stages = 0, ring_bytes = 0, stg_off = 0, bar_off = 0, tile_outer = 0, epi_warps = EPI_WARPS;
-            int need_box[4] = {0, 0, 0, 0};
+            int tb = 1, b_stages = 0, ring_bytes = 0, stg_off = 0, bar_off = 0;
             size_t smem = 0;
-            // ---- pipelined plan (whole halo resident, >= 2 tiles per CTA): tile after tile with the taps re-streamed per tile through a
-            // >= 3 deep ring (3 stages ahead of the MMAs cover the L2 round trip; with 2 the MMA warp starved: 90 cycles/MMA,
-            // profiles/r01/flat_timeline_v3.log), one barrier per halo box so tile 0 starts when ITS rows have landed, and a 4-warp epilogue
-            // with its own staging area that drains tile t while tile t+1 is multiplied
-            if (n_groups == 1 && MT >= 2 && !g_flat_no_pipe) {
-                int nb = 2 * MT;
-                int br = ((rows + nb - 1) / nb + 7) / 8 * 8;
-                if (br > 256) { nb = (rows + 255) / 256; br = ((rows + nb - 1) / nb + 7) / 8 * 8; }
-                nb = (rows + br - 1) / br;
-                const size_t a_b = (size_t)a_planes * nb * br * ROW_BYTES;
-                const int halo = (G - 1) * Wp + (KW - 1);
-                for (int want = 4; want >= 3 && nb <= 8; --want) {
-                    int bs = want < MT * taps_per_group ? want : MT * taps_per_group;
-                    const size_t ring = a_b + (size_t)bs * tap_bytes;
-                    const size_t stg = (size_t)4 * 32 * STG_PITCH * 4;
-                    const size_t need = ring + stg + 256 + (size_t)(pl.n_tile + 32) * 4 + 1024;
-                    if (need <= budget) {
-                        tile_outer = 1; epi_warps = 4; n_box = nb; box_rows = br; a_stages = 1; tb = 1; b_stages = bs; smem = need;
-                        ring_bytes = (int)ring; stg_off = (int)ring; bar_off = (int)(ring + stg);
-                        for (int t = 0; t < MT; ++t) {
-                            int nbx = (TILE_M * (t + 1) + halo + br - 1) / br;
-                            need_box[t] = nbx < nb ? nbx : nb;
-                        }
-                        break;
-                    }
-                }
-            }
-            if (!tile_outer) {
-                n_box = (rows + 255) / 256;
-                box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8;
-                if (box_rows > 256) { ++n_box; box_rows = ((rows + n_box - 1) / n_box + 7) / 8 * 8; }
-                // streamed A groups (one kernel row / channel block per stage): up to 4 stages in flight — with 2 the 9x1 stacked convs waited
-                // one L2 round trip per kernel row (profiles/r01: 154 us for the final conv)
-                a_stages = n_groups > 1 ? (n_groups < 4 ? n_groups : 4) : 1;
-                const size_t a_stage_b = (size_t)a_planes * n_box * box_rows * ROW_BYTES;
-                const size_t b_min = (size_t)2 * b_planes * pl.n_tile * ROW_BYTES * ((n_groups > 1 && KW > 1) ? KW : 1);
-                while (a_stages > 2 && a_stages * a_stage_b + b_min + 4096 > budget) --a_stages;
-                const size_t a_bytes = (size_t)a_stages * a_stage_b;
-                // B ring: one tap per stage, 4..2 deep (deepest that fits) — or one kernel row of taps per stage, 2 deep, when the tap tile
-                // is small and the kernel rows are streamed.  The epilogue staging area aliases the (drained) rings.
-                const bool row_stage = n_groups > 1 && KW > 1 && tap_bytes * KW <= 40 * 1024 && !pl.nstack;
-                for (int want = row_stage ? 2 : 4; want >= 2; --want) {
-                    tb = row_stage ? KW : 1;
-                    int bs = want;
-                    const int total_b = n_groups * (taps_per_group / tb);
-                    if (bs > total_b) bs = total_b;
-                    size_t ring = a_bytes + (size_t)bs * tb * tap_bytes;
-                    if (ring < (size_t)STG_BYTES) ring = STG_BYTES;
-                    const size_t need = ring + 256 /*barriers*/ + (size_t)(pl.n_tile + 32) * 4 /*bias*/ + 1024 /*align*/;
-                    if (need <= budget) { b_stages = bs; smem = need; ring_bytes = (int)ring; stg_off = 0; bar_off = (int)ring; break; }
-                }
+            const bool row_stage = !tile_outer && n_groups > 1 && KW > 1 && tap_bytes * KW <= 40 * 1024 && !pl.nstack;
+            for (int want = row_stage ? 2 : 4; want >= 2; --want) {
+                tb = row_stage ? KW : 1;
+                int bs = want;
+                const int total_b = (tile_outer ? MT : n_groups) * (taps_per_group / tb);
+                if (bs > total_b) bs = total_b;
+                size_t ring = a_bytes + (size_t)bs * tb * tap_bytes;
+                if (!tile_outer && ring < (size_t)STG_BYTES) ring = STG_BYTES;
+                const size_t so = tile_outer ? ring : 0;
+                const size_t bo = tile_outer ? ring + STG_BYTES : ring;
+                const size_t need = bo + 256 /*barriers*/ + (size_t)(pl.n_tile + 32) * 4 /*bias*/ + 1024 /*align*/;
+                if (need <= budget) { b_stages = bs; smem = need; ring_bytes = (int)ring; stg_off = (int)so; bar_off = (int)bo; break; }
             }
             if (b_stages == 0) continue;
             const long long ctas = (tiles + MT - 1) / MT * pl.n_tiles;
@@ -650,8 +598,7 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
             best_cost = cost;
             pl.MT = MT; pl.G = G; pl.kgroups = kgroups; pl.n_groups = n_groups; pl.a_stages = a_stages; pl.box_rows = box_rows; pl.n_box = n_box;
             pl.tb = tb; pl.b_stages = b_stages; pl.smem = smem; pl.ring_bytes = ring_bytes; pl.stg_off = stg_off; pl.bar_off = bar_off;
-            pl.tile_outer = tile_outer; pl.epi_warps = epi_warps;
-            for (int t = 0; t < 4; ++t) pl.need_box[t] = need_box[t];
+            pl.tile_outer = tile_outer;
             pl.grid_x = (int)((tiles + MT - 1) / MT);
         }
         if (best_cost >= 0) return TPGSR_OK;
@@ -898,13 +845,11 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
 
 // developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][16]
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
-// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes; bit 3: plan for two CTAs per SM (experimental);
-// bit 4: no pipelined plan
+// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes; bit 3: plan for two CTAs per SM (experimental)
 int tpgsr_conv2d_flat_set_debug_skip(int bits) {
     g_flat_dbg_skip = bits & 3;
     g_flat_no_nstack = (bits >> 2) & 1;
     g_flat_occ2 = (bits >> 3) & 1;
-    g_flat_no_pipe = (bits >> 4) & 1;
     return TPGSR_OK;
 }
 
@@ -965,9 +910,6 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     p.a_stages = pl.a_stages;
     p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
     p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off; p.nstack = pl.nstack;
-    p.epi_warps = pl.epi_warps;
-    for (int t = 0; t < 4; ++t) p.need_box[t] = pl.need_box[t];
-    const int threads = (2 + pl.epi_warps) * 32;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
     p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg; p.dbg_skip = g_flat_dbg_skip;
     p.yp_hi = static_cast<__nv_bfloat16*>(yp_hi); p.yp_lo = static_cast<__nv_bfloat16*>(yp_lo);
@@ -990,19 +932,19 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     if (g_flat_occ2 && pl.smem <= 112 * 1024) {      // two-CTA plan: the register-capped build, or the CTAs would not co-reside
         auto kern = nprod == 3 ? conv_flat_kernel<3, 2> : (nprod == 2 ? conv_flat_kernel<2, 2> : conv_flat_kernel<1, 2>);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return TPGSR_ERR_LAUNCH;
-        kern<<<grid, threads, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+        kern<<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else if (nprod == 3) {
         if (cudaFuncSetAttribute(conv_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
-        conv_flat_kernel<3><<<grid, threads, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+        conv_flat_kernel<3><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else if (nprod == 2) {
         if (cudaFuncSetAttribute(conv_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
-        conv_flat_kernel<2><<<grid, threads, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+        conv_flat_kernel<2><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else {
         if (cudaFuncSetAttribute(conv_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
-        conv_flat_kernel<1><<<grid, threads, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+        conv_flat_kernel<1><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     }
     return tpgsr_launch_status();
 }

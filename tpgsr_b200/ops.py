@@ -285,10 +285,8 @@ FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', 'infer')
 # EXPERIMENTAL, not measured yet (written after round 1's GPU minutes were spent): tile the flat convs for two co-resident CTAs per SM
 # (112 KB of shared memory, 256 TMEM columns each) so that one CTA's loads / epilogue overlap the other's MMAs.  Off by default.
 FLAT_OCC2 = os.environ.get('TPGSR_FLAT_OCC2', '0') != '0'
-# developer A/B switch: TPGSR_FLAT_PIPE=0 disables the pipelined plan of the flat convs (tile after tile, epilogue under the next tile's MMAs)
-FLAT_PIPE = os.environ.get('TPGSR_FLAT_PIPE', '1') != '0'
-if FLAT_OCC2 or not FLAT_PIPE:
-    LIB.tpgsr_conv2d_flat_set_debug_skip((8 if FLAT_OCC2 else 0) | (0 if FLAT_PIPE else 16))
+if FLAT_OCC2:
+    LIB.tpgsr_conv2d_flat_set_debug_skip(8)
 
 
 class FlatPlanes:
