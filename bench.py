@@ -522,7 +522,7 @@ def run_ours(args):
                    'l2': 'no explicit flush: the step touches >1 GB of activations/stashes per replay (>> 126 MB L2); inputs rotate over 8 distinct batches',
                    'last_loss': last_loss,
                    # non-default (experimental) switches in force, so that A/B lines describe themselves
-                   'switches': {k: True for k, on in (('TPGSR_PREPACK', ops.PREPACK), ('TPGSR_FLAT_OCC2', ops.FLAT_OCC2),
+                   'switches': {k: True for k, on in (('TPGSR_PREPACK', ops.PREPACK),
                                                       ('TPGSR_BWD_PRODUCTS=2', ops.BWD2), ('TPGSR_WGRAD_PRODUCTS=1', ops.WGRAD1)) if on}},
         'e2e': {'value': e2e_val, 'unit': 'images/s', 'h2d_bytes_per_step': B * (4 * 16 * 64 + 4 * 32 * 128) * 4, 'd2h_bytes_per_step': 4,
                 'ms_per_step': sec_e2e / args.steps * 1e3, 'api': api},

@@ -160,35 +160,6 @@ def test_flat_conv_plans_fit_the_sm(nprod):
         assert taps * n_tile <= 512 and n_tile * n_tiles == cpad and splits * kb_per_split >= total_kb
 
 
-def test_flat_conv_two_cta_plans_fit_half_an_sm():
-    """The experimental two-CTAs-per-SM tiling (debug bit 3 / TPGSR_FLAT_OCC2): every plan it produces fits half the shared memory and half
-    the TMEM columns of an SM and still covers every output row; geometries that do not fit keep the one-CTA plan."""
-    import ctypes
-    from tpgsr_b200._lib import LIB
-    geoms = [(48, 16, 64, 1, 64, 64, 3, 3), (48, 16, 64, 0, 64, 64, 1, 1), (48, 16, 64, 0, 64, 192, 1, 1), (48, 16, 64, 1, 64, 256, 3, 3),
-             (48, 32, 128, 4, 64, 36, 9, 1), (48, 16, 64, 4, 64, 64, 9, 1), (1248, 1, 1, 0, 512, 2048, 1, 1), (2, 16, 64, 1, 64, 64, 3, 3)]
-    try:
-        LIB.tpgsr_conv2d_flat_set_debug_skip(8)
-        halved = 0
-        for nprod in (1, 3):
-            for (B, H, W, P, Ci, Co, KH, KW) in geoms:
-                out = (ctypes.c_int * 13)()
-                smem = LIB.tpgsr_conv2d_flat_plan(B, H, W, P, Ci, Co, KH, KW, KH // 2, KW // 2, nprod, out)
-                MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer = list(out)
-                assert 0 < smem <= 227 * 1024
-                if smem <= 112 * 1024:
-                    halved += 1
-                    assert MT * tm_stride <= 256
-                assert n_box * box_rows >= 128 * MT + (G - 1) * (W + P) + (KW - 1) and box_rows % 8 == 0 and box_rows <= 256
-                assert grid_x * MT * 128 >= B * (H + P) * (W + P) and b_stages >= 1
-        assert halved >= 8                      # the hot 3x3 64->64 and the 1x1 convs do fit
-    finally:
-        LIB.tpgsr_conv2d_flat_set_debug_skip(0)
-    out = (ctypes.c_int * 13)()
-    assert LIB.tpgsr_conv2d_flat_plan(48, 16, 64, 1, 64, 64, 3, 3, 1, 1, 3, out) > 112 * 1024      # default plan unchanged: one CTA per SM, MT = 3
-    assert out[0] == 3
-
-
 def test_pack_store_job_table_layout():
     """ops.PackStore builds the device table tpgsr_pack_weights_batched reads: record size, field order and grid bound (host logic only)."""
     import struct

@@ -270,3 +270,37 @@ def test_srresnet_tl_config5_vs_golden_and_oracle(shapes):
         net.eval()
         assert rel_err(net(lr, prior.detach()), g['sr_eval']) < 2e-4
         assert rel_err(net(lr), g['sr_eval_noprior']) < 2e-4
+
+
+def test_tsrn_without_mask_channel_vs_oracle():
+    """``mask=False`` (3 input planes; ``--mask`` is a CLI flag the reference passes through, interfaces/base.py:296-297): train-mode forward
+    + backward and eval forward vs the CPU oracle."""
+    from oracle import models, ops as o, step
+    from oracle.ops import tps_buffers
+    from oracle.weights import synth_images, synth_state_dict
+    from tpgsr_b200.loss.image_loss import ImageLoss
+    from tpgsr_b200.model.tsrn import TSRN
+    kw = dict(KW, mask=False)
+    net = TSRN(**kw)
+    assert net.in_planes == 3 and net.block1[0].weight.shape[1] == 3 and net.block8[1].weight.shape[0] == 3
+    sd = synth_state_dict({k: list(v.shape) for k, v in net.state_dict().items()}, 4)
+    sd.update({'tps.' + k: v for k, v in tps_buffers(16, 64).items()})
+    net.load_state_dict(sd, strict=False)
+    net = net.to(_dev()).train()
+    lr, hr = synth_images(3, seed=33, smooth=True)
+    lr, hr = lr[:, :3].contiguous(), hr[:, :3].contiguous()
+    p = {k: v.clone() for k, v in sd.items()}
+    leaves = {k: v.requires_grad_(True) for k, v in p.items() if step.is_param(k)}
+    sr_o = models.tsrn(lr, p, True, stn=True)
+    loss_o = o.image_loss(sr_o, hr) * 100
+    loss_o.backward()
+    sr = net(lr.to(_dev()))
+    loss = ImageLoss(gradient=True, loss_weight=[1, 1e-4])(sr, hr.to(_dev())).mean() * 100
+    loss.backward()
+    assert sr.shape == (3, 3, 32, 128) and rel_err(sr, sr_o) < 3e-4, rel_err(sr, sr_o)
+    assert abs(float(loss) - float(loss_o)) < 1e-4 * abs(float(loss_o))
+    og = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    _grad_report(net.named_parameters(), og, 3e-3, skip=('stn_head.',))
+    net.eval()
+    with torch.no_grad():
+        assert rel_err(net(lr.to(_dev())), models.tsrn(lr, {k: v.detach() for k, v in p.items()}, False, stn=True)) < 1e-4

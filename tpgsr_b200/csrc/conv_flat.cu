@@ -154,9 +154,8 @@ __device__ __forceinline__ void mma_tap_stacked(uint32_t d, uint32_t ah, uint32_
     }
 }
 
-// OCC = CTAs the register allocation must leave room for per SM (2 only for the experimental two-CTA plan: 320 x 2 threads -> <= 102 registers)
-template <int NPROD, int OCC = 1>
-__global__ void __launch_bounds__(FWD_THREADS, OCC)
+template <int NPROD>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, FlatConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -521,7 +520,6 @@ struct FlatPlan {
 long long* g_flat_dbg = nullptr;
 int g_flat_dbg_skip = 0;
 int g_flat_no_nstack = 0;
-int g_flat_occ2 = 0;      // experimental: plan for two co-resident CTAs per SM (see plan_flat)
 
 // budget: dynamic shared memory a CTA may use; tmem_max: TMEM columns it may allocate; slots: CTAs resident on the GPU at once
 int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, size_t budget, int tmem_max, int slots,
@@ -606,13 +604,10 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
     return TPGSR_ERR_UNSUPPORTED;
 }
 
-// One CTA per SM with up to 226 KB of the 227 KB a CTA may use and all 512 TMEM columns — or, experimentally (debug bit 3 /
-// TPGSR_FLAT_OCC2=1), two co-resident CTAs per SM with 112 KB and 256 columns each: smaller tiles per CTA (more halo and weight traffic from
-// L2), but one CTA's loads and epilogue overlap the other's MMAs — the phases that run back to back in the one-CTA plan.
-// The default build of the kernel takes 128 registers x 320 threads (one CTA per SM); the two-CTA plan launches a second instantiation
-// compiled with __launch_bounds__(320, 2) (<= 102 registers).  Falls back to the one-CTA plan when a geometry does not fit the halved budget.
+// One CTA per SM with up to 226 KB of the 227 KB a CTA may use and all 512 TMEM columns.  (A two-CTAs-per-SM tiling — 112 KB, 256 columns,
+// one tile per CTA so that one CTA's loads / epilogue overlap the other's MMAs — was measured in round 2 and removed: 30.7 us against
+// 26.4 us for the 3x3 64->64 conv, step time unchanged, profiles/r02/call1_stdout.log.)
 int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
-    if (g_flat_occ2 && plan_flat_for(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 112 * 1024, 256, 2 * 148, pl) == TPGSR_OK) return TPGSR_OK;
     return plan_flat_for(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 226 * 1024, 512, 148, pl);
 }
 
@@ -845,11 +840,10 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
 
 // developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][16]
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
-// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes; bit 3: plan for two CTAs per SM (experimental)
+// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes
 int tpgsr_conv2d_flat_set_debug_skip(int bits) {
     g_flat_dbg_skip = bits & 3;
     g_flat_no_nstack = (bits >> 2) & 1;
-    g_flat_occ2 = (bits >> 3) & 1;
     return TPGSR_OK;
 }
 
@@ -929,11 +923,7 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     if (nprod == 3 && tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
     if (nprod >= 2 && tpgsr_make_tmap_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
     dim3 grid(pl.grid_x, pl.n_tiles);
-    if (g_flat_occ2 && pl.smem <= 112 * 1024) {      // two-CTA plan: the register-capped build, or the CTAs would not co-reside
-        auto kern = nprod == 3 ? conv_flat_kernel<3, 2> : (nprod == 2 ? conv_flat_kernel<2, 2> : conv_flat_kernel<1, 2>);
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return TPGSR_ERR_LAUNCH;
-        kern<<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
-    } else if (nprod == 3) {
+    if (nprod == 3) {
         if (cudaFuncSetAttribute(conv_flat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
         conv_flat_kernel<3><<<grid, FWD_THREADS, pl.smem, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);

@@ -148,8 +148,6 @@ class _TSRNBase(nn.Module):
             raise RuntimeError('tpgsr_b200 modules run on CUDA (sm_100a) only — there is no CPU fallback')
         if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != self.in_planes:
             raise ValueError(f'expected float32 NCHW input with {self.in_planes} channels, got {tuple(x.shape)} {x.dtype}')
-        if self.in_planes != 4:
-            raise NotImplementedError('mask=False (3 input planes) is not wired to the sm_100a kernels yet')
         if x.requires_grad and torch.is_grad_enabled():
             raise NotImplementedError('TSRN input-image gradients are not produced (the reference feeds data tensors; the cascade without '
                                       '--sr_share is out of scope) — detach the image or use tpgsr_b200.train.TPGSRTrainStep')

@@ -282,12 +282,6 @@ FLAT = os.environ.get('TPGSR_FLAT', '1') != '0'
 # '0' = never.  Measured on B200 (round 1): in training the fused path is neutral (5.77 vs 5.70 ms/step) — the backward pass has to
 # recompute the 1x1 output for dW_ih, which costs what the forward pass saves — so it is kept for inference only.
 FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', 'infer')
-# EXPERIMENTAL, not measured yet (written after round 1's GPU minutes were spent): tile the flat convs for two co-resident CTAs per SM
-# (112 KB of shared memory, 256 TMEM columns each) so that one CTA's loads / epilogue overlap the other's MMAs.  Off by default.
-FLAT_OCC2 = os.environ.get('TPGSR_FLAT_OCC2', '0') != '0'
-if FLAT_OCC2:
-    LIB.tpgsr_conv2d_flat_set_debug_skip(8)
-
 
 class FlatPlanes:
     """bf16 hi/lo planes of an NHWC activation in the padded-flat layout."""
@@ -301,12 +295,13 @@ def nprod() -> int:
     return 3 if CONV_MODE == 'bf16x3' else 1
 
 
-# EXPERIMENTAL, not measured yet: gradient GEMMs with TWO products — dY enters as ONE bf16 plane (no lo plane is split, staged or multiplied)
-# against the exact (hi + lo) weights / activations: dX = dY_hi (W_hi + W_lo), dW = (X_hi + X_lo) dY_hi.  The forward pass keeps three products,
-# so the SR output is untouched; on the oracle graph the non-STN gradients move from 1.7e-4 to 2.9e-4 relative L2 against fp32
-# (scripts/study_operand_precision.py, mode 'bwd2').  Off by default.
+# OPT-IN (default off: the parity mode keeps three products everywhere): gradient GEMMs with TWO products — dY enters as ONE bf16 plane (no lo
+# plane is split, staged or multiplied) against the exact (hi + lo) weights / activations: dX = dY_hi (W_hi + W_lo), dW = (X_hi + X_lo) dY_hi.
+# The forward pass keeps three products, so the SR output is untouched; on the oracle graph the non-STN gradients move from 1.7e-4 to 2.9e-4
+# relative L2 against fp32 (scripts/study_operand_precision.py, mode 'bwd2').  Measured on B200 (config 3, B = 48): 5 156 against 4 832 images/s
+# (+6.7%), with TPGSR_WGRAD_PRODUCTS=1 on top 5 283 (+9.3%) — profiles/r02/bench_c3_bwd2*_call5.json; tests/test_gpu_backward_products.py.
 BWD2 = os.environ.get('TPGSR_BWD_PRODUCTS', '3') == '2' and CONV_MODE == 'bf16x3'
-# EXPERIMENTAL, not measured yet: the flat weight gradient with ONE product (X_hi dY_hi, the kernel's bf16 instantiation).  A weight gradient
+# OPT-IN (default off): the flat weight gradient with ONE product (X_hi dY_hi, the kernel's bf16 instantiation).  A weight gradient
 # sums over every pixel of the batch (49 152 at B = 48), so the operands' independent rounding errors average out: on the oracle graph the
 # non-STN gradients are at 3.1e-4 relative L2 with it (2.9e-4 with two products, 1.7e-4 with three; study script, mode 'bwd2w1').  Off by default.
 WGRAD1 = os.environ.get('TPGSR_WGRAD_PRODUCTS', '3') == '1' and CONV_MODE == 'bf16x3'
