@@ -272,6 +272,11 @@ size_t tpgsr_resize_normalize_workspace_bytes(int B, int max_h, int W);
 int tpgsr_resize_normalize(const unsigned char* src, const long long* offsets, const int* hs, const int* ws, int B, int max_h, int max_w, int H,
                            int W, int mask, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* ---- input pipeline: label one-hot collate (collate.cu) — the text half of alignCollate_realWTL* (dataset/dataset.py:1172-1217, 1275-1323):
+ * codes [B][L] int32 = class index of character t of label b in the alphabet "-0123456789abcdefghijklmnopqrstuvwxyz" (-1 behind the end);
+ * out [B][C][1][L] fp32 one-hot, zero-padded to the longest label (the reference's label_rebatches). */
+int tpgsr_label_onehot(const int* codes, int B, int L, int C, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

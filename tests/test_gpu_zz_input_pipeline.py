@@ -88,3 +88,20 @@ def test_batch_prefetcher_matches_direct_transform_and_feeds_a_train_step():
         assert torch.equal(bh, tf_hr.batch(hr[sl])) and torch.equal(bl, tf_lr.batch(lr[sl]))
         seen += len(labels)
     assert seen == 22 and all(torch.isfinite(s) for s in sums)
+
+
+def test_label_onehot_collate_vs_reference_fixture():
+    """tpgsr_label_onehot through tpgsr_b200.dataset.label_onehot_collate: bit-exact against the arrays the reference's collate produced."""
+    from conftest import load_golden
+    from tpgsr_b200.dataset import label_onehot_collate
+    g = load_golden('label_collate')
+    for name in ('all', 'short', 'with_empty'):
+        strs = [str(s) for s in g[name + '/strs']]
+        reb, masks, tics = label_onehot_collate(strs)
+        assert reb.is_cuda and reb.dtype == torch.float32 and tuple(reb.shape) == g[name + '/label_rebatches'].shape
+        assert np.array_equal(reb.cpu().numpy(), g[name + '/label_rebatches']), name
+        assert np.array_equal(masks.numpy(), g[name + '/weighted_masks']) and np.array_equal(tics.numpy(), g[name + '/weighted_tics'])
+    big = ['w%d' % i * (1 + i % 5) for i in range(512)]          # a batch large enough for several CTAs
+    reb, _, _ = label_onehot_collate(big)
+    from oracle.collate import label_collate
+    assert np.array_equal(reb.cpu().numpy(), label_collate(big)[0])

@@ -335,3 +335,22 @@ def test_torch_eager_matches_oracle(shapes):
             continue
         du, dr = new[k] - sd[k], p_sr[k] - sd[k]
         assert float(((du - dr).abs() > 1e-4).float().mean()) < 0.01, k
+
+
+def test_label_collate_oracle_and_host_encoder_vs_reference_fixture():
+    """The label half of the collate (dataset/dataset.py:1263-1323): the numpy oracle AND the product's host-side character encoder reproduce
+    the arrays recorded from the reference's own ``alignCollate_realWTLAMask`` (empty labels, out-of-alphabet characters, 15-character cut)."""
+    from oracle.collate import label_collate
+    from tpgsr_b200.dataset.collate import ALPHABET, encode_labels
+    g = load_golden('label_collate')
+    for name in ('all', 'short', 'with_empty'):
+        strs = [str(s) for s in g[name + '/strs']]
+        reb, masks, tics = label_collate(strs)
+        assert reb.shape == g[name + '/label_rebatches'].shape and np.array_equal(reb, g[name + '/label_rebatches']), name
+        assert np.array_equal(masks, g[name + '/weighted_masks']) and np.array_equal(tics, g[name + '/weighted_tics']), name
+        codes, hm, ht, max_len = encode_labels(strs)
+        assert max_len == reb.shape[3] and hm == list(masks) and ht == list(tics)
+        onehot = (codes[:, None, :] == np.arange(len(ALPHABET))[None, :, None]).astype(np.float32)[:, :, None, :]
+        assert np.array_equal(onehot, reb), name
+    with pytest.raises(ValueError):
+        encode_labels(['', ''])                     # max_len 0: the reference's slice assignment fails on this batch as well
