@@ -96,3 +96,36 @@ def test_prefetcher_refuses_cpu_without_stub():
         pytest.skip('a GPU is present')
     with pytest.raises(RuntimeError):
         next(iter(BatchPrefetcher([], 1)))
+
+
+def test_lmdb_shaped_source_feeds_batches():
+    """TextZoom key layout (dataset/dataset.py:104-149) through an in-memory environment: counts, labels filtered by str_filt, images decoded
+    from encoded bytes, an undecodable sample replaced by the next one, and the sample iterable grouped by ``batches``."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from tpgsr_b200.dataset.loader import batches
+    from tpgsr_b200.dataset.lmdb_source import DictEnv, lmdbDataset_real
+
+    def png(h, w, seed):
+        buf = io.BytesIO()
+        Image.fromarray(np.random.RandomState(seed).randint(0, 255, (h, w, 3)).astype(np.uint8)).save(buf, format='PNG')
+        return buf.getvalue()
+
+    data = {b'num-samples': b'5'}
+    words = ['Hello!', 'wor-ld', 'A1', 'xyz?', 'Q']
+    for i, wd in enumerate(words, 1):
+        data[b'label-%09d' % i] = wd.encode()
+        data[b'image_hr-%09d' % i] = png(30 + i, 120 + i, i)
+        data[b'image_lr-%09d' % i] = png(15 + i, 60 + i, 100 + i)
+    data[b'image_lr-%09d' % 3] = b'not an image'
+    ds = lmdbDataset_real(DictEnv(data), voc_type='lower')
+    assert len(ds) == 5
+    hr, lr, lab = ds[0]
+    assert lab == 'hello' and hr.size == (121, 31) and lr.size == (61, 16) and hr.mode == 'RGB'
+    assert ds[1][2] == 'world' and ds[2][2] == 'xyz'            # sample 3 is undecodable -> the next one
+    got = list(batches(ds, 2, drop_last=False))
+    assert [len(b[0]) for b in got] == [2, 2, 1] and got[0][2] == ['hello', 'world']
+    import pytest
+    with pytest.raises(ImportError):
+        lmdbDataset_real('/nonexistent/path')                    # a PATH needs the lmdb package, which this image does not ship
