@@ -12,7 +12,7 @@
 //             coordinates = the 40 960 algorithmic bytes of SURVEY §8d (+ 94 KB / G of representation).
 //   backward: CTA = group of G images, whole map (4 pixels per thread at 16x64), the representation staged ONCE per CTA in shared memory;
 //             per image the 46 partial sums are reduced with warp shuffles and a fixed-order cross-warp sum (deterministic).
-// G grows with the batch (1 at the bench batch: 192 / 48 CTAs; 8 from B = 1024) so small batches keep their parallelism.
+// G = 1 at the bench batch (192 CTAs forward, 48 backward) and 2 forward from B = 1024; the backward kernel always takes one image per CTA.
 #include "common.cuh"
 
 namespace {
@@ -178,7 +178,7 @@ tps_sample_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ 
     }
 }
 
-inline int tps_group(int B) { return B >= 1024 ? GMAX : (B >= 256 ? 4 : 1); }
+inline int tps_group(int B) { return B >= 1024 ? 2 : 1; }
 
 }  // namespace
 
@@ -201,10 +201,10 @@ int tpgsr_tps_sample_bwd(const float* dout, const float* img, const float* src, 
                          float* dctrl, int B, int H, int W, int C, int accumulate, cudaStream_t stream) {
     if (!dout || !img || !src || !inv_kernel || !reprT || !dctrl || B <= 0) return TPGSR_ERR_BAD_ARG;
     if (C != 4 && C != 3) return TPGSR_ERR_UNSUPPORTED;
-    int G = tps_group(B);
-    size_t smem = (size_t)NK * H * W * sizeof(float);
-    if (smem > 200 * 1024) { G = 1; }                    // representation too large to stage: read it through L2 per image
-    if (G == 1) smem = 0;
+    // one image per CTA: staging the representation in shared memory for several images (94 KB, 2 CTAs / SM) was measured SLOWER than
+    // re-reading it through L2 (426 us against 224 us at B = 8192, profiles/r02/call6_stdout.log); the staged path stays for maps it helps
+    const int G = 1;
+    const size_t smem = 0;
     auto kern = C == 4 ? tps_sample_bwd_kernel<4> : tps_sample_bwd_kernel<3>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TPGSR_ERR_LAUNCH;
     kern<<<(B + G - 1) / G, 256, smem, stream>>>(dout, img, src, inv_kernel, reprT, dctrl, B, H, W, G, accumulate);
