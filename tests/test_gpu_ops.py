@@ -172,7 +172,7 @@ def test_pixelshuffle_mish_and_acts():
     d = _dev()
     xd = nhwc(x.detach()).to(d)
     yd = ops.pixelshuffle_mish_fwd(xd)
-    assert rel_err(nchw(yd), y) < 1e-6
+    assert rel_err(nchw(yd), y) < 3e-6          # mish through ex2.approx + fast division: a few ulp per element
     dx = ops.pixelshuffle_mish_bwd(nhwc(gy).to(d), xd)
     assert rel_err(nchw(dx), x.grad) < 1e-5
     # PReLU fwd/bwd with slope gradient
