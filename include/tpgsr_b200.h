@@ -133,6 +133,18 @@ int tpgsr_bn_eval_prepare(int C, const float* gamma, const float* beta, const fl
                           const float* running_var, float eps, float* mean_rstd, float* scale_shift, cudaStream_t stream);
 int tpgsr_bn_apply(const float* x, float* y, const float* scale_shift, long M, int C, int ldx, int ldy, int act,
                    const float* residual, int ldr, cudaStream_t stream);
+/* fused variants: reduction + finalize in ONE launch (the block that draws the last ticket finalizes; `ticket` = one zeroed unsigned in
+ * device memory private to the launching stream, left zero), and apply passes that also emit the result as the padded-flat bf16 hi/lo
+ * operand planes [B][H+P][W+P][C] of the neighbouring tensor-core conv (replacing a tpgsr_split_bf16_flat pass).  nn.BatchNorm2d train
+ * forward / backward: model/tsrn.py:377,382,38; model/crnn/crnn.py:48; model/stn_head.py:19. */
+int tpgsr_bn_stats_fused(const float* x, long M, int C, int ldx, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, float* mean_rstd, float* scale_shift, void* workspace,
+                         size_t workspace_bytes, unsigned* ticket, cudaStream_t stream);
+int tpgsr_bn_apply_planes(const float* x, float* y, const float* scale_shift, int B, int H, int W, int C, int act, const float* residual,
+                          int P, void* hi, void* lo, cudaStream_t stream);
+int tpgsr_bn_bwd_fused(const float* dy, const float* x, float* dx, const float* scale_shift, const float* mean_rstd, int B, int H, int W,
+                       int C, int act, int train, float* dgamma, float* dbeta, int accumulate, int P, void* hi, void* lo, void* workspace,
+                       size_t workspace_bytes, unsigned* ticket, cudaStream_t stream);
 size_t tpgsr_bn_bwd_workspace_bytes(long M, int C);
 int tpgsr_bn_bwd(const float* dy, const float* x, float* dx, const float* scale_shift, const float* mean_rstd, long M,
                  int C, int lddy, int ldx, int lddx, int act, int train, float* dgamma, float* dbeta, int accumulate,

@@ -326,3 +326,41 @@ def test_psnr_ssim_against_golden_and_oracle():
     assert abs(float(calculate_psnr(x.to(d), y.to(d))) - float(o.calculate_psnr(x, y))) < 1e-3
     assert abs(float(SSIM()(x.to(d), y.to(d))) - float(o.ssim(x, y))) < 1e-5
     assert float(calculate_psnr(a, a)) == float('inf')
+
+
+@pytest.mark.parametrize('act', ['none', 'relu', 'mish'])
+@pytest.mark.parametrize('P', [0, 1])
+def test_bn_fused_passes_match_three_launch_passes_bitwise(act, P):
+    """tpgsr_bn_stats_fused / tpgsr_bn_apply_planes / tpgsr_bn_bwd_fused ("last block finalizes", operand planes from the apply pass) against the
+    round-1 three-launch passes followed by tpgsr_split_bf16_flat: identical bits, twice in a row (the ticket resets itself)."""
+    from tpgsr_b200 import ops
+    d = _dev()
+    B, H, W, C = 5, 6, 9, 64
+    code = {'none': ops.ACT_NONE, 'relu': ops.ACT_RELU, 'mish': ops.ACT_MISH}[act]
+    x = rnd(B, H, W, C, seed=31).to(d) * 1.7 + 0.3
+    res = rnd(B, H, W, C, seed=32).to(d)
+    gy = rnd(B, H, W, C, seed=33).to(d)
+    g, b = (1 + 0.1 * rnd(C, seed=34)).to(d), (0.1 * rnd(C, seed=35)).to(d)
+    for rep in range(2):
+        rm1, rv1, rm2, rv2 = torch.zeros(C, device=d), torch.ones(C, device=d), torch.zeros(C, device=d), torch.ones(C, device=d)
+        old = ops.BN_FUSED
+        try:
+            ops.BN_FUSED = False
+            mr0, ss0 = ops.bn_stats(x.view(-1, C), g, b, rm1, rv1)
+            y0 = ops.bn_apply(x.view(-1, C), ss0, code, res.view(-1, C)).view(B, H, W, C)
+            p0 = ops.split_bf16_flat(y0, P, True)
+            dg0, db0 = torch.zeros(C, device=d), torch.zeros(C, device=d)
+            dx0 = ops.bn_bwd(gy.view(-1, C), x.view(-1, C), ss0, mr0, code, True, dg0, db0, False).view(B, H, W, C)
+            q0 = ops.split_bf16_flat(dx0, P, True)
+            ops.BN_FUSED = True
+            mr1, ss1 = ops.bn_stats(x.view(-1, C), g, b, rm2, rv2)
+            y1, p1 = ops.bn_apply_planes(x, ss1, code, res, P)
+            dg1, db1 = torch.zeros(C, device=d), torch.zeros(C, device=d)
+            dx1, q1 = ops.bn_bwd_fused(gy, x, ss1, mr1, code, True, dg1, db1, False, P)
+            dx2, none = ops.bn_bwd_fused(gy, x, ss1, mr1, code, True, dg1, db1, True, None)
+        finally:
+            ops.BN_FUSED = old
+        for a_, b_ in ((mr0, mr1), (ss0, ss1), (rm1, rm2), (rv1, rv2), (y0, y1), (dx0, dx1), (dx0, dx2), (dg0 * 2, dg1), (db0 * 2, db1),
+                       (p0.hi, p1.hi), (p0.lo, p1.lo), (q0.hi, q1.hi), (q0.lo, q1.lo)):
+            assert torch.equal(a_, b_), (act, P, rep)
+        assert none is None and (p1.B, p1.H, p1.W, p1.C, p1.P) == (B, H, W, C, P)

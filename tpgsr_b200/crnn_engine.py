@@ -84,7 +84,8 @@ def crnn_fwd(ctx: engine.Ctx, gray_nchw: torch.Tensor, need_input_grad: bool = F
                                  need_dgrad=(i > 0) or need_input_grad)
         s_bn = None
         if has_bn:
-            a, s_bn = engine.bn_fwd(ctx, c, f'cnn.batchnorm{i}.', ACT_RELU)
+            # conv2 / conv4's BN+ReLU output feeds the next 3x3 conv directly: emit its operand planes from the apply pass
+            a, s_bn = engine.bn_fwd(ctx, c, f'cnn.batchnorm{i}.', ACT_RELU, planes_P=1 if (pool is None and i < 6) else None)
         else:
             a = c
         s_pool = None
@@ -118,7 +119,7 @@ def crnn_bwd(ctx: engine.Ctx, saved_all, dlogits: torch.Tensor) -> Optional[torc
             arg, in_shape, pk, ps, pp = s_pool
             d = ops.maxpool_bwd(d, arg, in_shape, pk, ps, pp)
         if s_bn is not None:
-            d = engine.bn_bwd(ctx, s_bn, d)
+            d = engine.bn_bwd(ctx, s_bn, d, planes_P=1)          # dY planes of this conv's data / weight gradient (conv6: 'valid' -> padded by 1 too)
         else:
             d = ops.act_bwd(d, relu_out, ACT_RELU)
         d = engine.conv_bwd(ctx, s_c, d, need_dx=(idx > 0) or need_input_grad)

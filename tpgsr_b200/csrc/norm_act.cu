@@ -5,6 +5,7 @@
 // (model/stn_head.py:36-44, model/crnn/crnn.py:56-66), nn.PixelShuffle(2)+mish (model/tsrn.py:464-477), torch.tanh
 // (model/tsrn.py:74), bias gradients, NCHW<->NHWC boundary transposes.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -211,6 +212,201 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int ro
     sum_partials(partial, row_blocks, C, c, false, s, unused);
     if (c >= C || threadIdx.y != 0) return;
     out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused column reduction + finalize ("last block finalizes"): the blocks of the reduction take a ticket after publishing their partial
+// sums; the block that draws the last ticket sums the partials in the same fixed order as the stand-alone finalize kernels (so results are
+// bit-identical to the two-launch path) and resets the ticket, which therefore stays zero between launches and graph replays.  Saves one
+// dependent launch (~6 us of a latency-bound chain) per BatchNorm forward and per BatchNorm backward.
+// ------------------------------------------------------------------------------------------------
+struct BnFwdFin {
+    long M; const float* gamma; const float* beta; float* mean_rstd; float* scale_shift; float* running_mean; float* running_var;
+    float momentum, eps;
+    __device__ void operator()(int c, int C, double s1, double s2) const {
+        double mean = s1 / (double)M;
+        double var = s2 / (double)M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        mean_rstd[c] = (float)mean;
+        mean_rstd[C + c] = rstd;
+        float sc = gamma[c] * rstd;
+        scale_shift[c] = sc;
+        scale_shift[C + c] = beta[c] - (float)mean * sc;
+        if (running_mean) {
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    }
+};
+struct BnBwdFin {
+    long M; float* dgamma; float* dbeta; float* coef; int accumulate;
+    __device__ void operator()(int c, int C, double s1, double s2) const {
+        if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s1 : (float)s1;
+        if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)s2 : (float)s2;
+        coef[c] = (float)(s1 / (double)M);
+        coef[C + c] = (float)(s2 / (double)M);
+    }
+};
+
+template <class F, class FIN>
+__global__ void __launch_bounds__(256) col_reduce2_fin_kernel(F f, FIN fin, long M, int C, long rows_per_block, float* __restrict__ partial,
+                                                              unsigned* __restrict__ ticket) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long r0 = (long)blockIdx.y * rows_per_block;
+    long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    float s1 = 0.f, s2 = 0.f;
+    if (c < C)
+        for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+            float2 v = f(r, c);
+            s1 += v.x;
+            s2 += v.y;
+        }
+    __shared__ float sh[2][8][33];
+    __shared__ unsigned last;
+    sh[0][threadIdx.y][threadIdx.x] = s1;
+    sh[1][threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
+        partial[((size_t)blockIdx.y * 2 + 0) * C + c] = a;
+        partial[((size_t)blockIdx.y * 2 + 1) * C + c] = b;
+    }
+    __threadfence();                                      // partials visible device-wide before the ticket is taken
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int row_blocks = gridDim.y;
+    for (int c0 = 0; c0 < C; c0 += 32) {                  // the last block finalizes every channel, 32 at a time
+        const int cc = c0 + threadIdx.x;
+        // same summation tree as sum_partials (FIN_Y = 32 strided float sums, then doubles in order) so both paths agree bit for bit
+        double d1 = 0.0, d2 = 0.0;
+        __syncthreads();
+        for (int grp = 0; grp < FIN_Y / 8; ++grp) {
+            const int y = grp * 8 + threadIdx.y;
+            float a = 0.f, b = 0.f;
+            if (cc < C)
+                for (int rb = y; rb < row_blocks; rb += FIN_Y) {
+                    a += __ldcg(partial + ((size_t)rb * 2 + 0) * C + cc);
+                    b += __ldcg(partial + ((size_t)rb * 2 + 1) * C + cc);
+                }
+            sh[0][threadIdx.y][threadIdx.x] = a;
+            sh[1][threadIdx.y][threadIdx.x] = b;
+            __syncthreads();
+            if (threadIdx.y == 0)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { d1 += (double)sh[0][i][threadIdx.x]; d2 += (double)sh[1][i][threadIdx.x]; }
+            __syncthreads();
+        }
+        if (threadIdx.y == 0 && cc < C) fin(cc, C, d1, d2);
+    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) *ticket = 0u;
+}
+
+template <class F, class FIN>
+int launch_col_reduce_fin(F f, FIN fin, long M, int C, float* partial, unsigned* ticket, cudaStream_t s) {
+    long rpb;
+    int row_blocks;
+    reduce_plan(M, C, row_blocks, rpb);
+    dim3 grid(ceil_div(C, 32), row_blocks), block(32, 8);
+    col_reduce2_fin_kernel<F, FIN><<<grid, block, 0, s>>>(f, fin, M, C, rpb, partial, ticket);
+    return tpgsr_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply / BN backward apply that ALSO emit the result as padded-flat bf16 hi/lo operand planes of the next tensor-core conv
+// ([B][H+P][W+P][C], pad rows / columns zero: conv_flat.cu) — replaces a separate tpgsr_split_bf16_flat pass over the same tensor.
+// The grid walks the FLAT rows, so the pad positions are written (zeros) by the same kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float4 v) {
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(f[j]);
+        l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
+}
+
+__global__ void __launch_bounds__(256) bn_apply_planes_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               const float* __restrict__ scale_shift, int B, int H, int W, int C, int act,
+                                                               const float* __restrict__ residual, int P, __nv_bfloat16* __restrict__ hi,
+                                                               __nv_bfloat16* __restrict__ lo) {
+    const int cq = C >> 2, Hp = H + P, Wp = W + P;
+    const long total = (long)B * Hp * Wp * cq;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long q = i / cq;
+        const int c = (int)(i - q * cq) * 4;
+        const int col = (int)(q % Wp);
+        const long t = q / Wp;
+        const int r = (int)(t % Hp);
+        const int b = (int)(t / Hp);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < H && col < W) {
+            const size_t row = ((size_t)b * H + r) * W + col;
+            v = *reinterpret_cast<const float4*>(x + row * C + c);
+            const float4 sc = *reinterpret_cast<const float4*>(scale_shift + c);
+            const float4 sh = *reinterpret_cast<const float4*>(scale_shift + C + c);
+            v.x = apply_act(fmaf(v.x, sc.x, sh.x), act, 0.f);
+            v.y = apply_act(fmaf(v.y, sc.y, sh.y), act, 0.f);
+            v.z = apply_act(fmaf(v.z, sc.z, sh.z), act, 0.f);
+            v.w = apply_act(fmaf(v.w, sc.w, sh.w), act, 0.f);
+            if (residual) {
+                const float4 rr = *reinterpret_cast<const float4*>(residual + row * C + c);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(y + row * C + c) = v;
+        }
+        store_planes4(hi, lo, (size_t)q * C + c, v);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_planes_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                   float* __restrict__ dx, const float* __restrict__ scale_shift,
+                                                                   const float* __restrict__ mean_rstd, const float* __restrict__ coef,
+                                                                   int B, int H, int W, int C, int act, int train, int P,
+                                                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int cq = C >> 2, Hp = H + P, Wp = W + P;
+    const long total = (long)B * Hp * Wp * cq;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long q = i / cq;
+        const int c = (int)(i - q * cq) * 4;
+        const int col = (int)(q % Wp);
+        const long t = q / Wp;
+        const int r = (int)(t % Hp);
+        const int b = (int)(t / Hp);
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < H && col < W) {
+            const size_t row = ((size_t)b * H + r) * W + col;
+            const float4 xv4 = *reinterpret_cast<const float4*>(x + row * C + c);
+            const float4 g4 = *reinterpret_cast<const float4*>(dy + row * C + c);
+            const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float sc = scale_shift[c + j];
+                const float yp = fmaf(xv[j], sc, scale_shift[C + c + j]);
+                float g = gv[j];
+                if (act == TPGSR_ACT_RELU) g = yp > 0.f ? g : 0.f;
+                else if (act == TPGSR_ACT_MISH) g *= mish_grad_f(yp);
+                if (train) {
+                    const float xh = (xv[j] - mean_rstd[c + j]) * mean_rstd[C + c + j];
+                    o[j] = sc * (g - coef[c + j] - xh * coef[C + c + j]);
+                } else {
+                    o[j] = sc * g;
+                }
+            }
+            *reinterpret_cast<float4*>(dx + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        store_planes4(hi, lo, (size_t)q * C + c, make_float4(o[0], o[1], o[2], o[3]));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,6 +709,48 @@ int tpgsr_bn_bwd(const float* dy, const float* x, float* dx, const float* scale_
     rc = tpgsr_launch_status();
     if (rc) return rc;
     bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, stream>>>(dy, x, dx, scale_shift, mean_rstd, coef, M, C, lddy, ldx, lddx, act, train);
+    return tpgsr_launch_status();
+}
+
+// Fused variants (round 2).  `ticket`: one zero-initialised unsigned in device memory, private to the stream the call is enqueued on
+// (the kernel leaves it zero).  tpgsr_bn_stats_fused = tpgsr_bn_stats in ONE launch (bit-identical results).
+int tpgsr_bn_stats_fused(const float* x, long M, int C, int ldx, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, float* mean_rstd, float* scale_shift, void* workspace,
+                         size_t workspace_bytes, unsigned* ticket, cudaStream_t stream) {
+    if (!x || !gamma || !beta || !mean_rstd || !scale_shift || !workspace || !ticket || M <= 0 || C <= 0) return TPGSR_ERR_BAD_ARG;
+    if (workspace_bytes < tpgsr_colreduce_workspace_bytes(M, C)) return TPGSR_ERR_WORKSPACE;
+    return launch_col_reduce_fin(StatsF{x, ldx > 0 ? ldx : C}, BnFwdFin{M, gamma, beta, mean_rstd, scale_shift, running_mean, running_var, momentum, eps},
+                                 M, C, static_cast<float*>(workspace), ticket, stream);
+}
+
+// y = act(x*scale + shift) (+ residual) for a dense NHWC map [B,H,W,C], also written as padded-flat bf16 planes (pad P) for the next conv
+int tpgsr_bn_apply_planes(const float* x, float* y, const float* scale_shift, int B, int H, int W, int C, int act, const float* residual,
+                          int P, void* hi, void* lo, cudaStream_t stream) {
+    if (!x || !y || !scale_shift || !hi || (C & 3) || B < 1 || H < 1 || W < 1 || P < 0) return TPGSR_ERR_BAD_ARG;
+    bn_apply_planes_kernel<<<ew_grid((long)B * (H + P) * (W + P) * (C / 4)), 256, 0, stream>>>(
+        x, y, scale_shift, B, H, W, C, act, residual, P, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
+    return tpgsr_launch_status();
+}
+
+// tpgsr_bn_bwd in TWO launches (fused reduction + finalize, then the apply pass), dense tensors; when `hi` is given, dx is also written
+// as padded-flat bf16 planes [B][H+P][W+P][C] (the dY operand of the preceding conv's data / weight gradient)
+int tpgsr_bn_bwd_fused(const float* dy, const float* x, float* dx, const float* scale_shift, const float* mean_rstd, int B, int H, int W,
+                       int C, int act, int train, float* dgamma, float* dbeta, int accumulate, int P, void* hi, void* lo, void* workspace,
+                       size_t workspace_bytes, unsigned* ticket, cudaStream_t stream) {
+    if (!dy || !x || !dx || !scale_shift || !mean_rstd || !workspace || !ticket || (C & 3)) return TPGSR_ERR_BAD_ARG;
+    const long M = (long)B * H * W;
+    size_t need = tpgsr_colreduce_workspace_bytes(M, C) + 2 * (size_t)C * sizeof(float);
+    if (workspace_bytes < need) return TPGSR_ERR_WORKSPACE;
+    float* partial = static_cast<float*>(workspace);
+    float* coef = partial + tpgsr_colreduce_workspace_bytes(M, C) / sizeof(float);
+    int rc = launch_col_reduce_fin(BnBwdF{dy, x, scale_shift, mean_rstd, C, C, C, act}, BnBwdFin{M, dgamma, dbeta, coef, accumulate}, M, C, partial,
+                                   ticket, stream);
+    if (rc) return rc;
+    if (hi)
+        bn_bwd_apply_planes_kernel<<<ew_grid((long)B * (H + P) * (W + P) * (C / 4)), 256, 0, stream>>>(
+            dy, x, dx, scale_shift, mean_rstd, coef, B, H, W, C, act, train, P, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
+    else
+        bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, stream>>>(dy, x, dx, scale_shift, mean_rstd, coef, M, C, C, C, C, act, train);
     return tpgsr_launch_status();
 }
 

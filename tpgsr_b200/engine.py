@@ -305,9 +305,14 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
 
 
 # ------------------------------------------------------------------------------------------------------------ batch norm
+def _planes_ok(x: Tensor) -> bool:
+    return ops.BN_FUSED and ops.CONV_MODE != 'fp32' and x.dim() == 4 and x.shape[-1] % 64 == 0 and x.is_contiguous()
+
+
 def bn_fwd(ctx: Ctx, x: Tensor, pre: str, act=ACT_NONE, residual: Optional[Tensor] = None, out: Optional[Tensor] = None,
-           ldy: int = 0):
-    """x [...,C] -> act(BN(x)) (+ residual).  Training: batch stats + running-stat update; eval: running stats."""
+           ldy: int = 0, planes_P: Optional[int] = None):
+    """x [...,C] -> act(BN(x)) (+ residual).  Training: batch stats + running-stat update; eval: running stats.
+    ``planes_P``: the result feeds a tensor-core conv with padding P next — the apply pass then also writes its bf16 operand planes."""
     C = x.shape[-1]
     x2 = x.view(-1, C)
     if ctx.training:
@@ -316,6 +321,10 @@ def bn_fwd(ctx: Ctx, x: Tensor, pre: str, act=ACT_NONE, residual: Optional[Tenso
     else:
         mean_rstd, ss = ops.bn_eval_prepare(ctx.P(pre + 'weight'), ctx.P(pre + 'bias'), ctx.P(pre + 'running_mean'),
                                             ctx.P(pre + 'running_var'))
+    if planes_P is not None and out is None and _planes_ok(x):
+        y, yp = ops.bn_apply_planes(x, ss, act, residual, planes_P, ops.CONV_MODE == 'bf16x3')
+        ctx._planes[(id(y), 'flat', planes_P, C)] = (y, yp)
+        return y, (x, pre, act, mean_rstd, ss, ctx.training)
     y = ops.bn_apply(x2, ss, act, residual.view(-1, C) if residual is not None else None,
                      out=out.view(-1, out.shape[-1]) if out is not None else None, ldy=ldy)
     if out is None:
@@ -325,11 +334,19 @@ def bn_fwd(ctx: Ctx, x: Tensor, pre: str, act=ACT_NONE, residual: Optional[Tenso
     return y, (x, pre, act, mean_rstd, ss, ctx.training)
 
 
-def bn_bwd(ctx: Ctx, saved, dy: Tensor, lddy: int = 0) -> Tensor:
+def bn_bwd(ctx: Ctx, saved, dy: Tensor, lddy: int = 0, planes_P: Optional[int] = None) -> Tensor:
+    """``planes_P``: dx is the dY operand of a tensor-core conv backward with plane padding P — emitted by the apply pass."""
     x, pre, act, mean_rstd, ss, train = saved
     C = x.shape[-1]
     gg, acc = ctx.G(pre + 'weight')
     gb, _ = ctx.G(pre + 'bias')
+    if ops.BN_FUSED and lddy in (0, C) and x.dim() == 4 and C % 4 == 0 and x.is_contiguous() and dy.is_contiguous():
+        want_planes = planes_P is not None and _planes_ok(x)
+        need_lo = ops.CONV_MODE == 'bf16x3' and not ops.BWD2
+        dx, dxp = ops.bn_bwd_fused(dy.view(x.shape), x, ss, mean_rstd, act, train, gg, gb, acc, planes_P if want_planes else None, need_lo)
+        if dxp is not None:
+            ctx._planes[(id(dx), 'dflat' if ops.BWD2 else 'flat', planes_P, C)] = (dx, dxp)
+        return dx
     dx = ops.bn_bwd(dy.view(-1, dy.shape[-1]) if lddy == 0 else dy, x.view(-1, C), ss, mean_rstd, act, train, gg, gb, acc, lddy=lddy)
     return dx.view(x.shape)
 
@@ -427,10 +444,10 @@ def srb_fwd(ctx: Ctx, x: Tensor, pre: str, text: Optional[Tensor] = None):
     """RecurrentResidualBlock / RecurrentResidualBlockTL (model/tsrn.py:373-426)."""
     B, H, W, C = x.shape
     c1, s_c1 = conv_fwd(ctx, x, pre + 'conv1.weight', pre + 'conv1.bias', 3, 1)
-    a1, s_bn1 = bn_fwd(ctx, c1, pre + 'bn1.', ACT_MISH)
+    a1, s_bn1 = bn_fwd(ctx, c1, pre + 'bn1.', ACT_MISH, planes_P=1)                 # feeds conv2 (3x3)
     c2, s_c2 = conv_fwd(ctx, a1, pre + 'conv2.weight', pre + 'conv2.bias', 3, 1)
     if text is None:
-        r2, s_bn2 = bn_fwd(ctx, c2, pre + 'bn2.')
+        r2, s_bn2 = bn_fwd(ctx, c2, pre + 'bn2.', planes_P=0)                       # feeds gru1's 1x1 conv
         cat = r2
     else:
         Ct = text.shape[-1]
@@ -452,9 +469,9 @@ def srb_bwd(ctx: Ctx, saved, dout: Tensor, dtext: Optional[Tensor] = None):
         ops.copy_cols(dcat, Ctot, dtext, Ct, B * H * W, Ct, accumulate=True, src_off=C)
         dc2 = bn_bwd(ctx, s_bn2, dcat.view(-1, Ctot), lddy=Ctot)
     else:
-        dc2 = bn_bwd(ctx, s_bn2, dcat)
+        dc2 = bn_bwd(ctx, s_bn2, dcat, planes_P=1)                                  # dY of conv2's gradients
     da1 = conv_bwd(ctx, s_c2, dc2)
-    dc1 = bn_bwd(ctx, s_bn1, da1)
+    dc1 = bn_bwd(ctx, s_bn1, da1, planes_P=1)
     # dx = dgrad(conv1) + dsum : accumulate into the dsum buffer
     return conv_bwd(ctx, s_c1, dc1, True, dx_out=dsum, dx_accumulate=True)
 
@@ -534,7 +551,7 @@ def tsrn_fwd(ctx: Ctx, x_nchw: Tensor, stn: bool, srb_nums: int = 5, text: Optio
         s_srb.append(s)
     k = srb_nums + 2
     c7, s_c7 = conv_fwd(ctx, b, f'block{k}.0.weight', f'block{k}.0.bias', 3, 1)
-    s8, s_bn7 = bn_fwd(ctx, c7, f'block{k}.1.', ACT_NONE, residual=b1)
+    s8, s_bn7 = bn_fwd(ctx, c7, f'block{k}.1.', ACT_NONE, residual=b1, planes_P=1)   # feeds the 64 -> 256 conv
     k += 1
     u, s_up = conv_fwd(ctx, s8, f'block{k}.0.conv.weight', f'block{k}.0.conv.bias', 3, 1)
     v = ops.pixelshuffle_mish_fwd(u)
@@ -551,7 +568,7 @@ def tsrn_bwd(ctx: Ctx, saved, dsr_nchw: Tensor, dtext: Optional[Tensor] = None) 
     dv = conv_bwd(ctx, s_out, dpre)
     du = ops.pixelshuffle_mish_bwd(dv, u)
     ds8 = conv_bwd(ctx, s_up, du)                               # = d(b1 + bn7(c7)): flows to both operands
-    dc7 = bn_bwd(ctx, s_bn7, ds8)
+    dc7 = bn_bwd(ctx, s_bn7, ds8, planes_P=1)
     db = conv_bwd(ctx, s_c7, dc7)
     for s in reversed(s_srb):
         db = srb_bwd(ctx, s, db, dtext)

@@ -18,7 +18,7 @@ OUT_NHWC, OUT_NCHW = 0, 1
 # number of kernel launches issued by this process through the C ABI (bench.py reports it as `gpu_launches`)
 LAUNCHES = 0
 _KERNELS_PER_CALL = {
-    'tpgsr_conv2d_wgrad': 2, 'tpgsr_bn_stats': 2, 'tpgsr_bn_bwd': 3, 'tpgsr_colsum': 2, 'tpgsr_gru_bwd': 3,
+    'tpgsr_conv2d_wgrad': 2, 'tpgsr_bn_stats': 2, 'tpgsr_bn_bwd': 3, 'tpgsr_bn_bwd_fused': 2, 'tpgsr_colsum': 2, 'tpgsr_gru_bwd': 3,
     'tpgsr_image_loss_fwd': 2, 'tpgsr_semantic_loss_fwd': 2, 'tpgsr_optim_prepare': 2, 'tpgsr_lstm_bwd': 2,
     'tpgsr_conv2d_tc': 1, 'tpgsr_conv2d_wgrad_tc': 2, 'tpgsr_conv2d_flat': 1, 'tpgsr_conv2d_wgrad_flat': 2, 'tpgsr_gru_bwd_weights': 2,
     'tpgsr_psnr_ssim': 2,
@@ -491,14 +491,65 @@ def colsum(x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ batch norm
+_TICKETS = {}
+
+
+def ticket(device) -> int:
+    """One zeroed unsigned per (device, main / side stream) for the "last block finalizes" reductions: kernels that use it run on one
+    stream (ordered) and leave it zero, so the pointer is stable across CUDA-graph replays."""
+    idx = _dev_index(device)
+    side = _SIDE.get(idx)
+    on_side = side is not None and torch.cuda.current_stream(torch.device('cuda', idx)).cuda_stream == side.cuda_stream
+    t = _TICKETS.get((idx, on_side))
+    if t is None:
+        t = torch.zeros(4, dtype=torch.int32, device=torch.device('cuda', idx))
+        _TICKETS[(idx, on_side)] = t
+    return t.data_ptr()
+
+
+# TPGSR_BN_FUSED=0: the round-1 three-launch BatchNorm passes (A/B switch; results are bit-identical)
+BN_FUSED = os.environ.get('TPGSR_BN_FUSED', '1') != '0'
+
+
 def bn_stats(x2d: torch.Tensor, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5):
     M, C = x2d.shape
     mean_rstd = new((2, C), x2d)
     scale_shift = new((2, C), x2d)
     wp, wn = workspace(query('tpgsr_colreduce_workspace_bytes', M, C), x2d.device)
-    _call('tpgsr_bn_stats', ptr(x2d), M, C, C, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), momentum, eps,
-          ptr(mean_rstd), ptr(scale_shift), wp, wn, stream())
+    if BN_FUSED:
+        _call('tpgsr_bn_stats_fused', ptr(x2d), M, C, C, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), momentum, eps,
+              ptr(mean_rstd), ptr(scale_shift), wp, wn, ticket(x2d.device), stream())
+    else:
+        _call('tpgsr_bn_stats', ptr(x2d), M, C, C, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), momentum, eps,
+              ptr(mean_rstd), ptr(scale_shift), wp, wn, stream())
     return mean_rstd, scale_shift
+
+
+def bn_apply_planes(x: torch.Tensor, scale_shift: torch.Tensor, act: int, residual: Optional[torch.Tensor], P: int, need_lo: bool = True):
+    """x dense NHWC [B,H,W,C] -> (y dense fp32, FlatPlanes of y with padding P): BN apply + activation (+ residual) + operand planes."""
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    rows = B * (H + P) * (W + P)
+    hi = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device) if need_lo else None
+    _call('tpgsr_bn_apply_planes', ptr(x), ptr(y), ptr(scale_shift), B, H, W, C, act, ptr(residual), P, ptr(hi), ptr(lo), stream())
+    return y, FlatPlanes(hi, lo, B, H, W, C, P)
+
+
+def bn_bwd_fused(dy: torch.Tensor, x: torch.Tensor, scale_shift, mean_rstd, act: int, train: bool, dgamma, dbeta, accumulate: bool,
+                 P: Optional[int] = None, need_lo: bool = True):
+    """Dense NHWC [B,H,W,C] BN backward in two launches; with ``P`` also returns dx as padded-flat operand planes -> (dx, FlatPlanes | None)."""
+    B, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    hi = lo = None
+    if P is not None:
+        rows = B * (H + P) * (W + P)
+        hi = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device) if need_lo else None
+    wp, wn = workspace(query('tpgsr_bn_bwd_workspace_bytes', B * H * W, C), x.device)
+    _call('tpgsr_bn_bwd_fused', ptr(dy), ptr(x), ptr(dx), ptr(scale_shift), ptr(mean_rstd), B, H, W, C, act, int(train), ptr(dgamma), ptr(dbeta),
+          int(accumulate), P or 0, ptr(hi), ptr(lo), wp, wn, ticket(x.device), stream())
+    return dx, (FlatPlanes(hi, lo, B, H, W, C, P) if P is not None else None)
 
 
 def bn_eval_prepare(gamma, beta, running_mean, running_var, eps=1e-5):
