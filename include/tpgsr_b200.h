@@ -134,7 +134,8 @@ int tpgsr_bn_eval_prepare(int C, const float* gamma, const float* beta, const fl
 int tpgsr_bn_apply(const float* x, float* y, const float* scale_shift, long M, int C, int ldx, int ldy, int act,
                    const float* residual, int ldr, cudaStream_t stream);
 /* fused variants: reduction + finalize in ONE launch (the block that draws the last ticket finalizes; `ticket` = one zeroed unsigned in
- * device memory private to the launching stream, left zero), and apply passes that also emit the result as the padded-flat bf16 hi/lo
+ * device memory private to the launching stream, left zero; tpgsr_bn_bwd_fused with ticket == NULL keeps the stand-alone finalize kernel —
+ * the ticket path measured slower on B200 and is off by default), and apply passes that also emit the result as the padded-flat bf16 hi/lo
  * operand planes [B][H+P][W+P][C] of the neighbouring tensor-core conv (replacing a tpgsr_split_bf16_flat pass).  nn.BatchNorm2d train
  * forward / backward: model/tsrn.py:377,382,38; model/crnn/crnn.py:48; model/stn_head.py:19. */
 int tpgsr_bn_stats_fused(const float* x, long M, int C, int ldx, const float* gamma, const float* beta, float* running_mean,

@@ -352,7 +352,7 @@ def test_bn_fused_passes_match_three_launch_passes_bitwise(act, P):
             dg0, db0 = torch.zeros(C, device=d), torch.zeros(C, device=d)
             dx0 = ops.bn_bwd(gy.view(-1, C), x.view(-1, C), ss0, mr0, code, True, dg0, db0, False).view(B, H, W, C)
             q0 = ops.split_bf16_flat(dx0, P, True)
-            ops.BN_FUSED = True
+            ops.BN_FUSED = rep == 0                      # rep 1: planes from the apply passes behind the stand-alone finalize kernels
             mr1, ss1 = ops.bn_stats(x.view(-1, C), g, b, rm2, rv2)
             y1, p1 = ops.bn_apply_planes(x, ss1, code, res, P)
             dg1, db1 = torch.zeros(C, device=d), torch.zeros(C, device=d)

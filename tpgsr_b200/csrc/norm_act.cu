@@ -737,14 +737,23 @@ int tpgsr_bn_apply_planes(const float* x, float* y, const float* scale_shift, in
 int tpgsr_bn_bwd_fused(const float* dy, const float* x, float* dx, const float* scale_shift, const float* mean_rstd, int B, int H, int W,
                        int C, int act, int train, float* dgamma, float* dbeta, int accumulate, int P, void* hi, void* lo, void* workspace,
                        size_t workspace_bytes, unsigned* ticket, cudaStream_t stream) {
-    if (!dy || !x || !dx || !scale_shift || !mean_rstd || !workspace || !ticket || (C & 3)) return TPGSR_ERR_BAD_ARG;
+    if (!dy || !x || !dx || !scale_shift || !mean_rstd || !workspace || (C & 3)) return TPGSR_ERR_BAD_ARG;
     const long M = (long)B * H * W;
     size_t need = tpgsr_colreduce_workspace_bytes(M, C) + 2 * (size_t)C * sizeof(float);
     if (workspace_bytes < need) return TPGSR_ERR_WORKSPACE;
     float* partial = static_cast<float*>(workspace);
     float* coef = partial + tpgsr_colreduce_workspace_bytes(M, C) / sizeof(float);
-    int rc = launch_col_reduce_fin(BnBwdF{dy, x, scale_shift, mean_rstd, C, C, C, act}, BnBwdFin{M, dgamma, dbeta, coef, accumulate}, M, C, partial,
+    int rc;
+    if (ticket) {
+        rc = launch_col_reduce_fin(BnBwdF{dy, x, scale_shift, mean_rstd, C, C, C, act}, BnBwdFin{M, dgamma, dbeta, coef, accumulate}, M, C, partial,
                                    ticket, stream);
+    } else {                                              // ticket == NULL: the stand-alone finalize kernel (measured faster, see header)
+        int rb;
+        rc = launch_col_reduce(BnBwdF{dy, x, scale_shift, mean_rstd, C, C, C, act}, M, C, partial, rb, stream);
+        if (rc) return rc;
+        bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, FIN_Y), 0, stream>>>(partial, rb, M, C, dgamma, dbeta, coef, accumulate);
+        rc = tpgsr_launch_status();
+    }
     if (rc) return rc;
     if (hi)
         bn_bwd_apply_planes_kernel<<<ew_grid((long)B * (H + P) * (W + P) * (C / 4)), 256, 0, stream>>>(

@@ -306,7 +306,7 @@ def conv_bwd(ctx: Ctx, saved, dy: Tensor, need_dx: bool = True, dx_out: Optional
 
 # ------------------------------------------------------------------------------------------------------------ batch norm
 def _planes_ok(x: Tensor) -> bool:
-    return ops.BN_FUSED and ops.CONV_MODE != 'fp32' and x.dim() == 4 and x.shape[-1] % 64 == 0 and x.is_contiguous()
+    return ops.BN_PLANES and ops.CONV_MODE != 'fp32' and x.dim() == 4 and x.shape[-1] % 64 == 0 and x.is_contiguous()
 
 
 def bn_fwd(ctx: Ctx, x: Tensor, pre: str, act=ACT_NONE, residual: Optional[Tensor] = None, out: Optional[Tensor] = None,
@@ -340,8 +340,8 @@ def bn_bwd(ctx: Ctx, saved, dy: Tensor, lddy: int = 0, planes_P: Optional[int] =
     C = x.shape[-1]
     gg, acc = ctx.G(pre + 'weight')
     gb, _ = ctx.G(pre + 'bias')
-    if ops.BN_FUSED and lddy in (0, C) and x.dim() == 4 and C % 4 == 0 and x.is_contiguous() and dy.is_contiguous():
-        want_planes = planes_P is not None and _planes_ok(x)
+    want_planes = planes_P is not None and _planes_ok(x)
+    if (ops.BN_FUSED or want_planes) and lddy in (0, C) and x.dim() == 4 and C % 4 == 0 and x.is_contiguous() and dy.is_contiguous():
         need_lo = ops.CONV_MODE == 'bf16x3' and not ops.BWD2
         dx, dxp = ops.bn_bwd_fused(dy.view(x.shape), x, ss, mean_rstd, act, train, gg, gb, acc, planes_P if want_planes else None, need_lo)
         if dxp is not None:

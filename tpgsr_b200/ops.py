@@ -507,8 +507,11 @@ def ticket(device) -> int:
     return t.data_ptr()
 
 
-# TPGSR_BN_FUSED=0: the round-1 three-launch BatchNorm passes (A/B switch; results are bit-identical)
-BN_FUSED = os.environ.get('TPGSR_BN_FUSED', '1') != '0'
+# TPGSR_BN_FUSED=1: reduction + finalize in one launch ("last block finalizes").  Bit-identical results, MEASURED SLOWER on B200 (a graph
+# node costs 0.9 us; the fence + ticket + one-block finalize cost more: config 3 10.23 vs 9.61 ms, profiles/r02/call8_stdout.log) -> off.
+BN_FUSED = os.environ.get('TPGSR_BN_FUSED', '0') != '0'
+# TPGSR_BN_PLANES=0: BatchNorm apply passes do not emit the next conv's operand planes (a separate tpgsr_split_bf16_flat pass does)
+BN_PLANES = os.environ.get('TPGSR_BN_PLANES', '1') != '0'
 
 
 def bn_stats(x2d: torch.Tensor, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5):
@@ -548,7 +551,7 @@ def bn_bwd_fused(dy: torch.Tensor, x: torch.Tensor, scale_shift, mean_rstd, act:
         lo = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device) if need_lo else None
     wp, wn = workspace(query('tpgsr_bn_bwd_workspace_bytes', B * H * W, C), x.device)
     _call('tpgsr_bn_bwd_fused', ptr(dy), ptr(x), ptr(dx), ptr(scale_shift), ptr(mean_rstd), B, H, W, C, act, int(train), ptr(dgamma), ptr(dbeta),
-          int(accumulate), P or 0, ptr(hi), ptr(lo), wp, wn, ticket(x.device), stream())
+          int(accumulate), P or 0, ptr(hi), ptr(lo), wp, wn, ticket(x.device) if BN_FUSED else None, stream())
     return dx, (FlatPlanes(hi, lo, B, H, W, C, P) if P is not None else None)
 
 
