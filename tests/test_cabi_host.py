@@ -137,7 +137,12 @@ def test_flat_conv_plans_fit_the_sm(nprod):
         assert 0 < smem <= 227 * 1024, ((B, H, W, P, Ci, Co, KH, KW), smem)
         MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer = list(out)
         assert 1 <= MT <= 3 and MT * tm_stride <= 512 and n_tile % 16 == 0 and n_tile <= 128 and tm_stride <= 256
-        assert n_tile * n_tiles >= Co and box_rows % 8 == 0 and box_rows <= 256
+        assert n_tile * n_tiles >= Co and box_rows % 8 == 0
+        if tile_outer == 2:      # tall plan (KH x 1 kernels): MT tiles of 16 rows x 8 columns, one 4-D box [16 + KH - 1][8 MT] per plane
+            assert KW == 1 and G == KH and n_groups == 1 and n_box == 1 and box_rows == (16 + KH - 1) * 8 * MT and 8 * MT <= 256
+            assert grid_x == B * ((H + 15) // 16) * ((W + 8 * MT - 1) // (8 * MT))    # every output pixel belongs to a tile
+            continue
+        assert box_rows <= 256
         assert n_box * box_rows >= 128 * MT + (G - 1) * (W + P) + (KW - 1)          # the staged window covers every tap of every tile
         assert grid_x * MT * 128 >= B * (H + P) * (W + P)                           # every flat output row belongs to a tile
         assert b_stages >= 1 and a_stages >= 1 and (n_groups == 1 or a_stages >= 2)

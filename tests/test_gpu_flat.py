@@ -232,3 +232,46 @@ def test_valid_and_full_convs_through_engine(B, Ci, Co, H, W, k, pad, mode):
         assert rel_err(nchw(dx), x.grad) < tol, rel_err(nchw(dx), x.grad)
     finally:
         ops.CONV_MODE = old
+
+
+@pytest.mark.parametrize('B,Co,H,W,KH', [
+    (2, 36, 32, 128, 9),      # final conv after kw-stacking: 9 x 1, N = 36 partial sums
+    (48, 36, 32, 128, 9),     # ... at the bench batch
+    (3, 64, 16, 64, 9),       # block1 after kw-stacking (whole image height in one tile row)
+    (2, 64, 11, 29, 5),       # ragged map: rows / columns that are no multiple of the 16 x 8 tile
+    (1, 64, 40, 20, 7),
+])
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
+def test_tall_plan_kh_by_1_convs(B, Co, H, W, KH, mode):
+    """KH x 1 convs on 64 channels run the TALL plan (2-D halo tile through one 4-D TMA box, A descriptor SBO = tile pitch): against fp32
+    F.conv2d, and bit for bit against the flat plan (debug bit 3 disables the tall plan) — same MMAs in the same order, different tiling."""
+    from tpgsr_b200 import ops
+    from tpgsr_b200._lib import LIB
+    import ctypes
+    d = torch.device('cuda:0')
+    ph = KH // 2
+    x = rnd(B, 64, H, W, seed=91)
+    w = rnd(Co, 64, KH, 1, seed=92) / np.sqrt(64 * KH)
+    b = rnd(Co, seed=93, scale=0.1)
+    want = F.conv2d(x, w, b, padding=(ph, 0))
+    old = ops.CONV_MODE
+    ops.CONV_MODE = mode
+    lo = mode == 'bf16x3'
+    try:
+        out = (ctypes.c_int * 13)()
+        assert LIB.tpgsr_conv2d_flat_plan(B, H, W, ph, 64, Co, KH, 1, ph, 0, 3 if lo else 1, out) > 0 and out[12] == 2      # the tall plan is chosen
+        (wf, _) = ops.pack_conv_weights_bf16(w.to(d), False, lo)
+        xp = ops.split_bf16_flat(nhwc(x).to(d), ph, lo)
+        y = ops.conv_flat(xp, wf, b.to(d), Co, KH, 1, ph, 0)
+        assert rel_err(nchw(y), want) < (3e-5 if lo else 8e-3), rel_err(nchw(y), want)
+        y_nchw = ops.conv_flat(xp, wf, b.to(d), Co, KH, 1, ph, 0, act=ops.ACT_TANH, out_nchw=True)
+        assert rel_err(y_nchw, torch.tanh(want)) < (3e-5 if lo else 8e-3)
+        try:
+            LIB.tpgsr_conv2d_flat_set_debug_skip(8)
+            assert LIB.tpgsr_conv2d_flat_plan(B, H, W, ph, 64, Co, KH, 1, ph, 0, 3 if lo else 1, out) > 0 and out[12] != 2
+            y_flat = ops.conv_flat(xp, wf, b.to(d), Co, KH, 1, ph, 0)
+        finally:
+            LIB.tpgsr_conv2d_flat_set_debug_skip(0)
+        assert torch.equal(y, y_flat)
+    finally:
+        ops.CONV_MODE = old

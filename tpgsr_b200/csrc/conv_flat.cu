@@ -75,6 +75,20 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
 
 // D[tmem] (+)= A * B with descriptors given as (lo word, shared hi word); ACC is a compile-time accumulate flag
+// as umma_lo, with the high word of the A descriptor given (tall plan: SBO = the pitch of the 2-D halo tile instead of 1024 bytes)
+template <int ACC>
+__device__ __forceinline__ void umma_ab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %6};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC), "r"(DESC_HI), "r"(a_hi)
+        : "memory");
+}
 template <int ACC>
 __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
     asm volatile(
@@ -111,6 +125,10 @@ struct FlatConvParams {
     int nstack;                // 1 (bf16x3, n_tile <= 64): [B_hi; B_lo] is used as ONE N = 2*n_tile operand, 2 MMAs per K step instead of 3
     int tile_outer;            // 1: whole halo resident (n_groups == 1) -> finish tile after tile (weights re-streamed per tile from L2) so
                                //    that the epilogue of tile t overlaps the MMAs of tile t+1;  0: streamed A groups, taps outermost
+    int tall;                  // TALL plan (KW == 1, tall kernels: the kw-stacked 9x9 convs): a CTA owns MT tiles of 16 image rows x 8 columns;
+                               //   ONE 4-D TMA box stages the [16 + KH - 1][8 MT] pixel halo, tap kh is the same buffer kh * 8 MT rows further,
+                               //   the 8-row groups of a tile are 8 MT rows apart (A descriptor SBO = 8 MT * 128 bytes)
+    int tcols, n_hg, n_wg;     // tall: columns per CTA (8 MT); row groups / column groups per image
     int ring_bytes;            // bytes of the A+B rings
     int stg_off;               // byte offset of the epilogue staging area (== 0: aliases the rings, only legal when !tile_outer)
     int bar_off;               // byte offset of the barrier block
@@ -126,15 +144,15 @@ struct FlatConvParams {
 
 // the 4 K steps (x 1 or 3 products) of one (tile, tap): 128 x n_tile x 64 MACs.  FIRST: the first MMA overwrites the accumulator.
 template <int NPROD, int FIRST>
-__device__ __forceinline__ void mma_tap(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc) {
-    if (FIRST) umma_lo<0>(d, ah, bh, idesc); else umma_lo<1>(d, ah, bh, idesc);
-    if (NPROD >= 2) umma_lo<1>(d, ah, bl, idesc);
-    if (NPROD == 3) umma_lo<1>(d, al, bh, idesc);
+__device__ __forceinline__ void mma_tap(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc, uint32_t ahi) {
+    if (FIRST) umma_ab<0>(d, ah, ahi, bh, idesc); else umma_ab<1>(d, ah, ahi, bh, idesc);
+    if (NPROD >= 2) umma_ab<1>(d, ah, ahi, bl, idesc);
+    if (NPROD == 3) umma_ab<1>(d, al, ahi, bh, idesc);
 #pragma unroll
     for (int k = 1; k < 4; ++k) {          // 16 bf16 = 32 bytes = 2 descriptor units inside the 128-byte swizzle row
-        umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc);
-        if (NPROD >= 2) umma_lo<1>(d, ah + 2 * k, bl + 2 * k, idesc);
-        if (NPROD == 3) umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc);
+        umma_ab<1>(d, ah + 2 * k, ahi, bh + 2 * k, idesc);
+        if (NPROD >= 2) umma_ab<1>(d, ah + 2 * k, ahi, bl + 2 * k, idesc);
+        if (NPROD == 3) umma_ab<1>(d, al + 2 * k, ahi, bh + 2 * k, idesc);
     }
 }
 
@@ -144,13 +162,13 @@ __device__ __forceinline__ void mma_tap(uint32_t d, uint32_t ah, uint32_t al, ui
 // phase of an N = 64 conv is shared-memory-bandwidth bound (6 KB per 32-cycle MMA), so this is 112 instead of 144 smem cycles per K step.
 // NPROD = 2 (A has no lo plane): only the stacked MMA — ONE 128 x 2n x 16 MMA per K step.
 template <int NPROD, int FIRST>
-__device__ __forceinline__ void mma_tap_stacked(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t idesc1, uint32_t idesc2) {
-    if (FIRST) umma_lo<0>(d, ah, bh, idesc2); else umma_lo<1>(d, ah, bh, idesc2);
-    if (NPROD == 3) umma_lo<1>(d, al, bh, idesc1);
+__device__ __forceinline__ void mma_tap_stacked(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t idesc1, uint32_t idesc2, uint32_t ahi) {
+    if (FIRST) umma_ab<0>(d, ah, ahi, bh, idesc2); else umma_ab<1>(d, ah, ahi, bh, idesc2);
+    if (NPROD == 3) umma_ab<1>(d, al, ahi, bh, idesc1);
 #pragma unroll
     for (int k = 1; k < 4; ++k) {
-        umma_lo<1>(d, ah + 2 * k, bh + 2 * k, idesc2);
-        if (NPROD == 3) umma_lo<1>(d, al + 2 * k, bh + 2 * k, idesc1);
+        umma_ab<1>(d, ah + 2 * k, ahi, bh + 2 * k, idesc2);
+        if (NPROD == 3) umma_ab<1>(d, al + 2 * k, ahi, bh + 2 * k, idesc1);
     }
 }
 
@@ -223,7 +241,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const int cb = g / p.kgroups, gk = g - cb * p.kgroups;
                 const long long row0 = q0 + (long long)(gk * p.G - p.ph) * p.Wp - p.pw;
                 const int ch0 = cb * 64;
-                for (int bx = 0; bx < p.n_box; ++bx) {
+                if (p.tall) {          // one 4-D box [halo rows][8 MT columns][64 channels] per plane; rows / columns outside the plane grid arrive as zeros
+                    const int wg = blockIdx.x % p.n_wg, hb = blockIdx.x / p.n_wg, hg = hb % p.n_hg, bimg = hb / p.n_hg;
+                    tc::tma_load_4d(ast, &tmA_hi, &a_full[as], 0, wg * p.tcols, hg * 16 - p.ph, bimg);
+                    if (NPROD == 3) tc::tma_load_4d(ast + a_plane_bytes, &tmA_lo, &a_full[as], 0, wg * p.tcols, hg * 16 - p.ph, bimg);
+                }
+                for (int bx = 0; bx < (p.tall ? 0 : p.n_box); ++bx) {
                     const int r = (int)(row0 + (long long)bx * p.box_rows);
                     tc::tma_load_2d(ast + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_hi, &a_full[as], ch0, r);
                     if (NPROD == 3)
@@ -256,7 +279,9 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t idesc = tc::idesc_bf16(TILE_M, p.n_tile, 0, 0);
         const uint32_t idesc2 = tc::idesc_bf16(TILE_M, 2 * p.n_tile, 0, 0);
         const bool stacked = NPROD >= 2 && p.nstack;
-        const uint32_t tile_lo = (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
+        const uint32_t tile_lo = p.tall ? (8 * ROW_BYTES) >> 4 : (TILE_M * ROW_BYTES) >> 4;        // descriptor units (16 bytes) between consecutive tiles
+        const uint32_t tap_rows = p.tall ? (uint32_t)p.tcols : (uint32_t)p.Wp;                       // rows between vertically adjacent taps
+        const uint32_t ahi = p.tall ? (0x40004000u | (uint32_t)((p.tcols * ROW_BYTES) >> 4)) : DESC_HI;   // A descriptor: SBO = pitch of the 8-row groups
         uint32_t b_it = 0;
         if (p.tile_outer) {
             mbar_wait_safe(&a_full[0], 0);
@@ -272,15 +297,15 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     tc::tc_fence_after();
                     if (dbg && b_it == 0 && leader) dbg[3] = clock64();
                     const int khl = j / p.KW, kw = j - khl * p.KW;
-                    const uint32_t off = (uint32_t)(khl * p.Wp + kw) * (ROW_BYTES >> 4) + (uint32_t)t * tile_lo;
+                    const uint32_t off = (uint32_t)(khl * tap_rows + kw) * (ROW_BYTES >> 4) + (uint32_t)t * tile_lo;
                     const uint32_t bh = desc_lo(tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes), 16);
                     const uint32_t bl = bh + (b_plane_bytes >> 4);
                     if (leader) {
                         if (stacked) {
-                            if (j == 0) mma_tap_stacked<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
-                            else mma_tap_stacked<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2);
-                        } else if (j == 0) mma_tap<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
-                        else mma_tap<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc);
+                            if (j == 0) mma_tap_stacked<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2, ahi);
+                            else mma_tap_stacked<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2, ahi);
+                        } else if (j == 0) mma_tap<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc, ahi);
+                        else mma_tap<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc, ahi);
                         tc::tc_commit(&b_empty[bs]);
                     }
                 }
@@ -305,20 +330,20 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     for (int tt = 0; tt < p.tb; ++tt) {
                         const int tl = j * p.tb + tt;                  // tap index inside the group
                         const int khl = tl / p.KW, kw = tl - khl * p.KW;
-                        const uint32_t row_off = (uint32_t)(khl * p.Wp + kw) * (ROW_BYTES >> 4);
+                        const uint32_t row_off = (uint32_t)(khl * tap_rows + kw) * (ROW_BYTES >> 4);
                         const uint32_t bh = b_hi0 + tt * (b_tap_bytes >> 4), bl = b_lo0 + tt * (b_tap_bytes >> 4);
                         if (!leader) continue;
                         uint32_t ah = a_hi0 + row_off, al = a_lo0 + row_off, d = tmem_u;
                         if (stacked) {
                             if (g == 0 && tl == 0) {
-                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<NPROD, 1>(d, ah, al, bh, idesc, idesc2);
+                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<NPROD, 1>(d, ah, al, bh, idesc, idesc2, ahi);
                             } else {
-                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<NPROD, 0>(d, ah, al, bh, idesc, idesc2);
+                                for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap_stacked<NPROD, 0>(d, ah, al, bh, idesc, idesc2, ahi);
                             }
                         } else if (g == 0 && tl == 0) {
-                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 1>(d, ah, al, bh, bl, idesc);
+                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 1>(d, ah, al, bh, bl, idesc, ahi);
                         } else {
-                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 0>(d, ah, al, bh, bl, idesc);
+                            for (int t = 0; t < p.MT; ++t, ah += tile_lo, al += tile_lo, d += p.tm_stride) mma_tap<NPROD, 0>(d, ah, al, bh, bl, idesc, ahi);
                         }
                     }
                     if (leader) tc::tc_commit(&b_empty[bs]);
@@ -349,11 +374,18 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     waited = true;
                     if (dbg && e == 0 && lane == 0 && t == 0) dbg[5] = clock64();
                     // dense pixel index of this lane's output row (-1: pad position or beyond the last image)
+                    if (p.tall) {          // tile row m = 8 i + j  <->  image row 16 hg + i, column 8 MT wg + 8 t + j
+                        const int m = q * 32 + lane;
+                        const int wg = blockIdx.x % p.n_wg, hb = blockIdx.x / p.n_wg, hg = hb % p.n_hg;
+                        bi = hb / p.n_hg; r = hg * 16 + (m >> 3); c = wg * p.tcols + 8 * t + (m & 7);
+                        pix = (r < p.Ho && c < p.Wo) ? (bi * p.Ho + r) * p.Wo + c : -1;
+                    } else {
                     const unsigned qrow = (unsigned)q0 + (unsigned)(t * TILE_M + q * 32 + lane);
                     const unsigned ub = qrow / img, rem = qrow - ub * img;
                     const unsigned ur = rem / (unsigned)p.Wp, uc = rem - ur * (unsigned)p.Wp;
                     bi = (int)ub; r = (int)ur; c = (int)uc;
                     pix = (qrow < qtot && r < p.Ho && c < p.Wo) ? (bi * p.Ho + r) * p.Wo + c : -1;
+                    }
                 }
                 const int c0 = ch * 32;
                 const int cw = (p.n_tile - c0) >= 32 ? 32 : (p.n_tile - c0);       // 32 or 16 columns in this chunk
@@ -513,6 +545,7 @@ split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __re
 
 struct FlatPlan {
     int MT, n_tile, n_tiles, tm_stride, nstack, pointwise, G, kgroups, n_groups, a_stages, box_rows, n_box, tb, b_stages, tile_outer, ring_bytes, stg_off, bar_off;
+    int tall, tcols, n_hg, n_wg;
     size_t smem;
     int grid_x;
 };
@@ -520,6 +553,7 @@ struct FlatPlan {
 long long* g_flat_dbg = nullptr;
 int g_flat_dbg_skip = 0;
 int g_flat_no_nstack = 0;
+int g_flat_no_tall = 0;     // developer switch (debug bit 3): disable the tall plan (A/B measurements)
 
 // budget: dynamic shared memory a CTA may use; tmem_max: TMEM columns it may allocate; slots: CTAs resident on the GPU at once
 int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, size_t budget, int tmem_max, int slots,
@@ -543,6 +577,32 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
     pl.pointwise = pointwise;
     const long long Qtot = (long long)B * (H + P) * Wp;
     if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
+    pl.tall = 0; pl.tcols = 0; pl.n_hg = 0; pl.n_wg = 0;
+    // ---- TALL plan: KH x 1 kernels with KH >= 5 on 64 channels (the kw-stacked 9x9 convs, 9 x 1 after stacking).  In the flat plans a tap
+    // shifts the window by a whole image row (W + P >= 68 flat rows), more than a 128-row tile: nothing is shared between the taps and
+    // every pixel row is fetched KH times (525 MB through L2 for the final conv: 150 us).  Here a tile is 16 image rows x 8 columns, a CTA
+    // owns MT such tiles side by side, and ONE 4-D TMA box [16 + KH - 1][8 MT][64] is the halo of all of them: 1.5x traffic instead of 9x.
+    if (!g_flat_no_tall && KW == 1 && KH >= 5 && cbs == 1 && pw == 0) {
+        const int Ho = H + 2 * ph - KH + 1, halo_rows = 16 + KH - 1;
+        for (int MT = 2; MT >= 1; --MT) {
+            if (MT * pl.tm_stride > tmem_max) continue;
+            const int tcols = 8 * MT;
+            const size_t a_b = (size_t)a_planes * halo_rows * tcols * ROW_BYTES;
+            const size_t tap_bytes = (size_t)b_planes * pl.n_tile * ROW_BYTES;
+            for (int want = 4; want >= 2; --want) {
+                const int bs = want < KH ? want : KH;
+                size_t ring = a_b + (size_t)bs * tap_bytes;
+                if (ring < (size_t)STG_BYTES) ring = STG_BYTES;
+                const size_t need = ring + 256 + (size_t)(pl.n_tile + 32) * 4 + 1024;
+                if (need > budget) continue;
+                pl.tall = 1; pl.tcols = tcols; pl.n_hg = (Ho + 15) / 16; pl.n_wg = (W + tcols - 1) / tcols;
+                pl.MT = MT; pl.G = KH; pl.kgroups = 1; pl.n_groups = 1; pl.a_stages = 1; pl.box_rows = halo_rows * tcols; pl.n_box = 1;
+                pl.tb = 1; pl.b_stages = bs; pl.smem = need; pl.ring_bytes = (int)ring; pl.stg_off = 0; pl.bar_off = (int)ring; pl.tile_outer = 0;
+                pl.grid_x = B * pl.n_hg * pl.n_wg;
+                return TPGSR_OK;
+            }
+        }
+    }
     // candidate configurations, best first: whole kernel resident (G = KH) with MT = 3, 2, 1; then one kernel row per stage
     // among the feasible MT the one with the fewest (waves x tiles per CTA) wins; near-ties go to the larger MT (less weight traffic)
     const long long tiles = (Qtot + TILE_M - 1) / TILE_M;
@@ -840,10 +900,11 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
 
 // developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][16]
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
-// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes
+// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes; bit 3: no tall plan
 int tpgsr_conv2d_flat_set_debug_skip(int bits) {
     g_flat_dbg_skip = bits & 3;
     g_flat_no_nstack = (bits >> 2) & 1;
+    g_flat_no_tall = (bits >> 3) & 1;
     return TPGSR_OK;
 }
 
@@ -854,7 +915,7 @@ size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH
     if (plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl)) return 0;
     if (out) {
         const int v[13] = {pl.MT, pl.n_tile, pl.n_tiles, pl.tm_stride, pl.G, pl.n_groups, pl.a_stages, pl.box_rows, pl.n_box, pl.tb,
-                           pl.b_stages, pl.grid_x, pl.tile_outer};
+                           pl.b_stages, pl.grid_x, pl.tall ? 2 : pl.tile_outer};
         for (int i = 0; i < 13; ++i) out[i] = v[i];
     }
     return pl.smem;
@@ -904,6 +965,7 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     p.a_stages = pl.a_stages;
     p.box_rows = pl.box_rows; p.n_box = pl.n_box; p.tb = pl.tb; p.b_stages = pl.b_stages; p.ring_bytes = pl.ring_bytes;
     p.tile_outer = pl.tile_outer; p.stg_off = pl.stg_off; p.bar_off = pl.bar_off; p.nstack = pl.nstack;
+    p.tall = pl.tall; p.tcols = pl.tcols; p.n_hg = pl.n_hg; p.n_wg = pl.n_wg;
     p.ldy = ldy > 0 ? ldy : Co; p.act = act; p.out_mode = out_mode; p.accumulate = accumulate;
     p.bias = bias; p.act_param = act_param; p.y = y; p.dbg = g_flat_dbg; p.dbg_skip = g_flat_dbg_skip;
     p.yp_hi = static_cast<__nv_bfloat16*>(yp_hi); p.yp_lo = static_cast<__nv_bfloat16*>(yp_lo);
@@ -916,11 +978,16 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     uint64_t bdims[2] = {K, (uint64_t)Co};
     uint64_t bstr[1] = {K * 2};
     uint32_t bbox[2] = {64, (uint32_t)pl.n_tile};
-    if (tpgsr_make_tmap_bf16(&tmA_hi, x_hi, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
+    // tall plan: the planes as a 4-D tensor [B][H+P][W+P][Ci]; the box is the 2-D halo tile of MT x (16 x 8) outputs
+    uint64_t tdims[4] = {(uint64_t)Ci, (uint64_t)p.Wp, (uint64_t)p.Hp, (uint64_t)B};
+    uint64_t tstr[3] = {(uint64_t)Ci * 2, (uint64_t)p.Wp * Ci * 2, (uint64_t)p.Hp * p.Wp * Ci * 2};
+    uint32_t tbox[4] = {64, (uint32_t)pl.tcols, (uint32_t)(16 + KH - 1), 1};
+    if (pl.tall ? tpgsr_make_tmap_bf16(&tmA_hi, x_hi, 4, tdims, tstr, tbox) : tpgsr_make_tmap_bf16(&tmA_hi, x_hi, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
     if (tpgsr_make_tmap_bf16(&tmB_hi, w_hi, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
     tmA_lo = tmA_hi;
     tmB_lo = tmB_hi;
-    if (nprod == 3 && tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 2, adims, astr, abox)) return TPGSR_ERR_DRIVER;
+    if (nprod == 3 && (pl.tall ? tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 4, tdims, tstr, tbox) : tpgsr_make_tmap_bf16(&tmA_lo, x_lo, 2, adims, astr, abox)))
+        return TPGSR_ERR_DRIVER;
     if (nprod >= 2 && tpgsr_make_tmap_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox)) return TPGSR_ERR_DRIVER;
     dim3 grid(pl.grid_x, pl.n_tiles);
     if (nprod == 3) {

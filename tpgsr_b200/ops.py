@@ -283,6 +283,12 @@ FLAT = os.environ.get('TPGSR_FLAT', '1') != '0'
 # recompute the 1x1 output for dW_ih, which costs what the forward pass saves — so it is kept for inference only.
 FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', 'infer')
 
+# developer A/B switch: TPGSR_FLAT_TALL=0 disables the tall plan of the flat convs (KH x 1 kernels: the kw-stacked 9x9 convs)
+FLAT_TALL = os.environ.get('TPGSR_FLAT_TALL', '1') != '0'
+if not FLAT_TALL:
+    LIB.tpgsr_conv2d_flat_set_debug_skip(8)
+
+
 class FlatPlanes:
     """bf16 hi/lo planes of an NHWC activation in the padded-flat layout."""
     __slots__ = ('hi', 'lo', 'B', 'H', 'W', 'C', 'P')
