@@ -39,6 +39,10 @@ __global__ void lstm_transpose_whh_kernel(const float* __restrict__ whh, float* 
 // FMA phase: warp w covers k in [32w, 32w+32), lane u = hidden unit: 4 gates x BG batch accumulators, W as one LDS.128 per k (layout
 // [k][u][gate]), h as broadcast LDS.128; the 8 warps' partial sums meet in shared memory.  Gate phase: thread (b, u).
 // ---------------------------------------------------------------------------------------------------------------------------------
+// split cluster barrier: work that the peers do not wait for (HBM stores, next-step loads) goes between arrive and wait
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 constexpr int LS = 8;             // CTAs per cluster = hidden slices
 constexpr int LU = LH / LS;       // hidden units per CTA (32)
 
@@ -76,7 +80,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
     // gate-phase role: thread (pb, u) owns hidden unit 32r + u of batch item b0 + pb
     const int pb = w;
     const bool gate_thread = pb < BG;
-    float bias[4], c = 0.f;
+    float bias[4], c = 0.f, ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, hval = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = __ldg(bhh + dir * 4 * LH + g * LH + LU * r + u);
     cluster.sync();                                           // every CTA of the cluster is running and has cleared its h buffer
@@ -126,17 +130,10 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
                 for (int ww = 0; ww < 8; ++ww) sacc += red[(ww * 4 * BG + g * BG + pb) * LU + u];
                 pre[g] = sacc;
             }
-            const float ig = sigmoid_f(pre[0]), fg = sigmoid_f(pre[1]), gg = tanhf(pre[2]), og = sigmoid_f(pre[3]);
+            ig = sigmoid_f(pre[0]); fg = sigmoid_f(pre[1]); gg = tanhf(pre[2]); og = sigmoid_f(pre[3]);
             c = fg * c + ig * gg;
-            const float h = og * tanhf(c);
-            if (pb < nb) {
-                y[LROW(t, b0 + pb) * 2 * LH + dir * LH + LU * r + u] = h;
-                if (stash) {
-                    float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + LU * r + u;
-                    sp[0] = ig; sp[LH] = fg; sp[2 * LH] = gg; sp[3 * LH] = og; sp[4 * LH] = c;
-                }
-            }
-            hloc[u * BG + pb] = pb < nb ? h : 0.f;
+            hval = og * tanhf(c);
+            hloc[u * BG + pb] = pb < nb ? hval : 0.f;
         }
         __syncthreads();
         // push this CTA's [32 units][BG] block of h_t into the next-step h buffer of every CTA of the cluster (itself included)
@@ -147,8 +144,17 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
             float* remote = cluster.map_shared_rank(hs, dst);
             *reinterpret_cast<float4*>(remote + nxt * LH * BG + (LU * r) * BG + 4 * q) = v;
         }
-        cluster.sync();                                       // h_t complete everywhere (release / acquire at cluster scope)
+        cluster_arrive_release();                             // h_t is on its way to every CTA ...
+        if (gate_thread && pb < nb) {                         // ... the HBM outputs are written behind the arrive: the release need not wait for them
+            y[LROW(t, b0 + pb) * 2 * LH + dir * LH + LU * r + u] = hval;
+            if (stash) {
+                float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + LU * r + u;
+                sp[0] = ig; sp[LH] = fg; sp[2 * LH] = gg; sp[3 * LH] = og; sp[4 * LH] = c;
+            }
+        }
+        cluster_wait_acquire();                               // h_t complete everywhere (release / acquire at cluster scope)
     }
+    cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
 }
 
 // BPTT: dy [T,B,2H] -> dgx [T,B,2,4H] (gradient w.r.t. the gate pre-activations).  whh: original [2][4H][H] layout.  Same cluster
