@@ -364,3 +364,19 @@ def test_bn_fused_passes_match_three_launch_passes_bitwise(act, P):
                        (p0.hi, p1.hi), (p0.lo, p1.lo), (q0.hi, q1.hi), (q0.lo, q1.lo)):
             assert torch.equal(a_, b_), (act, P, rep)
         assert none is None and (p1.B, p1.H, p1.W, p1.C, p1.P) == (B, H, W, C, P)
+
+
+@pytest.mark.parametrize('C', [2, 3, 4, 7])
+def test_standalone_gradient_prior_loss_covers_every_channel(C):
+    """GradientPriorLoss on its own (loss/image_loss.py:33-51) averages over ALL channels of its input (ImageLoss hands it the RGB slice)."""
+    from oracle import ops as o
+    from tpgsr_b200.loss.image_loss import GradientPriorLoss
+    a = rnd(3, C, 12, 20, seed=41).requires_grad_(True)
+    b = rnd(3, C, 12, 20, seed=42)
+    want = (o.gradient_map(a) - o.gradient_map(b)).abs().mean()
+    want.backward()
+    ad = a.detach().to(_dev()).requires_grad_(True)
+    got = GradientPriorLoss()(ad, b.to(_dev()))
+    got.backward()
+    assert abs(float(got) - float(want)) < 2e-6 * abs(float(want)) + 1e-7
+    assert rel_err(ad.grad, a.grad) < 2e-5

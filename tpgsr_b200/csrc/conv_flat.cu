@@ -123,8 +123,9 @@ struct FlatConvParams {
     int box_rows, n_box;       // one A stage = n_box TMA boxes of box_rows rows (box_rows % 8 == 0)
     int tb, b_stages;          // taps per B stage; B ring depth
     int nstack;                // 1 (bf16x3, n_tile <= 64): [B_hi; B_lo] is used as ONE N = 2*n_tile operand, 2 MMAs per K step instead of 3
-    int tile_outer;            // 1: whole halo resident (n_groups == 1) -> finish tile after tile (weights re-streamed per tile from L2) so
-                               //    that the epilogue of tile t overlaps the MMAs of tile t+1;  0: streamed A groups, taps outermost
+    int tile_outer;            // always 0: taps outermost, the MT tiles innermost (a weight stage feeds MT x 8..12 MMAs).  Tile-after-tile order
+                               //    with the weights re-streamed per tile was built twice (round 1, round 2 with per-box barriers + overlapped
+                               //    epilogue) and measured slower both times: L2-bound on the weight refetch — DESIGN.md §4
     int tall;                  // TALL plan (KW == 1, tall kernels: the kw-stacked 9x9 convs): a CTA owns MT tiles of 16 image rows x 8 columns;
                                //   ONE 4-D TMA box stages the [16 + KH - 1][8 MT] pixel halo, tap kh is the same buffer kh * 8 MT rows further,
                                //   the 8-row groups of a tile are 8 MT rows apart (A descriptor SBO = 8 MT * 128 bytes)
@@ -252,7 +253,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (NPROD == 3)
                         tc::tma_load_2d(ast + a_plane_bytes + (size_t)bx * p.box_rows * ROW_BYTES, &tmA_lo, &a_full[as], ch0, r);
                 }
-                const int reps = p.tile_outer ? p.MT : 1;             // tile_outer: the taps are streamed once per tile
+                const int reps = 1;
                 for (int rep = 0; rep < reps; ++rep) {
                     for (int j = 0; j < b_per_group; ++j, ++b_it) {
                         const int bs = b_it % p.b_stages;
@@ -283,36 +284,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t tap_rows = p.tall ? (uint32_t)p.tcols : (uint32_t)p.Wp;                       // rows between vertically adjacent taps
         const uint32_t ahi = p.tall ? (0x40004000u | (uint32_t)((p.tcols * ROW_BYTES) >> 4)) : DESC_HI;   // A descriptor: SBO = pitch of the 8-row groups
         uint32_t b_it = 0;
-        if (p.tile_outer) {
-            mbar_wait_safe(&a_full[0], 0);
-            tc::tc_fence_after();
-            if (dbg && leader) dbg[2] = clock64();
-            const uint32_t a_hi0 = desc_lo(tc::smem_u32(a_ring), 16);
-            const uint32_t a_lo0 = a_hi0 + (a_plane_bytes >> 4);
-            for (int t = 0; t < p.MT; ++t) {
-                const uint32_t d = tmem_u + (uint32_t)(t * p.tm_stride);
-                for (int j = 0; j < taps_per_group; ++j, ++b_it) {            // tb == 1 in this mode
-                    const int bs = b_it % p.b_stages;
-                    mbar_wait_safe(&b_full[bs], (b_it / p.b_stages) & 1);
-                    tc::tc_fence_after();
-                    if (dbg && b_it == 0 && leader) dbg[3] = clock64();
-                    const int khl = j / p.KW, kw = j - khl * p.KW;
-                    const uint32_t off = (uint32_t)(khl * tap_rows + kw) * (ROW_BYTES >> 4) + (uint32_t)t * tile_lo;
-                    const uint32_t bh = desc_lo(tc::smem_u32(b_ring + (size_t)bs * b_stage_bytes), 16);
-                    const uint32_t bl = bh + (b_plane_bytes >> 4);
-                    if (leader) {
-                        if (stacked) {
-                            if (j == 0) mma_tap_stacked<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2, ahi);
-                            else mma_tap_stacked<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, idesc, idesc2, ahi);
-                        } else if (j == 0) mma_tap<NPROD, 1>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc, ahi);
-                        else mma_tap<NPROD, 0>(d, a_hi0 + off, a_lo0 + off, bh, bl, idesc, ahi);
-                        tc::tc_commit(&b_empty[bs]);
-                    }
-                }
-                if (leader) tc::tc_commit(&tmem_full[t]);             // tile t complete: its epilogue overlaps the next tile's MMAs
-            }
-            if (dbg && leader) dbg[4] = clock64();
-        } else {
+        {
             for (int g = 0; g < p.n_groups; ++g) {
                 const int as = g % p.a_stages;
                 mbar_wait_safe(&a_full[as], (g / p.a_stages) & 1);
@@ -369,7 +341,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             for (int ch = 0; ch < nchunks; ++ch, ++item) {
                 if ((item & 1) != half) continue;
                 if (!waited) {
-                    mbar_wait_safe(&tmem_full[p.tile_outer ? t : 0], 0);
+                    mbar_wait_safe(&tmem_full[0], 0);
                     tc::tc_fence_after();
                     waited = true;
                     if (dbg && e == 0 && lane == 0 && t == 0) dbg[5] = clock64();
@@ -626,12 +598,8 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
             while (a_stages > 2 && a_stages * a_stage_b + b_min + 4096 > budget) --a_stages;
             const size_t a_bytes = (size_t)a_stages * a_stage_b;
             // B ring: one tap per stage, 4..2 deep (deepest that fits) — or one kernel row of taps per stage, 2 deep, when the
-            // tap tile is small and the kernel rows are streamed.  tile_outer (whole halo resident): the epilogue of one tile runs while
-            // the next tile's MMAs read the rings, so its staging area is separate; otherwise it aliases the (drained) rings.
+            // tap tile is small and the kernel rows are streamed.  The epilogue staging area aliases the (drained) rings.
             const int taps_per_group = G * KW;
-            // tile_outer measured slower on B200 (profiles/r01/flat_timeline_v3.log): with the taps re-streamed per tile a B stage feeds
-            // only 12 MMAs and the 3-deep ring cannot cover the L2 round trip (90 cycles/MMA vs 63 with the taps outermost, where a
-            // stage feeds MT x 12 MMAs); the epilogue it would hide is ~2 us.  Kept in the kernel for geometries with many tiles per CTA.
             const int tile_outer = 0;
             const size_t tap_bytes = (size_t)b_planes * pl.n_tile * ROW_BYTES;
             int tb = 1, b_stages = 0, ring_bytes = 0, stg_off = 0, bar_off = 0;

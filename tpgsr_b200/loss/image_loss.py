@@ -31,7 +31,16 @@ class GradientPriorLoss(nn.Module):
     """mean |gm(out) - gm(target)| with gm = central-difference gradient magnitude (loss/image_loss.py:33-51)."""
 
     def forward(self, out_images, target_images):
-        return _ImageLossFn.apply(out_images, target_images, True, 0.0, 1.0)
+        # the reference applies the gradient map to EVERY channel of what it is given (ImageLoss hands it out[:, :3]); the kernel's
+        # gradient term covers up to three channels per call, so wider inputs are walked in groups of three (weighted back to one mean)
+        C = out_images.shape[1]
+        if C <= 3:
+            return _ImageLossFn.apply(out_images, target_images, True, 0.0, 1.0)
+        total = 0.0
+        for a in range(0, C, 3):
+            b = min(a + 3, C)
+            total = total + _ImageLossFn.apply(out_images[:, a:b], target_images[:, a:b], True, 0.0, 1.0) * ((b - a) / C)
+        return total
 
 
 class ImageLoss(nn.Module):
