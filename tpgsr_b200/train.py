@@ -171,9 +171,11 @@ class TPGSRTrainStep:
         self._g_opt = None
         # packed weight operands persist across steps (ops.PackStore): SR model and students are refreshed by one launch each after Adam,
         # the frozen teacher's are computed once
-        self.packs = {}
+        # the frozen teacher's packed weights are computed ONCE and kept (a PackStore that the optimiser never refreshes; call
+        # refresh_packs() after changing the teacher's parameters from outside)
+        self.packs = {'teacher': ops.PackStore()}
         if ops.PREPACK:
-            self.packs = {'teacher': ops.PackStore(), 'sr': ops.PackStore()}
+            self.packs['sr'] = ops.PackStore()
             self.packs.update({('stu', i): ops.PackStore() for i in range(len(self.students))})
         ops.prime_workspaces(256 << 20, self.dev)
 
