@@ -19,7 +19,7 @@ synthetic U[0,1) crops 16x64 -> 32x128, random-init weights of the
   e2e       images/s through the public API with HOST (pinned) input buffers: H2D of LR+HR and D2H of the loss inside the timed
             region, every step
   roofline  the dominant TSRN conv (3x3 64->64, 11 of 18 conv launches per SR forward) timed live with CUDA events on the launch
-            stream, cold L2; achieved = algorithmic FLOPs / launch time vs MEASURED_PEAKS.json.  roofline_crnn: the dominant CRNN
+            stream, operands larger than L2 (rotating sets; the flushed single-launch figure is kept beside it); achieved = algorithmic FLOPs / launch time vs MEASURED_PEAKS.json.  roofline_crnn: the dominant CRNN
             conv (conv5 3x3 512->512 on 4x26 maps) the same way.
   cpu_baseline   the oracle port of the same step on the box's host cores (bounded sample), rank 0, N=1 only
   gpu_eager_baseline  developer leg: the same step in stock PyTorch (cuDNN / cuBLAS / ATen, TF32 off, eager autograd) on the same GPU
@@ -60,7 +60,7 @@ CONFIGS = {
 }
 
 # DRAM traffic per launch of the roofline kernels from the committed ncu --set full captures (profiles/r0*/): bytes read + written
-NCU_TRAFFIC_BYTES = {('conv_flat_kernel', 3): 13.77e6, ('conv_tc_kernel', 3): 12.81e6}
+NCU_TRAFFIC_BYTES = {('conv_flat_kernel', 3): 13.77e6, ('conv_tc_kernel', 3): 12.81e6}      # (conv_ws_kernel: filled in from profiles/r02 once captured)
 
 
 def _peaks():
@@ -236,36 +236,80 @@ def _time_launch(run, flush, n=20):
     return sum(durs) / len(durs), min(durs)
 
 
+def _time_stream(runs, reps=5):
+    """Average device time per launch of a CUDA graph that holds one launch per operand set (``runs``), replayed ``reps`` times: the sets
+    together are larger than twice the L2, so every launch finds its operands in HBM — 'inputs larger than L2' instead of a flush kernel
+    between launches (whose dirty lines the measured kernel then has to evict)."""
+    st = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        for r in runs:
+            r()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for r in runs:
+                r()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    durs = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        durs.append(e0.elapsed_time(e1) * 1e-3 / len(runs))
+    return sum(durs) / len(durs), min(durs)
+
+
 def time_conv_kernel(device, batch: int, H: int, W: int, Ci: int, Co: int, peaks, flush):
     """One 3x3 'same' conv forward on [batch,H,W,Ci] NHWC through the tensor-core path the engine picks for that geometry, in the active
-    CONV_MODE: CUDA-event timing on the launch stream (torch's current stream = the stream the C ABI is handed), L2 flushed between
-    launches.  achieved = ALGORITHMIC flops (2*M*N*K, one product — the 3 MMAs of split-bf16 are not counted three times) / launch time."""
+    CONV_MODE, CUDA-event timing on the launch stream (torch's current stream = the stream the C ABI is handed).  Two figures:
+    launch_us = average over a graph of back-to-back launches on rotating operand sets that together exceed 2x the L2 (how the kernel runs
+    inside the step: graph-launched, operands not L2-resident); launch_us_flushed = single launches behind an L2 flush kernel (round 1's
+    figure).  achieved = ALGORITHMIC flops (2*M*N*K, one product — the MMAs of split-bf16 are not counted three times) / launch_us."""
     from tpgsr_b200 import ops
-    x = torch.randn(batch, H, W, Ci, device=device)
+    need_lo = ops.CONV_MODE == 'bf16x3'
     w = torch.randn(Co, Ci, 3, 3, device=device) * 0.05
     b = torch.zeros(Co, device=device)
-    need_lo = ops.CONV_MODE == 'bf16x3'
     (wf, _) = ops.pack_conv_weights_bf16(w, False, need_lo)
-    y = torch.empty(batch, H, W, Co, device=device)
     flat = ops.flat_supported(batch, H, W, 1, Ci, Co, 3, 3, 1, 1)
-    if flat:
-        fp = ops.split_bf16_flat(x, 1, need_lo)
-        run = lambda: ops.conv_flat(fp, wf, b, Co, 3, 3, 1, 1, out=y)
-    else:
-        xp = ops.split_bf16(x, need_lo)
-        run = lambda: ops.conv_tc(xp, wf, b, batch, H, W, Ci, Co, 3, 3, 1, 1, out=y)
-    dur, dmin = _time_launch(run, flush)
+    set_bytes = batch * (H + 1) * (W + 1) * Ci * 2 * (2 if need_lo else 1) + batch * H * W * Co * 4
+    n_sets = max(4, -(-(2 * 126 << 20) // set_bytes))
+    runs = []
+    for i in range(n_sets):
+        x = torch.randn(batch, H, W, Ci, device=device)
+        y = torch.empty(batch, H, W, Co, device=device)
+        if flat:
+            fp = ops.split_bf16_flat(x, 1, need_lo)
+            runs.append(lambda fp=fp, y=y: ops.conv_flat(fp, wf, b, Co, 3, 3, 1, 1, out=y))
+        else:
+            xp = ops.split_bf16(x, need_lo)
+            runs.append(lambda xp=xp, y=y: ops.conv_tc(xp, wf, b, batch, H, W, Ci, Co, 3, 3, 1, 1, out=y))
+        del x
+    dur, dmin = _time_stream(runs)
+    dur_f, dmin_f = _time_launch(runs[0], flush)
     flops = 2.0 * batch * H * W * Co * Ci * 9
     ach = flops / dur / 1e12
     nprod = 3 if need_lo else 1
-    kname = 'conv_flat_kernel' if flat else 'conv_tc_kernel'
-    return {'bound': 'tensor', 'kernel': '%s<%d> (tcgen05+TMA implicit GEMM, 3x3, %d->%d, M=%d, N=%d, K=%d, mode %s)' % (
-                kname, nprod, Ci, Co, batch * H * W, Co, 9 * Ci, ops.CONV_MODE),
+    kname, mmas = ('conv_flat_kernel', nprod) if flat else ('conv_tc_kernel', nprod)
+    if flat:
+        import ctypes
+        from tpgsr_b200._lib import LIB
+        plan = (ctypes.c_int * 13)()
+        LIB.tpgsr_conv2d_flat_plan(batch, H, W, 1, Ci, Co, 3, 3, 1, 1, nprod, plan)
+        if plan[12] == 3:      # weights-stationary plan: [W_hi; W_lo] x (X_hi, X_lo) = four products
+            kname, mmas = 'conv_ws_kernel', 4
+    return {'bound': 'tensor', 'kernel': '%s<%d products> (tcgen05+TMA implicit GEMM, 3x3, %d->%d, M=%d, N=%d, K=%d, mode %s)' % (
+                kname, mmas, Ci, Co, batch * H * W, Co, 9 * Ci, ops.CONV_MODE),
             'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops_burst'],
             'traffic': NCU_TRAFFIC_BYTES.get((kname, nprod)) if (Ci, Co) == (64, 64) else None,
             'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/',
-            'launch_us': dur * 1e6, 'launch_us_min': dmin * 1e6, 'algorithmic_flops_per_launch': flops,
-            'mma_flops_per_launch': flops * nprod, 'tensor_pipe_tflops': ach * nprod,
+            'launch_us': dur * 1e6, 'launch_us_min': dmin * 1e6, 'launch_us_flushed': dur_f * 1e6, 'frac_flushed': flops / dur_f / 1e12 / peaks['tflops_burst'],
+            'timing': 'CUDA events around a graph of %d back-to-back launches on %d rotating operand sets (%d MB > 2x L2); *_flushed: single '
+                      'launches behind a 256 MB L2 flush' % (n_sets, n_sets, n_sets * set_bytes >> 20),
+            'algorithmic_flops_per_launch': flops, 'mma_flops_per_launch': flops * mmas, 'tensor_pipe_tflops': ach * mmas,
             'peak_source': peaks['source'] + ', bf16 burst (kernel timed alone)'}
 
 

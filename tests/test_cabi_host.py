@@ -136,6 +136,12 @@ def test_flat_conv_plans_fit_the_sm(nprod):
         smem = LIB.tpgsr_conv2d_flat_plan(B, H, W, P, Ci, Co, KH, KW, KH // 2, KW // 2, nprod, out)
         assert 0 < smem <= 227 * 1024, ((B, H, W, P, Ci, Co, KH, KW), smem)
         MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer = list(out)
+        if tile_outer == 3:      # weights-stationary plan (64 -> 64, 3..12 taps, three products): {NT, 64, 1, N, ...}; weights + 2 accumulators in TMEM
+            NT, N = MT, tm_stride
+            assert nprod == 3 and (Ci, Co) == (64, 64) and N in (64, 96) and KH * KW * 32 + 2 * N <= 512 and box_rows == N // 2
+            assert n_box <= 24 and n_box * box_rows >= NT * N + (KH - 1) * (W + P) + KW - 1      # the halo covers every tap of every tile
+            assert grid_x * NT * N >= B * (H + P) * (W + P)                                       # every flat output row belongs to a tile
+            continue
         assert 1 <= MT <= 3 and MT * tm_stride <= 512 and n_tile % 16 == 0 and n_tile <= 128 and tm_stride <= 256
         assert n_tile * n_tiles >= Co and box_rows % 8 == 0
         if tile_outer == 2:      # tall plan (KH x 1 kernels): MT tiles of 16 rows x 8 columns, one 4-D box [16 + KH - 1][8 MT] per plane
@@ -155,6 +161,10 @@ def test_flat_conv_plans_fit_the_sm(nprod):
     assert LIB.tpgsr_conv2d_flat_supported(48, 2, 27, 0, 512, 512, 2, 2, 0, 0, nprod)
     assert LIB.tpgsr_conv2d_flat_supported(48, 1, 26, 1, 512, 512, 2, 2, 1, 1, nprod)
     assert LIB.tpgsr_conv2d_flat_supported(48, 16, 64, 1, 64, 64, 3, 3, 0, 0, nprod)
+    # the bench shape of the dominant conv: one wave of 139 CTAs x 4 tiles of 96 pixels under the weights-stationary plan
+    out = (ctypes.c_int * 13)()
+    LIB.tpgsr_conv2d_flat_plan(48, 16, 64, 1, 64, 64, 3, 3, 1, 1, nprod, out)
+    assert (out[12] == 3 and out[0] == 4 and out[3] == 96 and out[11] == 139) if nprod == 3 else out[12] == 0
     for (B, H, W, P, Co, K) in [(48, 16, 64, 1, 64, 3), (48, 16, 64, 0, 192, 1), (48, 16, 64, 1, 256, 3), (48, 32, 128, 4, 36, 9)]:
         out = (ctypes.c_int * 9)()
         cpad = (Co + 63) // 64 * 64

@@ -478,6 +478,335 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
 }
 
+// ============================================================================================================ weights-stationary plan
+// 3x3 (up to 12 taps) 64 -> 64 convolutions, forward and data gradient: the dominant kernel of the TSRN (11 of 18 convs per SR pass).
+// The plans above keep the PIXELS on the M side and stream the weights through shared memory once per CTA; with N = 64 outputs the MMA
+// phase is bound by shared-memory operand reads (14 KB per K step) and the load / MMA / store phases of a CTA cannot overlap because the
+// 144 KB of split weights do not fit beside the halo (tile-outer order re-streams them and becomes L2-bound).
+// Here the GEMM is transposed:  D^T[co][pixel] = W[co][k] * X^T[k][pixel]
+//   * A = the split weights, RESIDENT IN TENSOR MEMORY for the whole CTA: lanes 0..63 = W_hi rows, lanes 64..127 = W_lo rows,
+//     KH*KW*32 columns (two bf16 per 32-bit cell).  Loaded once from L2 by the epilogue warps (tcgen05.st) while the TMA fetches the halo.
+//   * B = the pixel halo in shared memory exactly as before (one 128-byte row per pixel, SWIZZLE_128B, tap = row offset), N = 96 or 64
+//     pixels per MMA.  Shared-memory operand traffic per K step drops to N x 32 bytes (64 B/cycle at the tensor rate).
+//   * two MMAs per K step (X_hi, X_lo) against the stacked [W_hi; W_lo] give all FOUR partial products; out[co] = D[co] + D[co + 64].
+//   * the accumulator is double buffered (2 x N columns beside the weights: 288 + 192 = 480 of 512 columns for a 3x3), the MMA warp
+//     runs tile after tile, the halo arrives in per-box barriers, and the 8 epilogue warps drain tile t while tile t + 1 is multiplied.
+constexpr int WS_MAXBOX = 24;
+
+struct WsParams {
+    int Hp, Wp, Ho, Wo;
+    long long Qtot;
+    int Co, KH, KW, ph, pw;
+    int NT;                    // pixel tiles per CTA
+    int box_rows, n_box;       // halo = n_box TMA boxes of box_rows rows per plane, one mbarrier each
+    int w_stages;              // depth of the weight staging ring of the prologue (one 16 KB tap per stage)
+    int K;                     // KH*KW*64
+    int stg_off, bar_off;
+    int ldy, act, accumulate;
+    const float* bias;
+    const float* act_param;
+    float* y;
+    __nv_bfloat16* yp_hi;
+    __nv_bfloat16* yp_lo;
+    const __nv_bfloat16* w_hi; // packed K-major weights [64][K]
+    const __nv_bfloat16* w_lo;
+    long long* dbg;
+};
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {              // 32 lanes x 16 consecutive columns
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+template <int ACC>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "n"(ACC), "r"(DESC_HI)
+        : "memory");
+}
+
+constexpr int WS_WSTAGES = 9;         // most stages of the weight staging ring: one tap (hi + lo tile, 16 KB) per stage; the ring starts in the
+                                      // epilogue staging area and takes whatever shared memory the halo leaves (plan: w_stages >= 3)
+constexpr int WS_MAXTAPS = 12;
+
+template <int N, int TAPS>      // TAPS: compile-time tap count with a fully unrolled issue sequence (9 = 3x3), 0 = any
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+conv_ws_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, WsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int NH = N / 2;          // pixels (TMEM columns) an epilogue warp reads per tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int plane_bytes = p.n_box * p.box_rows * ROW_BYTES;
+    uint8_t* halo = smem;                                          // [hi plane][lo plane]
+    uint8_t* stg = smem + p.stg_off;                               // prologue: weight ring; afterwards: T_hi [N][64], T_lo [N][64] floats
+    uint64_t* box_bar = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+    uint64_t* w_full = box_bar + WS_MAXBOX;                        // [WS_WSTAGES]
+    uint64_t* w_empty = w_full + WS_WSTAGES;
+    uint64_t* w_tap = w_empty + WS_WSTAGES;                        // [WS_MAXTAPS]: tap k of the weights is in tensor memory
+    uint64_t* acc_full = w_tap + WS_MAXTAPS;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    int* pixtab = reinterpret_cast<int*>(tmem_slot + 2);           // [N] dense pixel index of the current tile's rows (-1: dropped)
+
+    const long long q0 = (long long)blockIdx.x * p.NT * N;        // first flat output row of this CTA
+    int nt = (int)((p.Qtot - q0 + N - 1) / N);                     // tiles with at least one row inside the planes
+    nt = nt > p.NT ? p.NT : nt;
+    const int taps = p.KH * p.KW;
+    const int w_cols = taps * 32;
+    const int rot = blockIdx.x % taps;                             // this CTA's first weight tap
+    int nb = (nt * N + (p.KH - 1) * p.Wp + p.KW - 1 + p.box_rows - 1) / p.box_rows;
+    nb = nb > p.n_box ? p.n_box : nb;
+    long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;      // developer timeline: 32 slots per CTA (scripts/ws_timeline.py)
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmX_hi);
+        tc::prefetch_tmap(&tmX_lo);
+        tc::prefetch_tmap(&tmW_hi);
+        tc::prefetch_tmap(&tmW_lo);
+        for (int s = 0; s < WS_MAXBOX; ++s) tc::mbar_init(&box_bar[s], 1);
+        for (int s = 0; s < WS_WSTAGES; ++s) { tc::mbar_init(&w_full[s], 1); tc::mbar_init(&w_empty[s], EPI_WARPS); }
+        for (int s = 0; s < WS_MAXTAPS; ++s) tc::mbar_init(&w_tap[s], EPI_WARPS);
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], EPI_WARPS); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer: weight taps through the ring, the halo box after box.  Order = what tile 0 needs first.
+            // Every CTA needs the same 144 KB of weights at the same moment: CTA i starts with tap i % taps, so that concurrent CTAs pull
+            // different tiles through L2 (measured neutral: the prologue is bound by L2 -> SM throughput, profiles/r02/ws_timeline_history.md).
+            const long long row0 = q0 - (long long)p.ph * p.Wp - p.pw;
+            int bx = 0;
+            const int early = (N + (p.KH - 1) * p.Wp + p.KW - 1 + p.box_rows - 1) / p.box_rows;      // boxes tile 0 reads
+            for (int i = 0, k = rot; i < taps; ++i, k = (k + 1 == taps ? 0 : k + 1)) {
+                const int s = i % p.w_stages;
+                mbar_wait_safe(&w_empty[s], ((i / p.w_stages) & 1) ^ 1);
+                tc::mbar_expect_tx(&w_full[s], 2 * 64 * ROW_BYTES);
+                tc::tma_load_2d(stg + (size_t)s * 2 * 64 * ROW_BYTES, &tmW_hi, &w_full[s], k * 64, 0);
+                tc::tma_load_2d(stg + (size_t)s * 2 * 64 * ROW_BYTES + 64 * ROW_BYTES, &tmW_lo, &w_full[s], k * 64, 0);
+                if (i == 0) {
+                    for (; bx < early && bx < nb; ++bx) {
+                        tc::mbar_expect_tx(&box_bar[bx], (uint32_t)(2 * p.box_rows * ROW_BYTES));
+                        const int r = (int)(row0 + (long long)bx * p.box_rows);
+                        tc::tma_load_2d(halo + (size_t)bx * p.box_rows * ROW_BYTES, &tmX_hi, &box_bar[bx], 0, r);
+                        tc::tma_load_2d(halo + plane_bytes + (size_t)bx * p.box_rows * ROW_BYTES, &tmX_lo, &box_bar[bx], 0, r);
+                    }
+                }
+            }
+            for (; bx < nb; ++bx) {
+                tc::mbar_expect_tx(&box_bar[bx], (uint32_t)(2 * p.box_rows * ROW_BYTES));
+                const int r = (int)(row0 + (long long)bx * p.box_rows);
+                tc::tma_load_2d(halo + (size_t)bx * p.box_rows * ROW_BYTES, &tmX_hi, &box_bar[bx], 0, r);
+                tc::tma_load_2d(halo + plane_bytes + (size_t)bx * p.box_rows * ROW_BYTES, &tmX_lo, &box_bar[bx], 0, r);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (loops warp-uniform, no divisions per tap: an N = 96 MMA is 48 tensor cycles) =================
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+        const bool leader = elect_one();
+        const uint32_t idesc = tc::idesc_bf16(128, N, 0, 0);
+        const uint32_t x_hi0 = desc_lo(tc::smem_u32(halo), 16);
+        const uint32_t x_lo0 = x_hi0 + (plane_bytes >> 4);
+        int boxes_ready = 0;
+        const int kh0 = rot / p.KW, kw0 = rot - kh0 * p.KW;
+        uint32_t tap_off[TAPS > 0 ? TAPS : 1], tap_col[TAPS > 0 ? TAPS : 1];      // per tap (rotated order): B row offset in descriptor units, A column
+        if (TAPS > 0) {
+            int k = rot, kh = kh0, kw = kw0;
+#pragma unroll
+            for (int i = 0; i < (TAPS > 0 ? TAPS : 1); ++i) {
+                tap_off[i] = (uint32_t)(kh * p.Wp + kw) * (ROW_BYTES >> 4);
+                tap_col[i] = (uint32_t)(k * 32);
+                ++k; ++kw;
+                if (kw == p.KW) { kw = 0; ++kh; }
+                if (k == taps) { k = 0; kh = 0; kw = 0; }
+            }
+        }
+        for (int t = 0; t < nt; ++t) {
+            const int buf = t & 1;
+            mbar_wait_safe(&acc_empty[buf], ((t >> 1) & 1) ^ 1);
+            int need = (t * N + (p.KH - 1) * p.Wp + p.KW - 1 + N - 1) / p.box_rows;      // last halo box this tile reads
+            need = need >= nb ? nb - 1 : need;
+            while (boxes_ready <= need) {
+                mbar_wait_safe(&box_bar[boxes_ready], 0);
+                ++boxes_ready;
+                if (dbg && leader && boxes_ready == 1) dbg[2] = clock64();
+            }
+            tc::tc_fence_after();
+            const uint32_t d = tmem_u + (uint32_t)(w_cols + buf * N);
+            if (TAPS > 0 && t > 0) {
+                // straight-line issue: 8 TAPS MMAs with precomputed operand offsets.  (The looped form below costs ~150-190 cycles of
+                // address arithmetic and branches per tap and the tensor pipe does not queue deep enough to hide it: 66 instead of
+                // 48 cycles per MMA, profiles/r02/ws_timeline_history.md.)
+                if (leader) {
+                    const uint32_t base_h = x_hi0 + (uint32_t)(t * N) * (ROW_BYTES >> 4), base_l = x_lo0 + (uint32_t)(t * N) * (ROW_BYTES >> 4);
+#pragma unroll
+                    for (int i = 0; i < (TAPS > 0 ? TAPS : 1); ++i) {
+                        const uint32_t bh = base_h + tap_off[i], bl = base_l + tap_off[i], a = tmem_u + tap_col[i];
+                        if (i == 0) umma_ts<0>(d, a, bh, idesc); else umma_ts<1>(d, a, bh, idesc);
+                        umma_ts<1>(d, a, bl, idesc);
+#pragma unroll
+                        for (int kk = 1; kk < 4; ++kk) {
+                            umma_ts<1>(d, a + 8 * kk, bh + 2 * kk, idesc);
+                            umma_ts<1>(d, a + 8 * kk, bl + 2 * kk, idesc);
+                        }
+                    }
+                }
+                if (leader) tc::tc_commit(&acc_full[buf]);
+                if (dbg && leader && t < 4) dbg[4 + t] = clock64();
+                continue;
+            }
+            // taps in this CTA's rotated order (the order its weights arrive in); no divisions inside the loop
+            int k = rot, kh = kh0, kw = kw0;
+            for (int i = 0; i < taps; ++i) {
+                if (t == 0) {
+                    mbar_wait_safe(&w_tap[k], 0);
+                    tc::tc_fence_after();
+                    if (dbg && leader && i == taps - 1) dbg[3] = clock64();
+                }
+                if (leader) {
+                    const uint32_t off = (uint32_t)(t * N + kh * p.Wp + kw) * (ROW_BYTES >> 4);
+                    const uint32_t bh = x_hi0 + off, bl = x_lo0 + off;
+                    const uint32_t a = tmem_u + (uint32_t)(k * 32);
+                    if (i == 0) umma_ts<0>(d, a, bh, idesc); else umma_ts<1>(d, a, bh, idesc);
+                    umma_ts<1>(d, a, bl, idesc);
+#pragma unroll
+                    for (int kk = 1; kk < 4; ++kk) {                       // 16 K elements = 8 TMEM columns of A = 32 bytes of the B rows
+                        umma_ts<1>(d, a + 8 * kk, bh + 2 * kk, idesc);
+                        umma_ts<1>(d, a + 8 * kk, bl + 2 * kk, idesc);
+                    }
+                }
+                ++k; ++kw;
+                if (kw == p.KW) { kw = 0; ++kh; }
+                if (k == taps) { k = 0; kh = 0; kw = 0; }
+            }
+            if (leader) tc::tc_commit(&acc_full[buf]);
+            if (dbg && leader && t < 4) dbg[4 + t] = clock64();
+        }
+    } else {
+        // ================= warps 2..9: weights -> TMEM, then the epilogue =================
+        const int qq = warp & 3;                       // TMEM lane quarter this warp may access: lanes 32 qq ..
+        const int half = (warp - 2) >> 2;              // which half of a tile's pixel columns / of a tap's weight columns
+        const bool is_lo = qq >= 2;                    // lanes 64..127 hold the W_lo rows / their partial sums
+        const int co = (qq & 1) * 32 + lane;           // output channel of this thread
+        const int et = threadIdx.x - 64;               // 0..255 among the epilogue threads
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(qq * 32) << 16);
+        for (int i = 0, k = rot; i < taps; ++i, k = (k + 1 == taps ? 0 : k + 1)) {
+            // one tap = [64 co][64 ci] bf16 per plane in the ring (SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)); this
+            // thread moves 64 bytes (32 K elements = 16 TMEM columns) of its weight row
+            const int s = i % p.w_stages;
+            mbar_wait_safe(&w_full[s], (i / p.w_stages) & 1);
+            const uint8_t* row = stg + (size_t)s * 2 * 64 * ROW_BYTES + (is_lo ? 64 * ROW_BYTES : 0) + co * ROW_BYTES;
+            uint4 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const uint4*>(row + (((4 * half + j) ^ (co & 7)) << 4));
+            tmem_st_32x16(lane_addr + (uint32_t)(k * 32 + 16 * half), reinterpret_cast<const uint32_t*>(w));
+            tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(&w_empty[s]); tc::mbar_arrive(&w_tap[k]); }
+        }
+        named_bar_sync(1, EPI_WARPS * 32);            // every warp is done with the ring: the area becomes the output staging tile
+        float* T_hi = reinterpret_cast<float*>(stg);
+        float* T_lo = T_hi + N * 64;
+        const float slope = (p.act == TPGSR_ACT_PRELU && p.act_param) ? __ldg(p.act_param) : 0.f;
+        const float bias = (p.bias && !is_lo) ? __ldg(p.bias + co) : 0.f;
+        const unsigned img = (unsigned)(p.Hp * p.Wp);
+        const unsigned qtot = (unsigned)p.Qtot;
+        float* T_mine = (is_lo ? T_lo : T_hi) + (half * NH) * 64 + co;
+        for (int t = 0; t < nt; ++t) {
+            const int buf = t & 1;
+            mbar_wait_safe(&acc_full[buf], (t >> 1) & 1);
+            tc::tc_fence_after();
+            if (dbg && warp == 2 && lane == 0 && t < 4) dbg[8 + t] = clock64();
+            float v[NH];
+            const uint32_t taddr = lane_addr + (uint32_t)(w_cols + buf * N + half * NH);
+#pragma unroll
+            for (int c = 0; c < NH / 16; ++c) tmem_ld_32x16(taddr + 16 * c, v + 16 * c);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);           // the accumulator is in registers: the MMA warp may overwrite it
+            if (dbg && warp == 2 && lane == 0 && t < 4) dbg[12 + t] = clock64();
+            if (t > 0) named_bar_sync(1, EPI_WARPS * 32);               // the previous tile has left the staging tile
+            // transposed store: thread = channel, one row of T per pixel (32 lanes -> 32 consecutive floats: conflict-free)
+#pragma unroll
+            for (int j = 0; j < NH; ++j) T_mine[j * 64] = v[j] + bias;
+            if (et < N) {                                               // dense pixel index of tile row et (-1 = pad position / beyond the last image)
+                const unsigned qrow = (unsigned)q0 + (unsigned)(t * N + et);
+                const unsigned ub = qrow / img, rem = qrow - ub * img;
+                const unsigned ur = rem / (unsigned)p.Wp, uc = rem - ur * (unsigned)p.Wp;
+                pixtab[et] = (qrow < qtot && (int)ur < p.Ho && (int)uc < p.Wo) ? ((int)ub * p.Ho + (int)ur) * p.Wo + (int)uc : -1;
+            }
+            named_bar_sync(1, EPI_WARPS * 32);
+            if (dbg && warp == 2 && lane == 0 && t < 4) dbg[16 + t] = clock64();
+            // out = act(T_hi + T_lo): 16 float4 per pixel row, a thread takes every 256th float4 (coalesced 512 bytes per warp)
+#pragma unroll
+            for (int i = 0; i < N * 16 / (EPI_WARPS * 32); ++i) {
+                const int f = et + i * (EPI_WARPS * 32);
+                const int px = pixtab[f >> 4];
+                const float4 a4 = *reinterpret_cast<const float4*>(T_hi + 4 * f);
+                const float4 b4 = *reinterpret_cast<const float4*>(T_lo + 4 * f);
+                if (px < 0) continue;
+                float4 val = make_float4(a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w);
+                if (p.act != TPGSR_ACT_NONE) {
+                    val.x = apply_act(val.x, p.act, slope); val.y = apply_act(val.y, p.act, slope);
+                    val.z = apply_act(val.z, p.act, slope); val.w = apply_act(val.w, p.act, slope);
+                }
+                const int c4 = (f & 15) * 4;
+                float4* dst = reinterpret_cast<float4*>(p.y + (size_t)px * p.ldy + c4);
+                if (p.accumulate) {
+                    const float4 o = *dst;
+                    val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                }
+                *dst = val;
+                if (p.yp_hi) {
+                    const float fv[4] = {val.x, val.y, val.z, val.w};
+                    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        h[u] = __float2bfloat16_rn(fv[u]);
+                        l[u] = __float2bfloat16_rn(fv[u] - __bfloat162float(h[u]));
+                    }
+                    const size_t po = (size_t)px * p.Co + c4;
+                    *reinterpret_cast<uint2*>(p.yp_hi + po) = *reinterpret_cast<uint2*>(h);
+                    if (p.yp_lo) *reinterpret_cast<uint2*>(p.yp_lo + po) = *reinterpret_cast<uint2*>(l);
+                }
+            }
+            if (dbg && warp == 2 && lane == 0 && t < 4) dbg[20 + t] = clock64();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[24] = clock64();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // fp32 dense NHWC [B,H,W,C] (pixel pitch ldx) -> padded-flat bf16 hi/lo planes [B][H+P][W+P][Cout] (pads and channels >= C zero)
 __global__ void __launch_bounds__(256)
 split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int B,
@@ -637,6 +966,57 @@ int plan_flat_for(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, in
 // 26.4 us for the 3x3 64->64 conv, step time unchanged, profiles/r02/call1_stdout.log.)
 int plan_flat(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, FlatPlan& pl) {
     return plan_flat_for(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 226 * 1024, 512, 148, pl);
+}
+
+struct WsPlan {
+    int N, NT, box_rows, n_box, w_stages, stg_off, bar_off, grid;
+    size_t smem;
+};
+int g_flat_no_ws = 0;       // developer switch (debug bit 4): disable the weights-stationary plan (A/B measurements, cross-check tests)
+
+// weights-stationary plan (conv_ws_kernel): split-bf16, exactly 64 -> 64 channels, 3..12 taps, NHWC output
+int plan_ws(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, size_t budget, int slots, WsPlan& pl) {
+    if (g_flat_no_ws || nprod != 3 || Ci != 64 || Co != 64 || B < 1 || H < 1 || W < 1) return TPGSR_ERR_UNSUPPORTED;
+    const int taps = KH * KW;
+    if (taps < 3 || taps > 12) return TPGSR_ERR_UNSUPPORTED;
+    if (KW == 1 && KH >= 5) return TPGSR_ERR_UNSUPPORTED;      // tall kernels: the taps share nothing in the flat row order — the tall plan's 2-D tile is the right shape
+    if (ph < 0 || ph >= KH || pw < 0 || pw >= KW || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
+    if (H + 2 * ph - KH + 1 < 1 || W + 2 * pw - KW + 1 < 1 || H + 2 * ph - KH + 1 > H + P || W + 2 * pw - KW + 1 > W + P) return TPGSR_ERR_UNSUPPORTED;
+    const int Wp = W + P;
+    const long long Qtot = (long long)B * (H + P) * Wp;
+    if (Qtot + 4096 >= (1LL << 31)) return TPGSR_ERR_UNSUPPORTED;
+    long long best = -1;
+    const int cand[2] = {96, 64};
+    for (int ci = 0; ci < 2; ++ci) {
+        const int N = cand[ci];
+        if (taps * 32 + 2 * N > 512) continue;
+        const long long target = (Qtot + slots - 1) / slots;          // rows per CTA if the whole job were one wave
+        int NT = (int)((target + N - 1) / N);
+        const size_t tap_bytes = (size_t)2 * 64 * ROW_BYTES;
+        size_t stg = (size_t)2 * N * 64 * 4;                             // output staging T_hi, T_lo [N][64] floats ...
+        if (stg < 3 * tap_bytes) stg = 3 * tap_bytes;                    // ... aliasing the weight ring of the prologue (at least 3 taps deep)
+        int n_box = 0;
+        size_t smem = 0;
+        for (; NT >= 1; --NT) {
+            const int rows = NT * N + (KH - 1) * Wp + KW - 1;
+            n_box = (rows + N / 2 - 1) / (N / 2);
+            smem = (size_t)2 * n_box * (N / 2) * ROW_BYTES + stg + 1024 /*barriers + pixel table*/ + 1024 /*align*/;
+            if (n_box <= WS_MAXBOX && smem <= budget) break;
+        }
+        if (NT < 1) continue;
+        const long long grid = (Qtot + (long long)NT * N - 1) / ((long long)NT * N);
+        const long long cost = ((grid + slots - 1) / slots) * NT * N;
+        if (best >= 0 && cost >= best) continue;
+        best = cost;
+        // the weight ring takes the shared memory the halo leaves (up to one stage per tap)
+        int w_stages = (int)((budget - (smem - stg)) / tap_bytes);
+        w_stages = w_stages > taps ? taps : w_stages;
+        w_stages = w_stages > WS_WSTAGES ? WS_WSTAGES : w_stages;
+        if ((size_t)w_stages * tap_bytes > stg) { smem += (size_t)w_stages * tap_bytes - stg; stg = (size_t)w_stages * tap_bytes; }
+        pl.N = N; pl.NT = NT; pl.box_rows = N / 2; pl.n_box = n_box; pl.grid = (int)grid; pl.w_stages = w_stages;
+        pl.stg_off = 2 * n_box * (N / 2) * ROW_BYTES; pl.bar_off = pl.stg_off + (int)stg; pl.smem = smem;
+    }
+    return best >= 0 ? TPGSR_OK : TPGSR_ERR_UNSUPPORTED;
 }
 
 // ============================================================================================================ weight gradient
@@ -868,17 +1248,26 @@ int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int 
 
 // developer instrumentation: per-CTA clock64 timestamps of the next conv_flat launches are written to dbg[grid][16]
 int tpgsr_conv2d_flat_set_debug(long long* dbg) { g_flat_dbg = dbg; return TPGSR_OK; }
-// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes; bit 3: no tall plan
+// bits 0-1: skip phases (timeline experiments); bit 2: no N-stacking of the weight planes; bit 3: no tall plan; bit 4: no weights-stationary plan
 int tpgsr_conv2d_flat_set_debug_skip(int bits) {
     g_flat_dbg_skip = bits & 3;
     g_flat_no_nstack = (bits >> 2) & 1;
     g_flat_no_tall = (bits >> 3) & 1;
+    g_flat_no_ws = (bits >> 4) & 1;
     return TPGSR_OK;
 }
 
 // tiling decided for a geometry (host-only; lets tests / docs inspect the plan without a GPU):
 // out[13] = {MT, n_tile, n_tiles, tm_stride, G, n_groups, a_stages, box_rows, n_box, tb, b_stages, grid_x, tile_outer}; returns smem bytes (0 = unsupported)
 size_t tpgsr_conv2d_flat_plan(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, int* out) {
+    WsPlan ws;
+    if (plan_ws(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 226 * 1024, 148, ws) == TPGSR_OK) {      // mode 3: {NT, 64, 1, N, KH, 1, 1, box_rows, n_box, 0, 0, grid, 3}
+        if (out) {
+            const int v[13] = {ws.NT, 64, 1, ws.N, KH, 1, 1, ws.box_rows, ws.n_box, 0, 0, ws.grid, 3};
+            for (int i = 0; i < 13; ++i) out[i] = v[i];
+        }
+        return ws.smem;
+    }
     FlatPlan pl;
     if (plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl)) return 0;
     if (out) {
@@ -922,6 +1311,29 @@ int tpgsr_conv2d_flat_planes(const void* x_hi, const void* x_lo, const void* w_h
     if (!x_hi || !w_hi || !y || nprod < 1 || nprod > 3 || (nprod == 3 && !x_lo) || (nprod >= 2 && !w_lo)) return TPGSR_ERR_BAD_ARG;
     if (yp_hi && (Co % 32 != 0 || out_mode != TPGSR_OUT_NHWC || ((ldy > 0 ? ldy : Co) & 3) || (act != TPGSR_ACT_NONE && act != TPGSR_ACT_RELU)))
         return TPGSR_ERR_UNSUPPORTED;
+    WsPlan ws;
+    if (out_mode == TPGSR_OUT_NHWC && ((ldy > 0 ? ldy : Co) & 3) == 0 && plan_ws(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, 226 * 1024, 148, ws) == TPGSR_OK) {
+        WsParams q;
+        q.Hp = H + P; q.Wp = W + P; q.Ho = H + 2 * ph - KH + 1; q.Wo = W + 2 * pw - KW + 1; q.Qtot = (long long)B * q.Hp * q.Wp;
+        q.Co = Co; q.KH = KH; q.KW = KW; q.ph = ph; q.pw = pw; q.NT = ws.NT; q.box_rows = ws.box_rows; q.n_box = ws.n_box; q.w_stages = ws.w_stages; q.K = KH * KW * 64;
+        q.stg_off = ws.stg_off; q.bar_off = ws.bar_off; q.ldy = ldy > 0 ? ldy : Co; q.act = act; q.accumulate = accumulate;
+        q.bias = bias; q.act_param = act_param; q.y = y; q.yp_hi = static_cast<__nv_bfloat16*>(yp_hi); q.yp_lo = static_cast<__nv_bfloat16*>(yp_lo);
+        q.w_hi = static_cast<const __nv_bfloat16*>(w_hi); q.w_lo = static_cast<const __nv_bfloat16*>(w_lo); q.dbg = g_flat_dbg;
+        CUtensorMap tmX_hi, tmX_lo;
+        uint64_t xd[2] = {64, (uint64_t)q.Qtot};
+        uint64_t xs[1] = {128};
+        uint32_t xb[2] = {64, (uint32_t)ws.box_rows};
+        if (tpgsr_make_tmap_bf16(&tmX_hi, x_hi, 2, xd, xs, xb) || tpgsr_make_tmap_bf16(&tmX_lo, x_lo, 2, xd, xs, xb)) return TPGSR_ERR_DRIVER;
+        CUtensorMap tmW_hi, tmW_lo;
+        uint64_t wd[2] = {(uint64_t)q.K, 64};
+        uint64_t wst[1] = {(uint64_t)q.K * 2};
+        uint32_t wb[2] = {64, 64};
+        if (tpgsr_make_tmap_bf16(&tmW_hi, w_hi, 2, wd, wst, wb) || tpgsr_make_tmap_bf16(&tmW_lo, w_lo, 2, wd, wst, wb)) return TPGSR_ERR_DRIVER;
+        auto kern = ws.N == 96 ? (KH * KW == 9 ? conv_ws_kernel<96, 9> : conv_ws_kernel<96, 0>) : (KH * KW == 9 ? conv_ws_kernel<64, 9> : conv_ws_kernel<64, 0>);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.smem) != cudaSuccess) return TPGSR_ERR_LAUNCH;
+        kern<<<ws.grid, FWD_THREADS, ws.smem, stream>>>(tmX_hi, tmX_lo, tmW_hi, tmW_lo, q);
+        return tpgsr_launch_status();
+    }
     FlatPlan pl;
     int rc = plan_flat(B, H, W, P, Ci, Co, KH, KW, ph, pw, nprod, pl);
     if (rc) return rc;

@@ -84,7 +84,7 @@ image_loss_bwd_kernel(const float* __restrict__ o, const float* __restrict__ tg,
     const long total = (long)B * C * H * W;
     const float up = (upstream ? __ldg(upstream) : 1.f) * scale;
     const float k_mse = up * w0 * 2.f / (float)total;
-    const float k_gp = up * w1 / (float)((long)B * 3 * H * W);
+    const float k_gp = up * w1 / (float)((long)B * (C < 3 ? C : 3) * H * W);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         int w = (int)(i % W);
         long q = i / W;

@@ -285,8 +285,10 @@ FUSE_GRU_PROJ = os.environ.get('TPGSR_FUSE_GRU_PROJ', 'infer')
 
 # developer A/B switch: TPGSR_FLAT_TALL=0 disables the tall plan of the flat convs (KH x 1 kernels: the kw-stacked 9x9 convs)
 FLAT_TALL = os.environ.get('TPGSR_FLAT_TALL', '1') != '0'
-if not FLAT_TALL:
-    LIB.tpgsr_conv2d_flat_set_debug_skip(8)
+# developer A/B switch: TPGSR_FLAT_WS=0 disables the weights-stationary plan (weights resident in tensor memory) of the 3x3 64 -> 64 convs
+FLAT_WS = os.environ.get('TPGSR_FLAT_WS', '1') != '0'
+if not (FLAT_TALL and FLAT_WS):
+    LIB.tpgsr_conv2d_flat_set_debug_skip((0 if FLAT_TALL else 8) | (0 if FLAT_WS else 16))
 
 
 class FlatPlanes:
