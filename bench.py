@@ -60,7 +60,8 @@ CONFIGS = {
 }
 
 # DRAM traffic per launch of the roofline kernels from the committed ncu --set full captures (profiles/r0*/): bytes read + written
-NCU_TRAFFIC_BYTES = {('conv_flat_kernel', 3): 13.77e6, ('conv_tc_kernel', 3): 12.81e6}      # (conv_ws_kernel: filled in from profiles/r02 once captured)
+NCU_TRAFFIC_BYTES = {('conv_flat_kernel', 3): 13.77e6, ('conv_tc_kernel', 3): 12.81e6,
+                     ('conv_ws_kernel', 3): 13.79e6}      # profiles/r02/ncu_full_conv_ws.csv: 13.79 MB read, 0 written back (the output stays in L2)
 
 
 def _peaks():

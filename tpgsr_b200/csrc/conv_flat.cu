@@ -600,7 +600,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
             // different tiles through L2 (measured neutral: the prologue is bound by L2 -> SM throughput, profiles/r02/ws_timeline_history.md).
             const long long row0 = q0 - (long long)p.ph * p.Wp - p.pw;
             int bx = 0;
-            const int early = (N + (p.KH - 1) * p.Wp + p.KW - 1 + p.box_rows - 1) / p.box_rows;      // boxes tile 0 reads
+            const int early = ((nt >= 2 ? 2 : 1) * N + (p.KH - 1) * p.Wp + p.KW - 1 + p.box_rows - 1) / p.box_rows;      // boxes the first pass (tiles 0, 1) reads
             for (int i = 0, k = rot; i < taps; ++i, k = (k + 1 == taps ? 0 : k + 1)) {
                 const int s = i % p.w_stages;
                 mbar_wait_safe(&w_empty[s], ((i / p.w_stages) & 1) ^ 1);
@@ -644,10 +644,12 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 if (k == taps) { k = 0; kh = 0; kw = 0; }
             }
         }
-        for (int t = 0; t < nt; ++t) {
-            const int buf = t & 1;
-            mbar_wait_safe(&acc_empty[buf], ((t >> 1) & 1) ^ 1);
-            int need = (t * N + (p.KH - 1) * p.Wp + p.KW - 1 + N - 1) / p.box_rows;      // last halo box this tile reads
+        // ---- first pass: tiles 0 and 1 together, tap after tap as the weights arrive.  The prologue is bound by L2 -> SM throughput
+        // (~7 000 cycles for the weights + the first boxes) and one tile of MMAs is 4 500 cycles: two tiles keep the tensor pipe busy
+        // through all of it, and both accumulators are free anyway (15.9 against 16.7 us per launch, profiles/r02/call16_stdout.log).
+        const int first = nt >= 2 ? 2 : 1;
+        {
+            int need = ((first - 1) * N + (p.KH - 1) * p.Wp + p.KW - 1 + N - 1) / p.box_rows;
             need = need >= nb ? nb - 1 : need;
             while (boxes_ready <= need) {
                 mbar_wait_safe(&box_bar[boxes_ready], 0);
@@ -655,11 +657,49 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 if (dbg && leader && boxes_ready == 1) dbg[2] = clock64();
             }
             tc::tc_fence_after();
+            int k = rot, kh = kh0, kw = kw0;
+            for (int i = 0; i < taps; ++i) {
+                mbar_wait_safe(&w_tap[k], 0);
+                tc::tc_fence_after();
+                if (dbg && leader && i == taps - 1) dbg[3] = clock64();
+                for (int u = 0; u < first; ++u) {
+                    if (leader) {
+                        const uint32_t d = tmem_u + (uint32_t)(w_cols + u * N);
+                        const uint32_t off = (uint32_t)(u * N + kh * p.Wp + kw) * (ROW_BYTES >> 4);
+                        const uint32_t bh = x_hi0 + off, bl = x_lo0 + off;
+                        const uint32_t a = tmem_u + (uint32_t)(k * 32);
+                        if (i == 0) umma_ts<0>(d, a, bh, idesc); else umma_ts<1>(d, a, bh, idesc);
+                        umma_ts<1>(d, a, bl, idesc);
+#pragma unroll
+                        for (int kk = 1; kk < 4; ++kk) {                   // 16 K elements = 8 TMEM columns of A = 32 bytes of the B rows
+                            umma_ts<1>(d, a + 8 * kk, bh + 2 * kk, idesc);
+                            umma_ts<1>(d, a + 8 * kk, bl + 2 * kk, idesc);
+                        }
+                        if (i == taps - 1) tc::tc_commit(&acc_full[u]);
+                    }
+                    if (dbg && leader && i == taps - 1) dbg[4 + u] = clock64();
+                }
+                ++k; ++kw;
+                if (kw == p.KW) { kw = 0; ++kh; }
+                if (k == taps) { k = 0; kh = 0; kw = 0; }
+            }
+        }
+        // ---- the remaining tiles, one after the other (the epilogue of tile t - 2 has freed the accumulator)
+        for (int t = first; t < nt; ++t) {
+            const int buf = t & 1;
+            mbar_wait_safe(&acc_empty[buf], ((t >> 1) & 1) ^ 1);
+            int need = (t * N + (p.KH - 1) * p.Wp + p.KW - 1 + N - 1) / p.box_rows;      // last halo box this tile reads
+            need = need >= nb ? nb - 1 : need;
+            while (boxes_ready <= need) {
+                mbar_wait_safe(&box_bar[boxes_ready], 0);
+                ++boxes_ready;
+            }
+            tc::tc_fence_after();
             const uint32_t d = tmem_u + (uint32_t)(w_cols + buf * N);
-            if (TAPS > 0 && t > 0) {
+            if (TAPS > 0) {
                 // straight-line issue: 8 TAPS MMAs with precomputed operand offsets.  (The looped form below costs ~150-190 cycles of
                 // address arithmetic and branches per tap and the tensor pipe does not queue deep enough to hide it: 66 instead of
-                // 48 cycles per MMA, profiles/r02/ws_timeline_history.md.)
+                // 62 cycles per MMA, profiles/r02/ws_timeline_history.md.)
                 if (leader) {
                     const uint32_t base_h = x_hi0 + (uint32_t)(t * N) * (ROW_BYTES >> 4), base_l = x_lo0 + (uint32_t)(t * N) * (ROW_BYTES >> 4);
 #pragma unroll
@@ -674,33 +714,25 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                         }
                     }
                 }
-                if (leader) tc::tc_commit(&acc_full[buf]);
-                if (dbg && leader && t < 4) dbg[4 + t] = clock64();
-                continue;
-            }
-            // taps in this CTA's rotated order (the order its weights arrive in); no divisions inside the loop
-            int k = rot, kh = kh0, kw = kw0;
-            for (int i = 0; i < taps; ++i) {
-                if (t == 0) {
-                    mbar_wait_safe(&w_tap[k], 0);
-                    tc::tc_fence_after();
-                    if (dbg && leader && i == taps - 1) dbg[3] = clock64();
-                }
-                if (leader) {
-                    const uint32_t off = (uint32_t)(t * N + kh * p.Wp + kw) * (ROW_BYTES >> 4);
-                    const uint32_t bh = x_hi0 + off, bl = x_lo0 + off;
-                    const uint32_t a = tmem_u + (uint32_t)(k * 32);
-                    if (i == 0) umma_ts<0>(d, a, bh, idesc); else umma_ts<1>(d, a, bh, idesc);
-                    umma_ts<1>(d, a, bl, idesc);
+            } else {
+                int k = rot, kh = kh0, kw = kw0;
+                for (int i = 0; i < taps; ++i) {
+                    if (leader) {
+                        const uint32_t off = (uint32_t)(t * N + kh * p.Wp + kw) * (ROW_BYTES >> 4);
+                        const uint32_t bh = x_hi0 + off, bl = x_lo0 + off;
+                        const uint32_t a = tmem_u + (uint32_t)(k * 32);
+                        if (i == 0) umma_ts<0>(d, a, bh, idesc); else umma_ts<1>(d, a, bh, idesc);
+                        umma_ts<1>(d, a, bl, idesc);
 #pragma unroll
-                    for (int kk = 1; kk < 4; ++kk) {                       // 16 K elements = 8 TMEM columns of A = 32 bytes of the B rows
-                        umma_ts<1>(d, a + 8 * kk, bh + 2 * kk, idesc);
-                        umma_ts<1>(d, a + 8 * kk, bl + 2 * kk, idesc);
+                        for (int kk = 1; kk < 4; ++kk) {
+                            umma_ts<1>(d, a + 8 * kk, bh + 2 * kk, idesc);
+                            umma_ts<1>(d, a + 8 * kk, bl + 2 * kk, idesc);
+                        }
                     }
+                    ++k; ++kw;
+                    if (kw == p.KW) { kw = 0; ++kh; }
+                    if (k == taps) { k = 0; kh = 0; kw = 0; }
                 }
-                ++k; ++kw;
-                if (kw == p.KW) { kw = 0; ++kh; }
-                if (k == taps) { k = 0; kh = 0; kw = 0; }
             }
             if (leader) tc::tc_commit(&acc_full[buf]);
             if (dbg && leader && t < 4) dbg[4 + t] = clock64();
