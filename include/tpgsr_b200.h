@@ -223,6 +223,8 @@ int tpgsr_gru_fwd(const float* gx, const float* whh, const float* bhh, float* y,
                   int ldr, float* ysum, int ldys, float* stash, int S, int T, int inner, long outer_stride,
                   long inner_stride, long t_stride, cudaStream_t stream);
 size_t tpgsr_gru_bwd_workspace_bytes(int S);
+int tpgsr_gru_set_debug(long long* dbg);  /* developer instrumentation: per-step clock64 stamps of the tensor-core forward kernel */
+int tpgsr_gru_set_mode(int mma);      /* developer switch: 1 (default) kernel picked per shape, 0 the warp-per-sequence FFMA kernels, 2 the tensor-core kernels */
 int tpgsr_gru_bwd(const float* dy, int lddy, const float* y, int ldy, const float* stash, const float* whh, float* dgx,
                   float* dwhh, float* dbhh, float* dbih, int accumulate, int S, int T, int inner, long outer_stride,
                   long inner_stride, long t_stride, void* workspace, size_t workspace_bytes, cudaStream_t stream);

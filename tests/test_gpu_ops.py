@@ -380,3 +380,64 @@ def test_standalone_gradient_prior_loss_covers_every_channel(C):
     got.backward()
     assert abs(float(got) - float(want)) < 2e-6 * abs(float(want)) + 1e-7
     assert rel_err(ad.grad, a.grad) < 2e-5
+
+
+@pytest.mark.parametrize('B,H,W', [(3, 5, 24), (2, 16, 64), (48, 16, 64), (1, 7, 9)])
+@pytest.mark.parametrize('vertical', [False, True])
+def test_gru_tensor_core_forward_matches_ffma_kernel(B, H, W, vertical):
+    """The tensor-core forward recurrence (mma.sync on split-bf16 h and W_hh, 16 sequences per CTA, warp-specialised I/O) against the
+    warp-per-sequence FFMA kernel on the same inputs: every output (y, y + residual, the BPTT stash), ragged sequence counts, with and
+    without residual / stash (inference)."""
+    from tpgsr_b200 import ops
+    from tpgsr_b200._lib import LIB
+    d = _dev()
+    M = B * H * W
+    g = torch.Generator(device='cpu').manual_seed(B * 100 + H)
+    gx = torch.randn(M, 192, generator=g).to(d)
+    whh = (torch.rand(2, 96, 32, generator=g) * 2 - 1).mul(1 / np.sqrt(32)).to(d)
+    bhh = (torch.rand(2, 96, generator=g) * 2 - 1).mul(1 / np.sqrt(32)).to(d)
+    res = torch.randn(M, 64, generator=g).to(d)
+    try:
+        LIB.tpgsr_gru_set_mode(0)
+        y0, s0, st0 = ops.gru_fwd(gx, whh, bhh, B, H, W, vertical, residual=res)
+        LIB.tpgsr_gru_set_mode(2)
+        y1, s1, st1 = ops.gru_fwd(gx, whh, bhh, B, H, W, vertical, residual=res)
+        y2, s2, st2 = ops.gru_fwd(gx, whh, bhh, B, H, W, vertical, residual=None, need_stash=False)
+    finally:
+        LIB.tpgsr_gru_set_mode(1)
+    assert rel_err(y1, y0) < 5e-6 and rel_err(s1, s0) < 5e-6 and rel_err(st1, st0) < 5e-6, (rel_err(y1, y0), rel_err(st1, st0))
+    assert float((y1 - y0).abs().max()) < 2e-5
+    assert torch.equal(y2, y1) and s2 is None and st2 is None
+
+
+@pytest.mark.parametrize('B,H,W', [(3, 5, 24), (2, 16, 64), (48, 16, 64), (1, 7, 9)])
+@pytest.mark.parametrize('vertical', [False, True])
+def test_gru_tensor_core_bptt_matches_ffma_kernel(B, H, W, vertical):
+    """The tensor-core BPTT recurrence against the warp-per-sequence FFMA kernel on the same stash: dgx and, through the shared dW_hh /
+    reduction kernels, dW_hh and both bias gradients (the per-CTA partial slots of the two kernels differ; the sums must not)."""
+    from tpgsr_b200 import ops
+    from tpgsr_b200._lib import LIB
+    d = _dev()
+    M = B * H * W
+    g = torch.Generator(device='cpu').manual_seed(B * 10 + W)
+    gx = torch.randn(M, 192, generator=g).to(d)
+    whh = (torch.rand(2, 96, 32, generator=g) * 2 - 1).mul(1 / np.sqrt(32)).to(d)
+    bhh = (torch.rand(2, 96, generator=g) * 2 - 1).mul(1 / np.sqrt(32)).to(d)
+    dy = torch.randn(M, 64, generator=g).to(d)
+    outs = {}
+    try:
+        LIB.tpgsr_gru_set_mode(0)
+        y, _, stash = ops.gru_fwd(gx, whh, bhh, B, H, W, vertical)
+        for mode in (0, 2):
+            LIB.tpgsr_gru_set_mode(mode)
+            dwhh, dbhh, dbih = torch.zeros_like(whh), torch.zeros_like(bhh), torch.zeros(192, device=d)
+            dgx = ops.gru_bwd(dy, y, stash, whh, dwhh, dbhh, dbih, False, B, H, W, vertical)
+            dgx2, part = ops.gru_bwd_recurrence(dy, y, stash, whh, B, H, W, vertical)           # the two-call form the engine uses
+            dw2, db2, di2 = torch.ones_like(whh), torch.ones_like(bhh), torch.ones(192, device=d)
+            ops.gru_bwd_weights(dgx2, y, stash, part, dw2, db2, di2, True, B, H, W, vertical)
+            assert torch.equal(dgx2, dgx) and rel_err(dw2 - 1, dwhh) < 1e-5 and rel_err(db2 - 1, dbhh) < 1e-5 and rel_err(di2 - 1, dbih) < 1e-5
+            outs[mode] = (dgx, dwhh, dbhh, dbih)
+    finally:
+        LIB.tpgsr_gru_set_mode(1)
+    for name, a, b in zip(('dgx', 'dwhh', 'dbhh', 'dbih'), outs[2], outs[0]):
+        assert rel_err(a, b) < 1e-5, (name, rel_err(a, b))

@@ -664,6 +664,10 @@ def pixelshuffle_mish_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ GRU
+# developer A/B switch: TPGSR_GRU_MODE=0 forces the warp-per-sequence FFMA recurrence kernels, 2 the tensor-core kernels (default 1: per shape)
+GRU_MODE = int(os.environ.get('TPGSR_GRU_MODE', '1'))
+if GRU_MODE != 1:
+    LIB.tpgsr_gru_set_mode(GRU_MODE)
 def _seq_geom(B: int, H: int, W: int, vertical: bool):
     """(S, T, inner, outer_stride, inner_stride, t_stride) in pixel-row units."""
     if vertical:      # sequences run down the columns (gru1 in the reference, on the transposed map)
