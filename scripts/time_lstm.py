@@ -1,0 +1,44 @@
+"""GPU-box: cluster LSTM forward / backward per-launch time (CUDA graph) and the per-step timeline of the forward kernel's first CTA."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+from tpgsr_b200 import ops_prior
+from tpgsr_b200._lib import LIB
+d = torch.device('cuda:0')
+
+
+def batch_time(f, n=6, reps=5):
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream(); g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        f(); torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(n): f()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3 / n)
+    return best
+
+
+T = 26
+for B in (48, 8):
+    gx = torch.randn(B * T, 2048, device=d) * 0.5
+    whh = torch.randn(2, 1024, 256, device=d) * 0.06
+    bhh = torch.zeros(2, 1024, device=d)
+    whhT = ops_prior.lstm_transpose_whh(whh)
+    f = lambda: ops_prior.lstm_fwd(gx, whhT, bhh, T, B, True, batch_first=True)
+    y, stash = f()
+    dy = torch.randn_like(y)
+    b = lambda: ops_prior.lstm_bwd(dy, stash, whh, T, B, batch_first=True)
+    print(f'B={B}: lstm fwd {batch_time(f):.1f} us, bwd {batch_time(b):.1f} us per launch (T = {T})', flush=True)
+    dbg = torch.zeros(T * 6, dtype=torch.int64, device=d)
+    LIB.tpgsr_lstm_set_debug(dbg.data_ptr()); f(); torch.cuda.synchronize(); LIB.tpgsr_lstm_set_debug(None)
+    t = dbg.cpu().view(T, 6)
+    per = (t[1:, 0] - t[:-1, 0]).float()
+    names = ['FMA phase done', 'partials exchanged (sync)', 'gates done (sync)', 'h pushed + cluster arrive', 'cluster wait done']
+    print(f'   forward timeline, cycles per step median {per.median().item():.0f}: ' +
+          ', '.join(f'{n} +{(t[:, i + 1] - t[:, 0]).float().median().item():.0f}' for i, n in enumerate(names)), flush=True)

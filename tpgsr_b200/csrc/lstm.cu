@@ -59,7 +59,7 @@ struct LstmSmem {
 template <int BG>
 __global__ void __cluster_dims__(LS, 1, 1) __launch_bounds__(256, 1)
 lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ whhT, const float* __restrict__ bhh,
-                        float* __restrict__ y, float* __restrict__ stash, int T, int B, int bf) {
+                        float* __restrict__ y, float* __restrict__ stash, int T, int B, int bf, long long* dbg) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) float lsm[];
     float* Ws = lsm;
@@ -84,9 +84,11 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = __ldg(bhh + dir * 4 * LH + g * LH + LU * r + u);
     cluster.sync();                                           // every CTA of the cluster is running and has cleared its h buffer
+    const bool stamp = dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;      // developer timeline (scripts/time_lstm.py)
     for (int s = 0; s < T; ++s) {
         const int t = dir ? T - 1 - s : s;
         const float* hb = hs + (s & 1) * LH * BG;
+        if (stamp) dbg[s * 6] = clock64();
         float gxv[4] = {0.f, 0.f, 0.f, 0.f};
         if (gate_thread && pb < nb) {
             const float* gp = gx + (LROW(t, b0 + pb) * 2 + dir) * 4 * LH + LU * r + u;
@@ -116,11 +118,13 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
                 acc[3][b] = fmaf(wv.w, hv[b], acc[3][b]);
             }
         }
+        if (stamp) dbg[s * 6 + 1] = clock64() + (long long)(acc[0][0] * 0.f);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
             for (int b = 0; b < BG; ++b) red[(w * 4 * BG + g * BG + b) * LU + u] = acc[g][b];
         __syncthreads();
+        if (stamp) dbg[s * 6 + 2] = clock64();
         if (gate_thread) {
             float pre[4];
 #pragma unroll
@@ -136,6 +140,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
             hloc[u * BG + pb] = pb < nb ? hval : 0.f;
         }
         __syncthreads();
+        if (stamp) dbg[s * 6 + 3] = clock64();
         // push this CTA's [32 units][BG] block of h_t into the next-step h buffer of every CTA of the cluster (itself included)
         const int nxt = (s + 1) & 1;
         for (int i = tid; i < LS * LU * Q; i += 256) {
@@ -145,6 +150,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
             *reinterpret_cast<float4*>(remote + nxt * LH * BG + (LU * r) * BG + 4 * q) = v;
         }
         cluster_arrive_release();                             // h_t is on its way to every CTA ...
+        if (stamp) dbg[s * 6 + 4] = clock64();
         if (gate_thread && pb < nb) {                         // ... the HBM outputs are written behind the arrive: the release need not wait for them
             y[LROW(t, b0 + pb) * 2 * LH + dir * LH + LU * r + u] = hval;
             if (stash) {
@@ -153,6 +159,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
             }
         }
         cluster_wait_acquire();                               // h_t complete everywhere (release / acquire at cluster scope)
+        if (stamp) dbg[s * 6 + 5] = clock64();
     }
     cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
 }
@@ -272,9 +279,14 @@ __global__ void lstm_shift_h_kernel(const float* __restrict__ y, float* __restri
     }
 }
 
+long long* g_lstm_dbg = nullptr;
+
 }  // namespace
 
 extern "C" {
+
+// developer instrumentation: clock64 stamps of the first CTA of tpgsr_lstm_fwd, 6 per step
+int tpgsr_lstm_set_debug(long long* dbg) { g_lstm_dbg = dbg; return TPGSR_OK; }
 
 int tpgsr_lstm_transpose_whh(const float* whh, float* whhT, cudaStream_t stream) {
     if (!whh || !whhT) return TPGSR_ERR_BAD_ARG;
@@ -290,12 +302,12 @@ int tpgsr_lstm_fwd(const float* gx, const float* whhT, const float* bhh, float* 
         constexpr int BG = 4;
         if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
-        lstm_fwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first);
+        lstm_fwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first, g_lstm_dbg);
     } else {
         constexpr int BG = 8;
         if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
             return TPGSR_ERR_LAUNCH;
-        lstm_fwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first);
+        lstm_fwd_cluster_kernel<BG><<<dim3(LS, (B + BG - 1) / BG, 2), 256, LstmSmem<BG>::BYTES, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first, g_lstm_dbg);
     }
     return tpgsr_launch_status();
 }
