@@ -210,6 +210,7 @@ int tpgsr_pixelshuffle_bwd(const float* dy, float* dx, int B, int H, int W, int 
 
 /* ---- bidirectional LSTM recurrence -----------------------------------------------------------------------------------------------
  * nn.LSTM(nIn, 256, bidirectional=True) in BidirectionalLSTM: model/crnn/crnn.py:5-26 (cuDNN RNN). */
+int tpgsr_lstm_set_mode(int mma);               /* developer switch: 1 (default) tensor-core recurrence kernels, 0 the FFMA cluster kernels */
 int tpgsr_lstm_set_debug(long long* dbg);      /* developer instrumentation: per-step clock64 stamps of the forward kernel */
 int tpgsr_lstm_transpose_whh(const float* whh, float* whhT, cudaStream_t stream);
 int tpgsr_lstm_fwd(const float* gx, const float* whhT, const float* bhh, float* y, float* stash, int T, int B, int hidden,

@@ -1,4 +1,5 @@
-"""GPU-box: cluster LSTM forward / backward per-launch time (CUDA graph) and the per-step timeline of the forward kernel's first CTA."""
+"""GPU-box: cluster LSTM forward / backward per-launch time (CUDA graph), tensor-core kernels against the FFMA cluster kernels on the
+same inputs (tpgsr_lstm_set_mode), and the per-step timeline of the forward kernel's first CTA."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -24,21 +25,33 @@ def batch_time(f, n=6, reps=5):
     return best
 
 
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
 T = 26
-for B in (48, 8):
+for B in (48, 5):
     gx = torch.randn(B * T, 2048, device=d) * 0.5
     whh = torch.randn(2, 1024, 256, device=d) * 0.06
-    bhh = torch.zeros(2, 1024, device=d)
+    bhh = torch.randn(2, 1024, device=d) * 0.1
     whhT = ops_prior.lstm_transpose_whh(whh)
-    f = lambda: ops_prior.lstm_fwd(gx, whhT, bhh, T, B, True, batch_first=True)
-    y, stash = f()
-    dy = torch.randn_like(y)
-    b = lambda: ops_prior.lstm_bwd(dy, stash, whh, T, B, batch_first=True)
-    print(f'B={B}: lstm fwd {batch_time(f):.1f} us, bwd {batch_time(b):.1f} us per launch (T = {T})', flush=True)
-    dbg = torch.zeros(T * 6, dtype=torch.int64, device=d)
-    LIB.tpgsr_lstm_set_debug(dbg.data_ptr()); f(); torch.cuda.synchronize(); LIB.tpgsr_lstm_set_debug(None)
-    t = dbg.cpu().view(T, 6)
-    per = (t[1:, 0] - t[:-1, 0]).float()
-    names = ['FMA phase done', 'partials exchanged (sync)', 'gates done (sync)', 'h pushed + cluster arrive', 'cluster wait done']
-    print(f'   forward timeline, cycles per step median {per.median().item():.0f}: ' +
-          ', '.join(f'{n} +{(t[:, i + 1] - t[:, 0]).float().median().item():.0f}' for i, n in enumerate(names)), flush=True)
+    dy = torch.randn(B * T, 512, device=d)
+    outs = {}
+    for mode in (0, 1):
+        LIB.tpgsr_lstm_set_mode(mode)
+        f = lambda: ops_prior.lstm_fwd(gx, whhT, bhh, T, B, True, batch_first=True)
+        y, stash = f()
+        b = lambda: ops_prior.lstm_bwd(dy, stash, whh, T, B, batch_first=True)
+        dgx = b()
+        torch.cuda.synchronize()
+        outs[mode] = (y.clone(), stash.clone(), dgx.clone())
+        print(f'B={B} {"tensor-core" if mode else "FFMA       "}: lstm fwd {batch_time(f):6.1f} us, bwd {batch_time(b):6.1f} us per launch (T = {T})', flush=True)
+        dbg = torch.zeros(T * 6, dtype=torch.int64, device=d)
+        LIB.tpgsr_lstm_set_debug(dbg.data_ptr()); f(); torch.cuda.synchronize(); LIB.tpgsr_lstm_set_debug(None)
+        t = dbg.cpu().view(T, 6)
+        per = (t[1:, 0] - t[:-1, 0]).float()
+        names = ['mat-vec phase done', 'partials exchanged (sync)', 'gates done (sync)', 'h pushed + cluster arrive', 'cluster wait done']
+        print(f'   forward timeline, cycles per step median {per.median().item():.0f}: ' +
+              ', '.join(f'{n} +{(t[:, i + 1] - t[:, 0]).float().median().item():.0f}' for i, n in enumerate(names)), flush=True)
+    print('   tensor-core vs FFMA, rel L2: ' + '  '.join(f'{n} {rel(a, b_):.1e}' for n, a, b_ in zip(('y', 'stash', 'dgx'), outs[1], outs[0])), flush=True)
+LIB.tpgsr_lstm_set_mode(1)

@@ -215,3 +215,36 @@ def test_tsrn_tl_train_and_eval_vs_golden_and_oracle(shapes):
     with torch.no_grad():
         sr_eo = models.tsrn(T(ge['lr']), p, False, stn=True, text_emb=T(ge['prior']), tl=True)
     assert rel_err(sr_e, sr_eo) < 2e-4
+
+
+@pytest.mark.parametrize('B', [3, 8, 11, 48])
+def test_lstm_tensor_core_kernels_match_ffma_cluster_kernels(B):
+    """The tensor-core cluster recurrences (mma.sync on split-bf16 h / W_hh with the weight fragments resident in registers, forward and
+    BPTT) against the FFMA cluster kernels on the same inputs: y, the stash and dgx, ragged batch groups included."""
+    import numpy as np
+    from tpgsr_b200 import ops_prior
+    from tpgsr_b200._lib import LIB
+    d = torch.device('cuda:0')
+    T = 26
+    g = torch.Generator(device='cpu').manual_seed(B)
+    gx = (torch.randn(B * T, 2048, generator=g) * 0.5).to(d)
+    whh = ((torch.rand(2, 1024, 256, generator=g) * 2 - 1) / 16).to(d)
+    bhh = ((torch.rand(2, 1024, generator=g) * 2 - 1) / 16).to(d)
+    dy = torch.randn(B * T, 512, generator=g).to(d)
+    whhT = ops_prior.lstm_transpose_whh(whh)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            LIB.tpgsr_lstm_set_mode(mode)
+            for bf in (False, True):
+                y, stash = ops_prior.lstm_fwd(gx, whhT, bhh, T, B, True, batch_first=bf)
+                dgx = ops_prior.lstm_bwd(dy, stash, whh, T, B, batch_first=bf)
+                y2, st2 = ops_prior.lstm_fwd(gx, whhT, bhh, T, B, False, batch_first=bf)
+                assert st2 is None and torch.equal(y2, y)
+                outs[(mode, bf)] = (y, stash, dgx)
+    finally:
+        LIB.tpgsr_lstm_set_mode(1)
+    for bf in (False, True):
+        for name, a, b in zip(('y', 'stash', 'dgx'), outs[(1, bf)], outs[(0, bf)]):
+            err = float((a.double() - b.double()).norm() / b.double().norm())
+            assert err < 1e-5, (name, bf, err)

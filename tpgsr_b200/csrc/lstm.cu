@@ -6,6 +6,7 @@
 //
 // Latency-bound by construction (T = 26 serial steps): reported as us per step, not against the tensor roofline.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -164,6 +165,165 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
     cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Tensor-core recurrence (round 2).  The FMA phase above is 54 % of a step (3 160 of 5 840 cycles, profiles/r02/time_lstm.log).  Here
+// the step's GEMM runs on mma.sync m16n8k16 with the gate rows on the M side and the 8 batch items of the group as N:
+//   gates^T[128 gate rows of this CTA][8] = W_slice[128][256] . h^T[256][8]
+// warp w owns gate rows 16w .. 16w+15 and keeps their A fragments (bf16 hi + lo, 16 k-steps: 128 registers) for the whole launch — the
+// weights never leave the register file, there is no 128 KB weight tile in shared memory any more; B = h as bf16 hi / lo rows [b][k] in
+// shared memory (ldmatrix), three products, fp32 accumulate in four independent chains.  Each CTA still pushes its 32 new h values per
+// batch item (now as bf16 hi / lo, the same 1 KB) into the next-step buffers of all 8 CTAs through distributed shared memory.
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int MB = 8;             // batch items per cluster (the N of the MMAs)
+constexpr int HKP = 264;          // bf16 per row of an h tile: 256 + 8 (ldmatrix rows 528 bytes apart fall into distinct bank groups)
+constexpr int PRP = 132;          // floats per row of the pre-activation exchange tile [b][gate row]
+
+__device__ __forceinline__ void lstm_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void lstm_ldsm4(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+__device__ __forceinline__ void lstm_split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+}
+// gate non-linearities on the SFU (ex2.approx + rcp.approx, absolute error ~1e-7; the libm expf / tanhf sequences were ~770 cycles of a step)
+__device__ __forceinline__ float lstm_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float lstm_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+struct LstmMmaSmem {
+    static constexpr int H_ELEMS = 2 * 2 * MB * HKP;          // [step parity][hi, lo][b][k] bf16
+    static constexpr size_t BYTES = (size_t)H_ELEMS * 2 + (size_t)MB * PRP * 4 + (size_t)2 * MB * LU * 2;
+};
+
+__global__ void __cluster_dims__(LS, 1, 1) __launch_bounds__(256, 1)
+lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whhT, const float* __restrict__ bhh,
+                    float* __restrict__ y, float* __restrict__ stash, int T, int B, int bf, long long* dbg) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) uint8_t lsm_raw[];
+    __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(lsm_raw);                    // [2][2][MB][HKP]
+    float* pre = reinterpret_cast<float*>(hbuf + LstmMmaSmem::H_ELEMS);                 // [MB][PRP]: W h of this CTA's 128 gate rows
+    __nv_bfloat16* hloc = reinterpret_cast<__nv_bfloat16*>(pre + MB * PRP);             // [hi, lo][MB][32]: this CTA's new h values
+    const int r = (int)cluster.block_rank();
+    const int dir = blockIdx.z, b0 = blockIdx.y * MB;
+    const int nb = (B - b0) < MB ? (B - b0) : MB;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, u = lane;
+    const int gid = lane >> 2, tig = lane & 3;
+    // A fragments of this warp's 16 gate rows (local row n = gate * 32 + unit -> column gate * 256 + 32 r + unit of whhT [k][4H]):
+    //   a0 = (row 16w + gid, k = 16 ks + 2 tig, +1), a1 = (row + 8), a2 = (k + 8), a3 = (row + 8, k + 8)
+    uint32_t a_hi[16][4], a_lo[16][4];
+    {
+        const float* WT = whhT + (size_t)dir * 4 * LH * LH;
+        const int n0 = 16 * w + gid, n1 = n0 + 8;
+        const int c0 = (n0 >> 5) * LH + LU * r + (n0 & 31), c1 = (n1 >> 5) * LH + LU * r + (n1 & 31);
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+            const int k0 = 16 * ks + 2 * tig;
+            lstm_split_pair(__ldg(WT + (size_t)k0 * 4 * LH + c0), __ldg(WT + (size_t)(k0 + 1) * 4 * LH + c0), a_hi[ks][0], a_lo[ks][0]);
+            lstm_split_pair(__ldg(WT + (size_t)k0 * 4 * LH + c1), __ldg(WT + (size_t)(k0 + 1) * 4 * LH + c1), a_hi[ks][1], a_lo[ks][1]);
+            lstm_split_pair(__ldg(WT + (size_t)(k0 + 8) * 4 * LH + c0), __ldg(WT + (size_t)(k0 + 9) * 4 * LH + c0), a_hi[ks][2], a_lo[ks][2]);
+            lstm_split_pair(__ldg(WT + (size_t)(k0 + 8) * 4 * LH + c1), __ldg(WT + (size_t)(k0 + 9) * 4 * LH + c1), a_hi[ks][3], a_lo[ks][3]);
+        }
+    }
+    for (int i = tid; i < LstmMmaSmem::H_ELEMS / 2; i += 256) reinterpret_cast<uint32_t*>(hbuf)[i] = 0u;      // h_0 = 0
+    // gate-phase role: thread (pb, u) owns hidden unit 32r + u of batch item b0 + pb
+    const int pb = w;
+    float bias[4], c = 0.f, ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, hval = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias[g] = __ldg(bhh + dir * 4 * LH + g * LH + LU * r + u);
+    // ldmatrix source of this lane: matrix j = lane / 8 -> row (batch item) lane % 8, k offset 8 j (two k-steps per ldmatrix.x4)
+    const int lrow = lane & 7, lk = (lane >> 3) * 8;
+    // push role: 16-byte chunk q = i % 64 of hloc (plane q / 32, batch item (q / 4) % 8, units 8 (q % 4) ..) to CTA i / 64, i = tid, tid + 256
+    __nv_bfloat16* push_ptr[2];
+    int push_off[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = tid + 256 * j, dst = i >> 6, q = i & 63;
+        const int plane = q >> 5, bb = (q >> 2) & 7, part = q & 3;
+        push_ptr[j] = cluster.map_shared_rank(hbuf, dst) + (plane * MB + bb) * HKP + LU * r + 8 * part;
+        push_off[j] = q * 8;                                           // element offset of the chunk inside hloc
+    }
+    cluster.sync();                                           // every CTA of the cluster is running and has cleared its h buffers
+    const bool stamp = dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? T - 1 - s : s;
+        const __nv_bfloat16* hb = hbuf + (s & 1) * 2 * MB * HKP;
+        if (stamp) dbg[s * 6] = clock64();
+        float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pb < nb) {
+            const float* gp = gx + (LROW(t, b0 + pb) * 2 + dir) * 4 * LH + LU * r + u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gxv[g] = __ldg(gp + g * LH);
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 8; ++kp) {                      // two k-steps per iteration: one ldmatrix.x4 per plane
+            uint32_t bh[4], bl[4];
+            lstm_ldsm4(bh, hb + lrow * HKP + 32 * kp + lk);
+            lstm_ldsm4(bl, hb + MB * HKP + lrow * HKP + 32 * kp + lk);
+            lstm_mma(acc[(2 * kp) & 3], a_hi[2 * kp], bh[0], bh[1]);
+            lstm_mma(acc[(2 * kp + 1) & 3], a_hi[2 * kp + 1], bh[2], bh[3]);
+            lstm_mma(acc[(2 * kp) & 3], a_lo[2 * kp], bh[0], bh[1]);
+            lstm_mma(acc[(2 * kp + 1) & 3], a_lo[2 * kp + 1], bh[2], bh[3]);
+            lstm_mma(acc[(2 * kp) & 3], a_hi[2 * kp], bl[0], bl[1]);
+            lstm_mma(acc[(2 * kp + 1) & 3], a_hi[2 * kp + 1], bl[2], bl[3]);
+        }
+        {
+            // D fragment: (row 16w + gid, batch 2 tig, +1), (row + 8, ...) -> pre[b][gate row]
+            const int n0 = 16 * w + gid;
+            const float d0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]), d1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+            const float d2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]), d3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+            pre[(2 * tig) * PRP + n0] = d0; pre[(2 * tig + 1) * PRP + n0] = d1;
+            pre[(2 * tig) * PRP + n0 + 8] = d2; pre[(2 * tig + 1) * PRP + n0 + 8] = d3;
+        }
+        if (stamp) dbg[s * 6 + 1] = clock64();
+        __syncthreads();
+        if (stamp) dbg[s * 6 + 2] = clock64();
+        {
+            float p4[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) p4[g] = pre[pb * PRP + g * LU + u] + (bias[g] + gxv[g]);
+            ig = lstm_sigmoid(p4[0]); fg = lstm_sigmoid(p4[1]); gg = lstm_tanh(p4[2]); og = lstm_sigmoid(p4[3]);
+            c = fg * c + ig * gg;
+            hval = og * lstm_tanh(c);
+            const float hv = pb < nb ? hval : 0.f;
+            const __nv_bfloat16 hh = __float2bfloat16_rn(hv);
+            hloc[pb * LU + u] = hh;
+            hloc[MB * LU + pb * LU + u] = __float2bfloat16_rn(hv - __bfloat162float(hh));
+        }
+        __syncthreads();
+        if (stamp) dbg[s * 6 + 3] = clock64();
+        // push this CTA's [hi, lo][8][32 units] block of h_t into the next-step h buffer of every CTA of the cluster (itself included)
+        {
+            const int nxt = ((s + 1) & 1) * 2 * MB * HKP;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4*>(push_ptr[j] + nxt) = *reinterpret_cast<const uint4*>(hloc + push_off[j]);
+        }
+        cluster_arrive_release();                             // h_t is on its way to every CTA ...
+        if (stamp) dbg[s * 6 + 4] = clock64();
+        if (pb < nb) {                                        // ... the HBM outputs are written behind the arrive
+            y[LROW(t, b0 + pb) * 2 * LH + dir * LH + LU * r + u] = hval;
+            if (stash) {
+                float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + LU * r + u;
+                sp[0] = ig; sp[LH] = fg; sp[2 * LH] = gg; sp[3 * LH] = og; sp[4 * LH] = c;
+            }
+        }
+        cluster_wait_acquire();                               // h_t complete everywhere (release / acquire at cluster scope)
+        if (stamp) dbg[s * 6 + 5] = clock64();
+    }
+    cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
+}
+
 // BPTT: dy [T,B,2H] -> dgx [T,B,2,4H] (gradient w.r.t. the gate pre-activations).  whh: original [2][4H][H] layout.  Same cluster
 // decomposition: CTA r owns the gates of units [32r, 32r+32) (its 128 rows of W_hh, all 256 columns, resident); per step it forms its
 // dgates, multiplies them into a partial dh_prev for ALL 256 units, and reduce-scatters the partials through distributed shared memory
@@ -264,6 +424,133 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dy, const float* __restrict__ 
     cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
 }
 
+// Tensor-core BPTT (round 2): the transposed product on the same decomposition.  CTA r owns the gates of units [32r, 32r+32); per step
+// its gate threads form the 128 x 8 gate derivatives (bf16 hi / lo tile [b][gate row], the B operand), the MMAs give the partial
+//   dh_prev^T[256 units][8] = W_slice^T[256][128] . dgates^T[128][8]
+// (warp w: units 32w .. 32w+31 = exactly the units CTA w owns, A fragments of W^T resident in 128 registers), and every lane stores its
+// accumulator fragment straight into slot r of CTA w's receive buffer through distributed shared memory: no partial-sum staging, one
+// __syncthreads and one cluster barrier per step.  The owner sums the 8 slots in a fixed order (deterministic).
+constexpr int DGP = 136;          // bf16 per row of the gate-derivative tile [b][128 gate rows + 8]
+
+struct LstmBwdMmaSmem {
+    static constexpr size_t BYTES = (size_t)2 * MB * DGP * 2 + (size_t)2 * LS * LU * MB * 4;      // dgate tile (hi, lo) + receive slots [2][src][u][b]
+};
+
+__global__ void __cluster_dims__(LS, 1, 1) __launch_bounds__(256, 1)
+lstm_bwd_mma_kernel(const float* __restrict__ dy, const float* __restrict__ stash, const float* __restrict__ whh,
+                    float* __restrict__ dgx, int T, int B, int bf) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) uint8_t lsm_raw[];
+    __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(lsm_raw);                     // [hi, lo][MB][DGP]
+    float* recv = reinterpret_cast<float*>(dgs + 2 * MB * DGP);                         // [2][src][u][b]
+    const int r = (int)cluster.block_rank();
+    const int dir = blockIdx.z, b0 = blockIdx.y * MB;
+    const int nb = (B - b0) < MB ? (B - b0) : MB;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, u = lane;
+    const int gid = lane >> 2, tig = lane & 3;
+    // A fragments of W^T for this warp's two 16-unit tiles: a0 = (unit j = 32w + 16mt + gid, k = gate row 16ks + 2 tig, +1), a1 = (j + 8),
+    // a2 = (k + 8), a3 = (j + 8, k + 8); gate row n (local) = gate * 32 + unit  ->  row gate * 256 + 32 r + unit of whh [4H][H]
+    uint32_t a_hi[2][8][4], a_lo[2][8][4];
+    {
+        const float* W = whh + (size_t)dir * 4 * LH * LH;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int j0 = 32 * w + 16 * mt + gid, j1 = j0 + 8;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                for (int hk = 0; hk < 2; ++hk) {
+                    const int n = 16 * ks + 8 * hk + 2 * tig;                  // n and n + 1 lie in the same gate (n even, 32 | gate size)
+                    const size_t g0 = (size_t)((n >> 5) * LH + LU * r + (n & 31)) * LH;
+                    lstm_split_pair(__ldg(W + g0 + j0), __ldg(W + g0 + LH + j0), a_hi[mt][ks][2 * hk], a_lo[mt][ks][2 * hk]);
+                    lstm_split_pair(__ldg(W + g0 + j1), __ldg(W + g0 + LH + j1), a_hi[mt][ks][2 * hk + 1], a_lo[mt][ks][2 * hk + 1]);
+                }
+            }
+        }
+    }
+    const int pb = w;
+    const int lrow = lane & 7, lk = (lane >> 3) * 8;
+    // this lane's accumulator fragment goes to CTA w, slot r: rows u = 16 mt + gid (+ 8), columns b = 2 tig, +1
+    float* push_base = cluster.map_shared_rank(recv, w) + (size_t)r * LU * MB + gid * MB + 2 * tig;
+    float dc = 0.f;
+    cluster.sync();
+    for (int s = T - 1; s >= 0; --s) {                        // walk the processing order backwards
+        const int t = dir ? T - 1 - s : s;
+        const int tprev = dir ? t + 1 : t - 1;                // the step processed just before t (holds c_prev)
+        {
+            float di_p = 0.f, df_p = 0.f, dg_p = 0.f, do_p = 0.f;
+            if (pb < nb) {
+                float dh = 0.f;
+                if (s < T - 1) {
+                    const float* rv = recv + ((s + 1) & 1) * LS * LU * MB + u * MB + pb;
+#pragma unroll
+                    for (int src = 0; src < LS; ++src) dh += rv[src * LU * MB];
+                }
+                const size_t col = (size_t)LU * r + u;
+                const float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + col;
+                const float ig = sp[0], fg = sp[LH], gg = sp[2 * LH], og = sp[3 * LH], cc = sp[4 * LH];
+                const float cprev = s > 0 ? stash[((LROW(tprev, b0 + pb) * 2 + dir) * 5 + 4) * LH + col] : 0.f;
+                const float dht = dh + __ldg(dy + LROW(t, b0 + pb) * 2 * LH + dir * LH + col);
+                const float tcc = lstm_tanh(cc);
+                const float dct = dc + dht * og * (1.f - tcc * tcc);
+                do_p = dht * tcc * og * (1.f - og);
+                di_p = dct * gg * ig * (1.f - ig);
+                dg_p = dct * ig * (1.f - gg * gg);
+                df_p = dct * cprev * fg * (1.f - fg);
+                dc = dct * fg;
+                float* gp = dgx + (LROW(t, b0 + pb) * 2 + dir) * 4 * LH + col;
+                gp[0] = di_p; gp[LH] = df_p; gp[2 * LH] = dg_p; gp[3 * LH] = do_p;
+            }
+            const float dv[4] = {di_p, df_p, dg_p, do_p};
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const __nv_bfloat16 hh = __float2bfloat16_rn(dv[g]);
+                dgs[pb * DGP + g * LU + u] = hh;
+                dgs[MB * DGP + pb * DGP + g * LU + u] = __float2bfloat16_rn(dv[g] - __bfloat162float(hh));
+            }
+        }
+        if (s == 0) break;                                    // nothing consumes dh before the first processed step (uniform)
+        __syncthreads();
+        float acc[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) acc[mt][c2][0] = acc[mt][c2][1] = acc[mt][c2][2] = acc[mt][c2][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 4; ++kp) {                      // two k-steps (32 gate rows) per ldmatrix.x4
+            uint32_t bh[4], bl[4];
+            lstm_ldsm4(bh, dgs + lrow * DGP + 32 * kp + lk);
+            lstm_ldsm4(bl, dgs + MB * DGP + lrow * DGP + 32 * kp + lk);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                lstm_mma(acc[mt][0], a_hi[mt][2 * kp], bh[0], bh[1]);
+                lstm_mma(acc[mt][1], a_hi[mt][2 * kp + 1], bh[2], bh[3]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                lstm_mma(acc[mt][0], a_lo[mt][2 * kp], bh[0], bh[1]);
+                lstm_mma(acc[mt][1], a_lo[mt][2 * kp + 1], bh[2], bh[3]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                lstm_mma(acc[mt][0], a_hi[mt][2 * kp], bl[0], bl[1]);
+                lstm_mma(acc[mt][1], a_hi[mt][2 * kp + 1], bl[2], bl[3]);
+            }
+        }
+        // reduce-scatter: this warp's partial dh_prev of units [32w, 32w+32) goes to slot r of CTA w's receive buffer (parity s & 1)
+        {
+            float* dst = push_base + (s & 1) * LS * LU * MB;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                *reinterpret_cast<float2*>(dst + (16 * mt) * MB) = make_float2(acc[mt][0][0] + acc[mt][1][0], acc[mt][0][1] + acc[mt][1][1]);
+                *reinterpret_cast<float2*>(dst + (16 * mt + 8) * MB) = make_float2(acc[mt][0][2] + acc[mt][1][2], acc[mt][0][3] + acc[mt][1][3]);
+            }
+        }
+        cluster.sync();
+    }
+    cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
+}
+
 // hprev[t,b,dir,:] = y[t_prev,b,dir*H:] (the hidden state that entered step t), zero at each direction's first step
 __global__ void lstm_shift_h_kernel(const float* __restrict__ y, float* __restrict__ hprev, int T, int B, int bf) {
     const long total = (long)T * B * 2 * LH;
@@ -280,6 +567,7 @@ __global__ void lstm_shift_h_kernel(const float* __restrict__ y, float* __restri
 }
 
 long long* g_lstm_dbg = nullptr;
+int g_lstm_mma = 1;       // 1: tensor-core recurrence kernels; 0: the FFMA cluster kernels (tpgsr_lstm_set_mode: cross-check tests, A/B)
 
 }  // namespace
 
@@ -287,6 +575,8 @@ extern "C" {
 
 // developer instrumentation: clock64 stamps of the first CTA of tpgsr_lstm_fwd, 6 per step
 int tpgsr_lstm_set_debug(long long* dbg) { g_lstm_dbg = dbg; return TPGSR_OK; }
+// 1 (default): tensor-core recurrence kernels; 0: the FFMA cluster kernels
+int tpgsr_lstm_set_mode(int mma) { g_lstm_mma = mma ? 1 : 0; return TPGSR_OK; }
 
 int tpgsr_lstm_transpose_whh(const float* whh, float* whhT, cudaStream_t stream) {
     if (!whh || !whhT) return TPGSR_ERR_BAD_ARG;
@@ -298,6 +588,12 @@ int tpgsr_lstm_fwd(const float* gx, const float* whhT, const float* bhh, float* 
                    int batch_first, cudaStream_t stream) {
     if (!gx || !whhT || !bhh || !y || T <= 0 || B <= 0) return TPGSR_ERR_BAD_ARG;
     if (hidden != LH) return TPGSR_ERR_UNSUPPORTED;
+    if (g_lstm_mma) {
+        if (cudaFuncSetAttribute(lstm_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmMmaSmem::BYTES) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        lstm_fwd_mma_kernel<<<dim3(LS, (B + MB - 1) / MB, 2), 256, LstmMmaSmem::BYTES, stream>>>(gx, whhT, bhh, y, stash, T, B, batch_first, g_lstm_dbg);
+        return tpgsr_launch_status();
+    }
     if (B <= 4) {
         constexpr int BG = 4;
         if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
@@ -316,6 +612,12 @@ int tpgsr_lstm_bwd(const float* dy, const float* stash, const float* whh, float*
                    int batch_first, cudaStream_t stream) {
     if (!dy || !stash || !whh || !dgx || T <= 0 || B <= 0) return TPGSR_ERR_BAD_ARG;
     if (hidden != LH) return TPGSR_ERR_UNSUPPORTED;
+    if (g_lstm_mma) {
+        if (cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmBwdMmaSmem::BYTES) != cudaSuccess)
+            return TPGSR_ERR_LAUNCH;
+        lstm_bwd_mma_kernel<<<dim3(LS, (B + MB - 1) / MB, 2), 256, LstmBwdMmaSmem::BYTES, stream>>>(dy, stash, whh, dgx, T, B, batch_first);
+        return tpgsr_launch_status();
+    }
     if (B <= 4) {
         constexpr int BG = 4;
         if (cudaFuncSetAttribute(lstm_bwd_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem<BG>::BYTES) != cudaSuccess)
