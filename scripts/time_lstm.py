@@ -50,7 +50,7 @@ for B in (48, 5):
         LIB.tpgsr_lstm_set_debug(dbg.data_ptr()); f(); torch.cuda.synchronize(); LIB.tpgsr_lstm_set_debug(None)
         t = dbg.cpu().view(T, 6)
         per = (t[1:, 0] - t[:-1, 0]).float()
-        names = ['mat-vec phase done', 'partials exchanged (sync)', 'gates done (sync)', 'h pushed + cluster arrive', 'cluster wait done']
+        names = ['mat-vec phase done', 'partials exchanged (sync)', 'gates done (sync)', 'h pushed', 'h of the previous step landed (wait at the step start; FFMA kernel: cluster wait at the step end)']
         print(f'   forward timeline, cycles per step median {per.median().item():.0f}: ' +
               ', '.join(f'{n} +{(t[:, i + 1] - t[:, 0]).float().median().item():.0f}' for i, n in enumerate(names)), flush=True)
     print('   tensor-core vs FFMA, rel L2: ' + '  '.join(f'{n} {rel(a, b_):.1e}' for n, a, b_ in zip(('y', 'stash', 'dgx'), outs[1], outs[0])), flush=True)

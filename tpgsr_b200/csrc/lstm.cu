@@ -6,6 +6,7 @@
 //
 // Latency-bound by construction (T = 26 serial steps): reported as us per step, not against the tensor roofline.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -198,19 +199,48 @@ __device__ __forceinline__ void lstm_split_pair(float a, float b, uint32_t& hi, 
 __device__ __forceinline__ float lstm_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float lstm_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
+constexpr int HBP = 40;           // bf16 per (plane, batch item) row of a source block: 32 units + 8 pad (80-byte rows: conflict-free ldmatrix)
+constexpr int HBLK = 2 * MB * HBP;      // bf16 per source block [hi, lo][b][HBP] = 1280 bytes = what one CTA contributes per step
+
 struct LstmMmaSmem {
-    static constexpr int H_ELEMS = 2 * 2 * MB * HKP;          // [step parity][hi, lo][b][k] bf16
-    static constexpr size_t BYTES = (size_t)H_ELEMS * 2 + (size_t)MB * PRP * 4 + (size_t)2 * MB * LU * 2;
+    static constexpr int H_ELEMS = 2 * LS * HBLK;             // [step parity][source CTA][hi, lo][b][HBP] bf16
+    static constexpr size_t BYTES = (size_t)H_ELEMS * 2 + (size_t)2 * HBLK * 2 + (size_t)MB * PRP * 4 + 64;
 };
 
+// mbarrier wait that traps instead of hanging the GPU if the exchange ever deadlocks
+__device__ __forceinline__ void lstm_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+#pragma unroll 1
+    for (int it = 0; it < 400; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// The h exchange.  v1 pushed with per-thread st.shared::cluster + barrier.cluster arrive.release / wait.acquire: 1 160 + 240 cycles of a
+// 2 780-cycle step (profiles/r02/time_lstm_v2.log) — the release has to wait for the remote stores.  Here the h tiles are laid out by SOURCE
+// CTA ([parity][source][hi, lo][b][32 + 8]: a k-window of 32 = one source block, contiguous 1 280 bytes), each CTA sends its block to every
+// peer with ONE bulk copy (cp.async.bulk shared::cta -> shared::cluster) that completes on the receiver's mbarrier, and a step starts when
+// the local mbarrier has seen all 8 blocks: data and signal travel together, no cluster barrier inside the loop.
 __global__ void __cluster_dims__(LS, 1, 1) __launch_bounds__(256, 1)
 lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whhT, const float* __restrict__ bhh,
                     float* __restrict__ y, float* __restrict__ stash, int T, int B, int bf, long long* dbg) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) uint8_t lsm_raw[];
-    __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(lsm_raw);                    // [2][2][MB][HKP]
-    float* pre = reinterpret_cast<float*>(hbuf + LstmMmaSmem::H_ELEMS);                 // [MB][PRP]: W h of this CTA's 128 gate rows
-    __nv_bfloat16* hloc = reinterpret_cast<__nv_bfloat16*>(pre + MB * PRP);             // [hi, lo][MB][32]: this CTA's new h values
+    __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(lsm_raw);                    // [2][LS][HBLK]
+    __nv_bfloat16* hloc = hbuf + LstmMmaSmem::H_ELEMS;                                  // [2][HBLK]: this CTA's new h values (double buffered)
+    float* pre = reinterpret_cast<float*>(hloc + 2 * HBLK);                             // [MB][PRP]: W h of this CTA's 128 gate rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pre + MB * PRP);                       // [2]: all 8 blocks of a parity buffer have landed
     const int r = (int)cluster.block_rank();
     const int dir = blockIdx.z, b0 = blockIdx.y * MB;
     const int nb = (B - b0) < MB ? (B - b0) : MB;
@@ -232,29 +262,30 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whhT
             lstm_split_pair(__ldg(WT + (size_t)(k0 + 8) * 4 * LH + c1), __ldg(WT + (size_t)(k0 + 9) * 4 * LH + c1), a_hi[ks][3], a_lo[ks][3]);
         }
     }
-    for (int i = tid; i < LstmMmaSmem::H_ELEMS / 2; i += 256) reinterpret_cast<uint32_t*>(hbuf)[i] = 0u;      // h_0 = 0
+    for (int i = tid; i < (LstmMmaSmem::H_ELEMS + 2 * HBLK) / 2; i += 256) reinterpret_cast<uint32_t*>(hbuf)[i] = 0u;      // h_0 = 0 (and the pads)
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::fence_barrier_init();
+    }
     // gate-phase role: thread (pb, u) owns hidden unit 32r + u of batch item b0 + pb
     const int pb = w;
     float bias[4], c = 0.f, ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, hval = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = __ldg(bhh + dir * 4 * LH + g * LH + LU * r + u);
-    // ldmatrix source of this lane: matrix j = lane / 8 -> row (batch item) lane % 8, k offset 8 j (two k-steps per ldmatrix.x4)
+    // ldmatrix source of this lane: matrix j = lane / 8 -> row (batch item) lane % 8, unit offset 8 j inside a 32-unit source block
     const int lrow = lane & 7, lk = (lane >> 3) * 8;
-    // push role: 16-byte chunk q = i % 64 of hloc (plane q / 32, batch item (q / 4) % 8, units 8 (q % 4) ..) to CTA i / 64, i = tid, tid + 256
-    __nv_bfloat16* push_ptr[2];
-    int push_off[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int i = tid + 256 * j, dst = i >> 6, q = i & 63;
-        const int plane = q >> 5, bb = (q >> 2) & 7, part = q & 3;
-        push_ptr[j] = cluster.map_shared_rank(hbuf, dst) + (plane * MB + bb) * HKP + LU * r + 8 * part;
-        push_off[j] = q * 8;                                           // element offset of the chunk inside hloc
+    // push role (threads 0..7): this CTA's block -> slot r of CTA tid's buffers; shared::cluster addresses of the peer's buffer / barriers
+    uint32_t peer_buf = 0, peer_bar = 0;
+    if (tid < LS) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_buf) : "r"((uint32_t)__cvta_generic_to_shared(hbuf + r * HBLK)), "r"(tid));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"((uint32_t)__cvta_generic_to_shared(bars)), "r"(tid));
     }
-    cluster.sync();                                           // every CTA of the cluster is running and has cleared its h buffers
+    cluster.sync();                                           // every CTA of the cluster is running, has cleared its buffers and armed its barriers
     const bool stamp = dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
     for (int s = 0; s < T; ++s) {
         const int t = dir ? T - 1 - s : s;
-        const __nv_bfloat16* hb = hbuf + (s & 1) * 2 * MB * HKP;
+        const int par = s & 1;
         if (stamp) dbg[s * 6] = clock64();
         float gxv[4] = {0.f, 0.f, 0.f, 0.f};
         if (pb < nb) {
@@ -262,14 +293,17 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whhT
 #pragma unroll
             for (int g = 0; g < 4; ++g) gxv[g] = __ldg(gp + g * LH);
         }
+        if (s > 0) lstm_mbar_wait(&bars[par], ((s - 1) >> 1) & 1);      // the 8 blocks of h_{s-1} have landed in buffer `par`
+        if (stamp) dbg[s * 6 + 5] = clock64();
+        const __nv_bfloat16* hb = hbuf + par * LS * HBLK;
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll
-        for (int kp = 0; kp < 8; ++kp) {                      // two k-steps per iteration: one ldmatrix.x4 per plane
+        for (int kp = 0; kp < 8; ++kp) {                      // source block kp = units 32 kp .. = two k-steps: one ldmatrix.x4 per plane
             uint32_t bh[4], bl[4];
-            lstm_ldsm4(bh, hb + lrow * HKP + 32 * kp + lk);
-            lstm_ldsm4(bl, hb + MB * HKP + lrow * HKP + 32 * kp + lk);
+            lstm_ldsm4(bh, hb + kp * HBLK + lrow * HBP + lk);
+            lstm_ldsm4(bl, hb + kp * HBLK + MB * HBP + lrow * HBP + lk);
             lstm_mma(acc[(2 * kp) & 3], a_hi[2 * kp], bh[0], bh[1]);
             lstm_mma(acc[(2 * kp + 1) & 3], a_hi[2 * kp + 1], bh[2], bh[3]);
             lstm_mma(acc[(2 * kp) & 3], a_lo[2 * kp], bh[0], bh[1]);
@@ -297,31 +331,34 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whhT
             hval = og * lstm_tanh(c);
             const float hv = pb < nb ? hval : 0.f;
             const __nv_bfloat16 hh = __float2bfloat16_rn(hv);
-            hloc[pb * LU + u] = hh;
-            hloc[MB * LU + pb * LU + u] = __float2bfloat16_rn(hv - __bfloat162float(hh));
+            __nv_bfloat16* hl = hloc + par * HBLK;
+            hl[pb * HBP + u] = hh;
+            hl[MB * HBP + pb * HBP + u] = __float2bfloat16_rn(hv - __bfloat162float(hh));
         }
-        __syncthreads();
-        if (stamp) dbg[s * 6 + 3] = clock64();
-        // push this CTA's [hi, lo][8][32 units] block of h_t into the next-step h buffer of every CTA of the cluster (itself included)
-        {
-            const int nxt = ((s + 1) & 1) * 2 * MB * HKP;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-                *reinterpret_cast<uint4*>(push_ptr[j] + nxt) = *reinterpret_cast<const uint4*>(hloc + push_off[j]);
+        if (s + 1 < T) {
+            tc::fence_proxy_async();                          // the generic-proxy writes of hloc are ordered before the bulk copies read them
+            __syncthreads();
+            if (stamp) dbg[s * 6 + 3] = clock64();
+            const int nxt = par ^ 1;
+            if (tid < LS) {
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(peer_buf + (uint32_t)(nxt * LS * HBLK * 2)), "r"((uint32_t)__cvta_generic_to_shared(hloc + par * HBLK)),
+                               "r"((uint32_t)(HBLK * 2)), "r"(peer_bar + (uint32_t)(nxt * 8))
+                             : "memory");
+            } else if (tid == LS) {
+                tc::mbar_expect_tx(&bars[nxt], (uint32_t)(LS * HBLK * 2));      // this CTA expects the 8 blocks of h_s in buffer `nxt`
+            }
+            if (stamp) dbg[s * 6 + 4] = clock64();
         }
-        cluster_arrive_release();                             // h_t is on its way to every CTA ...
-        if (stamp) dbg[s * 6 + 4] = clock64();
-        if (pb < nb) {                                        // ... the HBM outputs are written behind the arrive
+        if (pb < nb) {
             y[LROW(t, b0 + pb) * 2 * LH + dir * LH + LU * r + u] = hval;
             if (stash) {
                 float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + LU * r + u;
                 sp[0] = ig; sp[LH] = fg; sp[2 * LH] = gg; sp[3 * LH] = og; sp[4 * LH] = c;
             }
         }
-        cluster_wait_acquire();                               // h_t complete everywhere (release / acquire at cluster scope)
-        if (stamp) dbg[s * 6 + 5] = clock64();
     }
-    cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
+    cluster.sync();                                           // no CTA leaves while a peer's copy may still be landing in its shared memory
 }
 
 // BPTT: dy [T,B,2H] -> dgx [T,B,2,4H] (gradient w.r.t. the gate pre-activations).  whh: original [2][4H][H] layout.  Same cluster
@@ -433,7 +470,8 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dy, const float* __restrict__ 
 constexpr int DGP = 136;          // bf16 per row of the gate-derivative tile [b][128 gate rows + 8]
 
 struct LstmBwdMmaSmem {
-    static constexpr size_t BYTES = (size_t)2 * MB * DGP * 2 + (size_t)2 * LS * LU * MB * 4;      // dgate tile (hi, lo) + receive slots [2][src][u][b]
+    // dgate tile (hi, lo) + receive slots [2][src][u][b] + send staging [2][dst][u][b] + 2 mbarriers
+    static constexpr size_t BYTES = (size_t)2 * MB * DGP * 2 + (size_t)2 * LS * LU * MB * 4 + (size_t)2 * LS * LU * MB * 4 + 64;
 };
 
 __global__ void __cluster_dims__(LS, 1, 1) __launch_bounds__(256, 1)
@@ -443,6 +481,8 @@ lstm_bwd_mma_kernel(const float* __restrict__ dy, const float* __restrict__ stas
     extern __shared__ __align__(16) uint8_t lsm_raw[];
     __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(lsm_raw);                     // [hi, lo][MB][DGP]
     float* recv = reinterpret_cast<float*>(dgs + 2 * MB * DGP);                         // [2][src][u][b]
+    float* pst = recv + 2 * LS * LU * MB;                                               // [2][dst][u][b]: partial dh_prev on its way to the owners
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pst + 2 * LS * LU * MB);               // [2]: the 8 partial blocks of a parity have landed
     const int r = (int)cluster.block_rank();
     const int dir = blockIdx.z, b0 = blockIdx.y * MB;
     const int nb = (B - b0) < MB ? (B - b0) : MB;
@@ -468,10 +508,20 @@ lstm_bwd_mma_kernel(const float* __restrict__ dy, const float* __restrict__ stas
             }
         }
     }
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::fence_barrier_init();
+    }
     const int pb = w;
     const int lrow = lane & 7, lk = (lane >> 3) * 8;
-    // this lane's accumulator fragment goes to CTA w, slot r: rows u = 16 mt + gid (+ 8), columns b = 2 tig, +1
-    float* push_base = cluster.map_shared_rank(recv, w) + (size_t)r * LU * MB + gid * MB + 2 * tig;
+    // exchange (as in the forward kernel): warp w's accumulator fragments are the partial dh_prev of the units CTA w owns; they are staged
+    // as block w, and thread j < 8 sends block j to slot r of CTA j's receive buffer with one bulk copy that completes on CTA j's mbarrier
+    uint32_t peer_buf = 0, peer_bar = 0;
+    if (tid < LS) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_buf) : "r"((uint32_t)__cvta_generic_to_shared(recv + r * LU * MB)), "r"(tid));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"((uint32_t)__cvta_generic_to_shared(bars)), "r"(tid));
+    }
     float dc = 0.f;
     cluster.sync();
     for (int s = T - 1; s >= 0; --s) {                        // walk the processing order backwards
@@ -479,6 +529,15 @@ lstm_bwd_mma_kernel(const float* __restrict__ dy, const float* __restrict__ stas
         const int tprev = dir ? t + 1 : t - 1;                // the step processed just before t (holds c_prev)
         {
             float di_p = 0.f, df_p = 0.f, dg_p = 0.f, do_p = 0.f;
+            float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cc = 0.f, cprev = 0.f, dyv = 0.f;
+            const size_t col = (size_t)LU * r + u;
+            if (pb < nb) {                                    // operands first: they do not depend on the exchange
+                const float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + col;
+                ig = sp[0]; fg = sp[LH]; gg = sp[2 * LH]; og = sp[3 * LH]; cc = sp[4 * LH];
+                cprev = s > 0 ? stash[((LROW(tprev, b0 + pb) * 2 + dir) * 5 + 4) * LH + col] : 0.f;
+                dyv = __ldg(dy + LROW(t, b0 + pb) * 2 * LH + dir * LH + col);
+            }
+            if (s < T - 1) lstm_mbar_wait(&bars[(s + 1) & 1], (((T - 2) - s) >> 1) & 1);      // the partials pushed during step s + 1 have landed
             if (pb < nb) {
                 float dh = 0.f;
                 if (s < T - 1) {
@@ -486,11 +545,7 @@ lstm_bwd_mma_kernel(const float* __restrict__ dy, const float* __restrict__ stas
 #pragma unroll
                     for (int src = 0; src < LS; ++src) dh += rv[src * LU * MB];
                 }
-                const size_t col = (size_t)LU * r + u;
-                const float* sp = stash + ((LROW(t, b0 + pb) * 2 + dir) * 5) * LH + col;
-                const float ig = sp[0], fg = sp[LH], gg = sp[2 * LH], og = sp[3 * LH], cc = sp[4 * LH];
-                const float cprev = s > 0 ? stash[((LROW(tprev, b0 + pb) * 2 + dir) * 5 + 4) * LH + col] : 0.f;
-                const float dht = dh + __ldg(dy + LROW(t, b0 + pb) * 2 * LH + dir * LH + col);
+                const float dht = dh + dyv;
                 const float tcc = lstm_tanh(cc);
                 const float dct = dc + dht * og * (1.f - tcc * tcc);
                 do_p = dht * tcc * og * (1.f - og);
@@ -537,18 +592,28 @@ lstm_bwd_mma_kernel(const float* __restrict__ dy, const float* __restrict__ stas
                 lstm_mma(acc[mt][1], a_hi[mt][2 * kp + 1], bl[2], bl[3]);
             }
         }
-        // reduce-scatter: this warp's partial dh_prev of units [32w, 32w+32) goes to slot r of CTA w's receive buffer (parity s & 1)
+        // reduce-scatter: block w of the staging area = this warp's partial dh_prev of the units CTA w owns: rows u = 16 mt + gid (+ 8), b = 2 tig, +1
         {
-            float* dst = push_base + (s & 1) * LS * LU * MB;
+            const int par = s & 1;
+            float* dst = pst + (size_t)(par * LS + w) * LU * MB + gid * MB + 2 * tig;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 *reinterpret_cast<float2*>(dst + (16 * mt) * MB) = make_float2(acc[mt][0][0] + acc[mt][1][0], acc[mt][0][1] + acc[mt][1][1]);
                 *reinterpret_cast<float2*>(dst + (16 * mt + 8) * MB) = make_float2(acc[mt][0][2] + acc[mt][1][2], acc[mt][0][3] + acc[mt][1][3]);
             }
+            tc::fence_proxy_async();
+            __syncthreads();
+            if (tid < LS) {
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(peer_buf + (uint32_t)(par * LS * LU * MB * 4)), "r"((uint32_t)__cvta_generic_to_shared(pst + (size_t)(par * LS + tid) * LU * MB)),
+                               "r"((uint32_t)(LU * MB * 4)), "r"(peer_bar + (uint32_t)(par * 8))
+                             : "memory");
+            } else if (tid == LS) {
+                tc::mbar_expect_tx(&bars[par], (uint32_t)(LS * LU * MB * 4));
+            }
         }
-        cluster.sync();
     }
-    cluster.sync();                                           // no CTA leaves while a peer may still be writing into its shared memory
+    cluster.sync();                                           // no CTA leaves while a peer's copy may still be landing in its shared memory
 }
 
 // hprev[t,b,dir,:] = y[t_prev,b,dir*H:] (the hidden state that entered step t), zero at each direction's first step

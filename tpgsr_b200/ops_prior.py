@@ -1,10 +1,12 @@
 """Tensor-level wrappers for the text-prior branch kernels (resampling, prior formatting, LSTM recurrence)."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
+from ._lib import LIB
 from .ops import _call, new, ptr, stream
 
 
@@ -90,6 +92,11 @@ def softmax_prior_bwd(probs: torch.Tensor, dprobs: Optional[torch.Tensor], dprio
 
 
 # ------------------------------------------------------------------------------------------------ LSTM
+# developer A/B switch: TPGSR_LSTM_MODE=0 forces the FFMA cluster kernels of the LSTM recurrence (default 1: tensor-core kernels)
+if os.environ.get('TPGSR_LSTM_MODE', '1') == '0':
+    LIB.tpgsr_lstm_set_mode(0)
+
+
 def lstm_transpose_whh(whh: torch.Tensor) -> torch.Tensor:
     """[2,1024,256] -> [2,256,1024]"""
     out = new((2, 256, 1024), whh)
