@@ -840,20 +840,23 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
 }
 
 // fp32 dense NHWC [B,H,W,C] (pixel pitch ldx) -> padded-flat bf16 hi/lo planes [B][H+P][W+P][Cout] (pads and channels >= C zero)
+// IDX = unsigned whenever the element count allows: the three divisions per thread were 64-bit (round 1) and cost more than the 26 MB of traffic
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 split_bf16_flat_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int B,
                        int H, int W, int C, int Cout, int P) {
-    const int Hp = H + P, Wp = W + P;
-    const int cq = Cout >> 2;
-    const long long total = (long long)B * Hp * Wp * cq;
+    const IDX Hp = H + P, Wp = W + P;
+    const IDX cq = Cout >> 2;
+    const IDX total = (IDX)B * Hp * Wp * cq;
     const bool vec = ((ldx & 3) == 0) && ((C & 3) == 0);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long q = i / cq;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+        const IDX q = i / cq;
         const int c = (int)(i - q * cq) * 4;
-        const int col = (int)(q % Wp);
-        const long long t = q / Wp;
-        const int r = (int)(t % Hp);
-        const int b = (int)(t / Hp);
+        const IDX t = q / Wp;
+        const int col = (int)(q - t * Wp);
+        const IDX bb = t / Hp;
+        const int r = (int)(t - bb * Hp);
+        const int b = (int)bb;
         float f[4] = {0.f, 0.f, 0.f, 0.f};
         if (r < H && col < W) {
             const float* src = x + ((size_t)(b * H + r) * W + col) * ldx + c;
@@ -1268,8 +1271,11 @@ int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, in
                           cudaStream_t stream) {
     if (!x || !hi || (Cout & 3) || Cout < C || B < 1 || H < 1 || W < 1 || P < 0) return TPGSR_ERR_BAD_ARG;
     long long blocks = ((long long)B * (H + P) * (W + P) * (Cout / 4) + 255) / 256;
-    split_bf16_flat_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, stream>>>(
-        x, ldx, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, H, W, C, Cout, P);
+    const int grid = (int)(blocks > 148 * 16 ? 148 * 16 : blocks);
+    if ((long long)B * (H + P) * (W + P) * (Cout / 4) + (long long)grid * 256 < (1LL << 32))
+        split_bf16_flat_kernel<unsigned><<<grid, 256, 0, stream>>>(x, ldx, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, H, W, C, Cout, P);
+    else
+        split_bf16_flat_kernel<long long><<<grid, 256, 0, stream>>>(x, ldx, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, H, W, C, Cout, P);
     return tpgsr_launch_status();
 }
 

@@ -519,6 +519,64 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const int* __re
     }
 }
 
+// float4 versions of the two kernels above (C % 4 == 0, fewer than 2^31 elements): 16-byte accesses and 32-bit index arithmetic.  The scalar
+// kernels spent most of their time in three 64-bit divisions per element (CRNN pool0 at B = 48: 45 us forward, 60 us backward for 59 MB).
+__global__ void __launch_bounds__(256) maxpool_fwd_v4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int4* __restrict__ arg,
+                                                            unsigned total, int Hi, int Wi, int C4, int Ho, int Wo, int kh, int kw,
+                                                            int sh, int sw, int ph, int pw) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned p = i / (unsigned)C4, c = i - p * (unsigned)C4;
+        const unsigned q = p / (unsigned)Wo, wo = p - q * (unsigned)Wo;
+        const unsigned b = q / (unsigned)Ho, ho = q - b * (unsigned)Ho;
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        int4 bi = make_int4(-1, -1, -1, -1);
+        for (int a = 0; a < kh; ++a) {
+            const int h = (int)ho * sh - ph + a;
+            if ((unsigned)h >= (unsigned)Hi) continue;
+            for (int d = 0; d < kw; ++d) {
+                const int w = (int)wo * sw - pw + d;
+                if ((unsigned)w >= (unsigned)Wi) continue;
+                const int me = h * Wi + w;
+                const float4 v = x[((size_t)(b * Hi + h) * Wi + w) * C4 + c];
+                if (v.x > best.x || bi.x < 0) { best.x = v.x; bi.x = me; }   // first max wins, like ATen
+                if (v.y > best.y || bi.y < 0) { best.y = v.y; bi.y = me; }
+                if (v.z > best.z || bi.z < 0) { best.z = v.z; bi.z = me; }
+                if (v.w > best.w || bi.w < 0) { best.w = v.w; bi.w = me; }
+            }
+        }
+        y[i] = best;
+        if (arg) arg[i] = bi;
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_v4_kernel(const float4* __restrict__ dy, const int4* __restrict__ arg, float4* __restrict__ dx,
+                                                            unsigned total, int Hi, int Wi, int C4, int Ho, int Wo, int kh, int kw,
+                                                            int sh, int sw, int ph, int pw) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned p = i / (unsigned)C4, c = i - p * (unsigned)C4;
+        const unsigned q = p / (unsigned)Wi, w = p - q * (unsigned)Wi;
+        const unsigned b = q / (unsigned)Hi, h = q - b * (unsigned)Hi;
+        const int me = (int)(h * Wi + w);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ho_lo = ((int)h + ph - kh + sh) / sh;  if ((int)h + ph - kh + 1 <= 0) ho_lo = 0;
+        int wo_lo = ((int)w + pw - kw + sw) / sw;  if ((int)w + pw - kw + 1 <= 0) wo_lo = 0;
+        int ho_hi = ((int)h + ph) / sh, wo_hi = ((int)w + pw) / sw;
+        if (ho_hi > Ho - 1) ho_hi = Ho - 1;
+        if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+        for (int ho = ho_lo; ho <= ho_hi; ++ho)
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                const size_t o = ((size_t)(b * Ho + ho) * Wo + wo) * C4 + c;
+                const int4 a = arg[o];
+                const float4 g = dy[o];
+                if (a.x == me) s.x += g.x;
+                if (a.y == me) s.y += g.y;
+                if (a.z == me) s.z += g.z;
+                if (a.w == me) s.w += g.w;
+            }
+        dx[i] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // PixelShuffle(2) + mish on NHWC: x [B,H,W,4C] -> y [B,2H,2W,C];  y[b,2h+i,2w+j,c] = mish(x[b,h,w,4c+2i+j])
 // ------------------------------------------------------------------------------------------------
@@ -834,6 +892,12 @@ int tpgsr_maxpool_fwd(const float* x, float* y, int* argmax, int B, int Hi, int 
                       int ph, int pw, cudaStream_t stream) {
     if (!x || !y) return TPGSR_ERR_BAD_ARG;
     int Ho = (Hi + 2 * ph - kh) / sh + 1, Wo = (Wi + 2 * pw - kw) / sw + 1;
+    const long n4 = (long)B * Ho * Wo * (C / 4);
+    if ((C & 3) == 0 && (long)B * Hi * Wi * C < (1L << 31) && !(((uintptr_t)x | (uintptr_t)y | (uintptr_t)argmax) & 15)) {
+        maxpool_fwd_v4_kernel<<<ew_grid(n4), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), reinterpret_cast<int4*>(argmax),
+                                                                (unsigned)n4, Hi, Wi, C / 4, Ho, Wo, kh, kw, sh, sw, ph, pw);
+        return tpgsr_launch_status();
+    }
     maxpool_fwd_kernel<<<ew_grid((long)B * Ho * Wo * C), 256, 0, stream>>>(x, y, argmax, B, Hi, Wi, C, Ho, Wo, kh, kw, sh, sw, ph, pw);
     return tpgsr_launch_status();
 }
@@ -842,6 +906,12 @@ int tpgsr_maxpool_bwd(const float* dy, const int* argmax, float* dx, int B, int 
                       int sw, int ph, int pw, cudaStream_t stream) {
     if (!dy || !argmax || !dx) return TPGSR_ERR_BAD_ARG;
     int Ho = (Hi + 2 * ph - kh) / sh + 1, Wo = (Wi + 2 * pw - kw) / sw + 1;
+    const long n4 = (long)B * Hi * Wi * (C / 4);
+    if ((C & 3) == 0 && (long)B * Hi * Wi * C < (1L << 31) && !(((uintptr_t)dy | (uintptr_t)dx | (uintptr_t)argmax) & 15)) {
+        maxpool_bwd_v4_kernel<<<ew_grid(n4), 256, 0, stream>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const int4*>(argmax), reinterpret_cast<float4*>(dx),
+                                                                (unsigned)n4, Hi, Wi, C / 4, Ho, Wo, kh, kw, sh, sw, ph, pw);
+        return tpgsr_launch_status();
+    }
     maxpool_bwd_kernel<<<ew_grid((long)B * Hi * Wi * C), 256, 0, stream>>>(dy, argmax, dx, B, Hi, Wi, C, Ho, Wo, kh, kw, sh, sw, ph, pw);
     return tpgsr_launch_status();
 }
