@@ -45,12 +45,13 @@ def flushed_time(f, reps=20):
     return ts[len(ts) // 2]
 
 
+K = int(os.environ.get('WS_K', '3'))
 for (B, H, W) in [(48, 16, 64), (8, 16, 64), (192, 16, 64)]:
-    x = torch.randn(B, H, W, 64, device=d); w = torch.randn(64, 64, 3, 3, device=d) / 24.0; b = torch.randn(64, device=d) * 0.1
-    want = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
-    fp = ops.split_bf16_flat(x, 1, True); (wf, _) = ops.pack_conv_weights_bf16(w, False, True)
+    x = torch.randn(B, H, W, 64, device=d); w = torch.randn(64, 64, K, K, device=d) / (8.0 * K); b = torch.randn(64, device=d) * 0.1
+    want = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=K // 2).permute(0, 2, 3, 1).float()
+    fp = ops.split_bf16_flat(x, K // 2, True); (wf, _) = ops.pack_conv_weights_bf16(w, False, True)
     y = torch.empty(B, H, W, 64, device=d)
-    f = lambda: ops.conv_flat(fp, wf, b, 64, 3, 3, 1, 1, out=y)
+    f = lambda: ops.conv_flat(fp, wf, b, 64, K, K, K // 2, K // 2, out=y)
     for tag, bits in (('weights-stationary', 0), ('flat plan', 16)):
         LIB.tpgsr_conv2d_flat_set_debug_skip(bits)
         y.zero_(); f(); torch.cuda.synchronize()

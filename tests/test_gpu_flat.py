@@ -289,6 +289,8 @@ def test_tall_plan_kh_by_1_convs(B, Co, H, W, KH, mode):
     (4, 9, 33, 3, 1, 1, 0),       # 3x1
     (2, 8, 24, 2, 2, 0, 0),       # 2x2 valid
     (2, 8, 24, 3, 4, 1, 2),       # 12 taps: the most that fit beside two 64-pixel accumulators
+    (48, 16, 64, 1, 1, 0, 0),     # GruBlock 1x1 conv at the bench batch: no halo, one tap
+    (3, 5, 17, 1, 1, 0, 0),       # ... on a ragged map
 ])
 def test_weights_stationary_plan(B, H, W, KH, KW, ph, pw):
     """64 -> 64 convs with 3..12 taps run the weights-stationary plan (split weights resident in tensor memory as the A operand, pixels

@@ -32,7 +32,9 @@ def rnd(*shape, seed=0, scale=1.0):
     (1, 64, 4, 32, 128, 9, 4),      # final conv (small-N path)
     (2, 96, 64, 16, 64, 1, 0),      # gru1 1x1 conv (TL)
     (2, 64, 256, 16, 64, 3, 1),     # upsample conv
-    (3, 1, 64, 32, 100, 3, 1),      # CRNN conv0 (scalar gather path)
+    (3, 1, 64, 32, 100, 3, 1),      # CRNN conv0 (one input channel: the dedicated 3x3 kernel)
+    (2, 1, 64, 7, 13, 3, 1),        # ... on a ragged map (rows of 13 = three groups of 4 pixels + 1)
+    (2, 1, 24, 9, 10, 3, 1),        # ... with 24 output channels (6 channel quads per pixel)
     (3, 512, 512, 2, 27, 2, 0),     # CRNN conv6 (valid 2x2)
     (5, 36, 40, 1, 1, 1, 0),        # linear with ragged N/K
     (2, 3, 64, 32, 128, 9, 4),      # SRCNN conv1 (Cin=3)

@@ -1009,11 +1009,11 @@ struct WsPlan {
 };
 int g_flat_no_ws = 0;       // developer switch (debug bit 4): disable the weights-stationary plan (A/B measurements, cross-check tests)
 
-// weights-stationary plan (conv_ws_kernel): split-bf16, exactly 64 -> 64 channels, 3..12 taps, NHWC output
+// weights-stationary plan (conv_ws_kernel): split-bf16, exactly 64 -> 64 channels, 1..12 taps, NHWC output
 int plan_ws(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod, size_t budget, int slots, WsPlan& pl) {
     if (g_flat_no_ws || nprod != 3 || Ci != 64 || Co != 64 || B < 1 || H < 1 || W < 1) return TPGSR_ERR_UNSUPPORTED;
     const int taps = KH * KW;
-    if (taps < 3 || taps > 12) return TPGSR_ERR_UNSUPPORTED;
+    if (taps < 1 || taps > 12) return TPGSR_ERR_UNSUPPORTED;      // (1x1: no halo; the kernel is then its double-buffered epilogue)
     if (KW == 1 && KH >= 5) return TPGSR_ERR_UNSUPPORTED;      // tall kernels: the taps share nothing in the flat row order — the tall plan's 2-D tile is the right shape
     if (ph < 0 || ph >= KH || pw < 0 || pw >= KW || P < ph || P < pw) return TPGSR_ERR_UNSUPPORTED;
     if (H + 2 * ph - KH + 1 < 1 || W + 2 * pw - KW + 1 < 1 || H + 2 * ph - KH + 1 > H + P || W + 2 * pw - KW + 1 > W + P) return TPGSR_ERR_UNSUPPORTED;

@@ -422,6 +422,59 @@ int tpgsr_pack_conv_weights(const float* w_oihw, float* wk_fwd, float* wk_dgrad,
     return tpgsr_launch_status();
 }
 
+// 3x3 'same' convolution of a ONE-channel image (CRNN conv0: model/crnn/crnn.py:35, 1 -> 64 on the 32 x 100 grey crop).  K = 9: nothing for a
+// GEMM to do — the op is the 39 MB output write.  A thread owns 4 output channels of 4 horizontally adjacent pixels: 18 input loads (3 x 6
+// window, L1-resident), 144 FMAs, four float4 stores (the 16 threads of a pixel write its 256-byte row: whole lines).  The gather-GEMM
+// kernel took 73 us for this layer at B = 48 (profiles/r02/launches_c3_summary_call21.txt).
+__global__ void __launch_bounds__(256)
+conv_c1_3x3_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias, float* __restrict__ y,
+                   int B, int H, int W, int Co, int ldy, int act, const float* __restrict__ act_param) {
+    const unsigned cq = Co >> 2, WG = (W + 3) >> 2;
+    const unsigned total = (unsigned)B * H * WG * cq;
+    const unsigned stride = gridDim.x * blockDim.x;          // a multiple of cq (host): the channel quad of a thread never changes
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned cqi = i % cq;
+    float4 wv[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(wk + (size_t)t * Co) + cqi);
+    const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cqi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float slope = (act == TPGSR_ACT_PRELU && act_param) ? __ldg(act_param) : 0.f;
+    for (; i < total; i += stride) {
+        const unsigned g = i / cq;
+        const unsigned t = g / WG, wg = g - t * WG;
+        const unsigned b = t / (unsigned)H, h = t - b * (unsigned)H;
+        const int w0 = (int)wg * 4;
+        float xw[3][6];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int hh = (int)h - 1 + a;
+            const bool rok = (unsigned)hh < (unsigned)H;
+            const float* row = x + ((size_t)b * H + (rok ? hh : 0)) * W;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const int ww = w0 - 1 + d;
+                xw[a][d] = (rok && (unsigned)ww < (unsigned)W) ? __ldg(row + ww) : 0.f;
+            }
+        }
+        float* yrow = y + (((size_t)b * H + h) * W + w0) * ldy + 4 * cqi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (w0 + j >= W) break;
+            float4 o = bv;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float xv = xw[a][j + d];
+                    const float4 ww = wv[a * 3 + d];
+                    o.x = fmaf(xv, ww.x, o.x); o.y = fmaf(xv, ww.y, o.y); o.z = fmaf(xv, ww.z, o.z); o.w = fmaf(xv, ww.w, o.w);
+                }
+            if (act != TPGSR_ACT_NONE) { o.x = apply_act(o.x, act, slope); o.y = apply_act(o.y, act, slope); o.z = apply_act(o.z, act, slope); o.w = apply_act(o.w, act, slope); }
+            *reinterpret_cast<float4*>(yrow + (size_t)j * ldy) = o;
+        }
+    }
+}
+
 // Generic gather-GEMM used for both the forward conv (wk = Wk_fwd, geometry as given) and the data gradient
 // (x := dY, wk = Wk_dgrad, Ci := conv Co, Co := conv Ci, ph := KH-1-ph, pw := KW-1-pw, (Hi,Wi) := dY dims, (Ho,Wo) := dX dims).
 static int igemm_splits(const ConvGeom& g, bool small_n) {
@@ -448,6 +501,14 @@ int tpgsr_conv2d_igemm_ws(const float* x, const float* wk, const float* bias, fl
     int rc = fill_geom(g, B, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, ph, pw, ldx, ldy);
     if (rc) return rc;
     if (!x || !wk || !y) return TPGSR_ERR_BAD_ARG;
+    if (Ci == 1 && KH == 3 && KW == 3 && ph == 1 && pw == 1 && Ho == Hi && Wo == Wi && (Co & 3) == 0 && Co <= 256 && 256 % (Co >> 2) == 0 &&
+        out_mode == TPGSR_OUT_NHWC && !accumulate && g.ldx == 1 && (g.ldy & 3) == 0 && (long)B * Hi * Wi * Co < (1L << 31) &&
+        !((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(wk) | reinterpret_cast<uintptr_t>(bias)) & 15)) {
+        const long threads = (long)B * Hi * ((Wi + 3) / 4) * (Co / 4);
+        const long blocks = (threads + 255) / 256;
+        conv_c1_3x3_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, stream>>>(x, wk, bias, y, B, Hi, Wi, Co, g.ldy, act, act_param);
+        return tpgsr_launch_status();
+    }
     bool vec = (Ci % 4 == 0) && (g.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     bool small_n = Co <= 16;
     int splits = igemm_splits(g, small_n);
