@@ -176,5 +176,49 @@ for B in (48, 384):
     except Exception as e:
         print('section 4 failed at B =', B, repr(e), flush=True)
         torch.cuda.synchronize()
+
+
+def _section5(B):
+    # ---- CRNN pool0 (model/crnn/crnn.py:40: MaxPool2d(2, 2) on [B,32,100,64]): reads 819 200 B/img, writes 204 800 + 204 800 (argmax) B/img;
+    #      backward reads dy + argmax, writes dx
+    x = torch.randn(B, 32, 100, 64, device=d)
+    p, arg = ops.maxpool_fwd(x, (2, 2), (2, 2), (0, 0), need_argmax=True)
+    report('maxpool_fwd (pool0)', B, 819200 + 2 * 204800, timed(lambda: ops.maxpool_fwd(x, (2, 2), (2, 2), (0, 0), need_argmax=True)))
+    dp = torch.randn_like(p)
+    report('maxpool_bwd (pool0)', B, 819200 + 2 * 204800, timed(lambda: ops.maxpool_bwd(dp, arg, tuple(x.shape), (2, 2), (2, 2), (0, 0))))
+    # ---- CRNN conv0 (model/crnn/crnn.py:35: 1 -> 64, 3x3, ReLU): reads 12 800 B/img, writes 819 200 B/img
+    g = torch.randn(B, 32, 100, 1, device=d)
+    w = torch.randn(64, 1, 3, 3, device=d) * 0.3
+    b = torch.zeros(64, device=d)
+    wf, _ = ops.pack_conv_weights(w, False)
+    report('conv0 1->64 3x3 + ReLU', B, 12800 + 819200, timed(lambda: ops.conv_fwd(g, wf, b, 64, 3, 3, 1, 1, act=ops.ACT_RELU)))
+    del x, p, arg, dp, g
+
+
+for B in (48, 384):
+    try:
+        _section5(B)
+    except Exception as e:
+        print('section 5 failed at B =', B, repr(e), flush=True)
+        torch.cuda.synchronize()
+
+
+def _section6():
+    # ---- clip + Adam over the config-3 arena (11.9 M parameters): 28 B/param
+    from tpgsr_b200 import optim as topt
+    n = 11_900_000
+    flat = torch.randn(n, device=d) * 0.01
+    gflat = torch.randn(n, device=d) * 0.001
+    opt = topt.FlatAdam(flat, n_clipped=n // 4, grads=gflat)
+    us = timed(lambda: opt.step())
+    rows.append({'kernel': 'clip + adam (3 launches)', 'batch': 0, 'algorithmic_bytes': n * 28, 'us': us, 'GBs': n * 28 / us / 1e3 if us else 0.0})
+    print(f'clip + adam, 11.9 M params     {n * 28 / 1e6:9.1f} MB  {us:9.1f} us  {(n * 28 / us / 1e3 if us else 0):8.0f} GB/s', flush=True)
+
+
+try:
+    _section6()
+except Exception as e:
+    print('section 6 failed', repr(e), flush=True)
+    torch.cuda.synchronize()
 if args.json:
     json.dump({'hbm_peak_gbs': peak, 'rows': rows}, open(args.json, 'w'), indent=1)
