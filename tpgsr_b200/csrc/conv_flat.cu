@@ -1140,15 +1140,19 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);      // same value, provably warp-uniform
         const bool leader = elect_one();
         {
-            const uint32_t idesc = tc::idesc_bf16(64, p.n_tile, 1, 1);      // both operands MN-major
+            // NPROD = 3: the X_hi and X_lo windows are ONE M = 128 operand — MN-major, the two 64-channel chunks x_plane_bytes apart (LBO) —
+            // so that [X_hi; X_lo]^T dY_hi and [X_hi; X_lo]^T dY_lo are two full-rate MMAs per K step (all four partial products) instead of
+            // three half-rate M = 64 ones: 64 instead of 96 tensor cycles.  Lanes 0..63 of the accumulator hold the X_hi rows, 64..127 the X_lo rows.
+            constexpr bool STK = NPROD == 3;
+            const uint32_t idesc = tc::idesc_bf16(STK ? 128 : 64, p.n_tile, 1, 1);      // both operands MN-major
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % p.stages;
                 mbar_wait_safe(&full[s], (i / p.stages) & 1);
                 tc::tc_fence_after();
                 const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
-                // MN-major SWIZZLE_128B: LBO = bytes between 64-element M/N chunks (one chunk for A; dY groups for B), SBO = 1024
+                // MN-major SWIZZLE_128B: LBO = bytes between 64-element M/N chunks (X hi / lo windows for the stacked A; dY groups for B), SBO = 1024
                 const uint32_t dy_hi = desc_lo(st, dy_tile_bytes), dy_lo = dy_hi + (dy_plane_bytes >> 4);
-                const uint32_t x_hi = desc_lo(st + dy_planes * dy_plane_bytes, 1024), x_lo = x_hi + (x_plane_bytes >> 4);
+                const uint32_t x_hi = desc_lo(st + dy_planes * dy_plane_bytes, STK ? x_plane_bytes : 1024), x_lo = x_hi + (x_plane_bytes >> 4);
                 for (int t = 0; t < ntaps; ++t) {
                     if (!leader) continue;
                     const uint32_t d = tmem_u + (uint32_t)(t * p.n_tile);
@@ -1156,19 +1160,19 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
                     if (i == 0) {
                         umma_lo<0>(d, xh, dy_hi, idesc);
                         if (NPROD == 3) umma_lo<1>(d, xh, dy_lo, idesc);
-                        if (NPROD >= 2) umma_lo<1>(d, xl, dy_hi, idesc);
+                        if (NPROD == 2) umma_lo<1>(d, xl, dy_hi, idesc);
 #pragma unroll
                         for (int k = 1; k < WG_KB / 16; ++k) {      // 16 K rows = 2048 bytes = 128 descriptor units
                             umma_lo<1>(d, xh + 128 * k, dy_hi + 128 * k, idesc);
                             if (NPROD == 3) umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc);
-                            if (NPROD >= 2) umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc);
+                            if (NPROD == 2) umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc);
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < WG_KB / 16; ++k) {
                             umma_lo<1>(d, xh + 128 * k, dy_hi + 128 * k, idesc);
                             if (NPROD == 3) umma_lo<1>(d, xh + 128 * k, dy_lo + 128 * k, idesc);
-                            if (NPROD >= 2) umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc);
+                            if (NPROD == 2) umma_lo<1>(d, xl + 128 * k, dy_hi + 128 * k, idesc);
                         }
                     }
                 }
@@ -1177,12 +1181,38 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
             if (leader) tc::tc_commit(tmem_full);
         }
     } else {
-        // epilogue.  M = 64 accumulators use the half-subpartition layout: row ci = 16*q + l lives in TMEM lane 32*q + l (l < 16)
         const int q = warp & 3;
         mbar_wait_safe(tmem_full, 0);
         tc::tc_fence_after();
-        const int ci = cb * 64 + 16 * q + lane;
         const int K = p.KH * p.KW * p.Ci;
+        if (NPROD == 3) {
+            // M = 128 accumulators: lane = row; rows 0..63 = X_hi channels, 64..127 = X_lo channels of the same 64 input channels.  Warps q = 2, 3
+            // hand their 32 x 32 blocks over through shared memory (the operand ring is drained), warps q = 0, 1 add theirs and store.
+            float* scratch = reinterpret_cast<float*>(smem);            // [64 rows][33]
+            const int ci3 = cb * 64 + (q & 1) * 32 + lane;
+            for (int t = 0; t < ntaps; ++t) {
+                const int tap = kh * p.KW + kw0 + t;
+                for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                    float v[32];
+                    tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.n_tile + c0), v);
+                    tc::tmem_ld_wait();
+                    if (q >= 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) scratch[((q - 2) * 32 + lane) * 33 + j] = v[j];
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (q < 2) {
+                        float* dst = p.ws + ((size_t)blockIdx.x * K + (size_t)tap * p.Ci + ci3) * p.Co + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c0 + j < p.Co) dst[j] = nkb > 0 ? v[j] + scratch[(q * 32 + lane) * 33 + j] : 0.f;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+        } else {
+        // M = 64 accumulators use the half-subpartition layout: row ci = 16*q + l lives in TMEM lane 32*q + l (l < 16)
+        const int ci = cb * 64 + 16 * q + lane;
         for (int t = 0; t < ntaps; ++t) {
             const int tap = kh * p.KW + kw0 + t;
             for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
@@ -1196,6 +1226,7 @@ conv_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_
                         if (n0 + c0 + j < p.Co) dst[j] = nkb > 0 ? v[j] : 0.f;
                 }
             }
+        }
         }
     }
     tc::tc_fence_before();
