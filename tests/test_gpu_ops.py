@@ -443,3 +443,27 @@ def test_gru_tensor_core_bptt_matches_ffma_kernel(B, H, W, vertical):
         LIB.tpgsr_gru_set_mode(1)
     for name, a, b in zip(('dgx', 'dwhh', 'dbhh', 'dbih'), outs[2], outs[0]):
         assert rel_err(a, b) < 1e-5, (name, rel_err(a, b))
+
+
+def test_bn_statistics_of_channels_with_large_mean_to_std_ratio():
+    """Train-mode BatchNorm statistics of channels whose |mean| dwarfs their standard deviation (post-ReLU maps, large conv biases): the
+    kernels sum around a per-channel pivot, so E[x^2] - mean^2 does not cancel in the fp32 partial sums (ATen: Welford)."""
+    from tpgsr_b200 import ops
+    d = _dev()
+    M, C = 48 * 16 * 64, 64
+    g = torch.Generator(device='cpu').manual_seed(5)
+    base = torch.randn(M, C, generator=g, dtype=torch.float64)
+    mean = torch.tensor([0.0, 1.0, 30.0, 300.0, -1000.0, 3000.0] * 11)[:C].double()
+    std = torch.tensor([1.0, 0.5, 0.1, 0.05, 0.02, 0.3] * 11)[:C].double()
+    x64 = base * std + mean
+    x = x64.float()
+    want_mean, want_var = x.double().mean(0), x.double().var(0, unbiased=False)
+    gamma, beta = torch.ones(C, device=d), torch.zeros(C, device=d)
+    rm, rv = torch.zeros(C, device=d), torch.ones(C, device=d)
+    mean_rstd, scale_shift = ops.bn_stats(x.to(d), gamma, beta, rm, rv, momentum=1.0)
+    got_mean = mean_rstd[0].double().cpu()
+    got_var = (1.0 / mean_rstd[1].double().cpu() ** 2) - 1e-5
+    assert float(((got_mean - want_mean).abs() / (want_mean.abs() + std)).max()) < 1e-6
+    assert float(((got_var - want_var).abs() / want_var).max()) < 2e-4, ((got_var - want_var).abs() / want_var).max()
+    # running_var (momentum 1: the unbiased batch variance itself)
+    assert float(((rv.double().cpu() - want_var * M / (M - 1)).abs() / want_var).max()) < 2e-4

@@ -12,9 +12,12 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // generic 2-value column reduction over a [M, C] row-major matrix: partial[rb][v][c]
 // ------------------------------------------------------------------------------------------------
-struct StatsF {   // sum x, sum x^2
+// sum (x - p), sum (x - p)^2 with the per-channel pivot p = x[0][c]: the variance E[x^2] - mean^2 of a channel whose |mean| is much larger than
+// its standard deviation (post-ReLU maps, large conv biases) cancels catastrophically in fp32 partial sums; around a pivot inside the data it
+// does not (ATen uses Welford).  The finalize step adds the pivot back to the mean.
+struct StatsF {
     const float* x; int ld;
-    __device__ float2 operator()(long r, int c) const { float v = x[(size_t)r * ld + c]; return make_float2(v, v * v); }
+    __device__ float2 operator()(long r, int c) const { float v = x[(size_t)r * ld + c] - __ldg(x + c); return make_float2(v, v * v); }
 };
 struct SumF {     // sum x (bias gradients)
     const float* x; int ld;
@@ -105,13 +108,14 @@ __global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int ro
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ mean_rstd, float* __restrict__ scale_shift,
                                        float* __restrict__ running_mean, float* __restrict__ running_var,
-                                       float momentum, float eps) {
+                                       float momentum, float eps, const float* __restrict__ pivot) {
     int c = blockIdx.x * 32 + threadIdx.x;
     double s1, s2;
     sum_partials(partial, row_blocks, C, c, true, s1, s2);
     if (c >= C || threadIdx.y != 0) return;
-    double mean = s1 / (double)M;
+    double mean = s1 / (double)M;                    // of x - pivot
     double var = s2 / (double)M - mean * mean;
+    mean += (double)pivot[c];
     if (var < 0.0) var = 0.0;
     float rstd = (float)(1.0 / sqrt(var + (double)eps));
     mean_rstd[c] = (float)mean;
@@ -222,10 +226,11 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int ro
 // ------------------------------------------------------------------------------------------------
 struct BnFwdFin {
     long M; const float* gamma; const float* beta; float* mean_rstd; float* scale_shift; float* running_mean; float* running_var;
-    float momentum, eps;
+    float momentum, eps; const float* pivot;
     __device__ void operator()(int c, int C, double s1, double s2) const {
-        double mean = s1 / (double)M;
+        double mean = s1 / (double)M;                // of x - pivot
         double var = s2 / (double)M - mean * mean;
+        mean += (double)pivot[c];
         if (var < 0.0) var = 0.0;
         float rstd = (float)(1.0 / sqrt(var + (double)eps));
         mean_rstd[c] = (float)mean;
@@ -730,7 +735,7 @@ int tpgsr_bn_stats(const float* x, long M, int C, int ldx, const float* gamma, c
     int rc = launch_col_reduce(StatsF{x, ldx > 0 ? ldx : C}, M, C, static_cast<float*>(workspace), rb, stream);
     if (rc) return rc;
     bn_fwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, FIN_Y), 0, stream>>>(static_cast<float*>(workspace), rb, M, C, gamma, beta,
-                                                                 mean_rstd, scale_shift, running_mean, running_var, momentum, eps);
+                                                                 mean_rstd, scale_shift, running_mean, running_var, momentum, eps, x);
     return tpgsr_launch_status();
 }
 
@@ -777,7 +782,7 @@ int tpgsr_bn_stats_fused(const float* x, long M, int C, int ldx, const float* ga
                          size_t workspace_bytes, unsigned* ticket, cudaStream_t stream) {
     if (!x || !gamma || !beta || !mean_rstd || !scale_shift || !workspace || !ticket || M <= 0 || C <= 0) return TPGSR_ERR_BAD_ARG;
     if (workspace_bytes < tpgsr_colreduce_workspace_bytes(M, C)) return TPGSR_ERR_WORKSPACE;
-    return launch_col_reduce_fin(StatsF{x, ldx > 0 ? ldx : C}, BnFwdFin{M, gamma, beta, mean_rstd, scale_shift, running_mean, running_var, momentum, eps},
+    return launch_col_reduce_fin(StatsF{x, ldx > 0 ? ldx : C}, BnFwdFin{M, gamma, beta, mean_rstd, scale_shift, running_mean, running_var, momentum, eps, x},
                                  M, C, static_cast<float*>(workspace), ticket, stream);
 }
 
