@@ -81,7 +81,12 @@ int tpgsr_conv2d_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi,
 
 /* ---- "padded-flat" tensor-core convolutions: halo rows staged ONCE in shared memory, every tap = a row offset of the same buffer ----
  * Same reference ops as tpgsr_conv2d_tc (nn.Conv2d 'same', 64 input channels: model/tsrn.py:37,376,381,467,495,43), but the
- * bf16 planes are stored [B][H+P][W+P][C] with zero pad rows/columns (tpgsr_split_bf16_flat) so shifted taps are row offsets. */
+ * bf16 planes are stored [B][H+P][W+P][C] with zero pad rows/columns (tpgsr_split_bf16_flat) so shifted taps are row offsets.
+ * tpgsr_conv2d_flat picks a plan per geometry (tpgsr_conv2d_flat_plan reports it: out[12] = 0 flat, 2 tall = 2-D halo tiles for KH x 1
+ * kernels, 3 weights-stationary = split weights resident in tensor memory for 64 -> 64 convs with 1..12 taps).
+ * Developer hooks: tpgsr_conv2d_flat_set_debug(buf) = per-CTA clock64 stamps of the next launches ([grid][16] slots; the
+ * weights-stationary kernel writes [grid][32]); tpgsr_conv2d_flat_set_debug_skip(bits): bits 0-1 skip epilogue phases (timing
+ * experiments), bit 2 no N-stacking of the weight planes, bit 3 no tall plan, bit 4 no weights-stationary plan. */
 int tpgsr_split_bf16_flat(const float* x, int ldx, void* hi, void* lo, int B, int H, int W, int C, int Cout, int P,
                           cudaStream_t stream);
 int tpgsr_conv2d_flat_supported(int B, int H, int W, int P, int Ci, int Co, int KH, int KW, int ph, int pw, int nprod);
